@@ -1,0 +1,337 @@
+"""Pin the CPU oracle against every known answer the reference's tests/doctests hold for the
+hot path.  All citations relative to /root/reference.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import evolution as EV
+from oracle import fields as F
+from oracle import lattice as L
+from oracle import observables as OB
+from oracle import operators as OP
+from oracle import spectrum as SP
+
+
+# ---------------------------------------------------------------- geometry goldens
+def test_site_order_doctest_goldens():
+    # src/core/latticevalue.jl:71-81
+    l = L.square_lattice(2, 2)
+    assert l.coords[:, 0].tolist() == [1.0, 1.0, 2.0, 2.0]
+    l2 = L.square_lattice(3, 3)
+    assert l2.coords[:, 1].tolist() == [1.0, 2.0, 3.0, 1.0, 2.0, 3.0, 1.0, 2.0, 3.0]
+
+
+def test_site_index_roundtrip():
+    # test/test_lattice.jl:96-107  site_index(l, l[i]) == i
+    for lat in (L.square_lattice(4, 3), L.honeycomb_lattice(3, 5)):
+        for i, p in enumerate(lat.pointers, start=1):
+            assert lat.site_index(p) == i
+
+
+def test_honeycomb_nn_doctest():
+    # src/lattices/bravais/nearestneighbor.jl:149-153
+    lat = L.honeycomb_lattice(5, 5)
+    assert len(lat) == 50
+    nn = L.nearest_neighbor(lat, 1)
+    assert [(t.site_indices, t.translate_uc) for t in nn] == [
+        ((1, 2), (0, -1)), ((1, 2), (-1, 0)), ((1, 2), (0, 0))]
+
+
+def test_square_nn_doctest():
+    # src/zoo/lattices.jl:52-55: NN(1) = Bravais[1,0], Bravais[0,1]
+    nn = L.nearest_neighbor(L.square_lattice(3, 3), 1)
+    assert [(t.site_indices, t.translate_uc) for t in nn] == [((0, 0), (1, 0)), ((0, 0), (0, 1))]
+
+
+_BRAILLE_4x4 = ["⎡⠪⡢⠑⢄⠀⠀⠀⠀⎤", "⎢⠑⢄⠪⡢⠑⢄⠀⠀⎥", "⎢⠀⠀⠑⢄⠪⡢⠑⢄⎥", "⎣⠀⠀⠀⠀⠑⢄⠪⡢⎦"]
+
+
+def _decode_braille(rows):
+    bits = {0x01: (0, 0), 0x02: (1, 0), 0x04: (2, 0), 0x40: (3, 0),
+            0x08: (0, 1), 0x10: (1, 1), 0x20: (2, 1), 0x80: (3, 1)}
+    n = 4 * len(rows)
+    pat = np.zeros((n, n), bool)
+    for r, row in enumerate(rows):
+        for c, ch in enumerate(row[1:-1]):
+            code = ord(ch) - 0x2800
+            for b, (dr, dc) in bits.items():
+                if code & b:
+                    pat[4 * r + dr, 2 * c + dc] = True
+    return pat
+
+
+def test_tightbinding_stored_entries_and_pattern():
+    # src/operators/system.jl:345-364: 48 stored entries (4x4), 80 (5x5) + the spy plot
+    H = OP.tightbinding_hamiltonian(L.square_lattice(4, 4))
+    assert H.nnz == 48
+    assert OP.tightbinding_hamiltonian(L.square_lattice(5, 5)).nnz == 80
+    pat = _decode_braille(_BRAILLE_4x4)
+    assert pat.sum() == 48
+    assert np.array_equal(pat, H.toarray() != 0)
+
+
+def test_spectrum_range_doctest():
+    # src/spectrum.jl:104: eigenvalues in range -3.23607 .. 3.23607
+    E, _ = SP.diagonalize(OP.tightbinding_hamiltonian(L.square_lattice(4, 4)))
+    assert round(E[0], 5) == -3.23607 and round(E[-1], 5) == 3.23607
+
+
+def test_builder_field_doctest():
+    # src/operators/builder.jl:206-223: hand-built Landau H == tightbinding_hamiltonian(field)
+    l = L.square_lattice(5, 5)
+    fld = F.LandauGauge(0.1)
+    b = OP.Builder(l, 1, fld)
+    for tr in (L.bravais(1, 0), L.bravais(0, 1)):
+        for i, ri, j, rj, fac in L.iterate_bonds(l, tr):
+            b.add_bond(i, ri, j, rj, fac, [[1]])
+    H = b.to_csc()
+    H2 = OP.tightbinding_hamiltonian(l, field=fld)
+    assert H.nnz == 80
+    assert abs(H - H2).max() == 0
+
+
+# ---------------------------------------------------------------- field known answers
+def test_line_integrals_vs_quadrature():
+    # test/test_field.jl:23-41
+    p1, p2 = (1.0, 2.0), (3.0, 4.0)
+    la, sym, flx = F.LandauGauge(0.1), F.SymmetricGauge(0.1), F.PointFlux(0.1)
+    assert flx.point == (0, 0)
+    q = F.line_integral_quadrature
+    assert la.line_integral(p1, p2) == pytest.approx(q(la, p1, p2, 100), rel=1e-12)
+    assert sym.line_integral(p1, p2) == pytest.approx(q(sym, p1, p2, 1), rel=1e-12)
+    assert sym.line_integral(p1, p2) == pytest.approx(q(sym, p1, p2, 100), rel=1e-12)
+    assert abs(q(flx, p1, p2, 1000) - flx.line_integral(p1, p2)) < 1e-8
+    fs = flx + sym
+    assert abs(q(fs, p1, p2, 1000) - fs.line_integral(p1, p2)) < 1e-8
+    gf = F.GaugeField(lambda p: (0, p[0] * 0.1), n=10)
+    assert la.line_integral(p1, p2) == pytest.approx(gf.line_integral(p1, p2), rel=1e-12)
+    with pytest.raises(ValueError):
+        F.Field().vector_potential((1, 2, 3))
+
+
+def test_point_fluxes_known_answer():
+    # test/test_field.jl:43-67
+    p1, p2 = (0.0, 0.0), (4.0, 0.0)
+    pf1, pf2 = F.PointFlux(0.1, (1, 2)), F.PointFlux(0.1, (3, 4))
+    ps1 = F.PointFluxes([0.1, 0.1], [(1, 2), (3, 4)], "singular")
+    ps3 = F.PointFluxes([0.1, 0.1], [(1, 2), (3, 4)], "axial")
+    assert abs((pf1 + pf2).line_integral(p1, p2) - ps3.line_integral(p1, p2)) < 1e-8
+    # NB: flux points ABOVE the segment y=0 -> crossing below them -> +flux each
+    assert abs(ps1.line_integral(p1, p2) - 0.2) < 1e-8
+
+
+def test_adapt_field_counts():
+    # test/test_field.jl:80-97
+    lnb = L.square_lattice(5, 5)
+    lwb = L.square_lattice(5, 5, periodic=(1, 2))
+    flx = F.PointFlux(0.1, (0.5, 0.5), "singular")
+    assert isinstance(flx.adapt(lnb), F.PointFlux)
+    assert len(flx.adapt(lwb).points) == 9
+    many = F.PointFluxes([0.1] * 25, [(x + 0.5, y + 0.5) for x in range(5) for y in range(5)], "singular")
+    assert len(many.adapt(lnb).points) == 25
+    assert len(many.adapt(lwb).points) == 9 * 25
+
+
+def test_axial_vs_singular_spectra_equal():
+    # test/test_operators.jl:211-213: a gauge change must not move the spectrum
+    l = L.square_lattice(6, 6)
+    Ea, _ = SP.diagonalize(OP.tightbinding_hamiltonian(l, field=F.PointFlux(0.3, (3.5, 3.5), "axial")))
+    Es, _ = SP.diagonalize(OP.tightbinding_hamiltonian(l, field=F.PointFlux(0.3, (3.5, 3.5), "singular")))
+    assert np.allclose(Ea, Es, atol=1e-9)   # 1e-11 fudge in the axial acos gives ~1e-6 rad
+
+
+# ---------------------------------------------------------------- assembly equivalences
+def test_qwz_assembly_equivalence():
+    # test/test_operators.jl:51-88: explicit per-site builder loop == qwz(l, field)
+    l = L.square_lattice(10, 10)
+    fld = F.LandauGauge(0.1)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    sx = np.array([[0, 1], [1, 0]], complex)
+    sy = np.array([[0, -1j], [1j, 0]], complex)
+    b = OP.Builder(l, 2, fld)
+    hx, hy = L.translation(axis=1), L.translation(axis=2)
+    for i, p in enumerate(l.pointers, start=1):
+        b.add_onsite(i, sz, 1)
+        for tr, mat in ((hx, (sz - 1j * sx) / 2), (hy, (sz - 1j * sy) / 2)):
+            rs = L.resolve_site(l, L.destination_pointer(tr, p))
+            if rs is None:
+                continue
+            j, old, fac = rs
+            b.add_bond(i, l.coords[i - 1], j, l.unitcell.site_coords(*old), fac, mat)
+    H1 = b.to_csc()
+    H = OP.qwz(l, field=fld)
+    assert abs(H - H1).max() < 1e-15
+    assert abs(H - H.conj().T).max() < 1e-15
+
+
+def test_hermitian_and_pbc_landau():
+    l = L.square_lattice(6, 6, periodic=(1,))
+    H = OP.qwz(l, field=F.LandauGauge(0.5))
+    assert abs(H - H.conj().T).max() < 1e-14
+    assert H.shape == (72, 72)
+    Hh = OP.haldane(L.honeycomb_lattice(4, 4), 1.0, 0.2, 0.1)
+    assert abs(Hh - Hh.conj().T).max() < 1e-14
+    # bulk honeycomb site: 3 NN + 6 NNN + diagonal
+    assert np.diff(Hh.tocsr().indptr).max() == 10
+
+
+# ---------------------------------------------------------------- propagator pins
+def test_evolution_known_answer():
+    # test/test_timedeps.jl:42-68 restated: KrylovKitExp and CachedExp(threshold=1e-12) both
+    # track repeated multiplication by the dense exp(-i dt H) to atol 1e-10 over 100 steps.
+    l = L.square_lattice(10, 10)
+    Hs = OP.qwz(l)
+    Hd = Hs.toarray()
+    psi = SP.groundstate(Hs)
+    ts = np.arange(0, 101) * 0.1
+    correct_ev = EV.exact_propagator(Hd, 0.1)
+    import scipy.linalg
+    assert np.abs(correct_ev - scipy.linalg.expm(-1j * 0.1 * Hd)).max() < 1e-13
+    correct, v = [], psi.copy()
+    for _ in ts:
+        correct.append(v[1])
+        v = correct_ev @ v
+    val1 = [st[0][1] for st, H, t in EV.Evolution(Hs, [psi], solver="krylov")(ts)]
+    val2 = [st[0][1] for st, H, t in EV.Evolution(Hs, [psi], solver="cachedexp", threshold=1e-12)(ts)]
+    assert np.abs(np.array(val1) - np.array(correct)).max() < 1e-10
+    assert np.abs(np.array(val2) - np.array(correct)).max() < 1e-10
+
+
+def test_myexp_default_threshold_accuracy():
+    # default CachedExp (threshold 1e-10) on config 1 is ~2e-11 per step
+    H = OP.tightbinding_hamiltonian(L.square_lattice(10, 10))
+    U, nterms = EV.myexp(H, -0.1j)
+    err = np.abs(U.toarray() - EV.exact_propagator(H, 0.1)).max()
+    assert 8 <= nterms <= 10 and err < 1e-10
+
+
+def test_stepping_semantics():
+    # src/evolution.jl:238-250,266-275: frame k pairs state(t_k) with H(t_{k-1}); first frame
+    # has dt = 0 and exposes the untouched initial state with H(t_0).
+    l = L.square_lattice(3, 3)
+    calls = []
+
+    def h(t):
+        calls.append(t)
+        return OP.tightbinding_hamiltonian(l, field=F.LandauGauge(t))
+    psi = np.zeros(9, complex)
+    psi[4] = 1
+    ev = EV.Evolution(h, [psi], solver="exact")
+    frames = list(ev([0.0, 0.5, 1.0]))
+    assert calls == [0.0, 0.0, 0.5]
+    assert np.array_equal(frames[0][0][0], psi)
+    U0 = EV.exact_propagator(h(0.0), 0.5)
+    U1 = EV.exact_propagator(h(0.5), 0.5)
+    assert np.abs(frames[2][0][0] - U1 @ (U0 @ psi)).max() < 1e-14
+    with pytest.raises(ValueError):
+        ev.step(-0.1)
+    # stateful: continues from ev.time (src/evolution.jl:269)
+    nxt = list(ev([1.5]))
+    assert nxt[0][2] == pytest.approx(1.5)
+
+
+# ---------------------------------------------------------------- observables identities
+@pytest.fixture(scope="module")
+def qwz44():
+    l = L.square_lattice(4, 4)
+    H0 = OP.qwz(l)
+    H1 = OP.qwz(l, field=F.LandauGauge(0.1))
+    P, Psi, w = SP.densitymatrix(H0, T=0.0, mu=0.0)
+    return l, H0, H1, P, Psi, w
+
+
+def test_currents_basics(qwz44):
+    # test/test_currents.jl:11-26
+    l, H0, H1, P, Psi, w = qwz44
+    s1, s2 = 6, 11
+    assert OB.density_current(H1, P, s1, s2, 2) == -OB.density_current(H1, P, s2, s1, 2)
+    assert abs(OB.density_current(H1, P, s1, s1, 2)) < np.finfo(float).eps
+    # Heisenberg equation: sum over the 4 neighbours == tr(i [H1, n_s1] P)
+    p = l.pointers[s1 - 1]
+    nbrs = [l.site_index(L.destination_pointer(L.translation(axis=a, dist=d), p))
+            for a, d in ((1, 1), (2, 1), (1, -1), (2, -1))]
+    n_op = np.zeros((32, 32), complex)
+    for a in range(2):
+        n_op[(s1 - 1) * 2 + a, (s1 - 1) * 2 + a] = 1
+    Hd = H1.toarray()
+    dens_dt = np.trace(1j * (Hd @ n_op - n_op @ Hd) @ P)
+    tot = sum(OB.density_current(H1, P, s1, t, 2) for t in nbrs)
+    assert tot == pytest.approx(dens_dt.real, abs=1e-13)
+    assert abs(dens_dt.imag) < 1e-13
+    assert OB.currents_from(H1, P, s1, 2) == pytest.approx(dens_dt.real, abs=1e-13)
+
+
+def test_state_representations_agree(qwz44):
+    # test/test_currents.jl:28-32 (ket vs psi (x) psi') + the Psi-block reformulation
+    l, H0, H1, P, Psi, w = qwz44
+    gs = SP.groundstate(H0)
+    c1 = OB.currents_matrix(H1, gs, 2)
+    c2 = OB.currents_matrix(H1, np.outer(gs, gs.conj()), 2)
+    assert abs(c1 - c2).max() < 1e-14
+    cb = OB.currents_matrix(H1, OB.State(Psi, w, block=True), 2)
+    cp = OB.currents_matrix(H1, P, 2)
+    assert abs(cb - cp).max() < 1e-13
+    assert np.allclose(OB.localdensity(OB.State(Psi, w, block=True), 2), OB.localdensity(P, 2), atol=1e-14)
+
+
+def test_currents_adjacency_equals_allpairs(qwz44):
+    # test/test_currents.jl:54-63: Currents(dc) == Currents(dc, AdjacencyMatrix(H))
+    l, H0, H1, P, Psi, w = qwz44
+    full = OB.currents_matrix(H1, P, 2)
+    adj = OB.currents_matrix(H1, P, 2, pairs=OB.site_adjacency(H1, 2))
+    assert abs(full - adj).max() == 0
+    assert abs(full + full.T).max() == 0          # antisymmetric
+    Is, Js, Vs = OB.currents_findnz(H1, P, 2)
+    assert np.all(Is < Js) and np.all(np.abs(Vs) >= 1e-10)
+
+
+def test_von_neumann_localdensity(qwz44):
+    # test/test_operators.jl:36-42: localdensity(-i [H1, P])[site] == tr(i [H1, n_site] P)
+    l, H0, H1, P, Psi, w = qwz44
+    Hd = H1.toarray()
+    dts = OB.localdensity(-1j * (Hd @ P - P @ Hd), 2)
+    site = 11
+    n_op = np.zeros((32, 32), complex)
+    for a in range(2):
+        n_op[(site - 1) * 2 + a, (site - 1) * 2 + a] = 1
+    dens_dt = np.trace(1j * (Hd @ n_op - n_op @ Hd) @ P)
+    assert dts[site - 1] == pytest.approx(dens_dt.real, abs=1e-13)
+    # continuity in the reference's sign convention: d rho_i/dt = + sum_j J_ij
+    J = OB.currents_matrix(H1, P, 2).toarray()
+    assert np.allclose(dts, J.sum(axis=1), atol=1e-12)
+
+
+def test_densitymatrix_trace():
+    # test/test_operators.jl:226-230 flavour: tr(P) = number of occupied states
+    H = OP.tightbinding_hamiltonian(L.square_lattice(4, 4))
+    P, Psi, w = SP.fermisphere(H, 3)
+    assert np.trace(P).real == pytest.approx(3)
+    P2, Psi2, w2 = SP.densitymatrix(H, T=1.0, mu=0.0)
+    assert np.allclose(w2, 1 / (np.exp(np.linalg.eigvalsh(H.toarray())) + 1))
+
+
+def test_workflow_smoke_pbc_landau_ramp():
+    # test/test_workflows.jl:29-62 (PBC 2-orbital H, Landau ramp, density + currents per frame)
+    l = L.square_lattice(6, 6, periodic=(1,))
+    rng = np.random.default_rng(0)
+    ms = rng.random(len(l))
+    A = np.array([[1, 1j], [1j, -1]], complex) / 2
+    B = np.array([[1, 1], [-1, -1]], complex) / 2
+
+    def h(t):
+        return OP.construct_hamiltonian(l, 2, [
+            (np.array([[1, 0], [0, -1]], complex), ms),
+            (A, L.translation(axis=1)), (B, L.translation(axis=2))], field=F.LandauGauge(t))
+    P0, Psi0, w0 = SP.densitymatrix(h(0.5), mu=3)
+    ev = EV.Evolution(h, [P0], solver="exact")
+    evb = EV.Evolution(h, [Psi0], solver="exact", block=True)
+    for (st, H, t), (stb, Hb, tb) in zip(ev(np.arange(0, 6) * 0.1), evb(np.arange(0, 6) * 0.1)):
+        d = OB.localdensity(st[0], 2)
+        db = OB.localdensity(OB.State(stb[0], w0, block=True), 2)
+        assert np.allclose(d, db, atol=1e-12)
+        J = OB.currents_matrix(H, st[0], 2, pairs=OB.site_adjacency(H, 2))
+        Jb = OB.currents_matrix(H, OB.State(stb[0], w0, block=True), 2, pairs=OB.site_adjacency(H, 2))
+        assert abs(J - Jb).max() < 1e-12
+        assert d.sum() == pytest.approx(np.trace(P0).real, abs=1e-10)
