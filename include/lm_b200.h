@@ -1,0 +1,174 @@
+/*
+ * lm_b200.h - C ABI of the B200-native unitary-evolution backend for LatticeModels.jl.
+ *
+ * The reference (aryavorskiy/LatticeModels.jl v1.0.7, pure Julia) has no FFI; its plug-in
+ * surface for this path is Julia multiple dispatch on the `EvolutionSolver` interface
+ * (src/evolution.jl:25-33).  The entry points below are exactly what a Julia `ccall` glue
+ * (julia/B200Backend.jl) binds; every function cites the reference
+ * interface it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  One host thread per context.
+ *  - every call returns int32 status (LM_OK = 0); lm_last_error() gives the message of the
+ *    last failing call on the calling thread (Julia side: throw(ArgumentError(msg)),
+ *    mirroring src/evolution.jl:152,239).
+ *  - complex numbers are interleaved (re, im): double[2] for precision LM_C128 (Julia
+ *    ComplexF64 / numpy complex128), float[2] for LM_C64.
+ *  - matrices handed over by the host are COLUMN-major (Julia / Fortran order).
+ *  - `index_base` is 1 for Julia arrays, 0 for C/numpy; it applies to every index array of
+ *    the call (colptr, rowval, site indices).
+ *  - host pointers are borrowed for the duration of the call; the library owns all device
+ *    memory.  Calls are synchronous with respect to host buffers (results are complete on
+ *    return); device work that produces no host result is only enqueued on the context's
+ *    stream.
+ *  - one process drives one GPU.  Multi-GPU = one process per GPU, Psi columns sharded by
+ *    the host with lm_shard_range(), H replicated; the only collective is the per-frame
+ *    all-reduce inside lm_local_density / lm_observables (NCCL, opened lazily with dlopen).
+ */
+#ifndef LM_B200_H
+#define LM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK                0
+#define LM_ERR_INVALID       1   /* bad argument (Julia: ArgumentError) */
+#define LM_ERR_CUDA          2   /* CUDA runtime failure */
+#define LM_ERR_NOT_CONVERGED 3   /* propagator did not reach `tol` (src/evolution.jl:152) */
+#define LM_ERR_NCCL          4
+#define LM_ERR_UNSUPPORTED   5
+
+#define LM_C128 0                /* complex128 arithmetic (default, parity 1e-10) */
+#define LM_C64  1                /* complex64 arithmetic (optional mode, parity 1e-5) */
+
+/* lm_step `method` */
+#define LM_METHOD_AUTO      0    /* Taylor for small ||H||dt, Chebyshev otherwise */
+#define LM_METHOD_CHEBYSHEV 1    /* Clenshaw-Chebyshev expansion of exp(-iH dt) */
+#define LM_METHOD_TAYLOR    2    /* Horner-Taylor with sub-stepping (what myexp! sums, src/evolution.jl:93-128) */
+#define LM_METHOD_LANCZOS   3    /* per-column Lanczos (KrylovKit.exponentiate semantics, src/evolution.jl:150-154) */
+
+/* gauge-field kinds for lm_ham_set_fields; each field owns 3 doubles of `params` */
+#define LM_FIELD_LANDAU            1   /* (B, -, -)         src/zoo/magneticfields.jl:15  */
+#define LM_FIELD_SYMMETRIC         2   /* (B, -, -)         src/zoo/magneticfields.jl:31  */
+#define LM_FIELD_POINTFLUX_AXIAL   3   /* (flux, px, py)    src/zoo/magneticfields.jl:72-85 */
+#define LM_FIELD_POINTFLUX_SINGULAR 4  /* (flux, px, py)    src/zoo/magneticfields.jl:89-104 */
+
+typedef struct lm_ctx   lm_ctx;
+typedef struct lm_ham   lm_ham;
+typedef struct lm_state lm_state;
+
+/* ------------------------------------------------------------------ library / errors */
+int32_t     lm_version(void);
+const char* lm_last_error(void);
+
+/* ------------------------------------------------------------------ context
+ * Replaces: nothing in the reference (it is single-process CPU).  `stream` may be NULL (the
+ * library creates its own non-blocking stream) or an existing cudaStream_t handle so that a
+ * host framework can time / order the work on its own stream. */
+int32_t lm_ctx_create(int32_t device, int32_t precision, void* stream, lm_ctx** out);
+int32_t lm_ctx_destroy(lm_ctx* ctx);
+int32_t lm_ctx_synchronize(lm_ctx* ctx);
+int32_t lm_ctx_stream(lm_ctx* ctx, void** stream_out);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int32_t lm_ctx_launch_count(lm_ctx* ctx, int64_t* count_out);
+/* CUDA-event timer on the context's stream */
+int32_t lm_timer_start(lm_ctx* ctx);
+int32_t lm_timer_stop(lm_ctx* ctx, double* elapsed_ms_out);
+
+/* multi-GPU plumbing: rank 0 calls lm_comm_unique_id, the host broadcasts the 128 bytes by
+ * any means (torch.distributed, MPI, Julia Distributed), every rank calls lm_ctx_comm_init. */
+int32_t lm_comm_unique_id(void* id128_out);
+int32_t lm_ctx_comm_init(lm_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+/* contiguous column range [begin, end) of rank `rank` out of `nranks` for M columns */
+int32_t lm_shard_range(int64_t M, int32_t rank, int32_t nranks, int64_t* begin, int64_t* end);
+
+/* ------------------------------------------------------------------ Hamiltonian
+ * Replaces the host-resident `Hamiltonian.data::SparseMatrixCSC{ComplexF64,Int}`
+ * (src/operators/system.jl:380-387) as the operand of update_solver! (src/evolution.jl:83-92,
+ * 146-149).  N = Hilbert dimension = n_sites * n_int, composite index = internal index
+ * fastest (src/operators/system.jl:16). */
+int32_t lm_ham_create_csc(lm_ctx* ctx, int64_t N, int32_t n_int,
+                          const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                          int32_t index_base, lm_ham** out);
+/* same sparsity pattern, new values (time-dependent H assembled on the host: the parity
+ * fallback for arbitrary closures t -> H(t), src/evolution.jl:43) */
+int32_t lm_ham_update_values(lm_ham* ham, const void* nzval);
+
+/* Device-resident time-dependent Hamiltonian (the AbstractTimeDependentOperator branch,
+ * src/evolution.jl:44-47,243).  Restates OperatorBuilder.setindex! + expand_bond
+ * (src/operators/builder.jl:282-309) on the device: for every directed bond b
+ *     H[src_b block, dst_b block] += amp_b * f_b ;  H[dst_b block, src_b block] += amp_b' * conj(f_b)
+ *     f_b = bfac_b * exp(-2 pi i * line_integral(field, r_src_b, r_dst_b))
+ * with r_dst the UNWRAPPED destination coordinates and bfac the boundary phase
+ * (src/core/boundaries.jl:280-289).  `amp` holds nb column-major n_int x n_int blocks,
+ * `onsite` (nullable) n_sites column-major blocks added on the diagonal, r_* are (x, y)
+ * pairs.  The Hermitian partner is NOT added for self-bonds (src == dst). */
+int32_t lm_ham_create_bonds(lm_ctx* ctx, int64_t n_sites, int32_t n_int, int64_t nb,
+                            const int32_t* src, const int32_t* dst,
+                            const double* r_src, const double* r_dst,
+                            const void* amp, const void* bfac, const void* onsite,
+                            int32_t index_base, lm_ham** out);
+/* FieldSum of nfields closed-form fields (src/operators/magneticfield.jl:100-104); params
+ * has 3 doubles per field.  nfields = 0 is NoField.  Regenerates the stored values. */
+int32_t lm_ham_set_fields(lm_ham* ham, int32_t nfields, const int32_t* kinds, const double* params);
+/* same kinds, new parameters (a few doubles per step instead of a host re-assembly) */
+int32_t lm_ham_set_field_params(lm_ham* ham, const double* params);
+
+int32_t lm_ham_dims(lm_ham* ham, int64_t* N, int32_t* n_int, int64_t* nnz, int32_t* ell_width);
+/* CSC view of the current H (pattern + values), index_base as given at creation */
+int32_t lm_ham_get_csc(lm_ham* ham, int64_t* colptr, int64_t* rowval, void* nzval);
+/* Gershgorin bounds [emin, emax] of the spectrum used by the polynomial propagators */
+int32_t lm_ham_spectral_bounds(lm_ham* ham, double* emin, double* emax);
+int32_t lm_ham_destroy(lm_ham* ham);
+
+/* ------------------------------------------------------------------ states
+ * Replaces the `.data` of the evolved `Ket` / density `Operator` (EvolutionStateType,
+ * src/evolution.jl:36).  A Psi state is the block reformulation P = Psi diag(w) Psi'
+ * (SURVEY.md section 8, Appendix B); M = 1 with w = NULL is a plain Ket.  Under multi-GPU
+ * each rank passes ITS shard of the columns (lm_shard_range). */
+int32_t lm_state_create_psi(lm_ctx* ctx, int64_t N, int64_t M, const void* psi_colmajor,
+                            const double* weights, lm_state** out);
+/* dense density matrix P (N x N column-major): stepped as U P U' (src/evolution.jl:73-78) */
+int32_t lm_state_create_dense(lm_ctx* ctx, int64_t N, const void* P_colmajor, lm_state** out);
+int32_t lm_state_copy(lm_state* state, lm_state** out);           /* copy(state), src/evolution.jl:193 */
+int32_t lm_state_dims(lm_state* state, int64_t* N, int64_t* M, int32_t* is_dense);
+int32_t lm_state_download_psi(lm_state* state, void* psi_colmajor_out);
+/* dense P (N x N column-major); for a Psi state materialises Psi diag(w) Psi' (local columns
+ * only) - the escape hatch for arbitrary operator algebra on the yielded state */
+int32_t lm_state_download_dense(lm_state* state, void* P_colmajor_out);
+int32_t lm_state_destroy(lm_state* state);
+
+/* ------------------------------------------------------------------ hot path
+ * lm_step replaces step!(solver, state.data, cache) (src/evolution.jl:69-78,150-154):
+ * Psi <- exp(-i H dt) Psi, or P <- U P U' for a dense state.  dt < 0 is allowed here (the
+ * negative-time-step guard lives in step!(evol, dt), src/evolution.jl:239, host side).
+ * n_matvec_out (nullable) receives the number of H applications executed (the K of
+ * SURVEY.md section 8d). */
+int32_t lm_step(lm_ham* ham, lm_state* state, double dt, double tol, int32_t method,
+                int32_t* n_matvec_out);
+/* Y = H X on device-resident states (bandwidth sweep / unit parity) and on host buffers */
+int32_t lm_spmm_state(lm_ham* ham, lm_state* x, lm_state* y);
+int32_t lm_spmm(lm_ham* ham, const void* X_colmajor, void* Y_colmajor, int64_t N, int64_t M);
+
+/* ------------------------------------------------------------------ observables
+ * localdensity (src/operators/latticeutils.jl:41-45): rho_i = sum_alpha Re P[i', i'].
+ * All-reduced over ranks when a communicator is attached. */
+int32_t lm_local_density(lm_state* state, int32_t n_int, double* rho_out /* n_sites */);
+/* DensityCurrents over H's own site-level sparsity, pairs i < j ordered like findnz of a CSC
+ * matrix filtered by I < J (src/currents.jl:173-177); curr[i,j] = sum_ab 2 Im(H[i',j'] P[j',i'])
+ * (src/zoo/currents.jl:92-102).  lm_currents_pairs returns the static pair list. */
+int32_t lm_currents_npairs(lm_ham* ham, int64_t* npairs);
+int32_t lm_currents_pairs(lm_ham* ham, int32_t* I, int32_t* J);
+/* fused pass: density (nullable) and all pair currents (nullable) from ONE read of Psi */
+int32_t lm_observables(lm_ham* ham, lm_state* state, double* rho_out, double* J_out);
+/* Currents(curr, bonds) (src/currents.jl:238-255) on a host-given bond list */
+int32_t lm_bond_currents(lm_ham* ham, lm_state* state, int64_t nb, const int32_t* I,
+                         const int32_t* J, double* J_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM_B200_H */

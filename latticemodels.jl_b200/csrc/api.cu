@@ -1,0 +1,1104 @@
+// C ABI of the B200 evolution backend (include/lm_b200.h): host-side orchestration of the
+// kernels in kernels.cuh.  No torch types, no CPU compute fallback: every numerical result
+// returned through this ABI is produced by the CUDA kernels.
+#include "../../include/lm_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace lm;
+typedef std::complex<double> zc;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(expr)                                                                           \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(LM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+    } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) return fail(LM_ERR_INVALID, msg); } while (0)
+#define FWD(expr) do { int _s = (expr); if (_s != LM_OK) return _s; } while (0)
+
+extern "C" const char* lm_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t lm_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (only needed for nranks > 1)
+// ------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void* ncclComm_h;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+    int (*CommInitRank)(ncclComm_h*, int, ncclUniqueId_t, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_h) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return LM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) return fail(LM_ERR_NCCL, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId_t*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_h*, int, ncclUniqueId_t, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(ncclComm_h))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(LM_ERR_NCCL, "libnccl lacks required symbols");
+    return LM_OK;
+}
+#define NCK(expr)                                                                          \
+    do {                                                                                   \
+        int _r = (expr);                                                                   \
+        if (_r != 0)                                                                       \
+            return fail(LM_ERR_NCCL, std::string(#expr) + ": " +                           \
+                        (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error")); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct lm_ctx {
+    int device = 0;
+    int precision = LM_C128;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_h comm = nullptr;
+    int rank = 0, nranks = 1;
+    void* h_pinned = nullptr; size_t pinned_bytes = 0;   // staging for small D2H/H2D
+    void* d_stage = nullptr; size_t stage_bytes = 0;      // staging for layout changes
+    int l2_bytes = 0;
+    struct lm_ham* dens_helper = nullptr;                 // pattern-less ham owning density scratch
+    size_t esz() const { return precision == LM_C128 ? 16 : 8; }
+};
+
+struct Plan {          // cached propagator plan (host-side Bessel / Taylor bookkeeping)
+    bool valid = false; double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method_req = -1;
+    int method = 0, nsub = 1, K = 1; std::vector<zc> coef;
+};
+
+struct lm_ham {
+    lm_ctx* ctx = nullptr;
+    Plan plan;
+    long long N = 0, n_sites = 0; int n_int = 1; int W = 0; long long nnz = 0;
+    int index_base = 0;
+    long long band = 0;
+    int* d_cols = nullptr; void* d_vals = nullptr;            // ELL [N][W]
+    unsigned char* d_upper = nullptr;                          // ELL flag: site(col) > site(row)
+    // CSC view (pattern in the caller's index base) and its map into the ELL array
+    std::vector<long long> colptr, rowval; int* d_csc2ell = nullptr; void* d_nz = nullptr;
+    // site pairs (I < J) in findnz order and the ELL entries of every pair
+    long long npairs = 0; std::vector<int> pairI, pairJ; int* d_pair_ptr = nullptr; int* d_pair_ent = nullptr;
+    // bond mode
+    bool bond_mode = false; long long nb = 0;
+    double* d_r = nullptr; double2* d_bfac = nullptr; double2* d_phase = nullptr;
+    double2* d_static = nullptr; int* d_cptr = nullptr; int* d_cbond = nullptr; double2* d_camp = nullptr;
+    int nfields = 0; int* d_kinds = nullptr; double* d_params = nullptr;
+    // spectral enclosure
+    double emin = 0, emax = 0, norm_inf = 0;
+    long long version = 0;
+    // observable scratch
+    double* d_dens = nullptr; double2* d_G = nullptr; double* d_obs = nullptr;
+};
+
+struct lm_state {
+    lm_ctx* ctx = nullptr;
+    long long N = 0, M = 0, ld = 0; bool dense = false;
+    void* d_x = nullptr; double* d_w = nullptr;
+    void* d_s1 = nullptr; void* d_s2 = nullptr;               // propagator scratch
+    // dense path: cached propagator U (row-major [N][ld])
+    void* d_U = nullptr; lm_ham* U_ham = nullptr; long long U_version = -1; double U_dt = 0, U_tol = 0; int U_method = -1;
+};
+
+static int set_dev(lm_ctx* c) { CK(cudaSetDevice(c->device)); return LM_OK; }
+static int ensure_pinned(lm_ctx* c, size_t bytes) {
+    if (c->pinned_bytes >= bytes) return LM_OK;
+    if (c->h_pinned) CK(cudaFreeHost(c->h_pinned));
+    c->h_pinned = nullptr; c->pinned_bytes = 0;
+    CK(cudaMallocHost(&c->h_pinned, bytes));
+    c->pinned_bytes = bytes;
+    return LM_OK;
+}
+static int ensure_stage(lm_ctx* c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return LM_OK;
+    if (c->d_stage) CK(cudaFree(c->d_stage));
+    c->d_stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return LM_OK;
+}
+static long long pad_ld(long long M) { return M >= 32 ? ((M + 7) / 8) * 8 : M; }
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t lm_ctx_create(int32_t device, int32_t precision, void* stream, lm_ctx** out) {
+    REQUIRE(out, "lm_ctx_create: out is NULL");
+    REQUIRE(precision == LM_C128 || precision == LM_C64, "lm_ctx_create: precision must be LM_C128 or LM_C64");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "lm_ctx_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    lm_ctx* c = new lm_ctx();
+    c->device = device; c->precision = precision;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device));
+    *out = c;
+    return LM_OK;
+}
+static void ham_free(lm_ham* h);
+extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
+    if (!c) return LM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->dens_helper) { ham_free(c->dens_helper); c->dens_helper = nullptr; }
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->d_stage) cudaFree(c->d_stage);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LM_OK;
+}
+extern "C" int32_t lm_ctx_synchronize(lm_ctx* c) {
+    REQUIRE(c, "lm_ctx_synchronize: ctx is NULL");
+    FWD(set_dev(c)); CK(cudaStreamSynchronize(c->stream)); return LM_OK;
+}
+extern "C" int32_t lm_ctx_stream(lm_ctx* c, void** s) { REQUIRE(c && s, "lm_ctx_stream: NULL"); *s = (void*)c->stream; return LM_OK; }
+extern "C" int32_t lm_ctx_launch_count(lm_ctx* c, int64_t* n) { REQUIRE(c && n, "lm_ctx_launch_count: NULL"); *n = c->launches; return LM_OK; }
+extern "C" int32_t lm_timer_start(lm_ctx* c) { REQUIRE(c, "lm_timer_start: NULL"); FWD(set_dev(c)); CK(cudaEventRecord(c->ev0, c->stream)); return LM_OK; }
+extern "C" int32_t lm_timer_stop(lm_ctx* c, double* ms) {
+    REQUIRE(c && ms, "lm_timer_stop: NULL"); FWD(set_dev(c));
+    CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+    float f = 0; CK(cudaEventElapsedTime(&f, c->ev0, c->ev1)); *ms = f; return LM_OK;
+}
+extern "C" int32_t lm_comm_unique_id(void* id) {
+    REQUIRE(id, "lm_comm_unique_id: NULL"); FWD(nccl_load());
+    ncclUniqueId_t u; NCK(g_nccl.GetUniqueId(&u)); memcpy(id, &u, 128); return LM_OK;
+}
+extern "C" int32_t lm_ctx_comm_init(lm_ctx* c, const void* id, int32_t rank, int32_t nranks) {
+    REQUIRE(c && id, "lm_ctx_comm_init: NULL");
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "lm_ctx_comm_init: bad rank/nranks");
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return LM_OK;
+    FWD(nccl_load()); FWD(set_dev(c));
+    ncclUniqueId_t u; memcpy(&u, id, 128);
+    NCK(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    return LM_OK;
+}
+extern "C" int32_t lm_shard_range(int64_t M, int32_t rank, int32_t nranks, int64_t* b, int64_t* e) {
+    REQUIRE(b && e && nranks >= 1 && rank >= 0 && rank < nranks && M >= 0, "lm_shard_range: bad arguments");
+    // contiguous ranges [k*M/G, (k+1)*M/G)   
+    *b = (M * (int64_t)rank) / nranks; *e = (M * (int64_t)(rank + 1)) / nranks; return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Hamiltonian
+// ------------------------------------------------------------------------------------------
+static void ham_free(lm_ham* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
+                    h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
+                    h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete h;
+}
+extern "C" int32_t lm_ham_destroy(lm_ham* h) { ham_free(h); return LM_OK; }
+
+struct Entry { long long row, col; int bond; zc amp; };   // bond: INT_MIN = static value
+
+// Shared tail of both constructors: `ent` = unique (row, col) pattern sorted by (row, col),
+// builds ELL, CSC view, pair tables.  vals_host (N*W complex128, ELL order) optional.
+static int ham_finish_pattern(lm_ham* h, const std::vector<long long>& rows, const std::vector<long long>& cols_in,
+                              std::vector<long long>& ell_pos /* out: ELL index per unique entry */) {
+    lm_ctx* c = h->ctx;
+    const long long N = h->N, nu = (long long)rows.size();
+    std::vector<int> cnt(N, 0);
+    for (long long e = 0; e < nu; ++e) cnt[rows[e]]++;
+    int W = 1;
+    for (long long i = 0; i < N; ++i) W = std::max(W, cnt[i]);
+    h->W = W; h->nnz = nu;
+    REQUIRE(N * (long long)W < 2147483647LL, "Hamiltonian too large for int32 ELL indexing");
+    std::vector<int> ecols((size_t)N * W);
+    for (long long i = 0; i < N; ++i) for (int k = 0; k < W; ++k) ecols[i * W + k] = (int)i;
+    std::vector<int> fill(N, 0);
+    ell_pos.resize(nu);
+    long long band = 0;
+    for (long long e = 0; e < nu; ++e) {
+        const long long i = rows[e];
+        const long long p = i * W + fill[i]++;
+        ecols[p] = (int)cols_in[e];
+        ell_pos[e] = p;
+        band = std::max(band, std::llabs(i - cols_in[e]));
+    }
+    h->band = band;
+    // CSC view: sort entries by (col, row)
+    std::vector<long long> order(nu);
+    for (long long e = 0; e < nu; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) {
+        return cols_in[a] != cols_in[b] ? cols_in[a] < cols_in[b] : rows[a] < rows[b]; });
+    h->colptr.assign(N + 1, 0); h->rowval.resize(nu);
+    std::vector<int> csc2ell(nu);
+    for (long long q = 0; q < nu; ++q) {
+        const long long e = order[q];
+        h->colptr[cols_in[e] + 1]++;
+        h->rowval[q] = rows[e] + h->index_base;
+        csc2ell[q] = (int)ell_pos[e];
+    }
+    for (long long j = 0; j < N; ++j) h->colptr[j + 1] += h->colptr[j];
+    for (long long j = 0; j <= N; ++j) h->colptr[j] += h->index_base;
+    // pair tables: site(row) < site(col), ordered (J, I)
+    const int n = h->n_int;
+    std::vector<unsigned char> upper((size_t)N * W, 0);
+    struct PE { long long key; int ent; };
+    std::vector<PE> pe;
+    for (long long e = 0; e < nu; ++e) {
+        const long long si = rows[e] / n, sj = cols_in[e] / n;
+        if (si < sj) { upper[ell_pos[e]] = 1; pe.push_back({sj * h->n_sites + si, (int)ell_pos[e]}); }
+    }
+    std::stable_sort(pe.begin(), pe.end(), [](const PE& a, const PE& b) { return a.key < b.key; });
+    std::vector<int> pptr, pent(pe.size());
+    h->pairI.clear(); h->pairJ.clear();
+    long long last = -1;
+    for (size_t q = 0; q < pe.size(); ++q) {
+        if (pe[q].key != last) {
+            pptr.push_back((int)q); last = pe[q].key;
+            h->pairI.push_back((int)(pe[q].key % h->n_sites)); h->pairJ.push_back((int)(pe[q].key / h->n_sites));
+        }
+        pent[q] = pe[q].ent;
+    }
+    pptr.push_back((int)pe.size());
+    h->npairs = (long long)h->pairI.size();
+
+    FWD(set_dev(c));
+    cudaStream_t s = c->stream;
+    CK(cudaMalloc(&h->d_cols, sizeof(int) * (size_t)N * W));
+    CK(cudaMalloc(&h->d_vals, c->esz() * (size_t)N * W));
+    CK(cudaMalloc(&h->d_upper, (size_t)N * W));
+    CK(cudaMalloc(&h->d_csc2ell, sizeof(int) * std::max<size_t>(1, nu)));
+    CK(cudaMalloc(&h->d_nz, c->esz() * std::max<size_t>(1, nu)));
+    CK(cudaMalloc(&h->d_pair_ptr, sizeof(int) * pptr.size()));
+    CK(cudaMalloc(&h->d_pair_ent, sizeof(int) * std::max<size_t>(1, pent.size())));
+    CK(cudaMemcpyAsync(h->d_cols, ecols.data(), sizeof(int) * ecols.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_upper, upper.data(), upper.size(), cudaMemcpyHostToDevice, s));
+    if (nu) CK(cudaMemcpyAsync(h->d_csc2ell, csc2ell.data(), sizeof(int) * nu, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_pair_ptr, pptr.data(), sizeof(int) * pptr.size(), cudaMemcpyHostToDevice, s));
+    if (!pent.empty()) CK(cudaMemcpyAsync(h->d_pair_ent, pent.data(), sizeof(int) * pent.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_vals, 0, c->esz() * (size_t)N * W, s));
+    CK(cudaMalloc(&h->d_dens, sizeof(double) * (size_t)N));
+    CK(cudaMalloc(&h->d_G, sizeof(double2) * (size_t)N * W));
+    CK(cudaMalloc(&h->d_obs, sizeof(double) * (size_t)(h->n_sites + h->npairs + 1)));
+    CK(cudaMemsetAsync(h->d_G, 0, sizeof(double2) * (size_t)N * W, s));
+    CK(cudaStreamSynchronize(s));   // host vectors go out of scope
+    return LM_OK;
+}
+
+template <typename T>
+static void bounds_from_csc(lm_ham* h, const void* nzval) {
+    // Gershgorin: [min_i (H_ii - R_i), max_i (H_ii + R_i)], R_i = sum_{j != i} |H_ij|
+    const long long N = h->N;
+    std::vector<double> diag(N, 0.0), rad(N, 0.0);
+    const std::complex<T>* v = (const std::complex<T>*)nzval;
+    const int base = h->index_base;
+    for (long long j = 0; j < N; ++j)
+        for (long long q = h->colptr[j] - base; q < h->colptr[j + 1] - base; ++q) {
+            const long long i = h->rowval[q] - base;
+            if (i == j) diag[i] += (double)v[q].real(); else rad[i] += std::abs(std::complex<double>(v[q]));
+        }
+    double lo = 1e300, hi = -1e300, nrm = 0;
+    for (long long i = 0; i < N; ++i) {
+        lo = std::min(lo, diag[i] - rad[i]); hi = std::max(hi, diag[i] + rad[i]);
+        nrm = std::max(nrm, std::fabs(diag[i]) + rad[i]);
+    }
+    if (N == 0) { lo = hi = 0; }
+    h->emin = lo; h->emax = hi; h->norm_inf = nrm;
+}
+
+template <typename T>
+static int upload_nzval(lm_ham* h, const void* nzval) {
+    lm_ctx* c = h->ctx;
+    using T2 = typename cx2<T>::type;
+    if (h->nnz == 0) return LM_OK;
+    const size_t bytes = sizeof(T2) * (size_t)h->nnz;
+    CK(cudaMemcpyAsync(h->d_nz, nzval, bytes, cudaMemcpyHostToDevice, c->stream));
+    const int th = 256; const long long bl = (h->nnz + th - 1) / th;
+    k_scatter_vals<T><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const T2*)h->d_nz, h->d_csc2ell, (T2*)h->d_vals);
+    c->launches++;
+    CK(cudaGetLastError());
+    // the host buffer is borrowed only for the duration of the call
+    CK(cudaStreamSynchronize(c->stream));
+    return LM_OK;
+}
+
+extern "C" int32_t lm_ham_create_csc(lm_ctx* c, int64_t N, int32_t n_int, const int64_t* colptr,
+                                     const int64_t* rowval, const void* nzval, int32_t index_base,
+                                     lm_ham** out) {
+    REQUIRE(c && out && colptr && nzval, "lm_ham_create_csc: NULL argument");
+    REQUIRE(N > 0 && n_int >= 1 && N % n_int == 0, "lm_ham_create_csc: N must be a positive multiple of n_int");
+    REQUIRE(index_base == 0 || index_base == 1, "lm_ham_create_csc: index_base must be 0 or 1");
+    REQUIRE(colptr[0] == index_base, "lm_ham_create_csc: colptr[0] != index_base");
+    const long long nnz = colptr[N] - index_base;
+    REQUIRE(nnz >= 0 && (nnz == 0 || rowval), "lm_ham_create_csc: bad colptr/rowval");
+    lm_ham* h = new lm_ham();
+    h->ctx = c; h->N = N; h->n_int = n_int; h->n_sites = N / n_int; h->index_base = index_base;
+    // (row, col) sorted by (row, col): bucket by row, columns ascend because CSC columns do
+    std::vector<long long> cnt(N + 1, 0);
+    for (long long j = 0; j < N; ++j) {
+        if (colptr[j + 1] < colptr[j]) { delete h; return fail(LM_ERR_INVALID, "lm_ham_create_csc: colptr not monotone"); }
+        for (long long q = colptr[j] - index_base; q < colptr[j + 1] - index_base; ++q) {
+            const long long i = rowval[q] - index_base;
+            if (i < 0 || i >= N) { delete h; return fail(LM_ERR_INVALID, "lm_ham_create_csc: row index out of range"); }
+            cnt[i + 1]++;
+        }
+    }
+    for (long long i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+    std::vector<long long> rows(nnz), cols(nnz), src(nnz);
+    {
+        std::vector<long long> fillp(cnt.begin(), cnt.end() - 1);
+        for (long long j = 0; j < N; ++j)
+            for (long long q = colptr[j] - index_base; q < colptr[j + 1] - index_base; ++q) {
+                const long long i = rowval[q] - index_base;
+                const long long p = fillp[i]++;
+                rows[p] = i; cols[p] = j; src[p] = q;
+            }
+    }
+    for (long long p = 1; p < nnz; ++p)
+        if (rows[p] == rows[p - 1] && cols[p] == cols[p - 1]) { delete h; return fail(LM_ERR_INVALID, "lm_ham_create_csc: duplicate entries"); }
+    std::vector<long long> ell_pos;
+    int st = ham_finish_pattern(h, rows, cols, ell_pos);
+    if (st != LM_OK) { ham_free(h); return st; }
+    // ham_finish_pattern sorted its own CSC view by (col,row) = the caller's order when the
+    // caller's rows ascend inside each column; re-map explicitly so that ANY row order works.
+    {
+        std::vector<int> csc2ell(nnz);
+        for (long long p = 0; p < nnz; ++p) csc2ell[src[p]] = (int)ell_pos[p];
+        for (long long q = 0; q < nnz; ++q) h->rowval[q] = rowval[q];
+        if (nnz) { cudaError_t e = cudaMemcpy(h->d_csc2ell, csc2ell.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice);
+                   if (e != cudaSuccess) { ham_free(h); return fail(LM_ERR_CUDA, cudaGetErrorString(e)); } }
+    }
+    st = lm_ham_update_values(h, nzval);
+    if (st != LM_OK) { ham_free(h); return st; }
+    *out = h;
+    return LM_OK;
+}
+
+extern "C" int32_t lm_ham_update_values(lm_ham* h, const void* nzval) {
+    REQUIRE(h && nzval, "lm_ham_update_values: NULL argument");
+    REQUIRE(!h->bond_mode, "lm_ham_update_values: Hamiltonian was created from bonds; use lm_ham_set_field_params");
+    FWD(set_dev(h->ctx));
+    if (h->ctx->precision == LM_C128) { bounds_from_csc<double>(h, nzval); FWD(upload_nzval<double>(h, nzval)); }
+    else { bounds_from_csc<float>(h, nzval); FWD(upload_nzval<float>(h, nzval)); }
+    h->version++;
+    return LM_OK;
+}
+
+static int ham_regen(lm_ham* h) {
+    lm_ctx* c = h->ctx;
+    const int th = 256;
+    if (h->nb > 0) {
+        k_bond_phase<<<(unsigned)((h->nb + th - 1) / th), th, 0, c->stream>>>(
+            h->nb, h->d_r, h->d_bfac, h->nfields, h->d_kinds, h->d_params, h->d_phase);
+        c->launches++;
+    }
+    const long long E = h->N * h->W;
+    if (c->precision == LM_C128)
+        k_assemble<double><<<(unsigned)((E + th - 1) / th), th, 0, c->stream>>>(E, h->d_static, h->d_cptr, h->d_cbond, h->d_camp, h->d_phase, (double2*)h->d_vals);
+    else
+        k_assemble<float><<<(unsigned)((E + th - 1) / th), th, 0, c->stream>>>(E, h->d_static, h->d_cptr, h->d_cbond, h->d_camp, h->d_phase, (float2*)h->d_vals);
+    c->launches++;
+    CK(cudaGetLastError());
+    h->version++;
+    return LM_OK;
+}
+
+extern "C" int32_t lm_ham_create_bonds(lm_ctx* c, int64_t n_sites, int32_t n_int, int64_t nb,
+                                       const int32_t* src, const int32_t* dst, const double* r_src,
+                                       const double* r_dst, const void* amp_, const void* bfac_,
+                                       const void* onsite_, int32_t index_base, lm_ham** out) {
+    REQUIRE(c && out, "lm_ham_create_bonds: NULL argument");
+    REQUIRE(n_sites > 0 && n_int >= 1 && nb >= 0, "lm_ham_create_bonds: bad sizes");
+    REQUIRE(nb == 0 || (src && dst && r_src && r_dst && amp_), "lm_ham_create_bonds: NULL bond arrays");
+    REQUIRE(index_base == 0 || index_base == 1, "lm_ham_create_bonds: index_base must be 0 or 1");
+    REQUIRE(nb < 2147483647LL, "lm_ham_create_bonds: too many bonds");
+    const zc* amp = (const zc*)amp_; const zc* bfac = (const zc*)bfac_; const zc* onsite = (const zc*)onsite_;
+    const int n = n_int; const long long N = n_sites * n;
+    std::vector<Entry> ent;
+    ent.reserve((size_t)nb * n * n * 2 + (onsite ? (size_t)N * n : 0));
+    const int STATIC = -2147483647 - 1;
+    if (onsite)
+        for (long long s = 0; s < n_sites; ++s)
+            for (int b = 0; b < n; ++b) for (int a = 0; a < n; ++a) {
+                const zc v = onsite[s * n * n + b * n + a];     // column-major block: [a, b]
+                if (v != zc(0, 0)) ent.push_back({s * n + a, s * n + b, STATIC, v});
+            }
+    for (long long q = 0; q < nb; ++q) {
+        const long long i = src[q] - index_base, j = dst[q] - index_base;
+        REQUIRE(i >= 0 && i < n_sites && j >= 0 && j < n_sites, "lm_ham_create_bonds: site index out of range");
+        for (int b = 0; b < n; ++b) for (int a = 0; a < n; ++a) {
+            const zc v = amp[q * n * n + b * n + a];            // amp[a, b]
+            if (v == zc(0, 0)) continue;                        // builder.jl:64
+            ent.push_back({i * n + a, j * n + b, (int)q, v});
+            if (i != j) ent.push_back({j * n + b, i * n + a, ~(int)q, std::conj(v)});
+        }
+    }
+    std::stable_sort(ent.begin(), ent.end(), [](const Entry& x, const Entry& y) {
+        return x.row != y.row ? x.row < y.row : x.col < y.col; });
+    std::vector<long long> rows, cols; std::vector<int> first;   // unique pattern
+    for (size_t e = 0; e < ent.size(); ++e)
+        if (e == 0 || ent[e].row != ent[e - 1].row || ent[e].col != ent[e - 1].col) {
+            rows.push_back(ent[e].row); cols.push_back(ent[e].col); first.push_back((int)e);
+        }
+    first.push_back((int)ent.size());
+    lm_ham* h = new lm_ham();
+    h->ctx = c; h->N = N; h->n_int = n; h->n_sites = n_sites; h->index_base = index_base;
+    h->bond_mode = true; h->nb = nb;
+    std::vector<long long> ell_pos;
+    int st = ham_finish_pattern(h, rows, cols, ell_pos);
+    if (st != LM_OK) { ham_free(h); return st; }
+    const long long E = N * h->W;
+    std::vector<zc> stat(E, zc(0, 0));
+    std::vector<int> cptr(E + 1, 0), cbond; std::vector<zc> camp;
+    // counting pass
+    for (size_t u = 0; u + 1 < first.size(); ++u) {
+        const long long p = ell_pos[u];
+        for (int e = first[u]; e < first[u + 1]; ++e) if (ent[e].bond != STATIC) cptr[p + 1]++;
+    }
+    for (long long p = 0; p < E; ++p) cptr[p + 1] += cptr[p];
+    cbond.resize(cptr[E]); camp.resize(cptr[E]);
+    // Gershgorin enclosure valid for EVERY field configuration: |sum amp f| <= sum |amp|
+    std::vector<double> diag(N, 0.0), rad(N, 0.0);
+    {
+        std::vector<int> fillc(cptr.begin(), cptr.end() - 1);
+        for (size_t u = 0; u + 1 < first.size(); ++u) {
+            const long long p = ell_pos[u];
+            for (int e = first[u]; e < first[u + 1]; ++e) {
+                if (ent[e].bond == STATIC) {
+                    stat[p] += ent[e].amp;
+                    if (ent[e].row == ent[e].col) diag[ent[e].row] += ent[e].amp.real();
+                    else rad[ent[e].row] += std::abs(ent[e].amp);
+                } else {
+                    const int f = fillc[p]++;
+                    cbond[f] = ent[e].bond; camp[f] = ent[e].amp;
+                    rad[ent[e].row] += std::abs(ent[e].amp);
+                }
+            }
+        }
+    }
+    double lo = 1e300, hi = -1e300, nrm = 0;
+    for (long long i = 0; i < N; ++i) {
+        lo = std::min(lo, diag[i] - rad[i]); hi = std::max(hi, diag[i] + rad[i]);
+        nrm = std::max(nrm, std::fabs(diag[i]) + rad[i]);
+    }
+    h->emin = lo; h->emax = hi; h->norm_inf = nrm;
+    // bond geometry
+    std::vector<double> r4((size_t)nb * 4);
+    std::vector<zc> bf(nb, zc(1, 0));
+    for (long long q = 0; q < nb; ++q) {
+        r4[4 * q] = r_src[2 * q]; r4[4 * q + 1] = r_src[2 * q + 1];
+        r4[4 * q + 2] = r_dst[2 * q]; r4[4 * q + 3] = r_dst[2 * q + 1];
+        if (bfac) bf[q] = bfac[q];
+    }
+    cudaStream_t s = c->stream;
+    auto up = [&](void** d, const void* src_, size_t bytes) -> int {
+        CK(cudaMalloc(d, std::max<size_t>(bytes, 16)));
+        if (bytes) CK(cudaMemcpyAsync(*d, src_, bytes, cudaMemcpyHostToDevice, s));
+        return LM_OK;
+    };
+    st = up((void**)&h->d_r, r4.data(), sizeof(double) * r4.size());
+    if (st == LM_OK) st = up((void**)&h->d_bfac, bf.data(), sizeof(zc) * bf.size());
+    if (st == LM_OK) st = up((void**)&h->d_static, stat.data(), sizeof(zc) * stat.size());
+    if (st == LM_OK) st = up((void**)&h->d_cptr, cptr.data(), sizeof(int) * cptr.size());
+    if (st == LM_OK) st = up((void**)&h->d_cbond, cbond.data(), sizeof(int) * cbond.size());
+    if (st == LM_OK) st = up((void**)&h->d_camp, camp.data(), sizeof(zc) * camp.size());
+    if (st == LM_OK) { cudaError_t e = cudaMalloc((void**)&h->d_phase, sizeof(double2) * std::max<long long>(1, nb)); if (e != cudaSuccess) st = fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    if (st == LM_OK) st = ham_regen(h);
+    if (st == LM_OK) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) st = fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    if (st != LM_OK) { ham_free(h); return st; }
+    *out = h;
+    return LM_OK;
+}
+
+extern "C" int32_t lm_ham_set_fields(lm_ham* h, int32_t nfields, const int32_t* kinds, const double* params) {
+    REQUIRE(h, "lm_ham_set_fields: NULL");
+    REQUIRE(h->bond_mode, "lm_ham_set_fields: Hamiltonian was not created from bonds");
+    REQUIRE(nfields >= 0 && (nfields == 0 || (kinds && params)), "lm_ham_set_fields: bad arguments");
+    for (int f = 0; f < nfields; ++f)
+        REQUIRE(kinds[f] >= LM_FIELD_LANDAU && kinds[f] <= LM_FIELD_POINTFLUX_SINGULAR, "lm_ham_set_fields: unknown field kind");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h->d_kinds) CK(cudaFree(h->d_kinds));
+    if (h->d_params) CK(cudaFree(h->d_params));
+    h->d_kinds = nullptr; h->d_params = nullptr; h->nfields = nfields;
+    if (nfields) {
+        CK(cudaMalloc(&h->d_kinds, sizeof(int) * nfields));
+        CK(cudaMalloc(&h->d_params, sizeof(double) * 3 * nfields));
+        CK(cudaMemcpy(h->d_kinds, kinds, sizeof(int) * nfields, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_params, params, sizeof(double) * 3 * nfields, cudaMemcpyHostToDevice));
+    }
+    return ham_regen(h);
+}
+extern "C" int32_t lm_ham_set_field_params(lm_ham* h, const double* params) {
+    REQUIRE(h, "lm_ham_set_field_params: NULL");
+    REQUIRE(h->bond_mode, "lm_ham_set_field_params: Hamiltonian was not created from bonds");
+    REQUIRE(h->nfields == 0 || params, "lm_ham_set_field_params: params is NULL");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    if (h->nfields) {
+        // a few doubles: stage through pinned memory so the copy is ordered on the stream
+        FWD(ensure_pinned(c, 4096 + sizeof(double) * 3 * h->nfields));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(c->h_pinned, params, sizeof(double) * 3 * h->nfields);
+        CK(cudaMemcpyAsync(h->d_params, c->h_pinned, sizeof(double) * 3 * h->nfields, cudaMemcpyHostToDevice, c->stream));
+    }
+    return ham_regen(h);
+}
+extern "C" int32_t lm_ham_dims(lm_ham* h, int64_t* N, int32_t* n_int, int64_t* nnz, int32_t* W) {
+    REQUIRE(h, "lm_ham_dims: NULL");
+    if (N) *N = h->N; if (n_int) *n_int = h->n_int; if (nnz) *nnz = h->nnz; if (W) *W = h->W;
+    return LM_OK;
+}
+extern "C" int32_t lm_ham_get_csc(lm_ham* h, int64_t* colptr, int64_t* rowval, void* nzval) {
+    REQUIRE(h, "lm_ham_get_csc: NULL");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    if (colptr) for (long long j = 0; j <= h->N; ++j) colptr[j] = h->colptr[j];
+    if (rowval) for (long long q = 0; q < h->nnz; ++q) rowval[q] = h->rowval[q];
+    if (nzval && h->nnz) {
+        const int th = 256; const long long bl = (h->nnz + th - 1) / th;
+        if (c->precision == LM_C128) k_gather_vals<double><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (double2*)h->d_nz, h->d_csc2ell, (const double2*)h->d_vals);
+        else k_gather_vals<float><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (float2*)h->d_nz, h->d_csc2ell, (const float2*)h->d_vals);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(nzval, h->d_nz, c->esz() * (size_t)h->nnz, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return LM_OK;
+}
+extern "C" int32_t lm_ham_spectral_bounds(lm_ham* h, double* emin, double* emax) {
+    REQUIRE(h, "lm_ham_spectral_bounds: NULL");
+    if (emin) *emin = h->emin; if (emax) *emax = h->emax; return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// states
+// ------------------------------------------------------------------------------------------
+static void state_free(lm_state* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    void* ptrs[] = {s->d_x, s->d_w, s->d_s1, s->d_s2, s->d_U};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete s;
+}
+extern "C" int32_t lm_state_destroy(lm_state* s) { state_free(s); return LM_OK; }
+
+// host column-major (N x M) -> device row-major [N][ld], in column chunks through d_stage
+template <typename T2>
+static int upload_colmajor(lm_ctx* c, long long N, long long M, long long ld, const void* src, void* d_x) {
+    const long long chunk_cols = std::max<long long>(1, std::min<long long>(M, (256LL << 20) / (long long)(sizeof(T2) * N)));
+    FWD(ensure_stage(c, sizeof(T2) * (size_t)N * chunk_cols));
+    for (long long c0 = 0; c0 < M; c0 += chunk_cols) {
+        const long long mc = std::min(chunk_cols, M - c0);
+        CK(cudaMemcpyAsync(c->d_stage, (const char*)src + sizeof(T2) * (size_t)N * c0, sizeof(T2) * (size_t)N * mc, cudaMemcpyHostToDevice, c->stream));
+        dim3 g((unsigned)((N + 31) / 32), (unsigned)((mc + 31) / 32)), b(32, 8);
+        k_col2row<T2><<<g, b, 0, c->stream>>>(N, mc, (const T2*)c->d_stage, (T2*)d_x, ld, c0);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return LM_OK;
+}
+template <typename T2>
+static int download_colmajor(lm_ctx* c, long long N, long long M, long long ld, void* dst, const void* d_x) {
+    const long long chunk_cols = std::max<long long>(1, std::min<long long>(M, (256LL << 20) / (long long)(sizeof(T2) * N)));
+    FWD(ensure_stage(c, sizeof(T2) * (size_t)N * chunk_cols));
+    for (long long c0 = 0; c0 < M; c0 += chunk_cols) {
+        const long long mc = std::min(chunk_cols, M - c0);
+        dim3 g((unsigned)((N + 31) / 32), (unsigned)((mc + 31) / 32)), b(32, 8);
+        k_row2col<T2><<<g, b, 0, c->stream>>>(N, mc, (T2*)c->d_stage, (const T2*)d_x, ld, c0);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((char*)dst + sizeof(T2) * (size_t)N * c0, c->d_stage, sizeof(T2) * (size_t)N * mc, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return LM_OK;
+}
+
+static int state_alloc(lm_ctx* c, long long N, long long M, bool dense, lm_state** out) {
+    lm_state* s = new lm_state();
+    s->ctx = c; s->N = N; s->M = M; s->ld = pad_ld(M); s->dense = dense;
+    cudaError_t e = cudaMalloc(&s->d_x, c->esz() * (size_t)N * s->ld);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_x, 0, c->esz() * (size_t)N * s->ld, c->stream);
+    if (e != cudaSuccess) { state_free(s); return fail(LM_ERR_CUDA, std::string("state allocation: ") + cudaGetErrorString(e)); }
+    *out = s;
+    return LM_OK;
+}
+
+extern "C" int32_t lm_state_create_psi(lm_ctx* c, int64_t N, int64_t M, const void* psi, const double* w, lm_state** out) {
+    REQUIRE(c && out && psi, "lm_state_create_psi: NULL argument");
+    REQUIRE(N > 0 && M > 0, "lm_state_create_psi: N and M must be positive");
+    FWD(set_dev(c));
+    lm_state* s = nullptr;
+    FWD(state_alloc(c, N, M, false, &s));
+    int st = (c->precision == LM_C128) ? upload_colmajor<double2>(c, N, M, s->ld, psi, s->d_x)
+                                       : upload_colmajor<float2>(c, N, M, s->ld, psi, s->d_x);
+    if (st == LM_OK && w) {
+        cudaError_t e = cudaMalloc(&s->d_w, sizeof(double) * (size_t)s->ld);
+        if (e == cudaSuccess) e = cudaMemset(s->d_w, 0, sizeof(double) * (size_t)s->ld);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_w, w, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) st = fail(LM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (st != LM_OK) { state_free(s); return st; }
+    *out = s;
+    return LM_OK;
+}
+extern "C" int32_t lm_state_create_dense(lm_ctx* c, int64_t N, const void* P, lm_state** out) {
+    REQUIRE(c && out && P, "lm_state_create_dense: NULL argument");
+    REQUIRE(N > 0 && N <= 16384, "lm_state_create_dense: N must be in 1..16384 (dense path)");
+    FWD(set_dev(c));
+    lm_state* s = nullptr;
+    FWD(state_alloc(c, N, N, true, &s));
+    int st = (c->precision == LM_C128) ? upload_colmajor<double2>(c, N, N, s->ld, P, s->d_x)
+                                       : upload_colmajor<float2>(c, N, N, s->ld, P, s->d_x);
+    if (st != LM_OK) { state_free(s); return st; }
+    *out = s;
+    return LM_OK;
+}
+extern "C" int32_t lm_state_copy(lm_state* s, lm_state** out) {
+    REQUIRE(s && out, "lm_state_copy: NULL argument");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    lm_state* t = nullptr;
+    FWD(state_alloc(c, s->N, s->M, s->dense, &t));
+    cudaError_t e = cudaMemcpyAsync(t->d_x, s->d_x, c->esz() * (size_t)s->N * s->ld, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess && s->d_w) {
+        e = cudaMalloc(&t->d_w, sizeof(double) * (size_t)s->ld);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_w, s->d_w, sizeof(double) * (size_t)s->ld, cudaMemcpyDeviceToDevice, c->stream);
+    }
+    if (e != cudaSuccess) { state_free(t); return fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = t;
+    return LM_OK;
+}
+extern "C" int32_t lm_state_dims(lm_state* s, int64_t* N, int64_t* M, int32_t* dense) {
+    REQUIRE(s, "lm_state_dims: NULL");
+    if (N) *N = s->N; if (M) *M = s->M; if (dense) *dense = s->dense ? 1 : 0; return LM_OK;
+}
+extern "C" int32_t lm_state_download_psi(lm_state* s, void* out) {
+    REQUIRE(s && out, "lm_state_download_psi: NULL argument");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    return (c->precision == LM_C128) ? download_colmajor<double2>(c, s->N, s->M, s->ld, out, s->d_x)
+                                     : download_colmajor<float2>(c, s->N, s->M, s->ld, out, s->d_x);
+}
+
+// C = A op(B) on the tensor-core (c128) or FFMA (c64) dense kernels
+static int dense_gemm(lm_ctx* c, bool conj_b, int Mr, int Nc, int K, const void* A, long long lda,
+                      const void* B, long long ldb, void* C, long long ldc) {
+    if (c->precision == LM_C128) {
+        dim3 g((Nc + 31) / 32, (Mr + 31) / 32);
+        if (conj_b) k_zgemm_dmma<true><<<g, 128, 0, c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
+        else k_zgemm_dmma<false><<<g, 128, 0, c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
+    } else {
+        dim3 g((Nc + 15) / 16, (Mr + 15) / 16);
+        if (conj_b) k_cgemm_simple<true><<<g, 256, 0, c->stream>>>(Mr, Nc, K, (const float2*)A, lda, (const float2*)B, ldb, (float2*)C, ldc);
+        else k_cgemm_simple<false><<<g, 256, 0, c->stream>>>(Mr, Nc, K, (const float2*)A, lda, (const float2*)B, ldb, (float2*)C, ldc);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
+extern "C" int32_t lm_state_download_dense(lm_state* s, void* out) {
+    REQUIRE(s && out, "lm_state_download_dense: NULL argument");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    const long long N = s->N;
+    if (s->dense)
+        return (c->precision == LM_C128) ? download_colmajor<double2>(c, N, N, s->ld, out, s->d_x)
+                                         : download_colmajor<float2>(c, N, N, s->ld, out, s->d_x);
+    REQUIRE(N <= 16384, "lm_state_download_dense: N too large to materialise Psi Psi'");
+    // P = (Psi diag(w)) Psi^H
+    void *d_a = nullptr, *d_p = nullptr;
+    const long long ldp = pad_ld(N);
+    CK(cudaMalloc(&d_a, c->esz() * (size_t)N * s->ld));
+    cudaError_t e = cudaMalloc(&d_p, c->esz() * (size_t)N * ldp);
+    if (e != cudaSuccess) { cudaFree(d_a); return fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    const long long tot = N * s->ld; const int th = 256;
+    if (c->precision == LM_C128) k_scale_cols<double2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, s->M, s->ld, (const double2*)s->d_x, s->d_w, (double2*)d_a);
+    else k_scale_cols<float2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, s->M, s->ld, (const float2*)s->d_x, s->d_w, (float2*)d_a);
+    c->launches++;
+    int st = dense_gemm(c, true, (int)N, (int)N, (int)s->M, d_a, s->ld, s->d_x, s->ld, d_p, ldp);
+    if (st == LM_OK)
+        st = (c->precision == LM_C128) ? download_colmajor<double2>(c, N, N, ldp, out, d_p)
+                                       : download_colmajor<float2>(c, N, N, ldp, out, d_p);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_a); cudaFree(d_p);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// the polynomial propagators
+// ------------------------------------------------------------------------------------------
+template <typename T, int CPT>
+static void launch_apply_w(const ApplyArgs& a, unsigned grid, cudaStream_t s) {
+    switch (a.W) {
+#define LM_CASE(w) case w: k_apply<T, CPT, w><<<grid, 256, 0, s>>>(a); break;
+        LM_CASE(1) LM_CASE(2) LM_CASE(3) LM_CASE(4) LM_CASE(5) LM_CASE(6) LM_CASE(7) LM_CASE(8)
+        LM_CASE(9) LM_CASE(10) LM_CASE(11) LM_CASE(12) LM_CASE(13) LM_CASE(14) LM_CASE(15) LM_CASE(16)
+#undef LM_CASE
+        default: k_apply<T, CPT, 0><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+
+// y = alpha H x + gamma x + beta z + delta u
+static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                 zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    ApplyArgs a;
+    a.cols = h->d_cols; a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    int lc = 0; while ((1LL << lc) < ld && lc < 5) lc++;
+    const int LC = 1 << lc, LR = 32 >> lc;
+    const int cpt = (ld >= 64) ? 2 : 1;
+    a.lc_log2 = lc;
+    a.tiles_r = (h->N + 8LL * LR - 1) / (8LL * LR);
+    a.tiles_c = (ld + (long long)LC * cpt - 1) / ((long long)LC * cpt);
+    // column strips sized so that the re-read window (2 x bandwidth rows) stays in L2
+    const double budget = 0.35 * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    const double row_bytes_per_tile = (double)LC * cpt * (double)c->esz();
+    long long tps = (long long)(budget / (2.0 * (double)(h->band + 8 * LR) * row_bytes_per_tile));
+    tps = std::max<long long>(1, std::min<long long>(tps, a.tiles_c));
+    a.tiles_per_strip = (int)std::min<long long>(tps, 1 << 30);
+    const long long grid = a.tiles_r * a.tiles_c;
+    REQUIRE(grid > 0 && grid < 2147483647LL, "apply: grid too large");
+    if (c->precision == LM_C128) { if (cpt == 2) launch_apply_w<double, 2>(a, (unsigned)grid, c->stream); else launch_apply_w<double, 1>(a, (unsigned)grid, c->stream); }
+    else { if (cpt == 2) launch_apply_w<float, 2>(a, (unsigned)grid, c->stream); else launch_apply_w<float, 1>(a, (unsigned)grid, c->stream); }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
+static int ensure_scratch(lm_state* s) {
+    lm_ctx* c = s->ctx;
+    const size_t bytes = c->esz() * (size_t)s->N * s->ld;
+    if (!s->d_s1) CK(cudaMalloc(&s->d_s1, bytes));
+    if (!s->d_s2) CK(cudaMalloc(&s->d_s2, bytes));
+    return LM_OK;
+}
+
+// Horner-Taylor:  w <- psi + (f/n) H w,  n = K..1  (f = -i dt / nsub), nsub sub-steps.
+// Buffers rotate among {x, s1, s2}; on return *px holds the result.
+static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
+    int s = std::max(1, (int)std::ceil(theta_total / 1.0));
+    const double th = theta_total / s;
+    const double target = std::max(tol, 1e-17) / s;
+    int k = 1; double term = th;            // term = th^k / k!
+    while (k < 200) {
+        // remainder after degree k: th^(k+1)/(k+1)! * 1/(1 - th/(k+2))
+        const double next = term * th / (k + 1);
+        const double rem = next / (1.0 - th / (k + 2));
+        if (rem <= target) break;
+        term = next; ++k;
+    }
+    if (k >= 200) return fail(LM_ERR_NOT_CONVERGED, "Taylor propagator did not converge");
+    *nsub = s; *K = k;
+    return LM_OK;
+}
+static int step_taylor(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, int* nmv) {
+    const int nsub = h->plan.nsub, K = h->plan.K;
+    const zc f(0.0, -dt / nsub);
+    for (int sub = 0; sub < nsub; ++sub) {
+        void* psi = *px; void* a = *ps1; void* b = *ps2;
+        const void* w = psi;
+        for (int n = K; n >= 1; --n) {
+            void* y = (w == a) ? b : a;
+            FWD(apply(h, ld, w, y, psi, nullptr, f / (double)n, zc(0, 0), zc(1, 0), zc(0, 0)));
+            w = y;
+        }
+        // result in w (a or b): rotate so that *px = result
+        if (w == a) { *px = a; *ps1 = psi; } else { *px = b; *ps2 = psi; }
+        *nmv += K;
+    }
+    return LM_OK;
+}
+
+// Clenshaw-Chebyshev: exp(-i H dt) = e^{-i b dt} sum_k a_k T_k(Ht), Ht = (H - b)/a,
+// a_0 = J_0(R), a_k = 2 (-i)^k J_k(R), R = a dt.
+static int cheb_plan(double R, double tol, std::vector<zc>& coef) {
+    const double Rabs = std::fabs(R);
+    const int kmax = (int)(Rabs + 60 + 4 * std::sqrt(Rabs + 1));
+    std::vector<double> J(kmax + 2);
+    for (int k = 0; k <= kmax + 1; ++k) J[k] = std::cyl_bessel_j((double)k, Rabs);
+    int K = kmax;
+    double tail = 0.0;
+    for (int k = kmax; k >= 1; --k) {       // smallest K with sum_{k>K} 2|J_k| <= tol
+        tail += 2.0 * std::fabs(J[k]);
+        if (tail > std::max(tol, 1e-17)) { K = k; break; }
+        K = k - 1;
+    }
+    if (K >= kmax) return fail(LM_ERR_NOT_CONVERGED, "Chebyshev propagator did not converge");
+    K = std::max(K, 1);
+    coef.resize(K + 1);
+    const zc mi(0.0, R >= 0 ? -1.0 : 1.0);   // J_k(-R) = (-1)^k J_k(R)
+    zc p(1.0, 0.0);
+    for (int k = 0; k <= K; ++k) { coef[k] = (k == 0 ? 1.0 : 2.0) * p * J[k]; p *= mi; }
+    return LM_OK;
+}
+struct SymVec { int kind; zc coef; void* buf; };   // 0 zero, 1 coef*psi, 2 buffer
+static int step_cheb(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, int* nmv) {
+    const double a = std::max(0.5 * (h->emax - h->emin), 1e-300), b = 0.5 * (h->emax + h->emin);
+    const std::vector<zc>& coef = h->plan.coef;
+    const int K = (int)coef.size() - 1;
+    void* psi = *px; void* bufs[2] = {*ps1, *ps2};
+    // b_{K+1} = 0, b_K = a_K psi  (symbolic, no pass over memory)
+    SymVec b1{1, coef[K], nullptr}, b2{0, zc(0, 0), nullptr};
+    const zc ph = std::exp(zc(0.0, -b * dt));
+    for (int k = K - 1; k >= 0; --k) {
+        // k >= 1: y = a_k psi + 2 Ht b1 - b2 ;  k == 0: y = ph (a_0 psi + Ht b1 - b2)
+        const double two = (k == 0) ? 1.0 : 2.0;
+        const zc scale = (k == 0) ? ph : zc(1, 0);
+        const void* x = (b1.kind == 1) ? psi : b1.buf;
+        const zc xs = (b1.kind == 1) ? b1.coef : zc(1, 0);
+        zc alpha = scale * xs * (two / a), gamma = scale * xs * (-two * b / a);
+        zc beta = scale * coef[k], delta(0, 0);
+        const void* u = nullptr; void* y;
+        if (b2.kind == 1) beta -= scale * b2.coef;
+        if (b2.kind == 2) { u = b2.buf; delta = -scale; y = b2.buf; }
+        else y = (b1.kind == 2 && b1.buf == bufs[0]) ? bufs[1] : bufs[0];
+        FWD(apply(h, ld, x, y, psi, u, alpha, gamma, beta, delta));
+        (*nmv)++;
+        b2 = b1; b1 = SymVec{2, zc(1, 0), y};
+    }
+    // result is b1.buf; rotate it into the state slot
+    if (b1.buf == bufs[0]) { *px = bufs[0]; *ps1 = psi; } else { *px = bufs[1]; *ps2 = psi; }
+    return LM_OK;
+}
+
+// The plan (method, sub-steps, degree, Bessel coefficients) depends only on (dt, tol, method,
+// spectral enclosure): cached on the Hamiltonian so a run of equal steps pays for it once.
+static int get_plan(lm_ham* h, double dt, double tol, int method) {
+    Plan& p = h->plan;
+    if (p.valid && p.dt == dt && p.tol == tol && p.method_req == method && p.emin == h->emin &&
+        p.emax == h->emax && p.norm == h->norm_inf) return LM_OK;
+    p.valid = false;
+    int nsub = 1, K = 1; std::vector<zc> coef;
+    const int st_t = (method == LM_METHOD_CHEBYSHEV) ? LM_ERR_UNSUPPORTED : taylor_plan(h->norm_inf * std::fabs(dt), tol, &nsub, &K);
+    const double a = std::max(0.5 * (h->emax - h->emin), 1e-300);
+    const int st_c = (method == LM_METHOD_TAYLOR) ? LM_ERR_UNSUPPORTED : cheb_plan(a * dt, tol, coef);
+    int m = method;
+    if (method == LM_METHOD_AUTO) {
+        // cost model in memory streams per term: Horner-Taylor 3, Clenshaw-Chebyshev 4
+        if (st_t != LM_OK && st_c != LM_OK) return fail(LM_ERR_NOT_CONVERGED, "lm_step: no propagator plan converged");
+        if (st_t != LM_OK) m = LM_METHOD_CHEBYSHEV;
+        else if (st_c != LM_OK) m = LM_METHOD_TAYLOR;
+        else m = (3.0 * nsub * K <= 4.0 * ((double)coef.size() - 1)) ? LM_METHOD_TAYLOR : LM_METHOD_CHEBYSHEV;
+    } else if (method == LM_METHOD_TAYLOR) { FWD(st_t); }
+    else if (method == LM_METHOD_CHEBYSHEV) { FWD(st_c); }
+    else return fail(LM_ERR_UNSUPPORTED, "lm_step: method not implemented (use AUTO, CHEBYSHEV or TAYLOR)");
+    p.dt = dt; p.tol = tol; p.method_req = method; p.emin = h->emin; p.emax = h->emax; p.norm = h->norm_inf;
+    p.method = m; p.nsub = nsub; p.K = K; p.coef.swap(coef); p.valid = true;
+    return LM_OK;
+}
+
+static int propagate(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, double tol, int method, int* nmv) {
+    if (dt == 0.0) return LM_OK;
+    FWD(get_plan(h, dt, tol, method));
+    if (h->plan.method == LM_METHOD_TAYLOR) return step_taylor(h, ld, px, ps1, ps2, dt, nmv);
+    return step_cheb(h, ld, px, ps1, ps2, dt, nmv);
+}
+
+extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_t method, int32_t* n_matvec_out) {
+    REQUIRE(h && s, "lm_step: NULL argument");
+    REQUIRE(h->ctx == s->ctx, "lm_step: Hamiltonian and state belong to different contexts");
+    REQUIRE(h->N == s->N, "lm_step: dimension mismatch between Hamiltonian and state");
+    REQUIRE(std::isfinite(dt), "lm_step: dt is not finite");
+    REQUIRE(tol > 0 && tol < 1, "lm_step: tol must be in (0, 1)");
+    REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_LANCZOS, "lm_step: unknown method");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    int nmv = 0;
+    if (!s->dense) {
+        FWD(ensure_scratch(s));
+        FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
+    } else {
+        // P <- U P U^H with U = exp(-i H dt) built by applying the propagator to the identity
+        // block; cached while (H values, dt) are unchanged - CachedExp semantics,
+        // src/evolution.jl:83-92.
+        const long long N = s->N, ld = s->ld;
+        const size_t bytes = c->esz() * (size_t)N * ld;
+        FWD(ensure_scratch(s));
+        const bool hit = s->d_U && s->U_ham == h && s->U_version == h->version && s->U_dt == dt && s->U_tol == tol && s->U_method == method;
+        if (!hit) {
+            if (!s->d_U) CK(cudaMalloc(&s->d_U, bytes));
+            const long long tot = N * ld; const int th = 256;
+            if (c->precision == LM_C128) k_set_identity<double2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, ld, (double2*)s->d_U);
+            else k_set_identity<float2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, ld, (float2*)s->d_U);
+            c->launches++;
+            s->U_version = -1;
+            FWD(propagate(h, ld, &s->d_U, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
+            s->U_ham = h; s->U_version = h->version; s->U_dt = dt; s->U_tol = tol; s->U_method = method;
+        }
+        // T = U P ; P = T U^H      (two complex GEMMs, src/evolution.jl:76-77)
+        FWD(dense_gemm(c, false, (int)N, (int)N, (int)N, s->d_U, ld, s->d_x, ld, s->d_s1, ld));
+        FWD(dense_gemm(c, true, (int)N, (int)N, (int)N, s->d_s1, ld, s->d_U, ld, s->d_x, ld));
+    }
+    if (n_matvec_out) *n_matvec_out = nmv;
+    return LM_OK;
+}
+
+extern "C" int32_t lm_spmm_state(lm_ham* h, lm_state* x, lm_state* y) {
+    REQUIRE(h && x && y, "lm_spmm_state: NULL argument");
+    REQUIRE(x != y && x->d_x != y->d_x, "lm_spmm_state: x and y must be distinct");
+    REQUIRE(h->ctx == x->ctx && h->ctx == y->ctx, "lm_spmm_state: context mismatch");
+    REQUIRE(h->N == x->N && x->N == y->N && x->M == y->M && x->ld == y->ld, "lm_spmm_state: dimension mismatch");
+    FWD(set_dev(h->ctx));
+    return apply(h, x->ld, x->d_x, y->d_x, nullptr, nullptr, zc(1, 0), zc(0, 0), zc(0, 0), zc(0, 0));
+}
+extern "C" int32_t lm_spmm(lm_ham* h, const void* X, void* Y, int64_t N, int64_t M) {
+    REQUIRE(h && X && Y, "lm_spmm: NULL argument");
+    REQUIRE(N == h->N && M > 0, "lm_spmm: dimension mismatch");
+    lm_state *x = nullptr, *y = nullptr;
+    FWD(lm_state_create_psi(h->ctx, N, M, X, nullptr, &x));
+    int st = state_alloc(h->ctx, N, M, false, &y);
+    if (st == LM_OK) st = lm_spmm_state(h, x, y);
+    if (st == LM_OK) st = lm_state_download_psi(y, Y);
+    state_free(x); state_free(y);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// observables
+// ------------------------------------------------------------------------------------------
+template <typename T, int WB>
+static void launch_observe(lm_ham* h, lm_state* s, int k0, int write_dens) {
+    using T2 = typename cx2<T>::type;
+    lm_ctx* c = h->ctx;
+    if (s->M >= 512)
+        k_observe<T, WB, true><<<(unsigned)h->N, 256, 0, c->stream>>>(h->N, s->M, s->ld, (const T2*)s->d_x, s->d_w, h->d_cols, h->W, h->d_upper, k0, write_dens, h->d_dens, h->d_G);
+    else
+        k_observe<T, WB, false><<<(unsigned)((h->N + 7) / 8), 256, 0, c->stream>>>(h->N, s->M, s->ld, (const T2*)s->d_x, s->d_w, h->d_cols, h->W, h->d_upper, k0, write_dens, h->d_dens, h->d_G);
+    c->launches++;
+}
+template <typename T>
+static int observe(lm_ham* h, lm_state* s, bool want_j) {
+    // ELL slots are processed WB at a time; a density-only pass has no active slot (k0 = W)
+    const int W = want_j ? h->W : 0;
+    if (W <= 0) launch_observe<T, 1>(h, s, h->W, 1);
+    else if (W <= 4) launch_observe<T, 4>(h, s, 0, 1);
+    else if (W <= 8) launch_observe<T, 8>(h, s, 0, 1);
+    else for (int k0 = 0; k0 < W; k0 += 16) launch_observe<T, 16>(h, s, k0, k0 == 0);
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
+static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, double* J_out) {
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    REQUIRE(!s->dense, "observables of a dense state: download it with lm_state_download_dense (diagonal) instead");
+    const long long n_sites = s->N / n_int;
+    const long long npairs = (h && J_out) ? h->npairs : 0;
+    const bool want_j = J_out != nullptr;
+    if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
+    const long long tot = n_sites + npairs; const int th = 256;
+    if (c->precision == LM_C128)
+        k_finalize_obs<double><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const double2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
+    else
+        k_finalize_obs<float><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const float2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (c->nranks > 1 && c->comm)
+        NCK(g_nccl.AllReduce(h->d_obs, h->d_obs, (size_t)tot, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    FWD(ensure_pinned(c, sizeof(double) * (size_t)tot + 4096));
+    CK(cudaMemcpyAsync(c->h_pinned, h->d_obs, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double* src = (const double*)c->h_pinned;
+    if (rho_out) memcpy(rho_out, src, sizeof(double) * (size_t)n_sites);
+    if (J_out) memcpy(J_out, src + n_sites, sizeof(double) * (size_t)npairs);
+    return LM_OK;
+}
+
+extern "C" int32_t lm_currents_npairs(lm_ham* h, int64_t* n) { REQUIRE(h && n, "lm_currents_npairs: NULL"); *n = h->npairs; return LM_OK; }
+extern "C" int32_t lm_currents_pairs(lm_ham* h, int32_t* I, int32_t* J) {
+    REQUIRE(h && I && J, "lm_currents_pairs: NULL");
+    for (long long p = 0; p < h->npairs; ++p) { I[p] = h->pairI[p] + h->index_base; J[p] = h->pairJ[p] + h->index_base; }
+    return LM_OK;
+}
+extern "C" int32_t lm_observables(lm_ham* h, lm_state* s, double* rho_out, double* J_out) {
+    REQUIRE(h && s, "lm_observables: NULL argument");
+    REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_observables: Hamiltonian/state mismatch");
+    return run_observables(h, s, h->n_int, rho_out, J_out);
+}
+extern "C" int32_t lm_bond_currents(lm_ham* h, lm_state* s, int64_t nb, const int32_t* I, const int32_t* J, double* out) {
+    REQUIRE(h && s && out && (nb == 0 || (I && J)), "lm_bond_currents: NULL argument");
+    REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_bond_currents: Hamiltonian/state mismatch");
+    std::vector<double> all((size_t)std::max<long long>(1, h->npairs));
+    FWD(run_observables(h, s, h->n_int, nullptr, all.data()));
+    for (long long q = 0; q < nb; ++q) {
+        long long i = I[q] - h->index_base, j = J[q] - h->index_base;
+        REQUIRE(i >= 0 && i < h->n_sites && j >= 0 && j < h->n_sites, "lm_bond_currents: site index out of range");
+        double sign = 1.0;
+        if (i > j) { std::swap(i, j); sign = -1.0; }
+        double v = 0.0;
+        if (i != j) {
+            // pairs are sorted by (J, I): binary search
+            long long lo = 0, hi = h->npairs;
+            while (lo < hi) {
+                const long long mid = (lo + hi) / 2;
+                const bool less = h->pairJ[mid] != j ? h->pairJ[mid] < j : h->pairI[mid] < i;
+                if (less) lo = mid + 1; else hi = mid;
+            }
+            if (lo < h->npairs && h->pairI[lo] == i && h->pairJ[lo] == j) v = all[lo];
+        }
+        out[q] = sign * v;
+    }
+    return LM_OK;
+}
+
+// lm_local_density has no Hamiltonian at hand and needs only the row densities: a
+// pattern-less helper (W = 1, no pairs) owned by the context provides the scratch arrays.
+extern "C" int32_t lm_local_density(lm_state* s, int32_t n_int, double* rho_out) {
+    REQUIRE(s && rho_out, "lm_local_density: NULL argument");
+    REQUIRE(n_int >= 1 && s->N % n_int == 0, "lm_local_density: N is not a multiple of n_int");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    if (s->dense) {
+        // rho_i = sum_alpha Re P[i', i']: the diagonal of the row-major P
+        const long long N = s->N;
+        std::vector<char> diag(c->esz() * (size_t)N);
+        CK(cudaMemcpy2DAsync(diag.data(), c->esz(), s->d_x, c->esz() * (size_t)(s->ld + 1), c->esz(), (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (long long i = 0; i < N / n_int; ++i) {
+            double acc = 0;
+            for (int a = 0; a < n_int; ++a)
+                acc += (c->precision == LM_C128) ? ((const double*)diag.data())[2 * (i * n_int + a)] : (double)((const float*)diag.data())[2 * (i * n_int + a)];
+            rho_out[i] = acc;
+        }
+        return LM_OK;
+    }
+    lm_ham* helper = c->dens_helper;
+    if (!helper || helper->N != s->N || helper->n_int != n_int) {
+        if (helper) { ham_free(helper); c->dens_helper = nullptr; }
+        std::vector<int64_t> cp((size_t)s->N + 1, 0);
+        char nz[16] = {0};
+        int64_t rv = 0;
+        FWD(lm_ham_create_csc(c, s->N, n_int, cp.data(), &rv, nz, 0, &helper));
+        c->dens_helper = helper;
+    }
+    return run_observables(helper, s, n_int, rho_out, nullptr);
+}

@@ -1,0 +1,519 @@
+// Hand-written sm_100a kernels for the Psi-block unitary-evolution hot path.
+//
+// Device data layout:
+//   Psi  : row-major [N][ld] complex, the Hilbert (row) index slow, the orbital (column) index
+//          contiguous -> every non-zero H_ij scales a contiguous run of columns; a lane owns
+//          one 128-bit complex128 (or 64-bit complex64) element per load.
+//   H    : ELL, row-major [N][W] (int32 column, complex value); padding points at the row
+//          itself with value 0.  A warp reads its row's entries as broadcast loads.
+// All kernels are HBM/L2-bound FP64 (FP32 in c64 mode) stream kernels: no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lm {
+
+template <typename T> struct cx2;
+template <> struct cx2<double> { using type = double2; };
+template <> struct cx2<float>  { using type = float2; };
+
+template <typename T2> __device__ __forceinline__ T2 cmake(double re, double im) {
+    T2 r; r.x = (decltype(r.x))re; r.y = (decltype(r.y))im; return r;
+}
+template <typename T2> __device__ __forceinline__ void cfma(T2& acc, const T2 a, const T2 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+template <typename T2> __device__ __forceinline__ T2 cmul(const T2 a, const T2 b) {
+    T2 r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+
+// read-only (ld.global.nc) L1-allocating loads for the gathered Psi rows (re-used by the
+// neighbouring rows of the same CTA); evict-first streaming loads / stores for operands that
+// are touched exactly once per pass.  Intrinsics (not volatile asm) so that ptxas is free to
+// batch the independent gathers of a row ahead of the FMA chain (memory-level parallelism).
+__device__ __forceinline__ double2 ld_ro(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ld_ro(const float2* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double2* p, double2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+
+// ------------------------------------------------------------------------------------------
+// k_apply: one polynomial term of the propagator, fused around the ELL SpMM
+//     y = alpha * (H x) + gamma * x + beta * z + delta * u          (element-wise epilogue)
+// z / u may be null (HAS_Z / HAS_U); u may alias y (same element read then written by the
+// same thread).  x must not alias y.
+//
+// Tile mapping: a warp covers LR = 32/LC rows x (LC * CPT) columns (LC lanes along the
+// contiguous column index), a CTA of 8 warps covers 8*LR consecutive rows so that the +-1
+// neighbour rows of a lattice stencil are re-used out of L1.  Tiles are ordered column-STRIP
+// major (tiles_per_strip column tiles, all row tiles, next strip) so that the window of rows
+// a sweep keeps re-reading (2 x matrix bandwidth) stays L2-resident for wide Psi blocks.
+// ------------------------------------------------------------------------------------------
+struct ApplyArgs {
+    const int* cols; const void* vals; int W;
+    long long N; long long ld;
+    const void* x; void* y; const void* z; const void* u;
+    double alpha[2], gamma[2], beta[2], delta[2];
+    int lc_log2;            // log2(LC)
+    long long tiles_r;      // row tiles
+    long long tiles_c;      // column tiles in total
+    int tiles_per_strip;    // column tiles per strip
+};
+
+template <typename T, int CPT, int WX>   // WX = exact ELL width (fully unrolled), 0 = generic loop
+__global__ void __launch_bounds__(256)
+k_apply(const ApplyArgs a) {
+    using T2 = typename cx2<T>::type;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LC = 1 << a.lc_log2, LR = 32 >> a.lc_log2;
+    // strip-major tile decode
+    long long t = blockIdx.x;
+    const long long per_strip = a.tiles_r * a.tiles_per_strip;
+    const long long strip = t / per_strip;
+    long long rem = t - strip * per_strip;
+    long long tps = a.tiles_per_strip;
+    const long long c_first = strip * (long long)a.tiles_per_strip;
+    if (c_first + tps > a.tiles_c) tps = a.tiles_c - c_first;   // last (narrower) strip
+    // the last strip has fewer column tiles: re-derive (rt, ct) with its own width
+    long long rt, ct;
+    if (tps == a.tiles_per_strip) { rt = rem / tps; ct = c_first + (rem - rt * tps); }
+    else { if (rem >= a.tiles_r * tps) return; rt = rem / tps; ct = c_first + (rem - rt * tps); }
+
+    const long long row = rt * (8LL * LR) + (long long)warp * LR + (lane >> a.lc_log2);
+    const long long col0 = ct * ((long long)LC * CPT) + (lane & (LC - 1));
+    if (row >= a.N) return;
+
+    const T2* __restrict__ x = (const T2*)a.x;
+    const T2* __restrict__ vals = (const T2*)a.vals + row * a.W;
+    const int* __restrict__ cols = a.cols + row * a.W;
+
+    long long cidx[CPT];
+    bool ok[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        long long c = col0 + (long long)j * LC;
+        ok[j] = c < a.ld;
+        cidx[j] = ok[j] ? c : (a.ld - 1);
+    }
+    T2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { acc[j].x = 0; acc[j].y = 0; }
+
+    if (WX > 0) {
+#pragma unroll
+        for (int k = 0; k < WX; ++k) {
+            const long long c = cols[k];
+            const T2 v = vals[k];
+            const T2* xr = x + c * a.ld;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
+        }
+    } else {
+        for (int k = 0; k < a.W; ++k) {
+            const long long c = cols[k];
+            const T2 v = vals[k];
+            const T2* xr = x + c * a.ld;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
+        }
+    }
+
+    const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
+    const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
+    const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
+    const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
+    const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
+    T2* y = (T2*)a.y;
+    const T2* z = (const T2*)a.z;
+    const T2* u = (const T2*)a.u;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        if (!ok[j]) continue;
+        const long long e = row * a.ld + cidx[j];
+        T2 out = cmul(alpha, acc[j]);
+        if (has_gamma) cfma(out, gamma, ld_ro(x + e));
+        if (z) cfma(out, beta, ld_stream(z + e));
+        if (u) { T2 uu = u[e]; cfma(out, delta, uu); }
+        st_stream(y + e, out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Peierls phases regenerated on the device (src/operators/builder.jl:282-285 +
+// src/zoo/magneticfields.jl:15,31,72-104 restated; FP64 always).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sgn(double v) { return (v > 0.0) - (v < 0.0); }
+
+__device__ __forceinline__ double line_integral(int kind, const double* p, double x1, double y1,
+                                                double x2, double y2) {
+    switch (kind) {
+    case 1:  // LandauGauge: (x1 + x2)(y2 - y1) B / 2
+        return (x1 + x2) * (y2 - y1) * p[0] / 2;
+    case 2:  // SymmetricGauge: (x1 y2 - x2 y1) / 2 * B
+        return (x1 * y2 - x2 * y1) / 2 * p[0];
+    case 3: {  // PointFlux{:axial}
+        const double ax = x1 - p[1], ay = y1 - p[2], bx = x2 - p[1], by = y2 - p[2];
+        const double n1 = sqrt(ax * ax + ay * ay), n2 = sqrt(bx * bx + by * by);
+        if (n1 < 1e-11 || n2 < 1e-11) return 0.0;
+        const double nnorm = n1 * n2;
+        const double sinsign = ax * by - ay * bx;
+        const double c = (ax * bx + ay * by) / nnorm / (1 + 1e-11);
+        return acos(c) * sgn(sinsign) * p[0] / 6.283185307179586;
+    }
+    case 4: {  // PointFlux{:singular}
+        const double ax = x1 - p[1], ay = y1 - p[2], bx = x2 - p[1], by = y2 - p[2];
+        const double sg = bx - ax;
+        if (fabs(sg) < 1e-11) return 0.0;
+        if (ax * bx > 0 || fmax(ax, bx) == 0.0) return 0.0;
+        const double yint = (-ay * bx + by * ax) / (ax - bx);
+        return yint > 0 ? 0.0 : p[0] * sgn(sg);
+    }
+    default: return 0.0;
+    }
+}
+
+// one thread per bond: phase[b] = bfac[b] * exp(-2 pi i * sum_f line_integral_f)
+__global__ void k_bond_phase(long long nb, const double* __restrict__ r /* x1,y1,x2,y2 */,
+                             const double2* __restrict__ bfac, int nfields,
+                             const int* __restrict__ kinds, const double* __restrict__ params,
+                             double2* __restrict__ phase) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const double x1 = r[4 * b], y1 = r[4 * b + 1], x2 = r[4 * b + 2], y2 = r[4 * b + 3];
+    double L = 0.0;
+    for (int f = 0; f < nfields; ++f) L += line_integral(kinds[f], params + 3 * f, x1, y1, x2, y2);
+    double s, c;
+    sincos(-6.283185307179586 * L, &s, &c);
+    const double2 bf = bfac[b];
+    phase[b] = make_double2(bf.x * c - bf.y * s, bf.x * s + bf.y * c);
+}
+
+// one thread per ELL entry: vals[e] = static[e] + sum_c amp_c * (conj?)phase[bond_c]
+template <typename T>
+__global__ void k_assemble(long long E, const double2* __restrict__ stat,
+                           const int* __restrict__ cptr, const int* __restrict__ cbond,
+                           const double2* __restrict__ camp, const double2* __restrict__ phase,
+                           typename cx2<T>::type* __restrict__ vals) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double2 v = stat[e];
+    for (int c = cptr[e]; c < cptr[e + 1]; ++c) {
+        int b = cbond[c];
+        double2 f;
+        if (b >= 0) f = phase[b];
+        else { f = phase[~b]; f.y = -f.y; }
+        const double2 am = camp[c];
+        v.x += am.x * f.x - am.y * f.y;
+        v.y += am.x * f.y + am.y * f.x;
+    }
+    vals[e] = cmake<typename cx2<T>::type>(v.x, v.y);
+}
+
+// scatter CSC nzval (host-assembled H) into the ELL value array
+template <typename T>
+__global__ void k_scatter_vals(long long nnz, const typename cx2<T>::type* __restrict__ nz,
+                               const int* __restrict__ pos, typename cx2<T>::type* __restrict__ vals) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e < nnz) vals[pos[e]] = nz[e];
+}
+template <typename T>
+__global__ void k_gather_vals(long long nnz, typename cx2<T>::type* __restrict__ nz,
+                              const int* __restrict__ pos, const typename cx2<T>::type* __restrict__ vals) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e < nnz) nz[e] = vals[pos[e]];
+}
+
+// ------------------------------------------------------------------------------------------
+// layout change column-major (host) <-> row-major [N][ld] (device), 32x32 smem tiles.
+// src: N x Mc column-major with leading dimension N; dst rows i, columns c0 + [0, Mc).
+// ------------------------------------------------------------------------------------------
+template <typename T2>
+__global__ void k_col2row(long long N, long long Mc, const T2* __restrict__ src,
+                          T2* __restrict__ dst, long long ld, long long c0) {
+    __shared__ T2 tile[32][33];
+    const long long i0 = blockIdx.x * 32LL, m0 = blockIdx.y * 32LL;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {           // r: column (orbital) in tile
+        long long m = m0 + r, i = i0 + threadIdx.x;
+        if (m < Mc && i < N) tile[r][threadIdx.x] = src[m * N + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {           // r: row (site) in tile
+        long long i = i0 + r, m = m0 + threadIdx.x;
+        if (m < Mc && i < N) dst[i * ld + c0 + m] = tile[threadIdx.x][r];
+    }
+}
+template <typename T2>
+__global__ void k_row2col(long long N, long long Mc, T2* __restrict__ dst,
+                          const T2* __restrict__ src, long long ld, long long c0) {
+    __shared__ T2 tile[32][33];
+    const long long i0 = blockIdx.x * 32LL, m0 = blockIdx.y * 32LL;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        long long i = i0 + r, m = m0 + threadIdx.x;
+        if (m < Mc && i < N) tile[r][threadIdx.x] = src[i * ld + c0 + m];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        long long m = m0 + r, i = i0 + threadIdx.x;
+        if (m < Mc && i < N) dst[m * N + i] = tile[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_observe: ONE read of Psi yields the per-row densities and the bond correlators
+//   dens[i]  = sum_c w_c |x[i,c]|^2
+//   G[i,k]   = sum_c w_c x[col_k(i), c] * conj(x[i, c])     for ELL slots flagged `upper`
+// A team of TS threads (one warp, or a whole 256-thread CTA for wide blocks) owns a row;
+// lanes stride over the columns; partial sums are folded with warp shuffles (and one smem
+// hop for the CTA team).  Accumulation is FP64 in both precisions.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T, int WB, bool CTA_TEAM>
+__global__ void __launch_bounds__(256)
+k_observe(long long N, long long M, long long ld, const typename cx2<T>::type* __restrict__ x,
+          const double* __restrict__ w, const int* __restrict__ cols, int W,
+          const unsigned char* __restrict__ upper, int k0, int write_dens,
+          double* __restrict__ dens, double2* __restrict__ G) {
+    using T2 = typename cx2<T>::type;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = CTA_TEAM ? (long long)blockIdx.x : (long long)blockIdx.x * 8 + warp;
+    if (row >= N) return;            // whole team exits together
+    const int TS = CTA_TEAM ? 256 : 32;
+    const int tid = CTA_TEAM ? threadIdx.x : lane;
+
+    const T2* xi = x + row * ld;
+    const int* cr = cols + row * W;
+    const unsigned char* up = upper + row * W;
+    long long nb[WB];
+    bool act[WB];
+#pragma unroll
+    for (int k = 0; k < WB; ++k) {
+        const int kk = k0 + k;
+        act[k] = (kk < W) && up[kk];
+        nb[k] = act[k] ? cr[kk] : row;
+    }
+    double d = 0.0;
+    double gr[WB], gi[WB];
+#pragma unroll
+    for (int k = 0; k < WB; ++k) { gr[k] = 0; gi[k] = 0; }
+
+    for (long long c = tid; c < M; c += TS) {
+        const T2 a = ld_stream(xi + c);
+        const double wc = w ? w[c] : 1.0;
+        const double ar = wc * (double)a.x, ai = wc * (double)a.y;
+        d = fma(ar, (double)a.x, d); d = fma(ai, (double)a.y, d);
+#pragma unroll
+        for (int k = 0; k < WB; ++k) {
+            if (act[k]) {
+                const T2 b = ld_ro(x + nb[k] * ld + c);
+                // b * conj(a) * w
+                gr[k] = fma((double)b.x, ar, gr[k]); gr[k] = fma((double)b.y, ai, gr[k]);
+                gi[k] = fma((double)b.y, ar, gi[k]); gi[k] = fma(-(double)b.x, ai, gi[k]);
+            }
+        }
+    }
+    d = warp_sum(d);
+#pragma unroll
+    for (int k = 0; k < WB; ++k) if (act[k]) { gr[k] = warp_sum(gr[k]); gi[k] = warp_sum(gi[k]); }
+
+    if (!CTA_TEAM) {
+        if (lane == 0) {
+            if (write_dens) dens[row] = d;
+#pragma unroll
+            for (int k = 0; k < WB; ++k) if (act[k]) G[row * W + k0 + k] = make_double2(gr[k], gi[k]);
+        }
+    } else {
+        __shared__ double sm[8][2 * WB + 1];
+        if (lane == 0) {
+            sm[warp][0] = d;
+#pragma unroll
+            for (int k = 0; k < WB; ++k) { sm[warp][1 + 2 * k] = gr[k]; sm[warp][2 + 2 * k] = gi[k]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * WB + 1) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += sm[q][threadIdx.x];
+            if (threadIdx.x == 0) { if (write_dens) dens[row] = s; }
+            else {
+                const int k = (threadIdx.x - 1) >> 1;
+                if ((k0 + k) < W && up[k0 + k]) {
+                    double* g = (double*)(G + row * W + k0 + k);
+                    g[(threadIdx.x - 1) & 1] = s;
+                }
+            }
+        }
+    }
+}
+
+// obs[0 .. n_sites) = site densities, obs[n_sites .. n_sites + npairs) = pair currents
+//   J_p = sum_{e in pair p} 2 Im(H_e * G_e)      (src/zoo/currents.jl:92-102)
+template <typename T>
+__global__ void k_finalize_obs(long long n_sites, int n_int, const double* __restrict__ dens,
+                               long long npairs, const int* __restrict__ pair_ptr,
+                               const int* __restrict__ pair_ent,
+                               const typename cx2<T>::type* __restrict__ vals,
+                               const double2* __restrict__ G, double* __restrict__ obs,
+                               int want_rho, int want_j) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n_sites) {
+        if (want_rho) {
+            double s = 0.0;
+            for (int a = 0; a < n_int; ++a) s += dens[t * n_int + a];
+            obs[t] = s;
+        }
+    } else if (t < n_sites + npairs) {
+        if (want_j) {
+            const long long p = t - n_sites;
+            double s = 0.0;
+            for (int q = pair_ptr[p]; q < pair_ptr[p + 1]; ++q) {
+                const int e = pair_ent[q];
+                const double hr = (double)vals[e].x, hi = (double)vals[e].y;
+                const double2 g = G[e];
+                s += 2.0 * (hr * g.y + hi * g.x);
+            }
+            obs[t] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------
+template <typename T2>
+__global__ void k_set_identity(long long N, long long ld, T2* __restrict__ x) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long i = e / ld, c = e - i * ld;
+    T2 v; v.x = (i == c) ? 1 : 0; v.y = 0;
+    x[e] = v;
+}
+// y[i,c] = w_c * x[i,c]
+template <typename T2>
+__global__ void k_scale_cols(long long N, long long M, long long ld, const T2* __restrict__ x,
+                             const double* __restrict__ w, T2* __restrict__ y) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long c = e % ld;
+    T2 v = x[e];
+    const double wc = (c < M) ? (w ? w[c] : 1.0) : 0.0;
+    v.x = (decltype(v.x))(v.x * wc); v.y = (decltype(v.y))(v.y * wc);
+    y[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense small-N path: complex GEMM on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64).
+//   C[Mr x Nc] = A[Mr x K] * op(B);  all row-major.
+//   CONJ_B = false: op(B) = B,  B is [K x Nc]            (T = U P)
+//   CONJ_B = true : op(B) = B^H, B is [Nc x K] row-major  (P' = T U^H, and Psi W Psi^H)
+// A complex product is 4 real DMMA chains: Cr += Ar Br - Ai Bi ; Ci += Ar Bi + Ai Br.
+// CTA = 4 warps, 32 x 32 output tile, each warp a 16 x 16 quadrant (2 x 2 MMA tiles),
+// K staged through shared memory in slabs of 16.  (FP32 mode falls back to the same kernel
+// instantiated on float with FFMA - the dense path is only used for N <~ 4096.)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <bool CONJ_B>
+__global__ void __launch_bounds__(128)
+k_zgemm_dmma(int Mr, int Nc, int K, const double2* __restrict__ A, long long lda,
+             const double2* __restrict__ B, long long ldb, double2* __restrict__ C, long long ldc) {
+    __shared__ double sAr[32][17], sAi[32][17];     // [m][k]
+    __shared__ double sBr[16][33], sBi[16][33];     // [k][n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+    const int g = lane >> 2, q = lane & 3;           // fragment coordinates
+    double cr[2][2][2] = {}, ci[2][2][2] = {};
+
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // stage A slab: 32 x 16
+        for (int e = tid; e < 32 * 16; e += 128) {
+            const int m = e >> 4, k = e & 15;
+            double2 v = make_double2(0, 0);
+            if (m0 + m < Mr && k0 + k < K) v = A[(long long)(m0 + m) * lda + k0 + k];
+            sAr[m][k] = v.x; sAi[m][k] = v.y;
+        }
+        // stage op(B) slab: 16 x 32
+        if (!CONJ_B) {
+            for (int e = tid; e < 16 * 32; e += 128) {
+                const int k = e >> 5, n = e & 31;
+                double2 v = make_double2(0, 0);
+                if (k0 + k < K && n0 + n < Nc) v = B[(long long)(k0 + k) * ldb + n0 + n];
+                sBr[k][n] = v.x; sBi[k][n] = v.y;
+            }
+        } else {
+            for (int e = tid; e < 16 * 32; e += 128) {
+                const int n = e >> 4, k = e & 15;
+                double2 v = make_double2(0, 0);
+                if (k0 + k < K && n0 + n < Nc) v = B[(long long)(n0 + n) * ldb + k0 + k];
+                sBr[k][n] = v.x; sBi[k][n] = -v.y;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk += 4) {
+            double ar[2], ai[2], br[2], bi[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { ar[i] = sAr[wm + 8 * i + g][kk + q]; ai[i] = sAi[wm + 8 * i + g][kk + q]; }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { br[j] = sBr[kk + q][wn + 8 * j + g]; bi[j] = sBi[kk + q][wn + 8 * j + g]; }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+                    dmma(cr[i][j][0], cr[i][j][1], -ai[i], bi[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + wm + 8 * i + g, n = n0 + wn + 8 * j + 2 * q + h;
+                if (m < Mr && n < Nc) C[(long long)m * ldc + n] = make_double2(cr[i][j][h], ci[i][j][h]);
+            }
+}
+
+// FP32 (c64 mode) dense GEMM: plain FFMA tile kernel, same interface.
+template <bool CONJ_B>
+__global__ void __launch_bounds__(256)
+k_cgemm_simple(int Mr, int Nc, int K, const float2* __restrict__ A, long long lda,
+               const float2* __restrict__ B, long long ldb, float2* __restrict__ C, long long ldc) {
+    __shared__ float2 sA[16][17], sB[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+    float2 acc = make_float2(0, 0);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float2 va = make_float2(0, 0), vb = make_float2(0, 0);
+        if (m < Mr && k0 + tx < K) va = A[(long long)m * lda + k0 + tx];
+        if (!CONJ_B) { if (k0 + ty < K && n < Nc) vb = B[(long long)(k0 + ty) * ldb + n]; }
+        else {
+            const int nn = blockIdx.x * 16 + ty;   // load B[nn][k0+tx] -> sB[k=tx][n=ty]
+            if (nn < Nc && k0 + tx < K) { vb = B[(long long)nn * ldb + k0 + tx]; vb.y = -vb.y; }
+        }
+        sA[ty][tx] = va;
+        if (!CONJ_B) sB[ty][tx] = vb; else sB[tx][ty] = vb;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cfma(acc, sA[ty][k], sB[k][tx]);
+        __syncthreads();
+    }
+    if (m < Mr && n < Nc) C[(long long)m * ldc + n] = acc;
+}
+
+}  // namespace lm

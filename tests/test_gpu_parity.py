@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical
+seeded inputs.  Tolerances: complex128 1e-10 relative on localdensity / DensityCurrents (the
+north-star bar; most checks are far tighter), complex64 1e-5.  Reference scenarios cited per
+test (paths relative to /root/reference)."""
+import ctypes as C
+import warnings
+from importlib import import_module
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import lm_b200 as lm
+from oracle import evolution as EV
+from oracle import fields as F
+from oracle import lattice as L
+from oracle import observables as OB
+from oracle import operators as OP
+from oracle import spectrum as SP
+
+pytestmark = pytest.mark.gpu
+_lib = import_module("lm_b200._lib")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return lm.default_context("c128")
+
+
+@pytest.fixture(scope="module")
+def ctx64():
+    return lm.default_context("c64")
+
+
+def _rand_block(n, m, seed=1234, orth=True):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m))
+    if orth and m <= n:
+        a, _ = np.linalg.qr(a)
+    return np.ascontiguousarray(a)
+
+
+def _relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+# ------------------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("M", [1, 2, 3, 17, 32, 33, 64, 200, 515])
+def test_spmm_matches_oracle(ctx, M):
+    H = OP.qwz(L.square_lattice(7, 6), field=F.LandauGauge(0.13))
+    dev = lm.DeviceHam.from_csc(ctx, H, 2)
+    X = np.asfortranarray(_rand_block(H.shape[0], M, orth=False))
+    Y = np.zeros_like(X, order="F")
+    _lib.check(_lib.load().lm_spmm(dev.handle, _lib.ptr(X), _lib.ptr(Y), H.shape[0], M))
+    assert _relerr(Y, H @ X) < 1e-14
+
+
+@pytest.mark.parametrize("case", ["square_t123", "haldane", "honeycomb_pbc"])
+def test_spmm_stencils(ctx, case):
+    if case == "square_t123":
+        H = OP.tightbinding_hamiltonian(L.square_lattice(9, 8), t1=1, t2=0.4, t3=0.2)
+    elif case == "haldane":
+        H = OP.haldane(L.honeycomb_lattice(7, 6), 1.0, 0.2, 0.1)
+    else:
+        H = OP.haldane(L.honeycomb_lattice(4, 4, periodic=(1, 2)), 1.0, 0.3, 0.0)
+    dev = lm.DeviceHam.from_csc(ctx, H, 1)
+    X = np.asfortranarray(_rand_block(H.shape[0], 40, orth=False))
+    Y = np.zeros_like(X, order="F")
+    _lib.check(_lib.load().lm_spmm(dev.handle, _lib.ptr(X), _lib.ptr(Y), H.shape[0], 40))
+    assert _relerr(Y, H @ X) < 1e-14
+    assert abs(dev.to_csc() - H).max() == 0     # CSC round trip through the ELL layout
+
+
+def test_csc_julia_one_based(ctx):
+    """index_base = 1 (Julia SparseMatrixCSC) is accepted as is."""
+    H = OP.tightbinding_hamiltonian(L.square_lattice(5, 5), field=F.LandauGauge(0.2))
+    colptr = np.ascontiguousarray(H.indptr + 1, np.int64)
+    rowval = np.ascontiguousarray(H.indices + 1, np.int64)
+    nz = np.ascontiguousarray(H.data, np.complex128)
+    h = C.c_void_p()
+    lib = _lib.load()
+    _lib.check(lib.lm_ham_create_csc(ctx.handle, 25, 1, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz), 1, C.byref(h)))
+    X = np.asfortranarray(_rand_block(25, 6, orth=False))
+    Y = np.zeros_like(X, order="F")
+    _lib.check(lib.lm_spmm(h, _lib.ptr(X), _lib.ptr(Y), 25, 6))
+    assert _relerr(Y, H @ X) < 1e-14
+    cp2, rv2 = np.zeros(26, np.int64), np.zeros(H.nnz, np.int64)
+    _lib.check(lib.lm_ham_get_csc(h, _lib.ptr(cp2), _lib.ptr(rv2), None))
+    assert np.array_equal(cp2, colptr) and np.array_equal(rv2, rowval)
+    lib.lm_ham_destroy(h)
+
+
+# ------------------------------------------------------------------------------ device Peierls phases
+FIELD_CASES = {
+    "nofield": (lambda: lm.NoField(), lambda: F.NoField()),
+    "landau": (lambda: lm.LandauGauge(0.1), lambda: F.LandauGauge(0.1)),
+    "symmetric": (lambda: lm.SymmetricGauge(0.07), lambda: F.SymmetricGauge(0.07)),
+    "axial": (lambda: lm.PointFlux(0.13, (5.5, 5.5)), lambda: F.PointFlux(0.13, (5.5, 5.5))),
+    "axial_collinear": (lambda: lm.PointFlux(0.2, (5.0, 5.5)), lambda: F.PointFlux(0.2, (5.0, 5.5))),
+    "axial_onsite": (lambda: lm.PointFlux(0.2, (3.0, 4.0)), lambda: F.PointFlux(0.2, (3.0, 4.0))),
+    "singular": (lambda: lm.PointFlux(0.3, (4.5, 4.5), gauge="singular"), lambda: F.PointFlux(0.3, (4.5, 4.5), "singular")),
+    "fluxes": (lambda: lm.PointFluxes([0.1, -0.2], [(2.5, 2.5), (6.5, 7.5)]), lambda: F.PointFluxes([0.1, -0.2], [(2.5, 2.5), (6.5, 7.5)])),
+    "sum": (lambda: lm.LandauGauge(0.05) + lm.PointFlux(0.3, (3.5, 3.5)), lambda: F.LandauGauge(0.05) + F.PointFlux(0.3, (3.5, 3.5))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FIELD_CASES))
+@pytest.mark.parametrize("model", ["tb", "qwz"])
+def test_device_phases_match_oracle(ctx, name, model):
+    """Device-regenerated H == host-assembled reference H for every closed-form field
+    (src/zoo/magneticfields.jl:15,31,72-104 incl. the 1e-11 guards and the acos fudge)."""
+    fl, fo = FIELD_CASES[name]
+    if model == "tb":
+        Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(9, 10), t1=1, t2=0.3, field=fl())
+        Ho = OP.tightbinding_hamiltonian(L.square_lattice(9, 10), t1=1, t2=0.3, field=fo())
+    else:
+        Hd = lm.qwz(lm.SquareLattice(9, 10), field=fl())
+        Ho = OP.qwz(L.square_lattice(9, 10), field=fo())
+    got = Hd.device(ctx).to_csc()
+    assert abs(got - Ho).max() < 5e-15
+
+
+def test_device_phases_pbc_and_twist(ctx):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Hd = lm.tightbinding_hamiltonian(
+            lm.SquareLattice(5, 6, boundaries=[("axis1", True), ("axis2", 0.7)]), t1=1, t2=0.3, t3=0.1,
+            field=lm.PointFlux(0.2, (2.5, 2.5), gauge="singular") + lm.LandauGauge(0.2))
+    Ho = OP.tightbinding_hamiltonian(L.square_lattice(5, 6, periodic=(1,), twists={2: 0.7}), t1=1, t2=0.3, t3=0.1,
+                                     field=F.PointFlux(0.2, (2.5, 2.5), "singular") + F.LandauGauge(0.2))
+    assert abs(Hd.device(ctx).to_csc() - Ho).max() < 5e-15
+    Hh = lm.haldane(lm.HoneycombLattice(4, 5, boundaries=[("axis1", True)]), 1.0, 0.2, 0.3, field=lm.LandauGauge(0.11))
+    Hho = OP.haldane(L.honeycomb_lattice(4, 5, periodic=(1,)), 1.0, 0.2, 0.3, field=F.LandauGauge(0.11))
+    assert abs(Hh.device(ctx).to_csc() - Hho).max() < 5e-15
+
+
+def test_field_param_update_path(ctx):
+    """lm_ham_set_field_params (a few doubles) == full re-assembly, repeatedly."""
+    l = lm.SquareLattice(8, 8)
+    lo = L.square_lattice(8, 8)
+    for B in (0.0, 0.05, 0.2, 0.05):
+        got = lm.tightbinding_hamiltonian(l, field=lm.PointFlux(B, (4.5, 4.5))).device(ctx).to_csc()
+        want = OP.tightbinding_hamiltonian(lo, field=F.PointFlux(B, (4.5, 4.5)))
+        assert abs(got - want).max() < 5e-15
+    lo_b, hi_b = lm.tightbinding_hamiltonian(l).device(ctx).spectral_bounds()
+    assert lo_b <= -3.9 and hi_b >= 3.9        # Gershgorin encloses [-4, 4]
+
+
+# ------------------------------------------------------------------------------ propagator
+@pytest.mark.parametrize("method", ["taylor", "chebyshev", "auto"])
+@pytest.mark.parametrize("dt", [0.1, 0.7, 3.0, -0.4])
+def test_step_matches_exact_exponential(ctx, method, dt):
+    Ho = OP.qwz(L.square_lattice(6, 5), field=F.LandauGauge(0.1))
+    Psi = _rand_block(60, 13)
+    st = lm.DeviceState.from_psi(Psi, ctx=ctx)
+    sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx, n_int=2)
+    sol.update_solver(Ho, dt)
+    sol.step(st)
+    want = EV.exact_propagator(Ho, dt) @ Psi
+    assert _relerr(st.download(), want) < 2e-13
+    assert sol.n_matvec > 0
+
+
+def test_evolution_known_answer_gpu(ctx):
+    """test/test_timedeps.jl:42-68: qwz(SquareLattice(10,10)) ground state over 0:0.1:10,
+    component psi[2] every frame vs repeated dense exp(-i 0.1 H) products, atol 1e-10."""
+    H = lm.qwz(lm.SquareLattice(10, 10))
+    Hd = OP.qwz(L.square_lattice(10, 10)).toarray()
+    psi = SP.groundstate(Hd)
+    ts = np.arange(0, 101) * 0.1
+    U = EV.exact_propagator(Hd, 0.1)
+    correct, v = [], psi.copy()
+    for _ in ts:
+        correct.append(v[1])
+        v = U @ v
+    for method in ("taylor", "chebyshev"):
+        vals = [m.state.data[1] for m in lm.Evolution(lm.B200Exp(method=method, ctx=ctx), H, psi)(ts)]
+        assert np.abs(np.array(vals) - np.array(correct)).max() < 1e-10
+    # CachedExp-style constant sparse matrix passed as a raw CSC (update_solver! identity skip)
+    vals = [m[0].data[1] for m in lm.Evolution(lm.B200Exp(ctx=ctx, n_int=2), sp.csc_matrix(Hd), psi)(ts)]
+    assert np.abs(np.array(vals) - np.array(correct)).max() < 1e-10
+
+
+def test_stepping_semantics_and_errors(ctx):
+    """src/evolution.jl:238-250,266-275: H(t_old) pairing, dt = 0 first frame, negative dt."""
+    l = lm.SquareLattice(3, 3)
+    lo = L.square_lattice(3, 3)
+    calls = []
+
+    def h(t):
+        calls.append(t)
+        return lm.tightbinding_hamiltonian(l, field=lm.LandauGauge(t))
+    psi = np.zeros(9, complex)
+    psi[4] = 1
+    ev = lm.Evolution(lm.B200Exp(tol=1e-14, ctx=ctx), h, psi)
+    calls.clear()
+    frames = [(m.state.data.copy(), m.H, m.t) for m in ev([0.0, 0.5, 1.0])]
+    assert calls == [0.0, 0.0, 0.5]
+    assert np.array_equal(frames[0][0], psi)
+    U0 = EV.exact_propagator(OP.tightbinding_hamiltonian(lo, field=F.LandauGauge(0.0)), 0.5)
+    U1 = EV.exact_propagator(OP.tightbinding_hamiltonian(lo, field=F.LandauGauge(0.5)), 0.5)
+    assert np.abs(frames[2][0] - U1 @ (U0 @ psi)).max() < 1e-13
+    assert frames[2][1].field.B == 0.5 and frames[2][2] == pytest.approx(1.0)
+    with pytest.raises(lm.ArgumentError, match="negative time step"):
+        ev.step(-0.1)
+    nxt = list(ev([1.5]))                      # stateful continuation
+    assert nxt[0].t == pytest.approx(1.5)
+    with pytest.raises(lm.ArgumentError):
+        lm.Evolution(lm.B200Exp(ctx=ctx), h)   # no states
+    with pytest.raises(lm.ArgumentError):
+        lm.Evolution(lm.B200Exp(ctx=ctx), h, psi, P=psi)   # named + unnamed
+    # dimension mismatch surfaces as ArgumentError from the C ABI
+    with pytest.raises(lm.ArgumentError, match="dimension mismatch"):
+        sol = lm.B200Exp(ctx=ctx)
+        sol.update_solver(lm.tightbinding_hamiltonian(lm.SquareLattice(4, 4)), 0.1)
+        sol.step(lm.DeviceState.from_psi(psi, ctx=ctx))
+
+
+def test_host_assembled_closure_path(ctx):
+    """Arbitrary closure t -> sparse matrix: same pattern, nzval re-uploaded each step
+    (lm_ham_update_values), results equal the device-phase path."""
+    lo = L.square_lattice(6, 6)
+    l = lm.SquareLattice(6, 6)
+    Psi = _rand_block(36, 9)
+    ts = np.arange(0, 6) * 0.1
+    ev_a = lm.Evolution(lm.B200Exp(tol=1e-14, ctx=ctx), lambda t: OP.tightbinding_hamiltonian(lo, field=F.PointFlux(0.3 * t, (3.5, 3.5))), lm.PsiProjector(Psi))
+    ev_b = lm.Evolution(lm.B200Exp(tol=1e-14, ctx=ctx), lambda t: lm.tightbinding_hamiltonian(l, field=lm.PointFlux(0.3 * t, (3.5, 3.5))), lm.PsiProjector(Psi))
+    ref = EV.Evolution(lambda t: OP.tightbinding_hamiltonian(lo, field=F.PointFlux(0.3 * t, (3.5, 3.5))), [Psi], solver="exact", block=True)
+    for ma, mb, (st, H, t) in zip(ev_a(ts), ev_b(ts), ref(ts)):
+        assert _relerr(ma.state.download(), st[0]) < 1e-12
+        assert _relerr(mb.state.download(), st[0]) < 1e-12
+
+
+# ------------------------------------------------------------------------------ observables
+@pytest.mark.parametrize("M", [1, 5, 16, 40, 600])
+def test_observables_match_oracle(ctx, M):
+    lo = L.square_lattice(20, 20) if M == 600 else L.square_lattice(6, 5)
+    l = lm.SquareLattice(20, 20) if M == 600 else lm.SquareLattice(6, 5)
+    Ho = OP.qwz(lo, field=F.LandauGauge(0.1))
+    Hd = lm.qwz(l, field=lm.LandauGauge(0.1))
+    N = Ho.shape[0]
+    Psi = _rand_block(N, M, seed=7)
+    w = np.random.default_rng(3).random(M)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=2)
+    ost = OB.State(Psi, w, block=True)
+    rho = lm.localdensity(st)
+    assert _relerr(rho.values, OB.localdensity(ost, 2)) < 1e-13
+    dc = lm.DensityCurrents(Hd, st)
+    I, J, V = dc.pair_values()
+    pairs = OB.site_adjacency(Ho, 2)
+    assert list(zip(I.tolist(), J.tolist())) == pairs          # findnz ordering (J major, I minor)
+    sub = pairs[:: max(1, len(pairs) // 60)]
+    idx = [pairs.index(p) for p in sub]
+    want = np.array([OB.density_current(Ho, ost, i, j, 2) for i, j in sub])
+    assert np.abs(V[idx] - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+    i0, j0 = sub[0]
+    assert dc[i0, j0] == pytest.approx(want[0], abs=1e-13)
+    assert dc[j0, i0] == pytest.approx(-want[0], abs=1e-13)      # antisymmetry (test_currents.jl:14)
+    assert dc[i0, i0] == 0.0                                     # zero self current (:15)
+
+
+def test_currents_reference_scenarios(ctx):
+    """test/test_currents.jl:1-63 on the device: Heisenberg sum, Ket vs block representation,
+    Currents(dc) == Currents(dc, adjacency), findnz filter."""
+    lo, l = L.square_lattice(4, 4), lm.SquareLattice(4, 4)
+    H0o, H1o = OP.qwz(lo), OP.qwz(lo, field=F.LandauGauge(0.1))
+    H1 = lm.qwz(l, field=lm.LandauGauge(0.1))
+    P, Psi, w = SP.densitymatrix(H0o, mu=0.0)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=2)
+    dc = lm.DensityCurrents(H1, st)
+    s1 = 6
+    nbrs = [s1 + 4, s1 + 1, s1 - 4, s1 - 1]
+    n_op = np.zeros((32, 32), complex)
+    for a in range(2):
+        n_op[(s1 - 1) * 2 + a, (s1 - 1) * 2 + a] = 1
+    Hd = H1o.toarray()
+    dens_dt = np.trace(1j * (Hd @ n_op - n_op @ Hd) @ P).real
+    assert sum(dc[s1, t] for t in nbrs) == pytest.approx(dens_dt, abs=1e-13)
+    assert lm.currentsfromto(dc, s1) == pytest.approx(dens_dt, abs=1e-12)
+    full = lm.Currents(dc)
+    want = OB.currents_matrix(H1o, P, 2)
+    assert abs(full.currents - want).max() < 1e-13
+    Is, Js, Vs = lm.findnz(dc)
+    Io, Jo, Vo = OB.currents_findnz(H1o, P, 2)
+    assert np.array_equal(Is, Io) and np.array_equal(Js, Jo) and np.abs(Vs - Vo).max() < 1e-13
+    adj = [(i, j) for i, j in OB.site_adjacency(H1o, 2)]
+    assert abs(lm.Currents(dc, adj).currents - full.currents).max() == 0
+    gs = SP.groundstate(H0o)
+    c1 = lm.Currents(lm.DensityCurrents(H1, lm.DeviceState.from_psi(gs, ctx=ctx, n_int=2)))
+    c2 = OB.currents_matrix(H1o, np.outer(gs, gs.conj()), 2)
+    assert abs(c1.currents - c2).max() < 1e-13
+    assert abs((full + full).currents - (2 * full).currents).max() == 0
+
+
+# ------------------------------------------------------------------------------ dense-P path (DMMA)
+def test_dense_density_matrix_step(ctx):
+    """P <- U P U' on the FP64 tensor cores == CachedExp semantics (src/evolution.jl:73-78)."""
+    Ho = OP.qwz(L.square_lattice(5, 4), field=F.LandauGauge(0.1))
+    N = Ho.shape[0]
+    P, Psi, w = SP.densitymatrix(Ho, T=0.5, mu=0.1)          # mixed state, all columns
+    st = lm.DeviceState.from_dense(P, ctx=ctx, n_int=2)
+    sol = lm.B200Exp(tol=1e-14, ctx=ctx, n_int=2)
+    U = EV.exact_propagator(Ho, 0.1)
+    want = P.copy()
+    for _ in range(3):
+        sol.update_solver(Ho, 0.1)
+        sol.step(st)
+        want = U @ want @ U.conj().T
+    assert _relerr(st.download(), want) < 1e-12
+    assert _relerr(lm.localdensity(st).values, OB.localdensity(want, 2)) < 1e-12
+    # Psi-block escape hatch: dense(P) materialises Psi W Psi'
+    stb = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=2)
+    assert _relerr(stb.dense(), P) < 1e-13
+
+
+def test_readme_workflow_config1(ctx):
+    """README.md:25-55 = BASELINE config 1: SquareLattice(10,10), PointFlux ramp, mu = 0 density
+    matrix, 0:0.1:20, localdensity + DensityCurrents per frame.  Dense-P state (as the reference
+    evolves it) and the Psi-block reformulation both track the oracle to 1e-10 relative."""
+    lo, l = L.square_lattice(10, 10), lm.SquareLattice(10, 10)
+    tau = 10.0
+
+    def h_ref(t):
+        return OP.tightbinding_hamiltonian(lo, field=F.PointFlux(0.2 * min(t, tau) / tau, (5.5, 5.5)))
+
+    def h_dev(t):
+        return lm.tightbinding_hamiltonian(l, field=lm.PointFlux(0.2 * min(t, tau) / tau, (5.5, 5.5)))
+    P0, Psi0, w0 = SP.densitymatrix(h_ref(0.0), mu=0.0)        # shared input (degenerate Fermi level)
+    ts = np.arange(0, 201) * 0.1
+    pairs = OB.site_adjacency(h_ref(0.0), 1)
+    ev_ref = EV.Evolution(h_ref, [P0], solver="exact")
+    ev_dense = lm.Evolution(lm.B200Exp(tol=1e-13, ctx=ctx), h_dev, P=P0)
+    ev_block = lm.Evolution(lm.B200Exp(tol=1e-13, ctx=ctx), h_dev, lm.PsiProjector(Psi0, w0))
+    worst_rho = worst_j = 0.0
+    for k, ((st, H, t), md, mb) in enumerate(zip(ev_ref(ts), ev_dense(ts), ev_block(ts))):
+        if k % 10 and k != 200:
+            continue
+        rho = OB.localdensity(st[0], 1)
+        Jw = np.array([OB.density_current(H, st[0], i, j, 1) for i, j in pairs])
+        rb = lm.localdensity(mb.state).values
+        rd = lm.localdensity(md.P).values
+        Pb, Hb, tb = mb
+        Jb = lm.DensityCurrents(Hb, Pb).pair_values()[2]
+        worst_rho = max(worst_rho, _relerr(rb, rho), _relerr(rd, rho))
+        big = np.abs(Jw) >= 1e-10
+        if big.any():
+            worst_j = max(worst_j, np.abs(Jb - Jw)[big].max() / np.abs(Jw).max())
+        assert tb == pytest.approx(t)
+    assert worst_rho < 1e-10 and worst_j < 1e-10
+
+
+# ------------------------------------------------------------------------------ complex64 mode
+def test_complex64_mode(ctx64):
+    Ho = OP.qwz(L.square_lattice(6, 6), field=F.LandauGauge(0.1))
+    Hd = lm.qwz(lm.SquareLattice(6, 6), field=lm.LandauGauge(0.1))
+    Psi = _rand_block(72, 20)
+    st = lm.DeviceState.from_psi(Psi, ctx=ctx64, n_int=2)
+    sol = lm.B200Exp(tol=1e-7, ctx=ctx64)
+    want = Psi.copy()
+    U = EV.exact_propagator(Ho, 0.1)
+    for _ in range(10):
+        sol.update_solver(Hd, 0.1)
+        sol.step(st)
+        want = U @ want
+    assert _relerr(st.download(), want) < 1e-5
+    rho = lm.localdensity(st).values
+    assert _relerr(rho, OB.localdensity(OB.State(want, None, block=True), 2)) < 1e-5
+    V = lm.DensityCurrents(Hd, st).pair_values()[2]
+    pairs = OB.site_adjacency(Ho, 2)
+    Jw = np.array([OB.density_current(Ho, OB.State(want, None, block=True), i, j, 2) for i, j in pairs])
+    assert np.abs(V - Jw).max() < 1e-5 * max(1.0, np.abs(Jw).max())
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_config2_properties(ctx):
+    """BASELINE config 2 (SquareLattice(100,100), N = 1e4, M = 5e3, complex128): size-independent
+    properties - unitarity (column norms / particle number), linearity, continuity
+    d rho_i/dt = sum_j J_ij by finite differences, round trip exp(-iHdt) exp(+iHdt) = 1."""
+    l = lm.SquareLattice(100, 100)
+    H = lm.tightbinding_hamiltonian(l, field=lm.LandauGauge(0.02))
+    N, M = 10000, 5000
+    rng = np.random.default_rng(1234)
+    Psi = (rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M))) / np.sqrt(2 * N)
+    st = lm.DeviceState.from_psi(Psi, ctx=ctx)
+    sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+    rho0 = lm.localdensity(st).values
+    J0 = lm.Currents(lm.DensityCurrents(H, st)).currents
+    n0 = rho0.sum()
+    eps = 1e-4
+    sol.update_solver(H, eps)
+    sol.step(st)
+    rho1 = lm.localdensity(st).values
+    assert abs(rho1.sum() - n0) < 1e-11 * n0                               # particle number
+    drho = (rho1 - rho0) / eps
+    assert np.abs(drho - np.asarray(J0.sum(axis=1)).ravel()).max() < 5e-3 * np.abs(drho).max()   # continuity (O(eps))
+    sol.update_solver(H, -eps)
+    sol.step(st)                                                           # back to t = 0
+    sol.update_solver(H, 0.1)
+    sol.step(st)
+    sol.update_solver(H, -0.1)
+    sol.step(st)
+    back = st.download()
+    assert np.abs(back - Psi).max() < 1e-12 * np.abs(Psi).max() * 50      # round trip
+    # linearity on a column slice against the oracle SpMM
+    Ho = H.data
+    Y = np.zeros((N, 8), complex, order="F")
+    X = np.asfortranarray(Psi[:, :8])
+    _lib.check(_lib.load().lm_spmm(H.device(ctx).handle, _lib.ptr(X), _lib.ptr(Y), N, 8))
+    assert _relerr(Y, Ho @ X) < 1e-14
