@@ -14,7 +14,7 @@
  *   (orth = ModifiedGramSchmidtIR), residual estimate beta_m |[exp(tau T_m)]_{m,1}| - is
  *   restated here exactly as in oracle/evolution.py::krylov_exponentiate.
  *   localdensity (src/operators/latticeutils.jl:41-45) for the per-frame density.
- * The reference itself is single-threaded Julia; columns are independent, so the OpenMP loop
+ * The reference itself is single-threaded Julia; columns are independent, so the pthread loop
  * over columns is the most favourable CPU arrangement (thread count is reported).
  */
 #include <complex.h>
@@ -22,9 +22,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+#include <pthread.h>
+#include <unistd.h>
 
 typedef double complex zc;
 
@@ -155,28 +154,53 @@ static int64_t krylov_column(int64_t n, const int64_t* rowptr, const int32_t* co
 }
 
 /* Evolve M kets (columns of psi, column-major n x M) by exp(-i H dt); H in CSR (0-based).
+ * Columns are distributed over `nthreads` pthreads through an atomic counter.
  * Returns total matvecs (negative if any column failed to converge). */
+typedef struct {
+    int64_t n, M; const int64_t* rowptr; const int32_t* col; const zc* val; zc* psi;
+    double dt, tol; int krylovdim, maxiter;
+    int64_t next; int64_t total; int failed; pthread_mutex_t mu;
+} job_t;
+
+static void* worker(void* arg) {
+    job_t* j = (job_t*)arg;
+    zc* work = (zc*)malloc(sizeof(zc) * (size_t)(j->krylovdim + 1) * j->n);
+    int64_t mine = 0; int bad = 0;
+    for (;;) {
+        int64_t c = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (c >= j->M) break;
+        int64_t k = krylov_column(j->n, j->rowptr, j->col, j->val, j->psi + (size_t)c * j->n, j->dt,
+                                  j->krylovdim, j->tol, j->maxiter, work);
+        if (k < 0) { bad = 1; k = -k; }
+        mine += k;
+    }
+    free(work);
+    pthread_mutex_lock(&j->mu); j->total += mine; j->failed |= bad; pthread_mutex_unlock(&j->mu);
+    return NULL;
+}
+
+int lm_ref_max_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
 int64_t lm_ref_krylov_block_step(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val_ri,
                                  int64_t M, double* psi_ri, double dt, int krylovdim, double tol, int maxiter,
                                  int nthreads) {
-    const zc* val = (const zc*)val_ri;
-    zc* psi = (zc*)psi_ri;
-    int64_t total = 0; int failed = 0;
-#ifdef _OPENMP
-    if (nthreads > 0) omp_set_num_threads(nthreads);
-#endif
-#pragma omp parallel reduction(+ : total) reduction(| : failed)
-    {
-        zc* work = (zc*)malloc(sizeof(zc) * (size_t)(krylovdim + 1) * n);
-#pragma omp for schedule(dynamic, 1)
-        for (int64_t c = 0; c < M; ++c) {
-            int64_t k = krylov_column(n, rowptr, col, val, psi + (size_t)c * n, dt, krylovdim, tol, maxiter, work);
-            if (k < 0) { failed = 1; k = -k; }
-            total += k;
-        }
-        free(work);
-    }
-    return failed ? -total : total;
+    job_t j;
+    j.n = n; j.M = M; j.rowptr = rowptr; j.col = col; j.val = (const zc*)val_ri; j.psi = (zc*)psi_ri;
+    j.dt = dt; j.tol = tol; j.krylovdim = krylovdim; j.maxiter = maxiter;
+    j.next = 0; j.total = 0; j.failed = 0;
+    pthread_mutex_init(&j.mu, NULL);
+    if (nthreads <= 0) nthreads = lm_ref_max_threads();
+    if (nthreads > M) nthreads = (int)(M > 0 ? M : 1);
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, &j);
+    worker(&j);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&j.mu);
+    return j.failed ? -j.total : j.total;
 }
 
 /* rho_i = sum_alpha sum_c w_c |psi[i*n_int + alpha, c]|^2  (src/operators/latticeutils.jl:41-45) */
@@ -193,10 +217,3 @@ void lm_ref_localdensity(int64_t n, int64_t M, int n_int, const double* psi_ri, 
     }
 }
 
-int lm_ref_max_threads(void) {
-#ifdef _OPENMP
-    return omp_get_max_threads();
-#else
-    return 1;
-#endif
-}
