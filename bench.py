@@ -181,7 +181,12 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: the default stream's handle is 0, which the C ABI reads as
+    # "create your own"; torch events must be recorded on the stream the kernels launch on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx = lm.Context(device=local, precision=args.precision, stream=stream)
     if world > 1:
         D.attach_communicator(ctx)
@@ -258,7 +263,7 @@ def main():
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get("%s_n%d" % (args.workload, world))
-    roofline = {"bound": "hbm", "kernel": "lm::k_apply (fused ELL SpMM + polynomial term)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "lm::k_apply_rows (fused ELL SpMM + product-form Taylor factor, tile-order register gather)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmm, "launches_timed": n_apply, "avg_launch_ms": avg_launch_ms,
                 "K_matvec_per_step": K}
@@ -275,7 +280,7 @@ def main():
     j_pinned = torch.empty(max(npairs, 1), dtype=torch.float64).pin_memory()
     rho_np, j_np = rho_pinned.numpy(), j_pinned.numpy()
     nmv = C.c_int32()
-    method = {"auto": 0, "chebyshev": 1, "taylor": 2}[args.method]
+    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4}[args.method]
 
     def e2e_step(k):
         _lib.check(lib.lm_ham_update_values(csc_dev.handle, _lib.ptr(nz_np)))                  # H2D

@@ -45,10 +45,12 @@ extern "C" {
 #define LM_C64  1                /* complex64 arithmetic (optional mode, parity 1e-5) */
 
 /* lm_step `method` */
-#define LM_METHOD_AUTO      0    /* Taylor for small ||H||dt, Chebyshev otherwise */
+#define LM_METHOD_AUTO      0    /* product-form Taylor for small ||H||dt, Chebyshev otherwise */
 #define LM_METHOD_CHEBYSHEV 1    /* Clenshaw-Chebyshev expansion of exp(-iH dt) */
-#define LM_METHOD_TAYLOR    2    /* Horner-Taylor with sub-stepping (what myexp! sums, src/evolution.jl:93-128) */
+#define LM_METHOD_TAYLOR    2    /* truncated Taylor series (the polynomial myexp! sums, src/evolution.jl:93-128)
+                                    applied in product form prod_j (I - A/r_j): 2 HBM streams per term */
 #define LM_METHOD_LANCZOS   3    /* per-column Lanczos (KrylovKit.exponentiate semantics, src/evolution.jl:150-154) */
+#define LM_METHOD_TAYLOR_HORNER 4 /* same polynomial in Horner form (3 streams per term; cross-check) */
 
 /* gauge-field kinds for lm_ham_set_fields; each field owns 3 doubles of `params` */
 #define LM_FIELD_LANDAU            1   /* (B, -, -)         src/zoo/magneticfields.jl:15  */
@@ -116,6 +118,11 @@ int32_t lm_ham_create_bonds(lm_ctx* ctx, int64_t n_sites, int32_t n_int, int64_t
 int32_t lm_ham_set_fields(lm_ham* ham, int32_t nfields, const int32_t* kinds, const double* params);
 /* same kinds, new parameters (a few doubles per step instead of a host re-assembly) */
 int32_t lm_ham_set_field_params(lm_ham* ham, const double* params);
+
+/* Site coordinates (n_sites (x, y) pairs, the lattice's own site_coords,
+ * src/lattices/bravais/unitcell.jl:119-122): lets the library group rows into compact 2-D
+ * patches for the TMA-staged SpMM.  Optional - without it the register-gather kernel is used. */
+int32_t lm_ham_set_site_coords(lm_ham* ham, const double* xy);
 
 int32_t lm_ham_dims(lm_ham* ham, int64_t* N, int32_t* n_int, int64_t* nnz, int32_t* ell_width);
 /* CSC view of the current H (pattern + values), index_base as given at creation */

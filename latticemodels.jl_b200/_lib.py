@@ -13,7 +13,7 @@ from . import build as _build
 
 LM_OK = 0
 LM_C128, LM_C64 = 0, 1
-METHOD_AUTO, METHOD_CHEBYSHEV, METHOD_TAYLOR, METHOD_LANCZOS = 0, 1, 2, 3
+METHOD_AUTO, METHOD_CHEBYSHEV, METHOD_TAYLOR, METHOD_LANCZOS, METHOD_TAYLOR_HORNER = 0, 1, 2, 3, 4
 FIELD_LANDAU, FIELD_SYMMETRIC, FIELD_POINTFLUX_AXIAL, FIELD_POINTFLUX_SINGULAR = 1, 2, 3, 4
 
 
@@ -47,6 +47,7 @@ PROTOTYPES = {
     "lm_ham_create_bonds": [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_set_fields": [_vp, _i32, _vp, _vp],
     "lm_ham_set_field_params": [_vp, _vp],
+    "lm_ham_set_site_coords": [_vp, _vp],
     "lm_ham_dims": [_vp, _pi64, _pi32, _pi64, _pi32],
     "lm_ham_get_csc": [_vp, _vp, _vp, _vp],
     "lm_ham_spectral_bounds": [_vp, _pf64, _pf64],

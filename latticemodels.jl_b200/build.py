@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "taylor_roots.h"),
         os.path.join(HERE, "..", "include", "lm_b200.h")]
 LIB = os.path.join(HERE, "lib", "liblm_b200.so")
 

@@ -3,6 +3,7 @@
 // returned through this ABI is produced by the CUDA kernels.
 #include "../../include/lm_b200.h"
 #include "kernels.cuh"
+#include "taylor_roots.h"
 
 #include <algorithm>
 #include <climits>
@@ -31,6 +32,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 #define REQUIRE(cond, msg) do { if (!(cond)) return fail(LM_ERR_INVALID, msg); } while (0)
 #define FWD(expr) do { int _s = (expr); if (_s != LM_OK) return _s; } while (0)
+// tuning knobs (environment overrides are for the sweep harness only)
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
 extern "C" const char* lm_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t lm_version(void) { return 100; }
@@ -117,6 +120,11 @@ struct lm_ham {
     long long version = 0;
     // observable scratch
     double* d_dens = nullptr; double2* d_G = nullptr; double* d_obs = nullptr;
+    // tile plan for the TMA-staged kernel (k_apply_tiled)
+    std::vector<int> h_cols;                       // host copy of the ELL columns
+    bool tiled = false; bool plan_from_coords = false; int ntiles = 0; int tile_max_rows = 0; long long tile_window_rows = 0;
+    double tile_halo_ratio = 0;
+    int* d_t_ptr = nullptr; int* d_t_nr = nullptr; int* d_t_rows = nullptr; unsigned short* d_lcols = nullptr;
 };
 
 struct lm_state {
@@ -221,7 +229,8 @@ static void ham_free(lm_ham* h) {
     cudaStreamSynchronize(h->ctx->stream);
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
-                    h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs};
+                    h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -254,6 +263,7 @@ static int ham_finish_pattern(lm_ham* h, const std::vector<long long>& rows, con
         band = std::max(band, std::llabs(i - cols_in[e]));
     }
     h->band = band;
+    h->h_cols = ecols;
     // CSC view: sort entries by (col, row)
     std::vector<long long> order(nu);
     for (long long e = 0; e < nu; ++e) order[e] = e;
@@ -312,6 +322,124 @@ static int ham_finish_pattern(lm_ham* h, const std::vector<long long>& rows, con
     CK(cudaMalloc(&h->d_obs, sizeof(double) * (size_t)(h->n_sites + h->npairs + 1)));
     CK(cudaMemsetAsync(h->d_G, 0, sizeof(double2) * (size_t)N * W, s));
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
+    return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile plan: rows grouped into compact patches (spatial bins of the site coordinates when the
+// host provides them, consecutive index blocks otherwise), halo lists and local ELL indices.
+// ------------------------------------------------------------------------------------------
+static int ham_build_tiles(lm_ham* h, const double* xy) {
+    lm_ctx* c = h->ctx;
+    const long long N = h->N, ns = h->n_sites; const int n = h->n_int, W = h->W;
+    static const int TR = std::max(16, env_int("LM_TILE_ROWS", 64));
+    const long long spt = std::max<long long>(1, TR / n);            // sites per tile (target)
+    std::vector<int> tile_of_site(ns, 0);
+    std::vector<std::vector<int>> tiles;                              // own SITES per tile, index order
+    long long rows_per_binrow = 0;
+    if (xy) {
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (long long s = 0; s < ns; ++s) {
+            x0 = std::min(x0, xy[2 * s]); x1 = std::max(x1, xy[2 * s]);
+            y0 = std::min(y0, xy[2 * s + 1]); y1 = std::max(y1, xy[2 * s + 1]);
+        }
+        const double Lx = std::max(x1 - x0, 1e-9), Ly = std::max(y1 - y0, 1e-9);
+        double hx, hy; long long nx, ny;
+        if (Ly <= 1e-6 * Lx) { nx = std::max<long long>(1, (ns + spt - 1) / spt); ny = 1; }
+        else if (Lx <= 1e-6 * Ly) { ny = std::max<long long>(1, (ns + spt - 1) / spt); nx = 1; }
+        else {
+            const double hside = std::sqrt(Lx * Ly * (double)spt / (double)ns);
+            nx = std::max<long long>(1, (long long)std::ceil(Lx / hside));
+            ny = std::max<long long>(1, (long long)std::ceil(Ly / hside));
+        }
+        hx = Lx / nx * (1 + 1e-12); hy = Ly / ny * (1 + 1e-12);
+        std::vector<std::vector<int>> bins((size_t)(nx * ny));
+        for (long long s = 0; s < ns; ++s) {
+            long long ix = std::min<long long>(nx - 1, (long long)((xy[2 * s] - x0) / hx));
+            long long iy = std::min<long long>(ny - 1, (long long)((xy[2 * s + 1] - y0) / hy));
+            bins[(size_t)(ix * ny + iy)].push_back((int)s);
+        }
+        for (long long ix = 0; ix < nx; ++ix) {
+            long long rows_here = 0;
+            for (long long iy = 0; iy < ny; ++iy) {
+                auto& b = bins[(size_t)(ix * ny + iy)];
+                rows_here += (long long)b.size() * n;
+                for (size_t q = 0; q < b.size(); q += (size_t)(2 * spt)) {     // split over-full bins
+                    const size_t e = std::min(b.size(), q + (size_t)(2 * spt));
+                    tiles.emplace_back(b.begin() + q, b.begin() + e);
+                }
+            }
+            rows_per_binrow = std::max(rows_per_binrow, rows_here);
+        }
+    } else {
+        for (long long s0 = 0; s0 < ns; s0 += spt) {
+            std::vector<int> t;
+            for (long long s = s0; s < std::min(ns, s0 + spt); ++s) t.push_back((int)s);
+            tiles.push_back(std::move(t));
+        }
+        rows_per_binrow = h->band + TR;
+    }
+    // drop empty tiles, number the rest
+    std::vector<std::vector<int>> kept;
+    for (auto& t : tiles) if (!t.empty()) kept.push_back(std::move(t));
+    tiles.swap(kept);
+    const int ntiles = (int)tiles.size();
+    for (int t = 0; t < ntiles; ++t) for (int s : tiles[t]) tile_of_site[s] = t;
+    // lists + local indices
+    std::vector<int> t_ptr(ntiles + 1, 0), t_nr(ntiles, 0), t_rows;
+    std::vector<unsigned short> lcols((size_t)N * W, 0);
+    std::vector<int> local(N, -1), stamp(N, -1);
+    t_rows.reserve((size_t)N * 2);
+    int max_rows = 0; double halo_sum = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int base = (int)t_rows.size();
+        int cnt = 0;
+        for (int s : tiles[t]) for (int a = 0; a < n; ++a) { const int g = s * n + a; local[g] = cnt++; stamp[g] = t; t_rows.push_back(g); }
+        t_nr[t] = cnt;
+        for (int s : tiles[t]) for (int a = 0; a < n; ++a) {
+            const long long g = (long long)s * n + a;
+            for (int k = 0; k < W; ++k) {
+                const int col = h->h_cols[g * W + k];
+                if (stamp[col] != t) { stamp[col] = t; local[col] = cnt++; t_rows.push_back(col); }
+                if (local[col] > 65535) return fail(LM_ERR_UNSUPPORTED, "tile plan: more than 65535 rows in a tile");
+                lcols[g * W + k] = (unsigned short)local[col];
+            }
+        }
+        t_ptr[t + 1] = (int)t_rows.size();
+        max_rows = std::max(max_rows, cnt);
+        halo_sum += (double)(cnt - t_nr[t]);
+        (void)base;
+    }
+    h->plan_from_coords = (xy != nullptr);
+    h->ntiles = ntiles; h->tile_max_rows = max_rows; h->tile_window_rows = 2 * rows_per_binrow;
+    h->tile_halo_ratio = halo_sum / (double)std::max<long long>(1, N);
+    // usable only if the staged rows of the widest tile fit comfortably in shared memory
+    static const int smem_cap = env_int("LM_TILE_SMEM_KB", 100) * 1024;
+    h->tiled = (long long)max_rows * 16 * (long long)c->esz() <= smem_cap;
+    FWD(set_dev(c));
+    CK(cudaStreamSynchronize(c->stream));
+    void* old[] = {h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols};
+    for (void* p : old) if (p) cudaFree(p);
+    h->d_t_ptr = h->d_t_nr = h->d_t_rows = nullptr; h->d_lcols = nullptr;
+    CK(cudaMalloc(&h->d_t_ptr, sizeof(int) * t_ptr.size()));
+    CK(cudaMalloc(&h->d_t_nr, sizeof(int) * std::max<size_t>(1, t_nr.size())));
+    CK(cudaMalloc(&h->d_t_rows, sizeof(int) * std::max<size_t>(1, t_rows.size())));
+    CK(cudaMalloc(&h->d_lcols, sizeof(unsigned short) * lcols.size()));
+    CK(cudaMemcpy(h->d_t_ptr, t_ptr.data(), sizeof(int) * t_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_t_nr, t_nr.data(), sizeof(int) * t_nr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_t_rows, t_rows.data(), sizeof(int) * t_rows.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_lcols, lcols.data(), sizeof(unsigned short) * lcols.size(), cudaMemcpyHostToDevice));
+    return LM_OK;
+}
+
+extern "C" int32_t lm_ham_set_site_coords(lm_ham* h, const double* xy) {
+    REQUIRE(h && xy, "lm_ham_set_site_coords: NULL argument");
+    return ham_build_tiles(h, xy);
+}
+extern "C" int32_t lm_dbg_tile_info(lm_ham* h, int32_t* ntiles, int32_t* max_rows, double* halo_ratio, int32_t* tiled) {
+    REQUIRE(h, "lm_dbg_tile_info: NULL");
+    if (ntiles) *ntiles = h->ntiles; if (max_rows) *max_rows = h->tile_max_rows;
+    if (halo_ratio) *halo_ratio = h->tile_halo_ratio; if (tiled) *tiled = h->tiled ? 1 : 0;
     return LM_OK;
 }
 
@@ -756,21 +884,142 @@ extern "C" int32_t lm_state_download_dense(lm_state* s, void* out) {
 // ------------------------------------------------------------------------------------------
 // the polynomial propagators
 // ------------------------------------------------------------------------------------------
-template <typename T, int CPT>
-static void launch_apply_w(const ApplyArgs& a, unsigned grid, cudaStream_t s) {
-    switch (a.W) {
-#define LM_CASE(w) case w: k_apply<T, CPT, w><<<grid, 256, 0, s>>>(a); break;
-        LM_CASE(1) LM_CASE(2) LM_CASE(3) LM_CASE(4) LM_CASE(5) LM_CASE(6) LM_CASE(7) LM_CASE(8)
-        LM_CASE(9) LM_CASE(10) LM_CASE(11) LM_CASE(12) LM_CASE(13) LM_CASE(14) LM_CASE(15) LM_CASE(16)
+template <typename T, int CPT, int MODE>
+static void launch_apply_w(const ApplyArgs& a, dim3 grid, cudaStream_t s) {
+    static const int generic_only = getenv("LM_APPLY_GENERIC") ? atoi(getenv("LM_APPLY_GENERIC")) : 0;
+    switch (generic_only ? 0 : a.W) {
+#define LM_CASE(w) case w: k_apply<T, CPT, w, MODE><<<grid, 256, 0, s>>>(a); break;
+        LM_CASE(4) LM_CASE(5) LM_CASE(9) LM_CASE(10)
 #undef LM_CASE
-        default: k_apply<T, CPT, 0><<<grid, 256, 0, s>>>(a); break;
+        default: k_apply<T, CPT, 0, MODE><<<grid, 256, 0, s>>>(a); break;
     }
+}
+template <typename T, int CPT>
+static void launch_apply_mode(const ApplyArgs& a, dim3 grid, cudaStream_t s) {
+    const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
+    if (!a.z && !a.u && !g) launch_apply_w<T, CPT, 0>(a, grid, s);
+    else if (a.z && !a.u && !g) launch_apply_w<T, CPT, 1>(a, grid, s);
+    else if (!a.z && !a.u && g) launch_apply_w<T, CPT, 3>(a, grid, s);
+    else launch_apply_w<T, CPT, 2>(a, grid, s);
+}
+template <typename T>
+static void launch_apply_cpt(const ApplyArgs& a, int cpt, dim3 grid, cudaStream_t s) {
+    if (cpt == 4) launch_apply_mode<T, 4>(a, grid, s);
+    else if (cpt == 2) launch_apply_mode<T, 2>(a, grid, s);
+    else launch_apply_mode<T, 1>(a, grid, s);
+}
+
+
+template <typename T, int CPT, int MODE>
+static int launch_tiled_inst(const TiledArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CK(cudaFuncSetAttribute(k_apply_tiled<T, CPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_apply_tiled<T, CPT, MODE><<<grid, 256, smem, s>>>(a);
+    return LM_OK;
+}
+template <typename T, int CPT>
+static int launch_tiled_mode(const TiledArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
+    if (!a.z && !a.u && !g) return launch_tiled_inst<T, CPT, 0>(a, grid, smem, s);
+    if (a.z && !a.u && !g) return launch_tiled_inst<T, CPT, 1>(a, grid, smem, s);
+    if (!a.z && !a.u && g) return launch_tiled_inst<T, CPT, 3>(a, grid, smem, s);
+    return launch_tiled_inst<T, CPT, 2>(a, grid, smem, s);
+}
+
+template <typename T, int CPT, int MODE>
+static void launch_rows_w(const RowsArgs& a, dim3 grid, cudaStream_t s) {
+    static const int generic_only = env_int("LM_APPLY_GENERIC", 0);
+    // exact unrolling only for narrow stencils: for W >= 8 ptxas front-loads every gather and
+    // spills; the generic loop (unrolled by 4) keeps 4 x CPT gathers in flight in 64 registers
+    switch (generic_only ? 0 : a.W) {
+#define LM_CASE(w) case w: k_apply_rows<T, CPT, w, MODE><<<grid, 256, 0, s>>>(a); break;
+        LM_CASE(3) LM_CASE(4) LM_CASE(5)
+#undef LM_CASE
+        default: k_apply_rows<T, CPT, 0, MODE><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+template <typename T, int CPT>
+static void launch_rows_mode(const RowsArgs& a, dim3 grid, cudaStream_t s) {
+    const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
+    if (!a.z && !a.u && !g) launch_rows_w<T, CPT, 0>(a, grid, s);
+    else if (a.z && !a.u && !g) launch_rows_w<T, CPT, 1>(a, grid, s);
+    else if (!a.z && !a.u && g) launch_rows_w<T, CPT, 3>(a, grid, s);
+    else launch_rows_w<T, CPT, 2>(a, grid, s);
+}
+static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                      zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    RowsArgs a;
+    a.t_ptr = h->d_t_ptr; a.t_nr = h->d_t_nr; a.t_rows = h->d_t_rows;
+    a.cols = h->d_cols; a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    static const int cpt_env = env_int("LM_ROWS_CPT", 0);
+    int cpt = (ld >= 128) ? 2 : 1;
+    if (cpt_env == 1 || cpt_env == 2) cpt = cpt_env;
+    const int CT = 32 * cpt;
+    const long long nchunks = (ld + CT - 1) / CT;
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    long long cps = (long long)(budget / ((double)std::max<long long>(1, h->tile_window_rows) * CT * (double)c->esz()));
+    cps = std::max<long long>(1, std::min<long long>(cps, nchunks));
+    const long long strips = (nchunks + cps - 1) / cps;
+    cps = (nchunks + strips - 1) / strips;
+    REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_rows: grid too large");
+    a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
+    dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
+    if (c->precision == LM_C128) { if (cpt == 2) launch_rows_mode<double, 2>(a, grid, c->stream); else launch_rows_mode<double, 1>(a, grid, c->stream); }
+    else { if (cpt == 2) launch_rows_mode<float, 2>(a, grid, c->stream); else launch_rows_mode<float, 1>(a, grid, c->stream); }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
+static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                       zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    TiledArgs a;
+    a.t_ptr = h->d_t_ptr; a.t_nr = h->d_t_nr; a.t_rows = h->d_t_rows; a.lcols = h->d_lcols;
+    a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    static const int cpt_env = env_int("LM_TILED_CPT", 0);
+    int cpt = (ld >= 32 && (long long)h->tile_max_rows * 32 * (long long)c->esz() <= 100 * 1024) ? 2 : 1;
+    if (cpt_env == 1 || cpt_env == 2) cpt = cpt_env;
+    const int CT = 16 * cpt;
+    const size_t smem = (size_t)h->tile_max_rows * CT * c->esz();
+    const long long nchunks = (ld + CT - 1) / CT;
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    long long cps = (long long)(budget / ((double)std::max<long long>(1, h->tile_window_rows) * CT * (double)c->esz()));
+    cps = std::max<long long>(1, std::min<long long>(cps, nchunks));
+    const long long strips = (nchunks + cps - 1) / cps;
+    cps = (nchunks + strips - 1) / strips;
+    REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_tiled: grid too large");
+    a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
+    dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
+    if (c->precision == LM_C128) { if (cpt == 2) FWD((launch_tiled_mode<double, 2>(a, grid, smem, c->stream))); else FWD((launch_tiled_mode<double, 1>(a, grid, smem, c->stream))); }
+    else { if (cpt == 2) FWD((launch_tiled_mode<float, 2>(a, grid, smem, c->stream))); else FWD((launch_tiled_mode<float, 1>(a, grid, smem, c->stream))); }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
 }
 
 // y = alpha H x + gamma x + beta z + delta u
 static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                  zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
+    static const int tiled_env = env_int("LM_APPLY_TILED", -1);
+    // LM_APPLY_TILED: 0 = register gather over consecutive rows, 1 = TMA-staged tiles,
+    //                 2 = register gather over plan tiles (L1 patch reuse)
+    // default: tile-order register gather whenever the host supplied site coordinates
+    if (h->plan_from_coords && ld >= 32 && (tiled_env == 2 || tiled_env < 0)) return apply_rows(h, ld, x, y, z, u, alpha, gamma, beta, delta);
+    if (h->tiled && ld >= 16 && tiled_env == 1) return apply_tiled(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     ApplyArgs a;
     a.cols = h->d_cols; a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
     a.x = x; a.y = y; a.z = z; a.u = u;
@@ -778,36 +1027,42 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
     int lc = 0; while ((1LL << lc) < ld && lc < 5) lc++;
     const int LC = 1 << lc, LR = 32 >> lc;
-    const int cpt = (ld >= 64) ? 2 : 1;
+    static const int cpt_env = env_int("LM_APPLY_CPT", 0);
+    int cpt = (ld >= 256) ? 4 : (ld >= 64 ? 2 : 1);
+    if (cpt_env == 1 || cpt_env == 2 || cpt_env == 4) cpt = cpt_env;
     a.lc_log2 = lc;
-    a.tiles_r = (h->N + 8LL * LR - 1) / (8LL * LR);
-    a.tiles_c = (ld + (long long)LC * cpt - 1) / ((long long)LC * cpt);
+    const long long tiles_r = (h->N + 8LL * LR - 1) / (8LL * LR);
+    const long long tiles_c = (ld + (long long)LC * cpt - 1) / ((long long)LC * cpt);
     // column strips sized so that the re-read window (2 x bandwidth rows) stays in L2
-    const double budget = 0.35 * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
     const double row_bytes_per_tile = (double)LC * cpt * (double)c->esz();
     long long tps = (long long)(budget / (2.0 * (double)(h->band + 8 * LR) * row_bytes_per_tile));
-    tps = std::max<long long>(1, std::min<long long>(tps, a.tiles_c));
-    a.tiles_per_strip = (int)std::min<long long>(tps, 1 << 30);
-    const long long grid = a.tiles_r * a.tiles_c;
-    REQUIRE(grid > 0 && grid < 2147483647LL, "apply: grid too large");
-    if (c->precision == LM_C128) { if (cpt == 2) launch_apply_w<double, 2>(a, (unsigned)grid, c->stream); else launch_apply_w<double, 1>(a, (unsigned)grid, c->stream); }
-    else { if (cpt == 2) launch_apply_w<float, 2>(a, (unsigned)grid, c->stream); else launch_apply_w<float, 1>(a, (unsigned)grid, c->stream); }
+    tps = std::max<long long>(1, std::min<long long>(tps, tiles_c));
+    const long long strips = (tiles_c + tps - 1) / tps;
+    tps = (tiles_c + strips - 1) / strips;                 // even strips
+    REQUIRE(tiles_r * tps < 2147483647LL && strips <= 65535, "apply: grid too large");
+    a.tiles_c = (unsigned)tiles_c; a.tps = (unsigned)tps;
+    dim3 grid((unsigned)(tiles_r * tps), (unsigned)strips);
+    if (c->precision == LM_C128) launch_apply_cpt<double>(a, cpt, grid, c->stream);
+    else launch_apply_cpt<float>(a, cpt, grid, c->stream);
     c->launches++;
     CK(cudaGetLastError());
     return LM_OK;
 }
 
-static int ensure_scratch(lm_state* s) {
+static int ensure_scratch(lm_state* s, int nbuf) {
     lm_ctx* c = s->ctx;
     const size_t bytes = c->esz() * (size_t)s->N * s->ld;
-    if (!s->d_s1) CK(cudaMalloc(&s->d_s1, bytes));
-    if (!s->d_s2) CK(cudaMalloc(&s->d_s2, bytes));
+    if (nbuf >= 1 && !s->d_s1) CK(cudaMalloc(&s->d_s1, bytes));
+    if (nbuf >= 2 && !s->d_s2) CK(cudaMalloc(&s->d_s2, bytes));
     return LM_OK;
 }
 
 // Horner-Taylor:  w <- psi + (f/n) H w,  n = K..1  (f = -i dt / nsub), nsub sub-steps.
 // Buffers rotate among {x, s1, s2}; on return *px holds the result.
 static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
+    if (!(theta_total < 1e7)) return fail(LM_ERR_NOT_CONVERGED, "Taylor propagator: ||H|| dt too large");
     int s = std::max(1, (int)std::ceil(theta_total / 1.0));
     const double th = theta_total / s;
     const double target = std::max(tol, 1e-17) / s;
@@ -819,10 +1074,30 @@ static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
         if (rem <= target) break;
         term = next; ++k;
     }
-    if (k >= 200) return fail(LM_ERR_NOT_CONVERGED, "Taylor propagator did not converge");
+    if (k > kTaylorKMax) return fail(LM_ERR_NOT_CONVERGED, "Taylor propagator did not converge");
     *nsub = s; *K = k;
     return LM_OK;
 }
+// Product-form Taylor: exp(A) ~ p_K(A) = prod_j (I - A / r_j), r_j the roots of the truncated
+// exponential (taylor_roots.h), A = -i H dt / nsub.  Each factor is ONE pass
+//     y = x + (i dt / (nsub r_j)) H x
+// i.e. an SpMM plus a diagonal term: two HBM streams per term and two buffers in total (the
+// Horner form below needs psi as a third stream and a third buffer).  |r_j| >= 3 for K >= 8, so
+// with ||A|| <= 1 every factor is a small perturbation of the identity (no cancellation).
+static int step_taylor_prod(lm_ham* h, long long ld, void** px, void** ps1, double dt, int* nmv) {
+    const int nsub = h->plan.nsub, K = h->plan.K;
+    const zc f(0.0, -dt / nsub);
+    const int off = kTaylorRootOffset[K];
+    for (int sub = 0; sub < nsub; ++sub)
+        for (int j = 0; j < K; ++j) {
+            const zc r(kTaylorRoots[off + j][0], kTaylorRoots[off + j][1]);
+            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, -f / r, zc(1, 0), zc(0, 0), zc(0, 0)));
+            std::swap(*px, *ps1);
+            (*nmv)++;
+        }
+    return LM_OK;
+}
+
 static int step_taylor(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, int* nmv) {
     const int nsub = h->plan.nsub, K = h->plan.K;
     const zc f(0.0, -dt / nsub);
@@ -903,15 +1178,15 @@ static int get_plan(lm_ham* h, double dt, double tol, int method) {
     int nsub = 1, K = 1; std::vector<zc> coef;
     const int st_t = (method == LM_METHOD_CHEBYSHEV) ? LM_ERR_UNSUPPORTED : taylor_plan(h->norm_inf * std::fabs(dt), tol, &nsub, &K);
     const double a = std::max(0.5 * (h->emax - h->emin), 1e-300);
-    const int st_c = (method == LM_METHOD_TAYLOR) ? LM_ERR_UNSUPPORTED : cheb_plan(a * dt, tol, coef);
+    const int st_c = (method == LM_METHOD_TAYLOR || method == LM_METHOD_TAYLOR_HORNER) ? LM_ERR_UNSUPPORTED : cheb_plan(a * dt, tol, coef);
     int m = method;
     if (method == LM_METHOD_AUTO) {
-        // cost model in memory streams per term: Horner-Taylor 3, Clenshaw-Chebyshev 4
+        // cost model in HBM streams per term: product-form Taylor 2, Clenshaw-Chebyshev 4
         if (st_t != LM_OK && st_c != LM_OK) return fail(LM_ERR_NOT_CONVERGED, "lm_step: no propagator plan converged");
         if (st_t != LM_OK) m = LM_METHOD_CHEBYSHEV;
         else if (st_c != LM_OK) m = LM_METHOD_TAYLOR;
-        else m = (3.0 * nsub * K <= 4.0 * ((double)coef.size() - 1)) ? LM_METHOD_TAYLOR : LM_METHOD_CHEBYSHEV;
-    } else if (method == LM_METHOD_TAYLOR) { FWD(st_t); }
+        else m = (2.0 * nsub * K <= 4.0 * ((double)coef.size() - 1)) ? LM_METHOD_TAYLOR : LM_METHOD_CHEBYSHEV;
+    } else if (method == LM_METHOD_TAYLOR || method == LM_METHOD_TAYLOR_HORNER) { FWD(st_t); }
     else if (method == LM_METHOD_CHEBYSHEV) { FWD(st_c); }
     else return fail(LM_ERR_UNSUPPORTED, "lm_step: method not implemented (use AUTO, CHEBYSHEV or TAYLOR)");
     p.dt = dt; p.tol = tol; p.method_req = method; p.emin = h->emin; p.emax = h->emax; p.norm = h->norm_inf;
@@ -922,7 +1197,8 @@ static int get_plan(lm_ham* h, double dt, double tol, int method) {
 static int propagate(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, double tol, int method, int* nmv) {
     if (dt == 0.0) return LM_OK;
     FWD(get_plan(h, dt, tol, method));
-    if (h->plan.method == LM_METHOD_TAYLOR) return step_taylor(h, ld, px, ps1, ps2, dt, nmv);
+    if (h->plan.method == LM_METHOD_TAYLOR) return step_taylor_prod(h, ld, px, ps1, dt, nmv);
+    if (h->plan.method == LM_METHOD_TAYLOR_HORNER) return step_taylor(h, ld, px, ps1, ps2, dt, nmv);
     return step_cheb(h, ld, px, ps1, ps2, dt, nmv);
 }
 
@@ -932,11 +1208,13 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
     REQUIRE(h->N == s->N, "lm_step: dimension mismatch between Hamiltonian and state");
     REQUIRE(std::isfinite(dt), "lm_step: dt is not finite");
     REQUIRE(tol > 0 && tol < 1, "lm_step: tol must be in (0, 1)");
-    REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_LANCZOS, "lm_step: unknown method");
+    REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_TAYLOR_HORNER, "lm_step: unknown method");
     lm_ctx* c = h->ctx; FWD(set_dev(c));
     int nmv = 0;
+    if (dt != 0.0) FWD(get_plan(h, dt, tol, method));
+    const int nbuf = (dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR) ? 1 : 2;
     if (!s->dense) {
-        FWD(ensure_scratch(s));
+        FWD(ensure_scratch(s, nbuf));
         FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
     } else {
         // P <- U P U^H with U = exp(-i H dt) built by applying the propagator to the identity
@@ -944,7 +1222,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
         // src/evolution.jl:83-92.
         const long long N = s->N, ld = s->ld;
         const size_t bytes = c->esz() * (size_t)N * ld;
-        FWD(ensure_scratch(s));
+        FWD(ensure_scratch(s, 2));
         const bool hit = s->d_U && s->U_ham == h && s->U_version == h->version && s->U_dt == dt && s->U_tol == tol && s->U_method == method;
         if (!hit) {
             if (!s->d_U) CK(cudaMalloc(&s->d_U, bytes));
@@ -1101,4 +1379,19 @@ extern "C" int32_t lm_local_density(lm_state* s, int32_t n_int, double* rho_out)
         c->dens_helper = helper;
     }
     return run_observables(helper, s, n_int, rho_out, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// calibration hook for tools/sweep.py (not part of the product ABI / header)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t lm_dbg_triad(lm_state* x, lm_state* z, lm_state* y) {
+    REQUIRE(x && y && z, "lm_dbg_triad: NULL");
+    lm_ctx* c = x->ctx; FWD(set_dev(c));
+    const long long n = x->N * x->ld;
+    const unsigned grid = (unsigned)((n + 1023) / 1024);
+    if (c->precision == LM_C128) k_dbg_triad<double2><<<grid, 256, 0, c->stream>>>(n, (const double2*)x->d_x, (const double2*)z->d_x, (double2*)y->d_x);
+    else k_dbg_triad<float2><<<grid, 256, 0, c->stream>>>(n, (const float2*)x->d_x, (const float2*)z->d_x, (float2*)y->d_x);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
 }

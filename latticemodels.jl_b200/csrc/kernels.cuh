@@ -38,6 +38,19 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p
 __device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double2* p, double2 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+// "pinned" variants: volatile asm keeps the load where it is written (ptxas otherwise sinks the
+// element-wise operand loads below the gather/FMA section to save registers, which serialises
+// two HBM latencies per thread).
+__device__ __forceinline__ double2 ld_stream_pin(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream_pin(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.cs.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // k_apply: one polynomial term of the propagator, fused around the ELL SpMM
@@ -57,86 +70,303 @@ struct ApplyArgs {
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], gamma[2], beta[2], delta[2];
     int lc_log2;            // log2(LC)
-    long long tiles_r;      // row tiles
-    long long tiles_c;      // column tiles in total
-    int tiles_per_strip;    // column tiles per strip
+    unsigned tiles_c;       // column tiles in total
+    unsigned tps;           // column tiles per strip (grid.x = tps * row tiles, grid.y = strips)
 };
 
-template <typename T, int CPT, int WX>   // WX = exact ELL width (fully unrolled), 0 = generic loop
+// WX = exact ELL width (fully unrolled), 0 = generic loop (unrolled by 4).
+// MODE 0: y = alpha H x ; 1: + beta z (Horner-Taylor term) ; 2: general (z, u, gamma at run time)
+// MODE 3: y = alpha H x + gamma x  (one factor (I - A/r_j) of the product-form Taylor
+//         propagator: TWO HBM streams per term, the own-row element rides on the gather window)
+template <typename T, int CPT, int WX, int MODE>
 __global__ void __launch_bounds__(256)
 k_apply(const ApplyArgs a) {
     using T2 = typename cx2<T>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int LC = 1 << a.lc_log2, LR = 32 >> a.lc_log2;
-    // strip-major tile decode
-    long long t = blockIdx.x;
-    const long long per_strip = a.tiles_r * a.tiles_per_strip;
-    const long long strip = t / per_strip;
-    long long rem = t - strip * per_strip;
-    long long tps = a.tiles_per_strip;
-    const long long c_first = strip * (long long)a.tiles_per_strip;
-    if (c_first + tps > a.tiles_c) tps = a.tiles_c - c_first;   // last (narrower) strip
-    // the last strip has fewer column tiles: re-derive (rt, ct) with its own width
-    long long rt, ct;
-    if (tps == a.tiles_per_strip) { rt = rem / tps; ct = c_first + (rem - rt * tps); }
-    else { if (rem >= a.tiles_r * tps) return; rt = rem / tps; ct = c_first + (rem - rt * tps); }
-
-    const long long row = rt * (8LL * LR) + (long long)warp * LR + (lane >> a.lc_log2);
-    const long long col0 = ct * ((long long)LC * CPT) + (lane & (LC - 1));
+    // CTA order (x fastest, then y): column tiles of one strip, next row tile, ..., next strip
+    const unsigned rt = blockIdx.x / a.tps;
+    const unsigned ct = blockIdx.y * a.tps + (blockIdx.x - rt * a.tps);
+    if (ct >= a.tiles_c) return;                    // ragged last strip
+    const long long row = (long long)rt * (8 * LR) + warp * LR + (lane >> a.lc_log2);
+    const long long col0 = (long long)ct * (LC * CPT) + (lane & (LC - 1));
     if (row >= a.N) return;
 
     const T2* __restrict__ x = (const T2*)a.x;
     const T2* __restrict__ vals = (const T2*)a.vals + row * a.W;
     const int* __restrict__ cols = a.cols + row * a.W;
+    T2* y = (T2*)a.y;
+    const T2* z = (const T2*)a.z;
+    const T2* u = (const T2*)a.u;
+    const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
 
     long long cidx[CPT];
     bool ok[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        long long c = col0 + (long long)j * LC;
+        const long long c = col0 + (long long)j * LC;
         ok[j] = c < a.ld;
         cidx[j] = ok[j] ? c : (a.ld - 1);
     }
+    // The element-wise operands do not depend on the gathers.  The accumulator is INITIALISED
+    // from them (acc = beta z + delta u + gamma x) and alpha is folded into the H values, so
+    // their loads are issued ahead of the gather section and all HBM requests of the thread
+    // are in flight together (one exposed latency instead of two).
+    const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
+    const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
+    const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
+    const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
     T2 acc[CPT];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) { acc[j].x = 0; acc[j].y = 0; }
+    for (int j = 0; j < CPT; ++j) {
+        const long long e = row * a.ld + cidx[j];
+        acc[j].x = 0; acc[j].y = 0;
+        if (MODE == 1) cfma(acc[j], beta, ld_stream(z + e));
+        if (MODE == 3) cfma(acc[j], gamma, ld_ro(x + e));
+        if (MODE == 2) {
+            if (z) cfma(acc[j], beta, ld_stream(z + e));
+            if (u) cfma(acc[j], delta, u[e]);
+            if (has_gamma) cfma(acc[j], gamma, ld_ro(x + e));
+        }
+    }
 
     if (WX > 0) {
+        int cc[WX > 0 ? WX : 1]; T2 vv[WX > 0 ? WX : 1];
+#pragma unroll
+        for (int k = 0; k < WX; ++k) { cc[k] = cols[k]; vv[k] = cmul(alpha, vals[k]); }
 #pragma unroll
         for (int k = 0; k < WX; ++k) {
-            const long long c = cols[k];
-            const T2 v = vals[k];
-            const T2* xr = x + c * a.ld;
+            const T2* xr = x + (long long)cc[k] * a.ld;
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
+            for (int j = 0; j < CPT; ++j) cfma(acc[j], vv[k], ld_ro(xr + cidx[j]));
         }
     } else {
+#pragma unroll 4
         for (int k = 0; k < a.W; ++k) {
             const long long c = cols[k];
-            const T2 v = vals[k];
+            const T2 v = cmul(alpha, vals[k]);
             const T2* xr = x + c * a.ld;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
         }
     }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+        if (ok[j]) st_stream(y + row * a.ld + cidx[j], acc[j]);
+}
 
+// ------------------------------------------------------------------------------------------
+// k_apply_rows: the register-gather kernel walking the rows of ONE TILE of the plan (a compact
+// 2-D lattice patch) instead of 8 consecutive rows: a warp still owns a whole row x (32 CPT)
+// columns - every H entry is loaded once per 32 CPT elements - while the gathered neighbour
+// rows of the patch are re-used out of L1 by the other rows of the same CTA.
+// ------------------------------------------------------------------------------------------
+struct RowsArgs {
+    const int* t_ptr; const int* t_nr; const int* t_rows;
+    const int* cols; const void* vals; int W;
+    long long N, ld;
+    const void* x; void* y; const void* z; const void* u;
+    double alpha[2], gamma[2], beta[2], delta[2];
+    unsigned cps, nchunks;
+};
+
+template <typename T, int CPT, int WX, int MODE>
+__global__ void __launch_bounds__(256, 4)
+k_apply_rows(const RowsArgs a) {
+    using T2 = typename cx2<T>::type;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile = blockIdx.x / a.cps;
+    const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
+    if (chunk >= a.nchunks) return;
+    const int p0 = a.t_ptr[tile];
+    const int nr = a.t_nr[tile];
+    const T2* __restrict__ x = (const T2*)a.x;
+    T2* y = (T2*)a.y;
+    const T2* z = (const T2*)a.z;
+    const T2* u = (const T2*)a.u;
+    const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
+    const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
+    const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
+    const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
+    const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
+    long long cidx[CPT];
+    bool ok[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const long long c = (long long)chunk * (32 * CPT) + lane + 32 * j;
+        ok[j] = c < a.ld;
+        cidx[j] = ok[j] ? c : (a.ld - 1);
+    }
+    for (int r = warp; r < nr; r += 8) {
+        const long long row = a.t_rows[p0 + r];
+        const T2* __restrict__ vals = (const T2*)a.vals + row * a.W;
+        const int* __restrict__ cols = a.cols + row * a.W;
+        T2 acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const long long e = row * a.ld + cidx[j];
+            acc[j].x = 0; acc[j].y = 0;
+            if (MODE == 1) cfma(acc[j], beta, ld_stream(z + e));
+            if (MODE == 2) {
+                if (z) cfma(acc[j], beta, ld_stream(z + e));
+                if (u) cfma(acc[j], delta, u[e]);
+                if (has_gamma) cfma(acc[j], gamma, ld_ro(x + e));
+            }
+        }
+        if (WX > 0) {
+            int cc[WX > 0 ? WX : 1]; T2 vv[WX > 0 ? WX : 1];
+#pragma unroll
+            for (int k = 0; k < WX; ++k) { cc[k] = cols[k]; vv[k] = cmul(alpha, vals[k]); }
+#pragma unroll
+            for (int k = 0; k < WX; ++k) {
+                const T2* xr = x + (long long)cc[k] * a.ld;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) cfma(acc[j], vv[k], ld_ro(xr + cidx[j]));
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < a.W; ++k) {
+                const long long c = cols[k];
+                const T2 v = cmul(alpha, vals[k]);
+                const T2* xr = x + c * a.ld;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            // product-form factor: the own-row element is (almost always) an L1 hit by now
+            if (MODE == 3) cfma(acc[j], gamma, ld_ro(x + row * a.ld + cidx[j]));
+            if (ok[j]) st_stream(y + row * a.ld + cidx[j], acc[j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_apply_tiled: the same fused term, staged through shared memory by the TMA engine.
+//
+// The Hamiltonian carries a TILE PLAN (built once per sparsity pattern on the host): rows are
+// grouped into compact 2-D lattice patches of <= TR rows; per tile the list of its own rows
+// followed by its halo rows (neighbours outside the patch), and per ELL entry the LOCAL index
+// (uint16) of the neighbour inside that list.  A CTA owns (tile, column chunk of CT columns):
+//   1. one elected thread arms an mbarrier with the expected byte count,
+//   2. every listed row contributes one cp.async.bulk (1-D TMA, SASS UBLKCP) of its CT-column
+//      segment global -> shared; all copies of the CTA are in flight at once, no registers,
+//   3. after the barrier flips, the 16 x 16 threads (column lane x row lane) run the stencil
+//      out of shared memory (conflict-free 128-bit LDS) and stream the result rows out.
+// Each Psi element crosses L2 -> SM (1 + halo/tile) ~ 1.4 times instead of ~W times, which is
+// what bounds the register-gather kernel above for W ~ 10 stencils (Haldane, QWZ).
+// ------------------------------------------------------------------------------------------
+struct TiledArgs {
+    const int* t_ptr;               // [ntiles + 1] offsets into t_rows
+    const int* t_nr;                // [ntiles] number of own rows (the rest of the list is halo)
+    const int* t_rows;              // concatenated global row ids
+    const unsigned short* lcols;    // [N][W] local index of every ELL neighbour in its tile list
+    const void* vals; int W;
+    long long N, ld;
+    const void* x; void* y; const void* z; const void* u;
+    double alpha[2], gamma[2], beta[2], delta[2];
+    unsigned cps;                   // column chunks per strip
+    unsigned nchunks;               // column chunks in total
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LM_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LM_DONE_%=;\n\t"
+        "bra LM_WAIT_%=;\n\t"
+        "LM_DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int CPT, int MODE>
+__global__ void __launch_bounds__(256)
+k_apply_tiled(const TiledArgs a) {
+    using T2 = typename cx2<T>::type;
+    constexpr int CT = 16 * CPT;
+    extern __shared__ __align__(128) unsigned char lm_smem[];
+    T2* sx = reinterpret_cast<T2*>(lm_smem);
+    __shared__ __align__(8) unsigned long long bar;
+
+    const unsigned tile = blockIdx.x / a.cps;
+    const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
+    if (chunk >= a.nchunks) return;
+    const long long c0 = (long long)chunk * CT;
+    const int cw = (int)((a.ld - c0) < CT ? (a.ld - c0) : CT);
+    const int p0 = a.t_ptr[tile];
+    const int nrows = a.t_ptr[tile + 1] - p0;
+    const int nr = a.t_nr[tile];
+    const int* __restrict__ rows = a.t_rows + p0;
+    const T2* __restrict__ x = (const T2*)a.x;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (unsigned)(nrows * cw * (int)sizeof(T2)));
+    }
+    __syncthreads();
+    for (int r = tid; r < nrows; r += 256)
+        tma_bulk_g2s(sx + r * CT, x + (long long)rows[r] * a.ld + c0, (unsigned)(cw * (int)sizeof(T2)), &bar);
+
+    const int lc = tid & 15, lr = tid >> 4;
     const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
     const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
     const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
     const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
     const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
-    T2* y = (T2*)a.y;
     const T2* z = (const T2*)a.z;
     const T2* u = (const T2*)a.u;
+    T2* y = (T2*)a.y;
+    const T2* __restrict__ vals = (const T2*)a.vals;
+    bool ok[CPT];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-        if (!ok[j]) continue;
-        const long long e = row * a.ld + cidx[j];
-        T2 out = cmul(alpha, acc[j]);
-        if (has_gamma) cfma(out, gamma, ld_ro(x + e));
-        if (z) cfma(out, beta, ld_stream(z + e));
-        if (u) { T2 uu = u[e]; cfma(out, delta, uu); }
-        st_stream(y + e, out);
+    for (int j = 0; j < CPT; ++j) ok[j] = (lc + 16 * j) < cw;
+
+    mbar_wait(&bar, 0);
+
+    for (int r = lr; r < nr; r += 16) {
+        const long long g = rows[r];
+        const long long e0 = g * a.ld + c0 + lc;
+        T2 acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            acc[j].x = 0; acc[j].y = 0;
+            if (MODE == 1 && ok[j]) cfma(acc[j], beta, ld_stream(z + e0 + 16 * j));
+            if (MODE == 3) cfma(acc[j], gamma, sx[r * CT + lc + 16 * j]);
+            if (MODE == 2) {
+                if (z && ok[j]) cfma(acc[j], beta, ld_stream(z + e0 + 16 * j));
+                if (u && ok[j]) cfma(acc[j], delta, u[e0 + 16 * j]);
+                if (has_gamma) cfma(acc[j], gamma, sx[r * CT + lc + 16 * j]);
+            }
+        }
+        const unsigned short* __restrict__ lcr = a.lcols + g * a.W;
+        const T2* __restrict__ vr = vals + g * a.W;
+#pragma unroll 5
+        for (int k = 0; k < a.W; ++k) {
+            const int l = lcr[k];
+            const T2 v = cmul(alpha, vr[k]);
+            const T2* sr = sx + l * CT + lc;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) cfma(acc[j], v, sr[16 * j]);
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (ok[j]) st_stream(y + e0 + 16 * j, acc[j]);
     }
 }
 
@@ -514,6 +744,16 @@ k_cgemm_simple(int Mr, int Nc, int K, const float2* __restrict__ A, long long ld
         __syncthreads();
     }
     if (m < Mr && n < Nc) C[(long long)m * ldc + n] = acc;
+}
+
+// calibration only (tools/sweep.py): 3-stream element-wise kernel y = a x + z, same tiling
+template <typename T2>
+__global__ void __launch_bounds__(256) k_dbg_triad(long long n, const T2* __restrict__ x, const T2* __restrict__ z, T2* __restrict__ y) {
+    const long long i = (blockIdx.x * 256LL + threadIdx.x) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i + j < n) { T2 a = __ldcs(x + i + j), b = __ldcs(z + i + j); a.x = 0.5 * a.x + b.x; a.y = 0.5 * a.y + b.y; __stcs(y + i + j, a); }
+    }
 }
 
 }  // namespace lm

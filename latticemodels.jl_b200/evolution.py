@@ -22,7 +22,7 @@ from .hamiltonian import DeviceHam, Hamiltonian
 from .states import DeviceState
 
 _METHODS = {"auto": _lib.METHOD_AUTO, "chebyshev": _lib.METHOD_CHEBYSHEV, "taylor": _lib.METHOD_TAYLOR,
-            "lanczos": _lib.METHOD_LANCZOS}
+            "lanczos": _lib.METHOD_LANCZOS, "taylor_horner": _lib.METHOD_TAYLOR_HORNER}
 
 
 class EvolutionSolver:

@@ -152,10 +152,17 @@ class DeviceHam:
             _lib.ptr(ons_cm), 0, C.byref(h)))
         d = cls(ctx, h, st.n_int, True)
         d.field_key = ((), b"")
+        d.set_site_coords(st.lat.coords)
         return d
 
+    def set_site_coords(self, coords):
+        xy = np.ascontiguousarray(np.asarray(coords, float)[:, :2])
+        if xy.shape != (self.N // self.n_int, 2):
+            raise _lib.ArgumentError("site coordinates must be (n_sites, 2)")
+        _lib.check(_lib.load().lm_ham_set_site_coords(self.handle, _lib.ptr(xy)))
+
     @classmethod
-    def from_csc(cls, ctx, mat, n_int=1):
+    def from_csc(cls, ctx, mat, n_int=1, coords=None):
         lib = _lib.load()
         m = sp.csc_matrix(mat)
         m.sort_indices()
@@ -167,6 +174,8 @@ class DeviceHam:
                                          _lib.ptr(nz), 0, C.byref(h)))
         d = cls(ctx, h, n_int, False)
         d.pattern = (colptr, rowval)
+        if coords is not None:
+            d.set_site_coords(coords)
         return d
 
     def update_values(self, nzval):

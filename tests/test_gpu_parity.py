@@ -147,7 +147,7 @@ def test_field_param_update_path(ctx):
 
 
 # ------------------------------------------------------------------------------ propagator
-@pytest.mark.parametrize("method", ["taylor", "chebyshev", "auto"])
+@pytest.mark.parametrize("method", ["taylor", "taylor_horner", "chebyshev", "auto"])
 @pytest.mark.parametrize("dt", [0.1, 0.7, 3.0, -0.4])
 def test_step_matches_exact_exponential(ctx, method, dt):
     Ho = OP.qwz(L.square_lattice(6, 5), field=F.LandauGauge(0.1))
