@@ -122,9 +122,13 @@ struct lm_ham {
     double* d_dens = nullptr; double2* d_G = nullptr; double* d_obs = nullptr;
     // tile plan for the TMA-staged kernel (k_apply_tiled)
     std::vector<int> h_cols;                       // host copy of the ELL columns
+    std::vector<unsigned char> h_upper;            // host copy of the upper flags
     bool tiled = false; bool plan_from_coords = false; int ntiles = 0; int tile_max_rows = 0; long long tile_window_rows = 0;
     double tile_halo_ratio = 0;
     int* d_t_ptr = nullptr; int* d_t_nr = nullptr; int* d_t_rows = nullptr; unsigned short* d_lcols = nullptr;
+    // observable items of the plan: (row, upper neighbour) pairs + one density item per row
+    int* d_it_ptr = nullptr; unsigned short* d_it_row = nullptr; unsigned short* d_it_nb = nullptr; int* d_it_out = nullptr;
+    bool obs_tiled = false;
 };
 
 struct lm_state {
@@ -153,7 +157,9 @@ static int ensure_stage(lm_ctx* c, size_t bytes) {
     c->stage_bytes = bytes;
     return LM_OK;
 }
-static long long pad_ld(long long M) { return M >= 32 ? ((M + 7) / 8) * 8 : M; }
+// leading dimension: 128-byte aligned rows for wide blocks; even for narrow ones so that every
+// row segment is 16-byte aligned in both precisions (TMA bulk copies); a single ket stays 1 wide
+static long long pad_ld(long long M) { return M >= 32 ? ((M + 7) / 8) * 8 : (M > 1 ? ((M + 1) / 2) * 2 : M); }
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -230,7 +236,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -301,6 +307,7 @@ static int ham_finish_pattern(lm_ham* h, const std::vector<long long>& rows, con
     }
     pptr.push_back((int)pe.size());
     h->npairs = (long long)h->pairI.size();
+    h->h_upper = upper;
 
     FWD(set_dev(c));
     cudaStream_t s = c->stream;
@@ -410,6 +417,21 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
         halo_sum += (double)(cnt - t_nr[t]);
         (void)base;
     }
+    // observable items per tile
+    std::vector<int> it_ptr(ntiles + 1, 0), it_out; std::vector<unsigned short> it_row, it_nb;
+    it_out.reserve((size_t)N * 4); it_row.reserve((size_t)N * 4); it_nb.reserve((size_t)N * 4);
+    for (int t = 0; t < ntiles; ++t) {
+        const int base = t_ptr[t];
+        for (int r = 0; r < t_nr[t]; ++r) {
+            const long long g = t_rows[base + r];
+            it_row.push_back((unsigned short)r); it_nb.push_back((unsigned short)0xFFFF); it_out.push_back((int)g);
+            for (int k = 0; k < W; ++k)
+                if (h->h_upper[g * W + k]) {
+                    it_row.push_back((unsigned short)r); it_nb.push_back(lcols[g * W + k]); it_out.push_back((int)(g * W + k));
+                }
+        }
+        it_ptr[t + 1] = (int)it_out.size();
+    }
     h->plan_from_coords = (xy != nullptr);
     h->ntiles = ntiles; h->tile_max_rows = max_rows; h->tile_window_rows = 2 * rows_per_binrow;
     h->tile_halo_ratio = halo_sum / (double)std::max<long long>(1, N);
@@ -418,9 +440,10 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
     h->tiled = (long long)max_rows * 16 * (long long)c->esz() <= smem_cap;
     FWD(set_dev(c));
     CK(cudaStreamSynchronize(c->stream));
-    void* old[] = {h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols};
+    void* old[] = {h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out};
     for (void* p : old) if (p) cudaFree(p);
     h->d_t_ptr = h->d_t_nr = h->d_t_rows = nullptr; h->d_lcols = nullptr;
+    h->d_it_ptr = h->d_it_out = nullptr; h->d_it_row = h->d_it_nb = nullptr;
     CK(cudaMalloc(&h->d_t_ptr, sizeof(int) * t_ptr.size()));
     CK(cudaMalloc(&h->d_t_nr, sizeof(int) * std::max<size_t>(1, t_nr.size())));
     CK(cudaMalloc(&h->d_t_rows, sizeof(int) * std::max<size_t>(1, t_rows.size())));
@@ -429,6 +452,16 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
     CK(cudaMemcpy(h->d_t_nr, t_nr.data(), sizeof(int) * t_nr.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_t_rows, t_rows.data(), sizeof(int) * t_rows.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_lcols, lcols.data(), sizeof(unsigned short) * lcols.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_it_ptr, sizeof(int) * it_ptr.size()));
+    CK(cudaMalloc(&h->d_it_row, sizeof(unsigned short) * std::max<size_t>(1, it_row.size())));
+    CK(cudaMalloc(&h->d_it_nb, sizeof(unsigned short) * std::max<size_t>(1, it_nb.size())));
+    CK(cudaMalloc(&h->d_it_out, sizeof(int) * std::max<size_t>(1, it_out.size())));
+    CK(cudaMemcpy(h->d_it_ptr, it_ptr.data(), sizeof(int) * it_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_it_row, it_row.data(), sizeof(unsigned short) * it_row.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_it_nb, it_nb.data(), sizeof(unsigned short) * it_nb.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_it_out, it_out.data(), sizeof(int) * it_out.size(), cudaMemcpyHostToDevice));
+    // staged rows of the widest tile for a 32-column chunk (padded stride 33)
+    h->obs_tiled = h->plan_from_coords && (long long)max_rows * 34 * (long long)c->esz() <= 200 * 1024;
     return LM_OK;
 }
 
@@ -1269,14 +1302,38 @@ template <typename T, int WB>
 static void launch_observe(lm_ham* h, lm_state* s, int k0, int write_dens) {
     using T2 = typename cx2<T>::type;
     lm_ctx* c = h->ctx;
-    if (s->M >= 512)
+    static const int cta_team_min = env_int("LM_OBS_CTA_MIN", 1 << 30);
+    if (s->M >= cta_team_min)
         k_observe<T, WB, true><<<(unsigned)h->N, 256, 0, c->stream>>>(h->N, s->M, s->ld, (const T2*)s->d_x, s->d_w, h->d_cols, h->W, h->d_upper, k0, write_dens, h->d_dens, h->d_G);
     else
         k_observe<T, WB, false><<<(unsigned)((h->N + 7) / 8), 256, 0, c->stream>>>(h->N, s->M, s->ld, (const T2*)s->d_x, s->d_w, h->d_cols, h->W, h->d_upper, k0, write_dens, h->d_dens, h->d_G);
     c->launches++;
 }
 template <typename T>
+static int observe_tiled(lm_ham* h, lm_state* s) {
+    using T2 = typename cx2<T>::type;
+    lm_ctx* c = h->ctx;
+    CK(cudaMemsetAsync(h->d_dens, 0, sizeof(double) * (size_t)h->N, c->stream));
+    CK(cudaMemsetAsync(h->d_G, 0, sizeof(double2) * (size_t)h->N * h->W, c->stream));
+    ObsTiledArgs a;
+    a.t_ptr = h->d_t_ptr; a.t_rows = h->d_t_rows; a.it_ptr = h->d_it_ptr; a.it_row = h->d_it_row; a.it_nb = h->d_it_nb; a.it_out = h->d_it_out;
+    a.N = h->N; a.M = s->M; a.ld = s->ld; a.x = s->d_x; a.w = s->d_w; a.dens = h->d_dens; a.G = h->d_G;
+    a.nchunks = (unsigned)((s->M + 31) / 32);
+    const size_t smem = (size_t)h->tile_max_rows * (sizeof(T2) == 16 ? 33 : 34) * sizeof(T2);
+    static size_t configured = 0;
+    if (smem > configured) { CK(cudaFuncSetAttribute(k_observe_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    const long long grid = (long long)h->ntiles * a.nchunks;
+    REQUIRE(grid < 2147483647LL, "observe_tiled: grid too large");
+    k_observe_tiled<T><<<(unsigned)grid, 256, smem, c->stream>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
+template <typename T>
 static int observe(lm_ham* h, lm_state* s, bool want_j) {
+    static const int obs_tiled_env = env_int("LM_OBS_TILED", -1);
+    if (h->obs_tiled && want_j && s->M >= 16 && obs_tiled_env != 0) return observe_tiled<T>(h, s);
     // ELL slots are processed WB at a time; a density-only pass has no active slot (k0 = W)
     const int W = want_j ? h->W : 0;
     if (W <= 0) launch_observe<T, 1>(h, s, h->W, 1);

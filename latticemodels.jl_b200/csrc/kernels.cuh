@@ -582,6 +582,83 @@ k_observe(long long N, long long M, long long ld, const typename cx2<T>::type* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_observe_tiled: the same reductions on the tile plan, staged by TMA.
+// CTA = (tile, chunk of 32 columns): the tile's own + halo rows of that chunk are bulk-copied
+// into shared memory (row stride padded to 33 elements: conflict-free column walks).  Work is
+// split into ITEMS - (row, upper neighbour) pairs plus one density item per row, listed per
+// tile by the host - and every thread runs the dot product of its item over the 32 columns
+// SERIALLY out of shared memory: no cross-lane reduction, one atomicAdd pair per item.
+// ------------------------------------------------------------------------------------------
+struct ObsTiledArgs {
+    const int* t_ptr; const int* t_rows;
+    const int* it_ptr;                  // [ntiles + 1] offsets into the item arrays
+    const unsigned short* it_row;       // local row of the item
+    const unsigned short* it_nb;        // local neighbour row, 0xFFFF = density item
+    const int* it_out;                  // ELL entry (G) or global row (density)
+    long long N, M, ld;
+    const void* x; const double* w;
+    double* dens; double2* G;
+    unsigned nchunks;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_observe_tiled(const ObsTiledArgs a) {
+    using T2 = typename cx2<T>::type;
+    constexpr int CT = 32, ST = (sizeof(T2) == 16) ? 33 : 34;   // padded, 16-byte aligned row stride
+    extern __shared__ __align__(128) unsigned char lm_smem[];
+    T2* sx = reinterpret_cast<T2*>(lm_smem);
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ double sw[CT];
+
+    const unsigned tile = blockIdx.x / a.nchunks;
+    const unsigned chunk = blockIdx.x - tile * a.nchunks;
+    const long long c0 = (long long)chunk * CT;
+    const int cw = (int)((a.M - c0) < CT ? (a.M - c0) : CT);
+    const int cwl = (int)((a.ld - c0) < CT ? (a.ld - c0) : CT);     // loadable (padded) columns
+    const int p0 = a.t_ptr[tile];
+    const int nrows = a.t_ptr[tile + 1] - p0;
+    const T2* __restrict__ x = (const T2*)a.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (unsigned)(nrows * cwl * (int)sizeof(T2)));
+    }
+    if (tid < CT) sw[tid] = (tid < cw) ? (a.w ? a.w[c0 + tid] : 1.0) : 0.0;
+    __syncthreads();
+    for (int r = tid; r < nrows; r += 256)
+        tma_bulk_g2s(sx + r * ST, x + (long long)a.t_rows[p0 + r] * a.ld + c0, (unsigned)(cwl * (int)sizeof(T2)), &bar);
+    const int i0 = a.it_ptr[tile], i1 = a.it_ptr[tile + 1];
+    mbar_wait(&bar, 0);
+    for (int it = i0 + tid; it < i1; it += 256) {
+        const int r = a.it_row[it], nb = a.it_nb[it];
+        const T2* pa = sx + r * ST;
+        if (nb == 0xFFFF) {
+            double d = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < cw; ++c) {
+                const T2 v = pa[c];
+                d = fma(sw[c] * (double)v.x, (double)v.x, d);
+                d = fma(sw[c] * (double)v.y, (double)v.y, d);
+            }
+            atomicAdd(a.dens + a.it_out[it], d);
+        } else {
+            const T2* pb = sx + nb * ST;
+            double gr = 0.0, gi = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < cw; ++c) {
+                const T2 va = pa[c], vb = pb[c];
+                const double ar = sw[c] * (double)va.x, ai = sw[c] * (double)va.y;
+                gr = fma((double)vb.x, ar, gr); gr = fma((double)vb.y, ai, gr);      // b * conj(a) * w
+                gi = fma((double)vb.y, ar, gi); gi = fma(-(double)vb.x, ai, gi);
+            }
+            double* g = reinterpret_cast<double*>(a.G + a.it_out[it]);
+            atomicAdd(g, gr); atomicAdd(g + 1, gi);
+        }
+    }
+}
+
 // obs[0 .. n_sites) = site densities, obs[n_sites .. n_sites + npairs) = pair currents
 //   J_p = sum_{e in pair p} 2 Im(H_e * G_e)      (src/zoo/currents.jl:92-102)
 template <typename T>
