@@ -270,7 +270,7 @@ def main():
 
     # ---------------- end to end through the C ABI with host buffers ----------------
     Hmat = H0.data                                    # host-assembled CSC (what t -> H(t) returns)
-    csc_dev = lm.DeviceHam.from_csc(ctx, Hmat, H0.n_int)
+    csc_dev = lm.DeviceHam.from_csc(ctx, Hmat, H0.n_int, coords=H0.lattice.coords)
     nz_pinned = torch.empty(nnz * (2 if esz == 16 else 1), dtype=torch.float64 if esz == 16 else torch.complex64).pin_memory()
     nz_np = nz_pinned.numpy().view(cdt)
     nz_np[:] = Hmat.data.astype(cdt)

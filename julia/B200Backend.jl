@@ -1,0 +1,167 @@
+# B200Backend.jl - thin Julia glue that plugs liblm_b200.so into LatticeModels.jl.
+#
+# NOT EXECUTED in the build container (Julia is not installed there); it is kept minimal and
+# line-for-line reviewable.  All logic lives in the shared library behind include/lm_b200.h;
+# this file only (a) declares the new `EvolutionSolver` subtype and the device state type,
+# (b) forwards the reference's extension points to `ccall`s.  No reference file is edited:
+# everything below is new methods on existing generic functions (multiple dispatch is the
+# reference's plug-in API, src/evolution.jl:25-33).
+#
+#   using LatticeModels, B200Backend
+#   P0 = densitymatrix(h(0), mu = 0)                        # host, as before
+#   ev = Evolution(B200Exp(tol = 1e-12), t -> h(t), PsiProjector(P0_eig...))   # or P0 itself
+#   for (P, H, t) in ev(0:0.1:20)
+#       localdensity(P); Currents(DensityCurrents(H, P))
+#   end
+module B200Backend
+
+using LatticeModels, SparseArrays, LinearAlgebra
+import LatticeModels: EvolutionSolver, update_solver!, step!, evolution_cache, localdensity,
+                      DensityCurrents, Currents, lattice, internal_length
+import QuantumOpticsBase: Operator, basis
+
+const LIB = get(ENV, "LM_B200_LIB", joinpath(@__DIR__, "..", "latticemodels.jl_b200", "lib", "liblm_b200.so"))
+
+# ---- status -> ArgumentError (mirrors src/evolution.jl:152,239) ---------------------------------
+lasterror() = unsafe_string(ccall((:lm_last_error, LIB), Cstring, ()))
+check(status::Int32) = status == 0 || throw(ArgumentError(lasterror()))
+
+# ---- context (one process drives one GPU) ------------------------------------------------------
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(; device::Integer = 0, precision::Symbol = :c128)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:lm_ctx_create, LIB), Int32, (Int32, Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                    device, precision === :c64 ? 1 : 0, C_NULL, h))
+        finalizer(c -> ccall((:lm_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.handle), new(h[]))
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing,Context}}(nothing)
+default_context() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context()))
+
+# ---- device Hamiltonian: upload of a Julia SparseMatrixCSC (1-based indices accepted as is) ----
+mutable struct DeviceHam
+    handle::Ptr{Cvoid}
+    colptr::Vector{Int64}
+    rowval::Vector{Int64}
+end
+function DeviceHam(ctx::Context, mat::SparseMatrixCSC{ComplexF64,Int64}, n_int::Integer; coords = nothing)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lm_ham_create_csc, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(mat, 1), n_int, mat.colptr, mat.rowval, mat.nzval, 1, h))
+    dev = DeviceHam(h[], copy(mat.colptr), copy(mat.rowval))
+    if coords !== nothing       # 2 x n_sites Float64 matrix of site coordinates (site.coords[1:2])
+        check(ccall((:lm_ham_set_site_coords, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), dev.handle, coords))
+    end
+    finalizer(d -> ccall((:lm_ham_destroy, LIB), Int32, (Ptr{Cvoid},), d.handle), dev)
+end
+samepattern(d::DeviceHam, m::SparseMatrixCSC) = d.colptr == m.colptr && d.rowval == m.rowval
+
+# ---- device state: P = Psi diag(w) Psi' (Psi-block) or a dense density matrix -----------------
+# An AbstractMatrix so that Operator(basis, PsiProjector) IS a DataOperator of the reference
+# (EvolutionStateType, src/evolution.jl:36; StateType, src/operators/bases.jl:35).
+mutable struct PsiProjector <: AbstractMatrix{ComplexF64}
+    handle::Ptr{Cvoid}
+    n::Int
+    ctx::Context
+end
+function PsiProjector(psi::AbstractMatrix{ComplexF64}, w::Union{Nothing,Vector{Float64}} = nothing;
+                      ctx::Context = default_context())
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    p = Matrix(psi)                                      # column-major N x M
+    check(ccall((:lm_state_create_psi, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Ptr{ComplexF64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(p, 1), size(p, 2), p, w === nothing ? C_NULL : w, h))
+    finalizer(s -> ccall((:lm_state_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle), PsiProjector(h[], size(p, 1), ctx))
+end
+Base.size(s::PsiProjector) = (s.n, s.n)
+function Base.copy(s::PsiProjector)                      # copy(state), src/evolution.jl:193
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lm_state_copy, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), s.handle, h))
+    finalizer(t -> ccall((:lm_state_destroy, LIB), Int32, (Ptr{Cvoid},), t.handle), PsiProjector(h[], s.n, s.ctx))
+end
+function Base.Matrix(s::PsiProjector)                    # escape hatch: materialise Psi W Psi'
+    P = Matrix{ComplexF64}(undef, s.n, s.n)
+    check(ccall((:lm_state_download_dense, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}), s.handle, P))
+    P
+end
+Base.getindex(s::PsiProjector, i::Int, j::Int) = Matrix(s)[i, j]     # slow, debugging only
+
+# ---- the solver ---------------------------------------------------------------------------------
+mutable struct B200Exp <: EvolutionSolver
+    ctx::Context
+    dev::Union{Nothing,DeviceHam}
+    mat::Any
+    dt::Float64
+    tol::Float64
+    method::Int32
+    n_int::Int
+    coords::Any
+end
+# B200Exp(; kw...) without a Hamiltonian comes for free via IncompleteSolver (src/evolution.jl:219-231)
+function B200Exp(ham; tol = 1e-12, method = 0, precision = :c128, ctx = default_context(), coords = nothing)
+    n_int = ham isa LatticeModels.Hamiltonian ? internal_length(ham) : 1
+    if coords === nothing && ham isa LatticeModels.Hamiltonian
+        l = lattice(ham)
+        coords = Float64[site.coords[k] for k in 1:2, site in l]
+    end
+    B200Exp(ctx, nothing, nothing, 0.0, tol, Int32(method), n_int, coords)
+end
+
+function update_solver!(s::B200Exp, mat::SparseMatrixCSC, dt, force = false)      # src/evolution.jl:83-92
+    s.dt = dt
+    !force && s.mat === mat && s.dev !== nothing && return
+    if s.dev !== nothing && samepattern(s.dev, mat)
+        check(ccall((:lm_ham_update_values, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}), s.dev.handle, mat.nzval))
+    else
+        s.dev = DeviceHam(s.ctx, mat, s.n_int; coords = s.coords)
+    end
+    s.mat = mat
+    return
+end
+update_solver!(s::B200Exp, mat::AbstractMatrix, dt, force = false) =
+    update_solver!(s, sparse(ComplexF64.(mat)), dt, force)
+
+evolution_cache(::B200Exp, ::PsiProjector) = nothing
+function step!(s::B200Exp, state::PsiProjector, _cache)                            # src/evolution.jl:69-78
+    check(ccall((:lm_step, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Int32}),
+                s.dev.handle, state.handle, s.dt, s.tol, s.method, C_NULL))
+    state
+end
+# A plain dense Matrix state means a density matrix: upload once, keep it on the device.
+# (Evolution copies the state at construction; convert there.)
+PsiProjector(P::Matrix{ComplexF64}; ctx::Context = default_context()) = begin
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lm_state_create_dense, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(P, 1), P, h))
+    finalizer(s -> ccall((:lm_state_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle), PsiProjector(h[], size(P, 1), ctx))
+end
+
+# ---- observables --------------------------------------------------------------------------------
+const DevOp = Operator{B,B,<:PsiProjector} where {B}
+function localdensity(state::DevOp)                                               # latticeutils.jl:41-45
+    l = lattice(state); n = internal_length(state)
+    rho = Vector{Float64}(undef, length(l))
+    check(ccall((:lm_local_density, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), state.data.handle, n, rho))
+    LatticeValue(l, rho)
+end
+
+# Currents(DensityCurrents(H, P)): all bonds of H in one fused pass (src/currents.jl:223-237).
+# The solver's device Hamiltonian currently holds exactly the H yielded with this frame.
+function Currents(curr::DensityCurrents{<:Any,<:DevOp}, solver::B200Exp)
+    dev = solver.dev
+    np = Ref{Int64}(0)
+    check(ccall((:lm_currents_npairs, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), dev.handle, np))
+    I = Vector{Int32}(undef, np[]); J = similar(I); V = Vector{Float64}(undef, np[])
+    check(ccall((:lm_currents_pairs, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), dev.handle, I, J))
+    check(ccall((:lm_observables, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                dev.handle, curr.state.data.handle, C_NULL, V))
+    keep = abs.(V) .>= 1e-10                                                       # CURRENTS_EPS, src/currents.jl:4
+    l = lattice(curr); n = length(l)
+    Currents(l, sparse(vcat(I[keep], J[keep]), vcat(J[keep], I[keep]), vcat(V[keep], -V[keep]), n, n))
+end
+
+export B200Exp, PsiProjector, Context
+
+end # module
