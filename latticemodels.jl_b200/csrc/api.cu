@@ -98,8 +98,11 @@ struct Plan {          // cached propagator plan (host-side Bessel / Taylor book
     int method = 0, nsub = 1, K = 1; std::vector<zc> coef;
 };
 
+static unsigned long long g_ham_uid = 0;
 struct lm_ham {
     lm_ctx* ctx = nullptr;
+    unsigned long long uid = ++g_ham_uid;   // identity for cached step graphs (addresses get recycled)
+    unsigned long long layout_epoch = 0;     // bumped whenever device pointers of the operator change
     Plan plan;
     long long N = 0, n_sites = 0; int n_int = 1; int W = 0; long long nnz = 0;
     int index_base = 0;
@@ -136,6 +139,10 @@ struct lm_state {
     long long N = 0, M = 0, ld = 0; bool dense = false;
     void* d_x = nullptr; double* d_w = nullptr;
     void* d_s1 = nullptr; void* d_s2 = nullptr;               // propagator scratch
+    // CUDA graphs of one propagation step (the K term launches), keyed by plan + buffer roles
+    struct StepGraph { cudaGraphExec_t exec = nullptr; lm_ham* h = nullptr; unsigned long long uid = 0, epoch = 0; void* x = nullptr; void* s1 = nullptr;
+                       double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false; };
+    StepGraph graphs[4]; int graph_next = 0;
     // dense path: cached propagator U (row-major [N][ld])
     void* d_U = nullptr; lm_ham* U_ham = nullptr; long long U_version = -1; double U_dt = 0, U_tol = 0; int U_method = -1;
 };
@@ -432,6 +439,7 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
         }
         it_ptr[t + 1] = (int)it_out.size();
     }
+    h->layout_epoch++;
     h->plan_from_coords = (xy != nullptr);
     h->ntiles = ntiles; h->tile_max_rows = max_rows; h->tile_window_rows = 2 * rows_per_binrow;
     h->tile_halo_ratio = halo_sum / (double)std::max<long long>(1, N);
@@ -711,7 +719,7 @@ extern "C" int32_t lm_ham_set_fields(lm_ham* h, int32_t nfields, const int32_t* 
     CK(cudaStreamSynchronize(c->stream));
     if (h->d_kinds) CK(cudaFree(h->d_kinds));
     if (h->d_params) CK(cudaFree(h->d_params));
-    h->d_kinds = nullptr; h->d_params = nullptr; h->nfields = nfields;
+    h->d_kinds = nullptr; h->d_params = nullptr; h->nfields = nfields; h->layout_epoch++;
     if (nfields) {
         CK(cudaMalloc(&h->d_kinds, sizeof(int) * nfields));
         CK(cudaMalloc(&h->d_params, sizeof(double) * 3 * nfields));
@@ -767,6 +775,7 @@ static void state_free(lm_state* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {s->d_x, s->d_w, s->d_s1, s->d_s2, s->d_U};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete s;
@@ -1248,7 +1257,43 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
     const int nbuf = (dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR) ? 1 : 2;
     if (!s->dense) {
         FWD(ensure_scratch(s, nbuf));
-        FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
+        static const int use_graph = env_int("LM_STEP_GRAPH", 1);
+        const bool graphable = use_graph && dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR;
+        if (!graphable) {
+            FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
+        } else {
+            // The step is K back-to-back launches with fixed arguments: replay it as one graph
+            // (launch-bound regimes: single kets, narrow shards).  H VALUES may change between
+            // replays (same pointers); a new sparsity/plan/buffer role gets its own graph.
+            lm_state::StepGraph* g = nullptr;
+            for (auto& c2 : s->graphs)
+                if (c2.exec && c2.h == h && c2.uid == h->uid && c2.epoch == h->layout_epoch && c2.x == s->d_x && c2.s1 == s->d_s1 && c2.dt == dt && c2.tol == tol && c2.method == method &&
+                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf) { g = &c2; break; }
+            if (!g) {
+                g = &s->graphs[s->graph_next]; s->graph_next = (s->graph_next + 1) % 4;
+                if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+                void *x0 = s->d_x, *s10 = s->d_s1;
+                const long long l0 = c->launches;
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int st = propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv);
+                cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                if (st != LM_OK) { if (graph) cudaGraphDestroy(graph); s->d_x = x0; s->d_s1 = s10; return st; }
+                if (e != cudaSuccess) { s->d_x = x0; s->d_s1 = s10; return fail(LM_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+                e = cudaGraphInstantiate(&g->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) { g->exec = nullptr; s->d_x = x0; s->d_s1 = s10; return fail(LM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+                g->h = h; g->uid = h->uid; g->epoch = h->layout_epoch; g->x = x0; g->s1 = s10; g->dt = dt; g->tol = tol; g->method = method;
+                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv;
+                g->launches = c->launches - l0; g->swap = (s->d_x != x0);
+                c->launches = l0;                       // counted at replay
+                s->d_x = x0; s->d_s1 = s10;             // capture did not execute anything
+            }
+            CK(cudaGraphLaunch(g->exec, c->stream));
+            c->launches += g->launches;
+            nmv = g->nmv;
+            if (g->swap) std::swap(s->d_x, s->d_s1);
+        }
     } else {
         // P <- U P U^H with U = exp(-i H dt) built by applying the propagator to the identity
         // block; cached while (H values, dt) are unchanged - CachedExp semantics,
