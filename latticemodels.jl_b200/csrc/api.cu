@@ -1052,11 +1052,13 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
     return LM_OK;
 }
 
+static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles
 // y = alpha H x + gamma x + beta z + delta u
 static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                  zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
-    static const int tiled_env = env_int("LM_APPLY_TILED", -1);
+    static const int tiled_env0 = env_int("LM_APPLY_TILED", -1);
+    const int tiled_env = g_apply_path_override >= 0 ? g_apply_path_override : tiled_env0;
     // LM_APPLY_TILED: 0 = register gather over consecutive rows, 1 = TMA-staged tiles,
     //                 2 = register gather over plan tiles (L1 patch reuse)
     // default: tile-order register gather whenever the host supplied site coordinates
@@ -1497,3 +1499,5 @@ extern "C" int32_t lm_dbg_triad(lm_state* x, lm_state* z, lm_state* y) {
     CK(cudaGetLastError());
     return LM_OK;
 }
+
+extern "C" int32_t lm_dbg_set_apply_path(int32_t path) { g_apply_path_override = path; return LM_OK; }

@@ -90,6 +90,66 @@ def test_csc_julia_one_based(ctx):
     lib.lm_ham_destroy(h)
 
 
+@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("model", ["square", "qwz_pbc", "haldane"])
+def test_all_spmm_kernels_on_plan(ctx, path, model):
+    """Every SpMM kernel generation (consecutive-row gather, TMA-staged tiles, tile-order gather)
+    against the oracle on device-built Hamiltonians with site coordinates, ragged widths."""
+    lib = _lib.load()
+    if model == "square":
+        Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(23, 17), t1=1, t2=0.3, field=lm.LandauGauge(0.07))
+        Ho = OP.tightbinding_hamiltonian(L.square_lattice(23, 17), t1=1, t2=0.3, field=F.LandauGauge(0.07))
+    elif model == "qwz_pbc":
+        Hd = lm.qwz(lm.SquareLattice(14, 15, boundaries=[("axis1", True)]), field=lm.LandauGauge(0.5))
+        Ho = OP.qwz(L.square_lattice(14, 15, periodic=(1,)), field=F.LandauGauge(0.5))
+    else:
+        Hd = lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1, field=lm.SymmetricGauge(0.03))
+        Ho = OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1, field=F.SymmetricGauge(0.03))
+    dev = Hd.device(ctx)
+    N = Ho.shape[0]
+    try:
+        lib.lm_dbg_set_apply_path(path)
+        for M in (16, 31, 32, 40, 64, 100, 131, 300):
+            X = _rand_block(N, M, seed=M, orth=False)
+            x = lm.DeviceState.from_psi(X, ctx=ctx)
+            y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+            _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+            assert _relerr(y.download(), Ho @ X) < 1e-14, (path, model, M)
+        # one propagator step per kernel path (product form, Horner, Chebyshev epilogues)
+        X = _rand_block(N, 40, seed=5)
+        want = EV.exact_propagator(Ho, 0.3) @ X
+        for method in ("taylor", "taylor_horner", "chebyshev"):
+            st = lm.DeviceState.from_psi(X, ctx=ctx)
+            sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx)
+            sol.update_solver(Hd, 0.3)
+            sol.step(st)
+            assert _relerr(st.download(), want) < 2e-13, (path, model, method)
+    finally:
+        lib.lm_dbg_set_apply_path(-1)
+
+
+def test_csc_hamiltonian_with_site_coords(ctx):
+    """A raw CSC Hamiltonian (host-assembled closure path) gets the tile plan through
+    lm_ham_set_site_coords and must give the same results as without it."""
+    lo, l = L.honeycomb_lattice(9, 8), lm.HoneycombLattice(9, 8)
+    Ho = OP.haldane(lo, 1.0, 0.2, 0.1, field=F.LandauGauge(0.05))
+    X = _rand_block(Ho.shape[0], 48, seed=3, orth=False)
+    outs = []
+    for coords in (None, l.coords):
+        dev = lm.DeviceHam.from_csc(ctx, Ho, 1, coords=coords)
+        Y = np.zeros_like(X, order="F")
+        Xf = np.asfortranarray(X)
+        _lib.check(_lib.load().lm_spmm(dev.handle, _lib.ptr(Xf), _lib.ptr(Y), Ho.shape[0], 48))
+        outs.append(Y)
+        st = lm.DeviceState.from_psi(X, np.linspace(0.1, 1, 48), ctx=ctx)
+        V = lm.DensityCurrents(dev, st).pair_values()[2]
+        outs.append(V)
+    assert _relerr(outs[0], Ho @ X) < 1e-14 and _relerr(outs[2], Ho @ X) < 1e-14
+    assert np.abs(outs[1] - outs[3]).max() < 1e-13
+    with pytest.raises(lm.ArgumentError):
+        lm.DeviceHam.from_csc(ctx, Ho, 1, coords=l.coords[:5])
+
+
 # ------------------------------------------------------------------------------ device Peierls phases
 FIELD_CASES = {
     "nofield": (lambda: lm.NoField(), lambda: F.NoField()),
