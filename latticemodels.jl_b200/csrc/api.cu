@@ -1002,7 +1002,7 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
     static const int cpt_env = env_int("LM_ROWS_CPT", 0);
     int cpt = (ld >= 128) ? 2 : 1;
-    if (cpt_env == 1 || cpt_env == 2) cpt = cpt_env;
+    if (cpt_env == 1 || cpt_env == 2 || cpt_env == 4) cpt = cpt_env;
     const int CT = 32 * cpt;
     const long long nchunks = (ld + CT - 1) / CT;
     static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
@@ -1014,8 +1014,8 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_rows: grid too large");
     a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
     dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
-    if (c->precision == LM_C128) { if (cpt == 2) launch_rows_mode<double, 2>(a, grid, c->stream); else launch_rows_mode<double, 1>(a, grid, c->stream); }
-    else { if (cpt == 2) launch_rows_mode<float, 2>(a, grid, c->stream); else launch_rows_mode<float, 1>(a, grid, c->stream); }
+    if (c->precision == LM_C128) { if (cpt == 4) launch_rows_mode<double, 4>(a, grid, c->stream); else if (cpt == 2) launch_rows_mode<double, 2>(a, grid, c->stream); else launch_rows_mode<double, 1>(a, grid, c->stream); }
+    else { if (cpt == 4) launch_rows_mode<float, 4>(a, grid, c->stream); else if (cpt == 2) launch_rows_mode<float, 2>(a, grid, c->stream); else launch_rows_mode<float, 1>(a, grid, c->stream); }
     c->launches++;
     CK(cudaGetLastError());
     return LM_OK;

@@ -171,7 +171,7 @@ struct RowsArgs {
 };
 
 template <typename T, int CPT, int WX, int MODE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (CPT >= 4 ? 2 : 4))
 k_apply_rows(const RowsArgs a) {
     using T2 = typename cx2<T>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
