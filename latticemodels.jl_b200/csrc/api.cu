@@ -143,6 +143,9 @@ struct lm_state {
     struct StepGraph { cudaGraphExec_t exec = nullptr; lm_ham* h = nullptr; unsigned long long uid = 0, epoch = 0; void* x = nullptr; void* s1 = nullptr;
                        double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false; };
     StepGraph graphs[4]; int graph_next = 0;
+    // block-Lanczos workspace (LM_METHOD_LANCZOS): Krylov basis + per-column scalars
+    std::vector<void*> kry; double2* d_alpha = nullptr; double* d_beta = nullptr; double2* d_coef = nullptr;
+    double* d_err = nullptr; unsigned long long* d_max = nullptr; double2* d_dot = nullptr;
     // dense path: cached propagator U (row-major [N][ld])
     void* d_U = nullptr; lm_ham* U_ham = nullptr; long long U_version = -1; double U_dt = 0, U_tol = 0; int U_method = -1;
 };
@@ -776,6 +779,8 @@ static void state_free(lm_state* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (void* p : s->kry) if (p) cudaFree(p);
+    { void* q[] = {s->d_alpha, s->d_beta, s->d_coef, s->d_err, s->d_max, s->d_dot}; for (void* p : q) if (p) cudaFree(p); }
     void* ptrs[] = {s->d_x, s->d_w, s->d_s1, s->d_s2, s->d_U};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete s;
@@ -1212,6 +1217,96 @@ static int step_cheb(lm_ham* h, long long ld, void** px, void** ps1, void** ps2,
     return LM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Block Lanczos exponential (KrylovKit.exponentiate semantics, src/evolution.jl:150-154):
+// every column runs its own Lanczos process (own alpha_j, beta_j); the subspace grows until
+// max_c beta_m |[exp(-i dt T_m)]_{m,1}| ||psi_c|| <= tol (checked every iteration), at most
+// krylovdim = 30 vectors; if that is not enough the step is split in two halves (restart).
+// ------------------------------------------------------------------------------------------
+static const int kKrylovDim = 30;
+template <typename T>
+static int coldot(lm_state* s, const void* a, const void* b, double2* out) {
+    using T2 = typename cx2<T>::type;
+    lm_ctx* c = s->ctx;
+    CK(cudaMemsetAsync(out, 0, sizeof(double2) * (size_t)s->ld, c->stream));
+    int lc = 0; while ((1LL << lc) < s->ld && lc < 5) lc++;
+    const int LC = 1 << lc;
+    const int rows_per_cta = 256;
+    dim3 grid((unsigned)((s->N + rows_per_cta - 1) / rows_per_cta), (unsigned)((s->M + LC - 1) / LC));
+    k_coldot<T2><<<grid, 256, 0, c->stream>>>(s->N, s->M, s->ld, (const T2*)a, (const T2*)b, out, lc, rows_per_cta);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+template <typename T>
+static int lanczos_once(lm_ham* h, lm_state* s, double dt, double tol, int* nmv, bool* converged) {
+    using T2 = typename cx2<T>::type;
+    lm_ctx* c = s->ctx;
+    const long long N = s->N, M = s->M, ld = s->ld, tot = N * ld;
+    const size_t bytes = sizeof(T2) * (size_t)tot;
+    const int th = 256; const unsigned gb = (unsigned)((tot + th - 1) / th), gc = (unsigned)((M + th - 1) / th);
+    if (!s->d_alpha) {
+        CK(cudaMalloc(&s->d_alpha, sizeof(double2) * (size_t)(kKrylovDim + 2) * ld));
+        CK(cudaMalloc(&s->d_beta, sizeof(double) * (size_t)(kKrylovDim + 2) * ld));
+        CK(cudaMalloc(&s->d_coef, sizeof(double2) * (size_t)(kKrylovDim + 2) * ld));
+        CK(cudaMalloc(&s->d_err, sizeof(double) * (size_t)ld));
+        CK(cudaMalloc(&s->d_dot, sizeof(double2) * (size_t)ld));
+        CK(cudaMalloc(&s->d_max, sizeof(unsigned long long)));
+        s->kry.assign(kKrylovDim + 1, nullptr);
+    }
+    auto basis = [&](int j) -> int { if (!s->kry[j]) CK(cudaMalloc(&s->kry[j], bytes)); return LM_OK; };
+    FWD(ensure_pinned(c, 4096));
+    // v_0 = psi / beta_0
+    FWD(basis(0));
+    FWD(coldot<T>(s, s->d_x, s->d_x, s->d_dot));
+    k_sqrt_cols<<<gc, th, 0, c->stream>>>(M, s->d_dot, s->d_beta);
+    k_scale_inv<T2><<<gb, th, 0, c->stream>>>(N, M, ld, (const T2*)s->d_x, s->d_beta, (T2*)s->kry[0]);
+    c->launches += 2;
+    *converged = false;
+    int m = 0;
+    for (int j = 0; j < kKrylovDim; ++j) {
+        FWD(basis(j + 1));
+        void* w = s->kry[j + 1];
+        FWD(apply(h, ld, s->kry[j], w, nullptr, nullptr, zc(1, 0), zc(0, 0), zc(0, 0), zc(0, 0)));
+        (*nmv)++;
+        FWD(coldot<T>(s, s->kry[j], w, s->d_alpha + (size_t)j * ld));
+        k_lanczos_update<T2><<<gb, th, 0, c->stream>>>(N, M, ld, (T2*)w, (const T2*)s->kry[j], j > 0 ? (const T2*)s->kry[j - 1] : nullptr,
+                                                       s->d_alpha + (size_t)j * ld, s->d_beta + (size_t)j * ld);
+        FWD(coldot<T>(s, w, w, s->d_dot));
+        k_sqrt_cols<<<gc, th, 0, c->stream>>>(M, s->d_dot, s->d_beta + (size_t)(j + 1) * ld);
+        m = j + 1;
+        CK(cudaMemsetAsync(s->d_max, 0, sizeof(unsigned long long), c->stream));
+        k_lanczos_coef<<<gc, th, 0, c->stream>>>(M, m, ld, dt, s->d_alpha, s->d_beta, s->d_coef, s->d_err);
+        k_max_cols<<<gc, th, 0, c->stream>>>(M, s->d_err, s->d_max);
+        c->launches += 4;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_pinned, s->d_max, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        double maxerr; memcpy(&maxerr, c->h_pinned, sizeof(double));
+        if (maxerr <= tol) { *converged = true; break; }
+        if (j + 1 < kKrylovDim) {
+            k_scale_inv<T2><<<gb, th, 0, c->stream>>>(N, M, ld, (const T2*)w, s->d_beta + (size_t)(j + 1) * ld, (T2*)w);
+            c->launches++;
+        }
+    }
+    if (!*converged) return LM_OK;      // caller restarts with half the step; psi untouched
+    LanczosBasis B;
+    for (int j = 0; j < LM_KMAX; ++j) B.v[j] = j < m ? s->kry[j] : nullptr;
+    k_lanczos_combine<T2><<<gb, th, 0, c->stream>>>(N, M, ld, m, B, s->d_coef, ld, (T2*)s->d_x);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+static int step_lanczos(lm_ham* h, lm_state* s, double dt, double tol, int* nmv, int depth = 0) {
+    bool ok = false;
+    if (s->ctx->precision == LM_C128) FWD(lanczos_once<double>(h, s, dt, tol, nmv, &ok));
+    else FWD(lanczos_once<float>(h, s, dt, tol, nmv, &ok));
+    if (ok) return LM_OK;
+    if (depth >= 12) return fail(LM_ERR_NOT_CONVERGED, "`exponentiate` did not converge");
+    FWD(step_lanczos(h, s, 0.5 * dt, 0.5 * tol, nmv, depth + 1));
+    return step_lanczos(h, s, 0.5 * dt, 0.5 * tol, nmv, depth + 1);
+}
+
 // The plan (method, sub-steps, degree, Bessel coefficients) depends only on (dt, tol, method,
 // spectral enclosure): cached on the Hamiltonian so a run of equal steps pays for it once.
 static int get_plan(lm_ham* h, double dt, double tol, int method) {
@@ -1255,6 +1350,12 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
     REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_TAYLOR_HORNER, "lm_step: unknown method");
     lm_ctx* c = h->ctx; FWD(set_dev(c));
     int nmv = 0;
+    if (method == LM_METHOD_LANCZOS) {
+        REQUIRE(!s->dense, "lm_step: the Lanczos method evolves kets / Psi blocks only (src/evolution.jl:150), not dense density matrices");
+        if (dt != 0.0) FWD(step_lanczos(h, s, dt, tol, &nmv));
+        if (n_matvec_out) *n_matvec_out = nmv;
+        return LM_OK;
+    }
     if (dt != 0.0) FWD(get_plan(h, dt, tol, method));
     const int nbuf = (dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR) ? 1 : 2;
     if (!s->dense) {

@@ -823,6 +823,137 @@ k_cgemm_simple(int Mr, int Nc, int K, const float2* __restrict__ A, long long ld
     if (m < Mr && n < Nc) C[(long long)m * ldc + n] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Block Lanczos pieces (LM_METHOD_LANCZOS: KrylovKit.exponentiate semantics, every column is
+// its own Krylov process with its own alpha_j, beta_j).
+// ------------------------------------------------------------------------------------------
+// out[c] += sum_i conj(a[i,c]) * b[i,c]   (b == a gives squared column norms)
+// A warp covers LR = 32/LC rows x LC columns per pass over its row block; the LR row-lanes of
+// a column are folded with warp shuffles, then one atomicAdd pair per (warp, column).
+template <typename T2>
+__global__ void __launch_bounds__(256)
+k_coldot(long long N, long long M, long long ld, const T2* __restrict__ a, const T2* __restrict__ b,
+         double2* __restrict__ out, int lc_log2, int rows_per_cta) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LC = 1 << lc_log2, LR = 32 >> lc_log2;
+    const long long col = (long long)blockIdx.y * LC + (lane & (LC - 1));
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = (r0 + rows_per_cta < N) ? r0 + rows_per_cta : N;
+    double sr = 0.0, si = 0.0;
+    if (col < M)
+        for (long long r = r0 + warp * LR + (lane >> lc_log2); r < r1; r += 8 * LR) {
+            const T2 x = a[r * ld + col], y = b[r * ld + col];
+            sr = fma((double)x.x, (double)y.x, sr); sr = fma((double)x.y, (double)y.y, sr);
+            si = fma((double)x.x, (double)y.y, si); si = fma(-(double)x.y, (double)y.x, si);
+        }
+    for (int o = 16; o >= LC; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+    if (col < M && (lane >> lc_log2) == 0) { atomicAdd(&out[col].x, sr); atomicAdd(&out[col].y, si); }
+}
+
+// w[i,c] = (w[i,c] - alpha[c] v[i,c] - beta[c] vprev[i,c])            (vprev may be null)
+template <typename T2>
+__global__ void k_lanczos_update(long long N, long long M, long long ld, T2* __restrict__ w,
+                                 const T2* __restrict__ v, const T2* __restrict__ vprev,
+                                 const double2* __restrict__ alpha, const double* __restrict__ beta) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long c = e % ld;
+    if (c >= M) return;
+    T2 x = w[e];
+    const double al = alpha[c].x;                    // Hermitian H: alpha is real
+    const T2 y = v[e];
+    double xr = (double)x.x - al * (double)y.x, xi = (double)x.y - al * (double)y.y;
+    if (vprev) { const double be = beta[c]; const T2 z = vprev[e]; xr -= be * (double)z.x; xi -= be * (double)z.y; }
+    x.x = (decltype(x.x))xr; x.y = (decltype(x.y))xi;
+    w[e] = x;
+}
+// beta[c] = sqrt(nrm2[c].x);  y[i,c] = x[i,c] / beta[c]   (columns with beta == 0 stay 0)
+__global__ void k_sqrt_cols(long long M, const double2* __restrict__ nrm2, double* __restrict__ beta) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c < M) beta[c] = sqrt(fmax(nrm2[c].x, 0.0));
+}
+template <typename T2>
+__global__ void k_scale_inv(long long N, long long M, long long ld, const T2* __restrict__ x,
+                            const double* __restrict__ beta, T2* __restrict__ y) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long c = e % ld;
+    T2 v = x[e];
+    const double b = (c < M) ? beta[c] : 0.0;
+    const double inv = b > 0.0 ? 1.0 / b : 0.0;
+    v.x = (decltype(v.x))((double)v.x * inv); v.y = (decltype(v.y))((double)v.y * inv);
+    y[e] = v;
+}
+// Per column: coef[j][c] = beta0[c] * [exp(-i dt T_m) e_1]_j for the m x m real symmetric
+// tridiagonal T_m = tridiag(alpha[0..m), beta[1..m)); err[c] = beta[m][c] |coef[m-1][c]|
+// (residual estimate of the Lanczos exponential).  exp via sub-stepped Taylor on the m-vector.
+#define LM_KMAX 32
+__global__ void k_lanczos_coef(long long M, int m, long long ldc, double dt,
+                               const double2* __restrict__ alpha /*[j][ldc]*/, const double* __restrict__ beta /*[j][ldc], beta[0] = beta0*/,
+                               double2* __restrict__ coef /*[j][ldc]*/, double* __restrict__ err) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= M) return;
+    double a[LM_KMAX], b[LM_KMAX];
+    double nrm = 0.0;
+    for (int j = 0; j < m; ++j) {
+        a[j] = alpha[(long long)j * ldc + c].x;
+        b[j] = (j + 1 < m) ? beta[(long long)(j + 1) * ldc + c] : 0.0;     // T[j][j+1]
+        nrm = fmax(nrm, fabs(a[j]) + fabs(b[j]) + (j ? fabs(b[j - 1]) : 0.0));
+    }
+    const int nsub = (int)fmax(1.0, ceil(nrm * fabs(dt)));
+    const double h = dt / nsub;
+    double yr[LM_KMAX], yi[LM_KMAX], tr[LM_KMAX], ti[LM_KMAX], ur[LM_KMAX], ui[LM_KMAX];
+    for (int j = 0; j < m; ++j) { yr[j] = (j == 0); yi[j] = 0.0; }
+    for (int s = 0; s < nsub; ++s) {
+        for (int j = 0; j < m; ++j) { tr[j] = yr[j]; ti[j] = yi[j]; }          // term_0 = y
+        for (int n = 1; n <= 40; ++n) {
+            // term_n = (-i h / n) T term_{n-1}
+            double tmax = 0.0;
+            for (int j = 0; j < m; ++j) {
+                double pr = a[j] * tr[j], pi = a[j] * ti[j];
+                if (j > 0) { pr += b[j - 1] * tr[j - 1]; pi += b[j - 1] * ti[j - 1]; }
+                if (j + 1 < m) { pr += b[j] * tr[j + 1]; pi += b[j] * ti[j + 1]; }
+                ur[j] = (h / n) * pi; ui[j] = -(h / n) * pr;                 // (-i)(pr + i pi) = pi - i pr
+                tmax = fmax(tmax, fabs(ur[j]) + fabs(ui[j]));
+            }
+            for (int j = 0; j < m; ++j) { tr[j] = ur[j]; ti[j] = ui[j]; yr[j] += ur[j]; yi[j] += ui[j]; }
+            if (tmax < 1e-18) break;
+        }
+    }
+    const double b0 = beta[c];
+    for (int j = 0; j < m; ++j) coef[(long long)j * ldc + c] = make_double2(b0 * yr[j], b0 * yi[j]);
+    const double bm = beta[(long long)m * ldc + c];
+    err[c] = bm * b0 * sqrt(yr[m - 1] * yr[m - 1] + yi[m - 1] * yi[m - 1]);
+}
+// max over columns -> out[0] (bit pattern of a non-negative double compares like an integer)
+__global__ void k_max_cols(long long M, const double* __restrict__ err, unsigned long long* __restrict__ out) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double v = (c < M) ? fabs(err[c]) : 0.0;
+    if (!(v == v)) v = 1e300;                                              // NaN -> not converged
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+// y[i,c] = sum_j coef[j][c] * V_j[i,c]
+struct LanczosBasis { const void* v[LM_KMAX]; };
+template <typename T2>
+__global__ void k_lanczos_combine(long long N, long long M, long long ld, int m, LanczosBasis basis,
+                                  const double2* __restrict__ coef, long long ldc, T2* __restrict__ y) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long c = e % ld;
+    double sr = 0.0, si = 0.0;
+    if (c < M)
+        for (int j = 0; j < m; ++j) {
+            const T2 v = ((const T2*)basis.v[j])[e];
+            const double2 k = coef[(long long)j * ldc + c];
+            sr += k.x * (double)v.x - k.y * (double)v.y;
+            si += k.x * (double)v.y + k.y * (double)v.x;
+        }
+    T2 o; o.x = (decltype(o.x))sr; o.y = (decltype(o.y))si;
+    y[e] = o;
+}
+
 // calibration only (tools/sweep.py): 3-stream element-wise kernel y = a x + z, same tiling
 template <typename T2>
 __global__ void __launch_bounds__(256) k_dbg_triad(long long n, const T2* __restrict__ x, const T2* __restrict__ z, T2* __restrict__ y) {

@@ -207,7 +207,7 @@ def test_field_param_update_path(ctx):
 
 
 # ------------------------------------------------------------------------------ propagator
-@pytest.mark.parametrize("method", ["taylor", "taylor_horner", "chebyshev", "auto"])
+@pytest.mark.parametrize("method", ["taylor", "taylor_horner", "chebyshev", "lanczos", "auto"])
 @pytest.mark.parametrize("dt", [0.1, 0.7, 3.0, -0.4])
 def test_step_matches_exact_exponential(ctx, method, dt):
     Ho = OP.qwz(L.square_lattice(6, 5), field=F.LandauGauge(0.1))
@@ -233,7 +233,7 @@ def test_evolution_known_answer_gpu(ctx):
     for _ in ts:
         correct.append(v[1])
         v = U @ v
-    for method in ("taylor", "chebyshev"):
+    for method in ("taylor", "chebyshev", "lanczos"):      # lanczos = KrylovKitExp semantics
         vals = [m.state.data[1] for m in lm.Evolution(lm.B200Exp(method=method, ctx=ctx), H, psi)(ts)]
         assert np.abs(np.array(vals) - np.array(correct)).max() < 1e-10
     # CachedExp-style constant sparse matrix passed as a raw CSC (update_solver! identity skip)
@@ -289,6 +289,22 @@ def test_host_assembled_closure_path(ctx):
     for ma, mb, (st, H, t) in zip(ev_a(ts), ev_b(ts), ref(ts)):
         assert _relerr(ma.state.download(), st[0]) < 1e-12
         assert _relerr(mb.state.download(), st[0]) < 1e-12
+
+
+def test_lanczos_block_restart_and_dense_rejection(ctx):
+    """Large dt forces the krylovdim = 30 restart path; dense states are rejected like
+    KrylovKitExp rejects matrices (src/evolution.jl:150, docs/src/manual/evolution.md:217)."""
+    Ho = OP.haldane(L.honeycomb_lattice(8, 8), 1.0, 0.3, 0.2, field=F.LandauGauge(0.05))
+    Psi = _rand_block(128, 37, seed=11)
+    st = lm.DeviceState.from_psi(Psi, ctx=ctx)
+    sol = lm.B200Exp(tol=1e-12, method="lanczos", ctx=ctx)
+    sol.update_solver(Ho, 25.0)
+    sol.step(st)
+    assert _relerr(st.download(), EV.exact_propagator(Ho, 25.0) @ Psi) < 1e-10
+    assert sol.n_matvec > 30
+    P = np.eye(128, dtype=complex) / 128
+    with pytest.raises(lm.ArgumentError, match="Lanczos"):
+        sol.step(lm.DeviceState.from_dense(P, ctx=ctx))
 
 
 # ------------------------------------------------------------------------------ observables
@@ -467,3 +483,60 @@ def test_full_size_config2_properties(ctx):
     X = np.asfortranarray(Psi[:, :8])
     _lib.check(_lib.load().lm_spmm(H.device(ctx).handle, _lib.ptr(X), _lib.ptr(Y), N, 8))
     assert _relerr(Y, Ho @ X) < 1e-14
+
+
+@pytest.mark.parametrize("config", ["c3_qwz300", "c4_haldane500"])
+def test_full_size_headline_configs_properties(ctx, config):
+    """BASELINE configs 3 / 4 at their full lattice sizes (N = 1.8e5 / 5e5) with a 256-column
+    block: size-independent properties - particle number, continuity d rho_i/dt = sum_j J_ij,
+    exp(+iHdt) exp(-iHdt) = 1, Lanczos (KrylovKit semantics) == product-form Taylor, and SpMM
+    linearity H(aX + bY) = aHX + bHY."""
+    if config == "c3_qwz300":
+        H = lm.qwz(lm.SquareLattice(300, 300), field=lm.LandauGauge(0.05))
+    else:
+        H = lm.haldane(lm.HoneycombLattice(500, 500), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.002))
+    dev = H.device(ctx)
+    N, M = dev.N, 256
+    rng = np.random.default_rng(1234)
+    blk = (rng.standard_normal((N, 32)) + 1j * rng.standard_normal((N, 32))) / np.sqrt(2 * N)
+    Psi = np.asfortranarray(np.concatenate([blk * np.exp(0.37j * k) * (1 + 0.01 * k) for k in range(M // 32)], axis=1))
+    w = np.linspace(0.2, 1.0, M)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=H.n_int)
+    sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+    rho0 = lm.localdensity(st).values
+    I, J, V = lm.DensityCurrents(H, st).pair_values()
+    n_sites = N // H.n_int
+    div = np.zeros(n_sites)
+    np.add.at(div, I - 1, V)          # sum_j J_ij with J_ji = -J_ij
+    np.add.at(div, J - 1, -V)
+    eps = 1e-4
+    sol.update_solver(H, eps)
+    sol.step(st)
+    rho1 = lm.localdensity(st).values
+    assert abs(rho1.sum() - rho0.sum()) < 1e-11 * rho0.sum()
+    drho = (rho1 - rho0) / eps
+    assert np.abs(drho - div).max() < 5e-3 * np.abs(drho).max()
+    sol.update_solver(H, -eps)
+    sol.step(st)
+    st2 = st.copy()
+    sol.update_solver(H, 0.1)
+    sol.step(st)
+    lz = lm.B200Exp(tol=1e-13, method="lanczos", ctx=ctx)
+    lz.update_solver(H, 0.1)
+    lz.step(st2)
+    a, b = st.download(), st2.download()
+    assert np.abs(a - b).max() < 1e-11 * np.abs(a).max() * 10
+    sol.update_solver(H, -0.1)
+    sol.step(st)
+    assert np.abs(st.download() - Psi).max() < 5e-11 * np.abs(Psi).max()
+    # linearity of the SpMM on device-resident blocks
+    x = lm.DeviceState.from_psi(Psi[:, :64], ctx=ctx)
+    y = lm.DeviceState.from_psi(Psi[:, 64:128], ctx=ctx)
+    zsum = lm.DeviceState.from_psi(2.0 * Psi[:, :64] - 0.5j * Psi[:, 64:128], ctx=ctx)
+    outs = []
+    for s_in in (x, y, zsum):
+        o = lm.DeviceState.from_psi(np.zeros((N, 64), complex), ctx=ctx)
+        _lib.check(_lib.load().lm_spmm_state(dev.handle, s_in.handle, o.handle))
+        outs.append(o.download())
+    lin = 2.0 * outs[0] - 0.5j * outs[1]
+    assert np.abs(outs[2] - lin).max() < 1e-13 * max(np.abs(lin).max(), 1e-300) * 10
