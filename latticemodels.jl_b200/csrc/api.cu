@@ -1008,7 +1008,8 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     static const int cpt_env = env_int("LM_ROWS_CPT", 0);
     int cpt = (ld >= 128) ? 2 : 1;
     if (cpt_env == 1 || cpt_env == 2 || cpt_env == 4) cpt = cpt_env;
-    const int CT = 32 * cpt;
+    const int ec = (c->precision == LM_C128) ? 1 : 2;       // complex columns per 128-bit lane element
+    const int CT = 32 * cpt * ec;                             // complex columns per chunk
     const long long nchunks = (ld + CT - 1) / CT;
     static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
     const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
@@ -1017,6 +1018,7 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     const long long strips = (nchunks + cps - 1) / cps;
     cps = (nchunks + strips - 1) / strips;
     REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_rows: grid too large");
+    REQUIRE(ld % ec == 0, "apply_rows: odd leading dimension in complex64 mode");
     a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
     dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
     if (c->precision == LM_C128) { if (cpt == 4) launch_rows_mode<double, 4>(a, grid, c->stream); else if (cpt == 2) launch_rows_mode<double, 2>(a, grid, c->stream); else launch_rows_mode<double, 1>(a, grid, c->stream); }

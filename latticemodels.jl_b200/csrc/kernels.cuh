@@ -52,6 +52,24 @@ __device__ __forceinline__ float2 ld_stream_pin(const float2* p) {
     return r;
 }
 
+// What ONE LANE moves per 128-bit access: one complex128, or TWO adjacent complex64 columns
+// (so that the complex64 mode keeps full-width L1 / HBM transactions).
+template <typename T> struct pack;
+template <> struct pack<double> { using E = double2; static constexpr int EC = 1; };
+template <> struct pack<float>  { using E = float4;  static constexpr int EC = 2; };
+__device__ __forceinline__ float4 ld_ro(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void pzero(double2& a) { a.x = 0; a.y = 0; }
+__device__ __forceinline__ void pzero(float4& a) { a.x = 0; a.y = 0; a.z = 0; a.w = 0; }
+__device__ __forceinline__ void pfma(double2& acc, const double2 v, const double2 x) { cfma(acc, v, x); }
+__device__ __forceinline__ void pfma(float4& acc, const float2 v, const float4 x) {
+    acc.x = fmaf(v.x, x.x, acc.x); acc.x = fmaf(-v.y, x.y, acc.x);
+    acc.y = fmaf(v.x, x.y, acc.y); acc.y = fmaf(v.y, x.x, acc.y);
+    acc.z = fmaf(v.x, x.z, acc.z); acc.z = fmaf(-v.y, x.w, acc.z);
+    acc.w = fmaf(v.x, x.w, acc.w); acc.w = fmaf(v.y, x.z, acc.w);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_apply: one polynomial term of the propagator, fused around the ELL SpMM
 //     y = alpha * (H x) + gamma * x + beta * z + delta * u          (element-wise epilogue)
@@ -174,16 +192,19 @@ template <typename T, int CPT, int WX, int MODE>
 __global__ void __launch_bounds__(256, (CPT >= 4 ? 2 : 4))
 k_apply_rows(const RowsArgs a) {
     using T2 = typename cx2<T>::type;
+    using E = typename pack<T>::E;                  // one 128-bit lane element
+    constexpr int EC = pack<T>::EC;                 // complex columns per lane element
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile = blockIdx.x / a.cps;
     const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
     if (chunk >= a.nchunks) return;
     const int p0 = a.t_ptr[tile];
     const int nr = a.t_nr[tile];
-    const T2* __restrict__ x = (const T2*)a.x;
-    T2* y = (T2*)a.y;
-    const T2* z = (const T2*)a.z;
-    const T2* u = (const T2*)a.u;
+    const long long lde = a.ld / EC;                // row length in lane elements (ld is even)
+    const E* __restrict__ x = (const E*)a.x;
+    E* y = (E*)a.y;
+    const E* z = (const E*)a.z;
+    const E* u = (const E*)a.u;
     const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
     const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
     const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
@@ -194,23 +215,23 @@ k_apply_rows(const RowsArgs a) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const long long c = (long long)chunk * (32 * CPT) + lane + 32 * j;
-        ok[j] = c < a.ld;
-        cidx[j] = ok[j] ? c : (a.ld - 1);
+        ok[j] = c < lde;
+        cidx[j] = ok[j] ? c : (lde - 1);
     }
     for (int r = warp; r < nr; r += 8) {
         const long long row = a.t_rows[p0 + r];
         const T2* __restrict__ vals = (const T2*)a.vals + row * a.W;
         const int* __restrict__ cols = a.cols + row * a.W;
-        T2 acc[CPT];
+        E acc[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-            const long long e = row * a.ld + cidx[j];
-            acc[j].x = 0; acc[j].y = 0;
-            if (MODE == 1) cfma(acc[j], beta, ld_stream(z + e));
+            const long long e = row * lde + cidx[j];
+            pzero(acc[j]);
+            if (MODE == 1) pfma(acc[j], beta, ld_stream(z + e));
             if (MODE == 2) {
-                if (z) cfma(acc[j], beta, ld_stream(z + e));
-                if (u) cfma(acc[j], delta, u[e]);
-                if (has_gamma) cfma(acc[j], gamma, ld_ro(x + e));
+                if (z) pfma(acc[j], beta, ld_stream(z + e));
+                if (u) pfma(acc[j], delta, u[e]);
+                if (has_gamma) pfma(acc[j], gamma, ld_ro(x + e));
             }
         }
         if (WX > 0) {
@@ -219,25 +240,25 @@ k_apply_rows(const RowsArgs a) {
             for (int k = 0; k < WX; ++k) { cc[k] = cols[k]; vv[k] = cmul(alpha, vals[k]); }
 #pragma unroll
             for (int k = 0; k < WX; ++k) {
-                const T2* xr = x + (long long)cc[k] * a.ld;
+                const E* xr = x + (long long)cc[k] * lde;
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) cfma(acc[j], vv[k], ld_ro(xr + cidx[j]));
+                for (int j = 0; j < CPT; ++j) pfma(acc[j], vv[k], ld_ro(xr + cidx[j]));
             }
         } else {
 #pragma unroll 4
             for (int k = 0; k < a.W; ++k) {
                 const long long c = cols[k];
                 const T2 v = cmul(alpha, vals[k]);
-                const T2* xr = x + c * a.ld;
+                const E* xr = x + c * lde;
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) cfma(acc[j], v, ld_ro(xr + cidx[j]));
+                for (int j = 0; j < CPT; ++j) pfma(acc[j], v, ld_ro(xr + cidx[j]));
             }
         }
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             // product-form factor: the own-row element is (almost always) an L1 hit by now
-            if (MODE == 3) cfma(acc[j], gamma, ld_ro(x + row * a.ld + cidx[j]));
-            if (ok[j]) st_stream(y + row * a.ld + cidx[j], acc[j]);
+            if (MODE == 3) pfma(acc[j], gamma, ld_ro(x + row * lde + cidx[j]));
+            if (ok[j]) st_stream(y + row * lde + cidx[j], acc[j]);
         }
     }
 }
