@@ -175,6 +175,15 @@ int32_t lm_observables(lm_ham* ham, lm_state* state, double* rho_out, double* J_
 int32_t lm_bond_currents(lm_ham* ham, lm_state* state, int64_t nb, const int32_t* I,
                          const int32_t* J, double* J_out);
 
+/* ------------------------------------------------------------------ local operators
+ * localexpect(op, state) (src/operators/latticeutils.jl:13-20):
+ *   out_i = sum_{j,k} op[j,k] P[(i,k),(i,j)];  op = n_int x n_int column-major complex128,
+ *   out = n_sites complex128.  All-reduced over ranks. */
+int32_t lm_local_expect(lm_state* state, int32_t n_int, const void* op, void* out);
+/* LocalOperatorCurrents(ham, state, op)[i,j] (src/zoo/currents.jl:150-184) for every site pair of
+ * lm_currents_pairs:  J_p = sum_{a,b} 2 Im( (op T_ij)_{ab} P[j_b, i_a] ),  T_ij the H block. */
+int32_t lm_operator_currents(lm_ham* ham, lm_state* state, const void* op, double* J_out);
+
 #ifdef __cplusplus
 }
 #endif

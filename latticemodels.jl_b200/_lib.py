@@ -67,6 +67,8 @@ PROTOTYPES = {
     "lm_currents_pairs": [_vp, _vp, _vp],
     "lm_observables": [_vp, _vp, _vp, _vp],
     "lm_bond_currents": [_vp, _vp, _i64, _vp, _vp, _vp],
+    "lm_local_expect": [_vp, _i32, _vp, _vp],
+    "lm_operator_currents": [_vp, _vp, _vp, _vp],
 }
 _SPECIAL = {"lm_version": ([], _i32), "lm_last_error": ([], C.c_char_p)}
 

@@ -90,6 +90,7 @@ struct lm_ctx {
     void* d_stage = nullptr; size_t stage_bytes = 0;      // staging for layout changes
     int l2_bytes = 0;
     struct lm_ham* dens_helper = nullptr;                 // pattern-less ham owning density scratch
+    long long le_N = 0; int le_n = 0; int* d_le_a = nullptr; int* d_le_b = nullptr; double2* d_le_G = nullptr; double2* d_le_out = nullptr;   // localexpect tables
     size_t esz() const { return precision == LM_C128 ? 16 : 8; }
 };
 
@@ -132,6 +133,9 @@ struct lm_ham {
     // observable items of the plan: (row, upper neighbour) pairs + one density item per row
     int* d_it_ptr = nullptr; unsigned short* d_it_row = nullptr; unsigned short* d_it_nb = nullptr; int* d_it_out = nullptr;
     bool obs_tiled = false;
+    // LocalOperatorCurrents tables (built on first use): correlator requests of every full
+    // n_int x n_int block of the site pairs, and the ELL entry of H[i_k, j_b] (or -1)
+    int* d_oc_a = nullptr; int* d_oc_b = nullptr; int* d_oc_ent = nullptr; double2* d_oc_G = nullptr; double* d_oc_J = nullptr;
 };
 
 struct lm_state {
@@ -199,6 +203,7 @@ extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->d_stage) cudaFree(c->d_stage);
+    { void* q[] = {c->d_le_a, c->d_le_b, c->d_le_G, c->d_le_out}; for (void* p : q) if (p) cudaFree(p); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -246,7 +251,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -1604,3 +1609,111 @@ extern "C" int32_t lm_dbg_triad(lm_state* x, lm_state* z, lm_state* y) {
 }
 
 extern "C" int32_t lm_dbg_set_apply_path(int32_t path) { g_apply_path_override = path; return LM_OK; }
+
+// ------------------------------------------------------------------------------------------
+// N3: localexpect and LocalOperatorCurrents
+// ------------------------------------------------------------------------------------------
+static int load_op(int n, const void* op_colmajor, OpMat* out) {
+    REQUIRE(n >= 1 && n <= 8, "local operator: n_int must be in 1..8");
+    const zc* o = (const zc*)op_colmajor;
+    for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) {       // column-major in: op[j,k] = o[k*n + j]
+        out->m[j * n + k].x = o[k * n + j].real(); out->m[j * n + k].y = o[k * n + j].imag();
+    }
+    return LM_OK;
+}
+template <typename T>
+static int corr_pairs(lm_state* s, long long nq, const int* d_a, const int* d_b, double2* d_out) {
+    using T2 = typename cx2<T>::type;
+    lm_ctx* c = s->ctx;
+    if (nq == 0) return LM_OK;
+    k_corr_pairs<T><<<(unsigned)((nq + 7) / 8), 256, 0, c->stream>>>(nq, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+static int reduce_and_fetch(lm_ctx* c, double* d_buf, size_t ndoubles, void* host_out) {
+    if (c->nranks > 1 && c->comm)
+        NCK(g_nccl.AllReduce(d_buf, d_buf, ndoubles, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    FWD(ensure_pinned(c, sizeof(double) * ndoubles + 4096));
+    CK(cudaMemcpyAsync(c->h_pinned, d_buf, sizeof(double) * ndoubles, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(host_out, c->h_pinned, sizeof(double) * ndoubles);
+    return LM_OK;
+}
+
+extern "C" int32_t lm_local_expect(lm_state* s, int32_t n_int, const void* op, void* out) {
+    REQUIRE(s && op && out, "lm_local_expect: NULL argument");
+    REQUIRE(!s->dense, "lm_local_expect: dense states are handled on the host from lm_state_download_dense");
+    REQUIRE(n_int >= 1 && s->N % n_int == 0, "lm_local_expect: N is not a multiple of n_int");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    OpMat O; FWD(load_op(n_int, op, &O));
+    const int n = n_int; const long long ns = s->N / n, nq = ns * n * n;
+    REQUIRE(nq < 2147483647LL, "lm_local_expect: too many correlators");
+    if (c->le_N != s->N || c->le_n != n) {
+        CK(cudaStreamSynchronize(c->stream));
+        void* q[] = {c->d_le_a, c->d_le_b, c->d_le_G, c->d_le_out}; for (void* p : q) if (p) cudaFree(p);
+        c->d_le_a = c->d_le_b = nullptr; c->d_le_G = c->d_le_out = nullptr;
+        std::vector<int> a((size_t)nq), b((size_t)nq);
+        for (long long st = 0; st < ns; ++st) for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) {
+            a[(st * n + j) * n + k] = (int)(st * n + j);          // conj'd row  -> G = P[(s,k),(s,j)]
+            b[(st * n + j) * n + k] = (int)(st * n + k);
+        }
+        CK(cudaMalloc(&c->d_le_a, sizeof(int) * nq)); CK(cudaMalloc(&c->d_le_b, sizeof(int) * nq));
+        CK(cudaMalloc(&c->d_le_G, sizeof(double2) * nq)); CK(cudaMalloc(&c->d_le_out, sizeof(double2) * ns));
+        CK(cudaMemcpy(c->d_le_a, a.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_le_b, b.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
+        c->le_N = s->N; c->le_n = n;
+    }
+    if (c->precision == LM_C128) FWD(corr_pairs<double>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G));
+    else FWD(corr_pairs<float>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G));
+    k_localexpect_fin<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(ns, n, O, c->d_le_G, c->d_le_out);
+    c->launches++;
+    CK(cudaGetLastError());
+    return reduce_and_fetch(c, (double*)c->d_le_out, (size_t)(2 * ns), out);
+}
+
+extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, double* J_out) {
+    REQUIRE(h && s && op && J_out, "lm_operator_currents: NULL argument");
+    REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_operator_currents: Hamiltonian/state mismatch");
+    REQUIRE(!s->dense, "lm_operator_currents: Psi-block states only");
+    REQUIRE(h->n_int >= 2, "System expected to have internal degrees of freedom");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    const int n = h->n_int; const int W = h->W;
+    OpMat O; FWD(load_op(n, op, &O));
+    const long long np = h->npairs, nq = np * n * n;
+    REQUIRE(nq < 2147483647LL, "lm_operator_currents: too many correlators");
+    if (np == 0) return LM_OK;
+    if (!h->d_oc_a) {
+        std::vector<int> a((size_t)nq), b((size_t)nq), ent((size_t)nq, -1);
+        for (long long p = 0; p < np; ++p) {
+            const long long I = h->pairI[p], Jn = h->pairJ[p];
+            for (int al = 0; al < n; ++al) for (int be = 0; be < n; ++be) {
+                a[(p * n + al) * n + be] = (int)(I * n + al);       // G = P[j_b, i_a]
+                b[(p * n + al) * n + be] = (int)(Jn * n + be);
+            }
+            for (int k = 0; k < n; ++k) {
+                const long long row = I * n + k;
+                for (int q = 0; q < W; ++q) {
+                    const long long col = h->h_cols[row * W + q];
+                    if (col / n == Jn) ent[(p * n + k) * n + (col % n)] = (int)(row * W + q);
+                }
+            }
+        }
+        CK(cudaMalloc(&h->d_oc_a, sizeof(int) * nq)); CK(cudaMalloc(&h->d_oc_b, sizeof(int) * nq));
+        CK(cudaMalloc(&h->d_oc_ent, sizeof(int) * nq)); CK(cudaMalloc(&h->d_oc_G, sizeof(double2) * nq));
+        CK(cudaMalloc(&h->d_oc_J, sizeof(double) * np));
+        CK(cudaMemcpy(h->d_oc_a, a.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_oc_b, b.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_oc_ent, ent.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
+    }
+    if (c->precision == LM_C128) {
+        FWD(corr_pairs<double>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G));
+        k_opcurrents_fin<double><<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(np, n, O, h->d_oc_G, h->d_oc_ent, (const double2*)h->d_vals, h->d_oc_J);
+    } else {
+        FWD(corr_pairs<float>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G));
+        k_opcurrents_fin<float><<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(np, n, O, h->d_oc_G, h->d_oc_ent, (const float2*)h->d_vals, h->d_oc_J);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return reduce_and_fetch(c, h->d_oc_J, (size_t)np, J_out);
+}

@@ -680,6 +680,71 @@ k_observe_tiled(const ObsTiledArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Generic correlators for localexpect / LocalOperatorCurrents:
+//   out[q] = P[rowB_q, rowA_q] = sum_c w_c x[rowB_q, c] conj(x[rowA_q, c])
+// one warp per requested pair, lanes stride over the columns, warp-shuffle reduction.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_corr_pairs(long long nq, long long M, long long ld, const typename cx2<T>::type* __restrict__ x,
+             const double* __restrict__ w, const int* __restrict__ rowA, const int* __restrict__ rowB,
+             double2* __restrict__ out) {
+    using T2 = typename cx2<T>::type;
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const T2* pa = x + (long long)rowA[q] * ld;
+    const T2* pb = x + (long long)rowB[q] * ld;
+    double gr = 0.0, gi = 0.0;
+#pragma unroll 2
+    for (long long c = lane; c < M; c += 32) {
+        const T2 va = ld_ro(pa + c), vb = ld_ro(pb + c);
+        const double wc = w ? w[c] : 1.0;
+        const double ar = wc * (double)va.x, ai = wc * (double)va.y;
+        gr = fma((double)vb.x, ar, gr); gr = fma((double)vb.y, ai, gr);
+        gi = fma((double)vb.y, ar, gi); gi = fma(-(double)vb.x, ai, gi);
+    }
+    gr = warp_sum(gr); gi = warp_sum(gi);
+    if (lane == 0) out[q] = make_double2(gr, gi);
+}
+struct OpMat { double2 m[64]; };     // n_int x n_int operator, row-major m[j * n + k], n_int <= 8
+// localexpect (src/operators/latticeutils.jl:13-20): out_s = sum_{j,k} op[j,k] P[(s,k),(s,j)],
+// G laid out [site][j][k] with G = P[(s,k),(s,j)]
+__global__ void k_localexpect_fin(long long n_sites, int n, OpMat op, const double2* __restrict__ G, double2* __restrict__ out) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n_sites) return;
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) {
+        const double2 o = op.m[j * n + k], g = G[(s * n + j) * n + k];
+        sr += o.x * g.x - o.y * g.y; si += o.x * g.y + o.y * g.x;
+    }
+    out[s] = make_double2(sr, si);
+}
+// LocalOperatorCurrents.getindex (src/zoo/currents.jl:169-181):
+//   J_p = sum_{a,b} 2 Im( (O T)_{ab} P[j_b, i_a] ),  T[k,b] = H[i_k, j_b]  (ELL entry ent[p][k][b] or -1)
+template <typename T>
+__global__ void k_opcurrents_fin(long long npairs, int n, OpMat op, const double2* __restrict__ G /*[p][a][b]*/,
+                                 const int* __restrict__ ent /*[p][k][b]*/,
+                                 const typename cx2<T>::type* __restrict__ vals, double* __restrict__ J) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    double acc = 0.0;
+    for (int a = 0; a < n; ++a) for (int b = 0; b < n; ++b) {
+        double otr = 0.0, oti = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const int e = ent[(p * n + k) * n + b];
+            if (e < 0) continue;
+            const double hr = (double)vals[e].x, hi = (double)vals[e].y;
+            const double2 o = op.m[a * n + k];
+            otr += o.x * hr - o.y * hi; oti += o.x * hi + o.y * hr;
+        }
+        const double2 g = G[(p * n + a) * n + b];
+        acc += 2.0 * (otr * g.y + oti * g.x);
+    }
+    J[p] = acc;
+}
+
 // obs[0 .. n_sites) = site densities, obs[n_sites .. n_sites + npairs) = pair currents
 //   J_p = sum_{e in pair p} 2 Im(H_e * G_e)      (src/zoo/currents.jl:92-102)
 template <typename T>

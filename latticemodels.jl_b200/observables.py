@@ -54,6 +54,22 @@ def localdensity(state, n_int=None):
     return LatticeValue(ds.lattice, rho)
 
 
+def localexpect(op, state, n_int=None):
+    """``localexpect(op, state)``: expectation of the on-site operator ``op`` (n_int x n_int) on
+    every site -> LatticeValue (complex in general, like the reference's un-real()ed sum)."""
+    ds = _device_state(state)
+    o = np.asarray(op, complex)
+    n = n_int or ds.n_int or o.shape[0]
+    if n < 2:
+        raise _lib.ArgumentError("Cannot compute local expectation value for a state without internal degrees of freedom")
+    if o.shape != (n, n):
+        raise _lib.ArgumentError("Operator must be defined on the internal basis of the state")
+    out = np.zeros(ds.N // n, complex)
+    o_cm = np.asfortranarray(o)
+    _lib.check(_lib.load().lm_local_expect(ds.handle, n, _lib.ptr(o_cm), _lib.ptr(out)))
+    return LatticeValue(ds.lattice, out)
+
+
 def _device_ham(ham, ctx, n_int):
     if isinstance(ham, Hamiltonian):
         return ham.device(ctx)
@@ -113,6 +129,37 @@ class DensityCurrents:
         return ns * (ns - 1) // 2
 
 
+class LocalOperatorCurrents(DensityCurrents):
+    """``LocalOperatorCurrents(hamiltonian, state, op)`` (e.g. spin currents)."""
+
+    def __init__(self, hamiltonian, state, op, n_int=None):
+        super().__init__(hamiltonian, state, n_int)
+        o = np.asarray(op, complex)
+        if self.n_int < 2:
+            raise _lib.ArgumentError("System expected to have internal degrees of freedom")
+        if o.shape != (self.n_int, self.n_int):
+            raise _lib.ArgumentError("Operator must be defined on the internal basis of the Hamiltonian.")
+        self.op = np.asfortranarray(o)
+
+    def pair_values(self):
+        if self._values is None:
+            dev = self._ham()
+            I, J = dev.pairs()
+            V = np.zeros(max(len(I), 1))
+            _lib.check(_lib.load().lm_operator_currents(dev.handle, self.state.handle, _lib.ptr(self.op), _lib.ptr(V)))
+            self._values = (I, J, V[:len(I)])
+        return self._values
+
+    def __getitem__(self, ij):
+        i, j = ij
+        I, J, V = self.pair_values()
+        if i == j:
+            return 0.0
+        a, b, sgn = (i, j, 1.0) if i < j else (j, i, -1.0)
+        hit = np.nonzero((I == a) & (J == b))[0]
+        return sgn * float(V[hit[0]]) if len(hit) else 0.0
+
+
 def findnz(curr):
     """(Is, Js, Vs) with Is < Js, |V| >= 1e-10, ordered like findnz of a CSC matrix."""
     if isinstance(curr, Currents):
@@ -130,7 +177,7 @@ class Currents:
     """Materialised antisymmetric site-current matrix ``Currents(lat, mat)``."""
 
     def __init__(self, curr, bonds=None, lattice=None):
-        if isinstance(curr, DensityCurrents):
+        if isinstance(curr, DensityCurrents):       # incl. LocalOperatorCurrents
             I, J, V = curr.pair_values()
             if bonds is not None:
                 # Currents(curr, bonds): only the listed (i, j) pairs (1-based), either order

@@ -109,3 +109,29 @@ def currents_from(H, state, src, n_int=1):
     st = state if isinstance(state, State) else State(state)
     ns = st.data.shape[0] // n_int
     return sum(density_current(H, st, src, j, n_int) for j in range(1, ns + 1) if j != src)
+
+
+def localexpect(op, state, n_int):
+    """localexpect(op, state) (src/operators/latticeutils.jl:13-20):
+    [sum(op[j,k] * matrix_element(state, (i-1)N + k, (i-1)N + j) for j, k) for i in sites]."""
+    st = state if isinstance(state, State) else State(state)
+    op = np.asarray(op, complex)
+    ns = st.data.shape[0] // n_int
+    out = np.zeros(ns, complex)
+    for i in range(ns):
+        out[i] = sum(op[j, k] * st.elem(i * n_int + k, i * n_int + j) for j in range(n_int) for k in range(n_int))
+    return out
+
+
+def operator_current(H, state, op, i, j, n_int):
+    """LocalOperatorCurrents.getindex (src/zoo/currents.jl:169-181), 1-based site indices."""
+    st = state if isinstance(state, State) else State(state)
+    Hc = H.tocsr() if sp.issparse(H) else np.asarray(H)
+    O = np.asarray(op, complex)
+    T = np.array([[Hc[(i - 1) * n_int + a, (j - 1) * n_int + b] for b in range(n_int)] for a in range(n_int)], complex)
+    out = 0.0
+    for a in range(n_int):
+        for b in range(n_int):
+            ot = sum(O[a, k] * T[k, b] for k in range(n_int))
+            out += 2 * np.imag(ot * st.elem((j - 1) * n_int + b, (i - 1) * n_int + a))
+    return float(out)

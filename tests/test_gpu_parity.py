@@ -540,3 +540,79 @@ def test_full_size_headline_configs_properties(ctx, config):
         outs.append(o.download())
     lin = 2.0 * outs[0] - 0.5j * outs[1]
     assert np.abs(outs[2] - lin).max() < 1e-13 * max(np.abs(lin).max(), 1e-300) * 10
+
+
+def test_localexpect_and_operator_currents(ctx):
+    """SURVEY 8f N3 on the device: localexpect (src/operators/latticeutils.jl:13-20) and
+    LocalOperatorCurrents (src/zoo/currents.jl:150-184) against the oracle + the reference's
+    identities (test/test_currents.jl:76-91, test/test_operators.jl:28)."""
+    lo, l = L.square_lattice(6, 5), lm.SquareLattice(6, 5)
+    Ho = OP.qwz(lo, field=F.LandauGauge(0.1))
+    Hd = lm.qwz(l, field=lm.LandauGauge(0.1))
+    Psi = _rand_block(60, 23, seed=9)
+    w = np.random.default_rng(2).random(23)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=2)
+    ost = OB.State(Psi, w, block=True)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    sy = np.array([[0, -1j], [1j, 0]], complex)
+    for op in (np.eye(2), sz, sy, sz + 0.3 * sy):
+        got = lm.localexpect(op, st).values
+        assert np.abs(got - OB.localexpect(op, ost, 2)).max() < 1e-13
+        loc = lm.LocalOperatorCurrents(Hd, st, op)
+        I, J, V = loc.pair_values()
+        want = np.array([OB.operator_current(Ho, ost, op, i, j, 2) for i, j in zip(I, J)])
+        assert np.abs(V - want).max() < 1e-13
+    assert np.abs(lm.localexpect(np.eye(2), st).values.real - lm.localdensity(st).values).max() < 1e-13
+    dc = lm.Currents(lm.DensityCurrents(Hd, st))
+    one = lm.Currents(lm.LocalOperatorCurrents(Hd, st, np.eye(2)))
+    up = lm.Currents(lm.LocalOperatorCurrents(Hd, st, [[1, 0], [0, 0]]))
+    dn = lm.Currents(lm.LocalOperatorCurrents(Hd, st, [[0, 0], [0, 1]]))
+    spin = lm.Currents(lm.LocalOperatorCurrents(Hd, st, sz))
+    assert abs(one.currents - dc.currents).max() < 1e-13
+    assert abs((up + dn).currents - dc.currents).max() < 1e-13
+    assert abs((up - dn).currents - spin.currents).max() < 1e-13
+    with pytest.raises(lm.ArgumentError):
+        lm.LocalOperatorCurrents(Hd, st, np.eye(3))
+    with pytest.raises(lm.ArgumentError):
+        lm.localexpect(np.eye(2), lm.DeviceState.from_psi(Psi, ctx=ctx, n_int=1), n_int=1)
+
+
+def test_c_abi_error_behaviour(ctx):
+    """Every misuse surfaces as a non-zero status + message (-> ArgumentError), never a crash."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    colptr = np.array([0, 1, 2], np.int64)
+    rowval = np.array([0, 5], np.int64)                # row index out of range
+    nz = np.ones(2, np.complex128)
+    assert lib.lm_ham_create_csc(ctx.handle, 2, 1, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz), 0, C.byref(h)) == 1
+    assert b"out of range" in lib.lm_last_error()
+    assert lib.lm_ham_create_csc(ctx.handle, 3, 2, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz), 0, C.byref(h)) == 1   # N % n_int
+    assert lib.lm_ham_create_csc(ctx.handle, 2, 1, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz), 7, C.byref(h)) == 1   # index_base
+    assert lib.lm_ham_create_csc(None, 2, 1, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz), 0, C.byref(h)) == 1        # NULL ctx
+    s = C.c_void_p()
+    psi = np.ones((4, 2), np.complex128, order="F")
+    assert lib.lm_state_create_psi(ctx.handle, 0, 2, _lib.ptr(psi), None, C.byref(s)) == 1
+    assert lib.lm_state_create_psi(ctx.handle, 4, 2, None, None, C.byref(s)) == 1
+    H = lm.tightbinding_hamiltonian(lm.SquareLattice(2, 2))
+    dev = H.device(ctx)
+    st = lm.DeviceState.from_psi(psi, ctx=ctx)
+    nmv = C.c_int32()
+    assert lib.lm_step(dev.handle, st.handle, float("nan"), 1e-12, 0, C.byref(nmv)) == 1
+    assert lib.lm_step(dev.handle, st.handle, 0.1, -1.0, 0, C.byref(nmv)) == 1
+    assert lib.lm_step(dev.handle, st.handle, 0.1, 1e-12, 99, C.byref(nmv)) == 1
+    assert lib.lm_step(dev.handle, st.handle, 0.0, 1e-12, 0, C.byref(nmv)) == 0 and nmv.value == 0      # dt = 0 is a no-op
+    assert lib.lm_ham_update_values(dev.handle, _lib.ptr(nz)) == 1                                         # bond-mode ham
+    assert b"lm_ham_set_field_params" in lib.lm_last_error()
+    kinds = np.array([9], np.int32)
+    assert lib.lm_ham_set_fields(dev.handle, 1, _lib.ptr(kinds), _lib.ptr(np.zeros(3))) == 1               # unknown field kind
+    assert lib.lm_spmm_state(dev.handle, st.handle, st.handle) == 1                                        # aliasing
+    with pytest.raises(lm.ArgumentError):
+        lm.Context(device=4096)
+    b, e = C.c_int64(), C.c_int64()
+    assert lib.lm_shard_range(10, 3, 2, C.byref(b), C.byref(e)) == 1
+    assert lib.lm_shard_range(10, 1, 2, C.byref(b), C.byref(e)) == 0 and (b.value, e.value) == (5, 10)
+    # the propagator refuses absurd ||H|| dt instead of looping
+    with pytest.raises(lm.ArgumentError):
+        sol = lm.B200Exp(method="taylor", ctx=ctx)
+        sol.update_solver(H, 1e9)
+        sol.step(st)

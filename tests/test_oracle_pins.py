@@ -335,3 +335,25 @@ def test_workflow_smoke_pbc_landau_ramp():
         Jb = OB.currents_matrix(H, OB.State(stb[0], w0, block=True), 2, pairs=OB.site_adjacency(H, 2))
         assert abs(J - Jb).max() < 1e-12
         assert d.sum() == pytest.approx(np.trace(P0).real, abs=1e-10)
+
+
+def test_operator_currents_and_localexpect_identities(qwz44):
+    # test/test_currents.jl:76-91 and test/test_operators.jl:28 on the oracle
+    l, H0, H1, P, Psi, w = qwz44
+    gs = SP.groundstate(H0)
+    pairs = OB.site_adjacency(H1, 2)
+    dc = np.array([OB.density_current(H1, gs, i, j, 2) for i, j in pairs])
+    cur = lambda op: np.array([OB.operator_current(H1, gs, op, i, j, 2) for i, j in pairs])
+    up, dn, one, sz = cur([[1, 0], [0, 0]]), cur([[0, 0], [0, 1]]), cur([[1, 0], [0, 1]]), cur([[1, 0], [0, -1]])
+    assert np.allclose(one, dc, atol=1e-14)
+    assert np.allclose(up + dn, dc, atol=1e-14) and np.allclose(up - dn, sz, atol=1e-14)
+    # Heisenberg equation for the spin density on site 6
+    site = 6
+    spin_op = np.zeros((32, 32), complex)
+    spin_op[(site - 1) * 2, (site - 1) * 2] = 1
+    spin_op[(site - 1) * 2 + 1, (site - 1) * 2 + 1] = -1
+    Hd = H1.toarray()
+    spin_dt = (gs.conj() @ (1j * (Hd @ spin_op - spin_op @ Hd)) @ gs).real
+    tot = sum(OB.operator_current(H1, gs, [[1, 0], [0, -1]], site, j, 2) for j in range(1, 17) if j != site)
+    assert tot == pytest.approx(spin_dt, abs=1e-13)
+    assert np.allclose(OB.localexpect(np.eye(2), P, 2).real, OB.localdensity(P, 2), atol=1e-14)
