@@ -133,6 +133,8 @@ struct lm_ham {
     // observable items of the plan: (row, upper neighbour) pairs + one density item per row
     int* d_it_ptr = nullptr; unsigned short* d_it_row = nullptr; unsigned short* d_it_nb = nullptr; int* d_it_out = nullptr;
     bool obs_tiled = false;
+    // site-blocked view for n_int >= 2 (k_apply_sites): neighbour sites, gather map, block values
+    int Ws = 0; int* d_scols = nullptr; int* d_bsrc = nullptr; void* d_bvals = nullptr; long long bvals_version = -1;
     // LocalOperatorCurrents tables (built on first use): correlator requests of every full
     // n_int x n_int block of the site pairs, and the ELL entry of H[i_k, j_b] (or -1)
     int* d_oc_a = nullptr; int* d_oc_b = nullptr; int* d_oc_ent = nullptr; double2* d_oc_G = nullptr; double* d_oc_J = nullptr;
@@ -251,7 +253,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -478,6 +480,41 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
     CK(cudaMemcpy(h->d_it_out, it_out.data(), sizeof(int) * it_out.size(), cudaMemcpyHostToDevice));
     // staged rows of the widest tile for a 32-column chunk (padded stride 33)
     h->obs_tiled = h->plan_from_coords && (long long)max_rows * 34 * (long long)c->esz() <= 200 * 1024;
+    // site-blocked view (n_int = 2): union of the neighbour sites over the orbitals of a site
+    { void* q[] = {h->d_scols, h->d_bsrc, h->d_bvals}; for (void* p : q) if (p) cudaFree(p); }
+    h->d_scols = h->d_bsrc = nullptr; h->d_bvals = nullptr; h->Ws = 0; h->bvals_version = -1;
+    if (n == 2 && h->plan_from_coords) {
+        std::vector<std::vector<int>> nbrs((size_t)ns);
+        int Ws = 1;
+        for (long long st = 0; st < ns; ++st) {
+            auto& v = nbrs[st];
+            for (int a2 = 0; a2 < n; ++a2) for (int k = 0; k < W; ++k) {
+                const int sj = h->h_cols[(st * n + a2) * W + k] / n;
+                if (std::find(v.begin(), v.end(), sj) == v.end()) v.push_back(sj);
+            }
+            std::sort(v.begin(), v.end());
+            Ws = std::max(Ws, (int)v.size());
+        }
+        std::vector<int> scols((size_t)ns * Ws), bsrc((size_t)ns * Ws * n * n, -1);
+        for (long long st = 0; st < ns; ++st) {
+            for (int ks = 0; ks < Ws; ++ks) scols[st * Ws + ks] = ks < (int)nbrs[st].size() ? nbrs[st][ks] : (int)st;
+            for (int a2 = 0; a2 < n; ++a2) for (int k = 0; k < W; ++k) {
+                const long long e = (st * n + a2) * W + k;
+                const int col = h->h_cols[e];
+                const int ks = (int)(std::find(nbrs[st].begin(), nbrs[st].end(), col / n) - nbrs[st].begin());
+                int& slot = bsrc[((st * Ws + ks) * n + a2) * n + (col % n)];
+                // real entries come first in a row (columns ascend, padding last), so ELL padding
+                // duplicates (col == own row, value 0) never shadow a real diagonal entry
+                if (slot < 0) slot = (int)e;
+            }
+        }
+        h->Ws = Ws;
+        CK(cudaMalloc(&h->d_scols, sizeof(int) * scols.size()));
+        CK(cudaMalloc(&h->d_bsrc, sizeof(int) * bsrc.size()));
+        CK(cudaMalloc(&h->d_bvals, c->esz() * bsrc.size()));
+        CK(cudaMemcpy(h->d_scols, scols.data(), sizeof(int) * scols.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_bsrc, bsrc.data(), sizeof(int) * bsrc.size(), cudaMemcpyHostToDevice));
+    }
     return LM_OK;
 }
 
@@ -1033,6 +1070,54 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     return LM_OK;
 }
 
+template <typename T, int CPT>
+static void launch_sites_mode(const SitesArgs& a, dim3 grid, cudaStream_t s) {
+    const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
+    if (!a.z && !a.u && !g) k_apply_sites<T, CPT, 2, 0><<<grid, 256, 0, s>>>(a);
+    else if (a.z && !a.u && !g) k_apply_sites<T, CPT, 2, 1><<<grid, 256, 0, s>>>(a);
+    else if (!a.z && !a.u && g) k_apply_sites<T, CPT, 2, 3><<<grid, 256, 0, s>>>(a);
+    else k_apply_sites<T, CPT, 2, 2><<<grid, 256, 0, s>>>(a);
+}
+static int apply_sites(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                       zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    if (h->bvals_version != h->version) {           // refresh the block copy of the ELL values
+        const long long nb = h->n_sites * h->Ws * h->n_int * h->n_int;
+        const int th = 256;
+        if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const double2*)h->d_vals, (double2*)h->d_bvals);
+        else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const float2*)h->d_vals, (float2*)h->d_bvals);
+        c->launches++;
+        h->bvals_version = h->version;
+    }
+    SitesArgs a;
+    a.t_ptr = h->d_t_ptr; a.t_nr = h->d_t_nr; a.t_rows = h->d_t_rows;
+    a.scols = h->d_scols; a.bvals = h->d_bvals; a.Ws = h->Ws; a.N = h->N; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    static const int cpt_env = env_int("LM_SITES_CPT", 0);
+    int cpt = (ld >= 128) ? 2 : 1;
+    if (cpt_env == 1 || cpt_env == 2) cpt = cpt_env;
+    const int ec = (c->precision == LM_C128) ? 1 : 2;
+    const int CT = 32 * cpt * ec;
+    const long long nchunks = (ld + CT - 1) / CT;
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    long long cps = (long long)(budget / ((double)std::max<long long>(1, h->tile_window_rows) * CT * (double)c->esz()));
+    cps = std::max<long long>(1, std::min<long long>(cps, nchunks));
+    const long long strips = (nchunks + cps - 1) / cps;
+    cps = (nchunks + strips - 1) / strips;
+    REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_sites: grid too large");
+    REQUIRE(ld % ec == 0, "apply_sites: odd leading dimension in complex64 mode");
+    a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
+    dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
+    if (c->precision == LM_C128) { if (cpt == 2) launch_sites_mode<double, 2>(a, grid, c->stream); else launch_sites_mode<double, 1>(a, grid, c->stream); }
+    else { if (cpt == 2) launch_sites_mode<float, 2>(a, grid, c->stream); else launch_sites_mode<float, 1>(a, grid, c->stream); }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
 static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                        zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
@@ -1073,6 +1158,9 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     const int tiled_env = g_apply_path_override >= 0 ? g_apply_path_override : tiled_env0;
     // LM_APPLY_TILED: 0 = register gather over consecutive rows, 1 = TMA-staged tiles,
     //                 2 = register gather over plan tiles (L1 patch reuse)
+    // n_int = 2 models: site-blocked gather (3 = force, default on when the block view exists)
+    static const int sites_env = env_int("LM_APPLY_SITES", 1);
+    if (h->d_scols && ld >= 32 && ((tiled_env < 0 && sites_env) || tiled_env == 3)) return apply_sites(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     // default: tile-order register gather whenever the host supplied site coordinates
     if (h->plan_from_coords && ld >= 32 && (tiled_env == 2 || tiled_env < 0)) return apply_rows(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     if (h->tiled && ld >= 16 && tiled_env == 1) return apply_tiled(h, ld, x, y, z, u, alpha, gamma, beta, delta);

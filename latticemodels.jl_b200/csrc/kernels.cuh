@@ -264,6 +264,112 @@ k_apply_rows(const RowsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_apply_sites: site-blocked variant for models with NI internal orbitals per site (QWZ,
+// Kane-Mele, ...).  All NI rows of a site couple to the same neighbour SITES through dense
+// NI x NI blocks, so a warp processes the NI rows of one site TOGETHER: every gathered
+// neighbour element x[nb*NI + b] is loaded once and feeds NI output rows (one gather per NI
+// complex FMAs instead of one per FMA) - the L1 data pipe is what bounds W ~ 9-10 stencils.
+// Block values are a gathered copy of the ELL values (k_gather_blocks after each H update).
+// ------------------------------------------------------------------------------------------
+struct SitesArgs {
+    const int* t_ptr; const int* t_nr; const int* t_rows;
+    const int* scols;               // [n_sites][Ws] neighbour site (padding: own site, zero block)
+    const void* bvals;              // [n_sites][Ws][NI*NI] complex, block element (a, b) at a*NI + b
+    int Ws;
+    long long N, ld;
+    const void* x; void* y; const void* z; const void* u;
+    double alpha[2], gamma[2], beta[2], delta[2];
+    unsigned cps, nchunks;
+};
+template <typename T2>
+__global__ void k_gather_blocks(long long n, const int* __restrict__ src, const T2* __restrict__ vals, T2* __restrict__ bvals) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T2 v; v.x = 0; v.y = 0;
+    const int e = src[i];
+    if (e >= 0) v = vals[e];
+    bvals[i] = v;
+}
+
+template <typename T, int CPT, int NI, int MODE>
+__global__ void __launch_bounds__(256, 3)
+k_apply_sites(const SitesArgs a) {
+    using T2 = typename cx2<T>::type;
+    using E = typename pack<T>::E;
+    constexpr int EC = pack<T>::EC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile = blockIdx.x / a.cps;
+    const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
+    if (chunk >= a.nchunks) return;
+    const int p0 = a.t_ptr[tile];
+    const int nsite = a.t_nr[tile] / NI;             // own rows are site-major, orbital fastest
+    const long long lde = a.ld / EC;
+    const E* __restrict__ x = (const E*)a.x;
+    E* y = (E*)a.y;
+    const E* z = (const E*)a.z;
+    const E* u = (const E*)a.u;
+    const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
+    const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
+    const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
+    const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
+    const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
+    long long cidx[CPT];
+    bool ok[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const long long c = (long long)chunk * (32 * CPT) + lane + 32 * j;
+        ok[j] = c < lde;
+        cidx[j] = ok[j] ? c : (lde - 1);
+    }
+    for (int q = warp; q < nsite; q += 8) {
+        const long long site = a.t_rows[p0 + q * NI] / NI;
+        const long long row0 = site * NI;
+        const int* __restrict__ sc = a.scols + site * a.Ws;
+        const T2* __restrict__ bv = (const T2*)a.bvals + site * a.Ws * (NI * NI);
+        E acc[NI][CPT];
+#pragma unroll
+        for (int al = 0; al < NI; ++al)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const long long e = (row0 + al) * lde + cidx[j];
+                pzero(acc[al][j]);
+                if (MODE == 1) pfma(acc[al][j], beta, ld_stream(z + e));
+                if (MODE == 2) {
+                    if (z) pfma(acc[al][j], beta, ld_stream(z + e));
+                    if (u) pfma(acc[al][j], delta, u[e]);
+                    if (has_gamma) pfma(acc[al][j], gamma, ld_ro(x + e));
+                }
+            }
+#pragma unroll 2
+        for (int ks = 0; ks < a.Ws; ++ks) {
+            const long long nb = sc[ks];
+            const T2* __restrict__ blk = bv + ks * (NI * NI);
+#pragma unroll
+            for (int be = 0; be < NI; ++be) {
+                E xv[CPT];
+                const E* xr = x + (nb * NI + be) * lde;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) xv[j] = ld_ro(xr + cidx[j]);
+#pragma unroll
+                for (int al = 0; al < NI; ++al) {
+                    const T2 v = cmul(alpha, blk[al * NI + be]);
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) pfma(acc[al][j], v, xv[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int al = 0; al < NI; ++al)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const long long e = (row0 + al) * lde + cidx[j];
+                if (MODE == 3) pfma(acc[al][j], gamma, ld_ro(x + e));
+                if (ok[j]) st_stream(y + e, acc[al][j]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_apply_tiled: the same fused term, staged through shared memory by the TMA engine.
 //
 // The Hamiltonian carries a TILE PLAN (built once per sparsity pattern on the host): rows are
