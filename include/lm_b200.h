@@ -123,6 +123,12 @@ int32_t lm_ham_set_field_params(lm_ham* ham, const double* params);
  * src/lattices/bravais/unitcell.jl:119-122): lets the library group rows into compact 2-D
  * patches for the TMA-staged SpMM.  Optional - without it the register-gather kernel is used. */
 int32_t lm_ham_set_site_coords(lm_ham* ham, const double* xy);
+/* Optional hint, to be given BEFORE lm_ham_set_site_coords: `rows` consecutive Hilbert rows form
+ * one block that is kept together (default n_int = the orbitals of a site; a Bravais lattice
+ * with an NB-site basis passes NB * n_int = all rows of a unit cell,
+ * src/lattices/bravais/unitcell.jl:126-132 orders the basis index innermost).  Blocks of 2 rows
+ * are processed by the site-blocked kernel. */
+int32_t lm_ham_set_row_block(lm_ham* ham, int32_t rows);
 
 int32_t lm_ham_dims(lm_ham* ham, int64_t* N, int32_t* n_int, int64_t* nnz, int32_t* ell_width);
 /* CSC view of the current H (pattern + values), index_base as given at creation */

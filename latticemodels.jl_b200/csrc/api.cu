@@ -134,6 +134,8 @@ struct lm_ham {
     int* d_it_ptr = nullptr; unsigned short* d_it_row = nullptr; unsigned short* d_it_nb = nullptr; int* d_it_out = nullptr;
     bool obs_tiled = false;
     // site-blocked view for n_int >= 2 (k_apply_sites): neighbour sites, gather map, block values
+    int blk = 0;                                   // rows per block for tiling / site-blocking (0 = n_int)
+    int grp = 1; long long ngroups = 0;            // effective group size / count used by the current plan
     int Ws = 0; int* d_scols = nullptr; int* d_bsrc = nullptr; void* d_bvals = nullptr; long long bvals_version = -1;
     // LocalOperatorCurrents tables (built on first use): correlator requests of every full
     // n_int x n_int block of the site pairs, and the ELL entry of H[i_k, j_b] (or -1)
@@ -355,7 +357,18 @@ static int ham_finish_pattern(lm_ham* h, const std::vector<long long>& rows, con
 // ------------------------------------------------------------------------------------------
 static int ham_build_tiles(lm_ham* h, const double* xy) {
     lm_ctx* c = h->ctx;
-    const long long N = h->N, ns = h->n_sites; const int n = h->n_int, W = h->W;
+    // rows are grouped in blocks of n consecutive rows that always share a tile: the n_int
+    // orbitals of a site, or (row-block hint) the sites of one Bravais unit cell x n_int
+    const int n = (h->blk > 0 && h->N % h->blk == 0 && h->blk % h->n_int == 0) ? h->blk : h->n_int;
+    const int sites_per_group = n / h->n_int;
+    const long long N = h->N, ns = h->N / n; const int W = h->W;
+    std::vector<double> gxy;
+    if (xy && sites_per_group > 1) {                 // a group sits at the coordinates of its first site
+        gxy.resize((size_t)ns * 2);
+        for (long long g = 0; g < ns; ++g) { gxy[2 * g] = xy[2 * g * sites_per_group]; gxy[2 * g + 1] = xy[2 * g * sites_per_group + 1]; }
+        xy = gxy.data();
+    }
+    h->grp = n; h->ngroups = ns;
     static const int TR = std::max(16, env_int("LM_TILE_ROWS", 64));
     const long long spt = std::max<long long>(1, TR / n);            // sites per tile (target)
     std::vector<int> tile_of_site(ns, 0);
@@ -403,6 +416,7 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
         }
         rows_per_binrow = h->band + TR;
     }
+    const bool have_xy = (xy != nullptr);
     // drop empty tiles, number the rest
     std::vector<std::vector<int>> kept;
     for (auto& t : tiles) if (!t.empty()) kept.push_back(std::move(t));
@@ -450,7 +464,7 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
         it_ptr[t + 1] = (int)it_out.size();
     }
     h->layout_epoch++;
-    h->plan_from_coords = (xy != nullptr);
+    h->plan_from_coords = have_xy;
     h->ntiles = ntiles; h->tile_max_rows = max_rows; h->tile_window_rows = 2 * rows_per_binrow;
     h->tile_halo_ratio = halo_sum / (double)std::max<long long>(1, N);
     // usable only if the staged rows of the widest tile fit comfortably in shared memory
@@ -521,6 +535,12 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
 extern "C" int32_t lm_ham_set_site_coords(lm_ham* h, const double* xy) {
     REQUIRE(h && xy, "lm_ham_set_site_coords: NULL argument");
     return ham_build_tiles(h, xy);
+}
+extern "C" int32_t lm_ham_set_row_block(lm_ham* h, int32_t rows) {
+    REQUIRE(h, "lm_ham_set_row_block: NULL");
+    REQUIRE(rows >= 1 && h->N % rows == 0 && rows % h->n_int == 0, "lm_ham_set_row_block: rows must divide N and be a multiple of n_int");
+    h->blk = rows;
+    return LM_OK;
 }
 extern "C" int32_t lm_dbg_tile_info(lm_ham* h, int32_t* ntiles, int32_t* max_rows, double* halo_ratio, int32_t* tiled) {
     REQUIRE(h, "lm_dbg_tile_info: NULL");
@@ -1082,7 +1102,7 @@ static int apply_sites(lm_ham* h, long long ld, const void* x, void* y, const vo
                        zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
     if (h->bvals_version != h->version) {           // refresh the block copy of the ELL values
-        const long long nb = h->n_sites * h->Ws * h->n_int * h->n_int;
+        const long long nb = h->ngroups * h->Ws * h->grp * h->grp;
         const int th = 256;
         if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const double2*)h->d_vals, (double2*)h->d_bvals);
         else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const float2*)h->d_vals, (float2*)h->d_bvals);

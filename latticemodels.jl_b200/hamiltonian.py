@@ -45,6 +45,17 @@ def _sig(x):
     return ("arr", a.shape, a.dtype.str, a.tobytes())
 
 
+def _row_block(lat, n_int):
+    """Rows of one Bravais unit cell (basis index innermost) when the lattice is unfiltered."""
+    import os
+    if os.environ.get("LM_ROW_BLOCK", "1") == "0":
+        return None
+    nb = getattr(lat, "nb", 1)
+    if nb > 1 and len(lat) == lat.sizes[0] * lat.sizes[1] * nb:
+        return nb * n_int
+    return None
+
+
 class Structure:
     """Field-independent part of a lattice Hamiltonian (OperatorBuilder restated as tables,
     src/operators/builder.jl:282-309, src/operators/constructoperator.jl:4-47)."""
@@ -152,13 +163,15 @@ class DeviceHam:
             _lib.ptr(ons_cm), 0, C.byref(h)))
         d = cls(ctx, h, st.n_int, True)
         d.field_key = ((), b"")
-        d.set_site_coords(st.lat.coords)
+        d.set_site_coords(st.lat.coords, row_block=_row_block(st.lat, st.n_int))
         return d
 
-    def set_site_coords(self, coords):
+    def set_site_coords(self, coords, row_block=None):
         xy = np.ascontiguousarray(np.asarray(coords, float)[:, :2])
         if xy.shape != (self.N // self.n_int, 2):
             raise _lib.ArgumentError("site coordinates must be (n_sites, 2)")
+        if row_block:
+            _lib.check(_lib.load().lm_ham_set_row_block(self.handle, int(row_block)))
         _lib.check(_lib.load().lm_ham_set_site_coords(self.handle, _lib.ptr(xy)))
 
     @classmethod
