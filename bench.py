@@ -263,7 +263,7 @@ def main():
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get("%s_n%d" % (args.workload, world))
-    roofline = {"bound": "hbm", "kernel": "lm::k_apply_rows (fused ELL SpMM + product-form Taylor factor, tile-order register gather)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "lm::k_apply_rows / k_apply_sites (fused ELL SpMM + one product-form propagator factor, tile-order register gather)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmm, "launches_timed": n_apply, "avg_launch_ms": avg_launch_ms,
                 "K_matvec_per_step": K}
@@ -280,7 +280,7 @@ def main():
     j_pinned = torch.empty(max(npairs, 1), dtype=torch.float64).pin_memory()
     rho_np, j_np = rho_pinned.numpy(), j_pinned.numpy()
     nmv = C.c_int32()
-    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4}[args.method]
+    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4, "chebyshev_clenshaw": 5}[args.method]
 
     def e2e_step(k):
         _lib.check(lib.lm_ham_update_values(csc_dev.handle, _lib.ptr(nz_np)))                  # H2D

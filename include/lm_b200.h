@@ -45,12 +45,14 @@ extern "C" {
 #define LM_C64  1                /* complex64 arithmetic (optional mode, parity 1e-5) */
 
 /* lm_step `method` */
-#define LM_METHOD_AUTO      0    /* product-form Taylor for small ||H||dt, Chebyshev otherwise */
-#define LM_METHOD_CHEBYSHEV 1    /* Clenshaw-Chebyshev expansion of exp(-iH dt) */
+#define LM_METHOD_AUTO      0    /* cheapest plan by HBM-stream count (normally product-form Chebyshev) */
+#define LM_METHOD_CHEBYSHEV 1    /* Chebyshev approximant of exp(-iH dt) on the Gershgorin interval, applied in
+                                    product form prod_j (I - Ht/x_j) (Leja-ordered roots): 2 HBM streams per term */
 #define LM_METHOD_TAYLOR    2    /* truncated Taylor series (the polynomial myexp! sums, src/evolution.jl:93-128)
                                     applied in product form prod_j (I - A/r_j): 2 HBM streams per term */
 #define LM_METHOD_LANCZOS   3    /* per-column Lanczos (KrylovKit.exponentiate semantics, src/evolution.jl:150-154) */
 #define LM_METHOD_TAYLOR_HORNER 4 /* same polynomial in Horner form (3 streams per term; cross-check) */
+#define LM_METHOD_CHEBYSHEV_CLENSHAW 5 /* same Chebyshev approximant by the Clenshaw recurrence (4 streams; fallback) */
 
 /* gauge-field kinds for lm_ham_set_fields; each field owns 3 doubles of `params` */
 #define LM_FIELD_LANDAU            1   /* (B, -, -)         src/zoo/magneticfields.jl:15  */

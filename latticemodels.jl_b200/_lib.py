@@ -13,7 +13,7 @@ from . import build as _build
 
 LM_OK = 0
 LM_C128, LM_C64 = 0, 1
-METHOD_AUTO, METHOD_CHEBYSHEV, METHOD_TAYLOR, METHOD_LANCZOS, METHOD_TAYLOR_HORNER = 0, 1, 2, 3, 4
+METHOD_AUTO, METHOD_CHEBYSHEV, METHOD_TAYLOR, METHOD_LANCZOS, METHOD_TAYLOR_HORNER, METHOD_CHEBYSHEV_CLENSHAW = 0, 1, 2, 3, 4, 5
 FIELD_LANDAU, FIELD_SYMMETRIC, FIELD_POINTFLUX_AXIAL, FIELD_POINTFLUX_SINGULAR = 1, 2, 3, 4
 
 

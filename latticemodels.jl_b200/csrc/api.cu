@@ -97,6 +97,7 @@ struct lm_ctx {
 struct Plan {          // cached propagator plan (host-side Bessel / Taylor bookkeeping)
     bool valid = false; double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method_req = -1;
     int method = 0, nsub = 1, K = 1; std::vector<zc> coef;
+    std::vector<zc> croots; zc cpref; int csub = 1;   // product-form Chebyshev: Leja-ordered roots of q_K, prefactor q_K(0), sub-steps
 };
 
 static unsigned long long g_ham_uid = 0;
@@ -1302,6 +1303,112 @@ static int cheb_plan(double R, double tol, std::vector<zc>& coef) {
     for (int k = 0; k <= K; ++k) { coef[k] = (k == 0 ? 1.0 : 2.0) * p * J[k]; p *= mi; }
     return LM_OK;
 }
+// ------------------------------------------------------------------------------------------
+// Product-form Chebyshev.  q_K(x) = sum_k a_k T_k(x) is the degree-K Chebyshev approximant of
+// exp(-i R x) on [-1, 1]; q_K(x) = q_K(0) prod_j (1 - x / x_j).  Applying the K factors
+// (I - Ht / x_j) one after the other costs ONE SpMM + diagonal term each (two HBM streams, two
+// buffers) instead of the four streams of a Clenshaw step, with the same (near-minimax) K.
+// The roots are found at plan time by Aberth-Ehrlich iteration in long double, ordered by the
+// Leja rule (keeps the partial products O(1): stable up to R ~ 40+), and the factorisation is
+// validated against the Clenshaw evaluation of q_K; any failure falls back to Clenshaw.
+// ------------------------------------------------------------------------------------------
+typedef std::complex<long double> lzc;
+static void cheb_eval(const std::vector<lzc>& a, lzc z, lzc* q, lzc* dq) {
+    const int K = (int)a.size() - 1;
+    lzc t0(1, 0), t1 = z, d0(0, 0), d1(1, 0);
+    lzc sum = a[0], dsum(0, 0);
+    if (K >= 1) { sum += a[1] * t1; dsum += a[1] * d1; }
+    for (int k = 2; k <= K; ++k) {
+        const lzc t2 = 2.0L * z * t1 - t0;
+        const lzc d2 = 2.0L * t1 + 2.0L * z * d1 - d0;
+        sum += a[k] * t2; dsum += a[k] * d2;
+        t0 = t1; t1 = t2; d0 = d1; d1 = d2;
+    }
+    *q = sum; if (dq) *dq = dsum;
+}
+static bool cheb_product_plan(const std::vector<zc>& coef, double R, std::vector<zc>& roots_out, zc* pref_out) {
+    const int K = (int)coef.size() - 1;
+    if (K < 1 || K > 128 || R == 0.0) return false;
+    std::vector<lzc> a(K + 1);
+    for (int k = 0; k <= K; ++k) a[k] = lzc(coef[k].real(), coef[k].imag());
+    // initial guesses: exp(-iRx) ~ Taylor in w = -iRx, whose roots have modulus between 0.28 K and K
+    std::vector<lzc> z(K);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int j = 0; j < K; ++j) {
+        const long double th = 2 * pi * (j + 0.37L) / K;
+        const long double rad = std::max<long double>(1.2L, 0.55L * K / fabsl((long double)R));
+        z[j] = lzc(0, 1) * lzc(rad * cosl(th), rad * sinl(th)) * (long double)(R > 0 ? 1 : -1);
+    }
+    bool conv = false; int polish = -1;
+    for (int it = 0; it < 400 && !conv; ++it) {
+        long double worst = 0;
+        for (int j = 0; j < K; ++j) {
+            lzc q, dq; cheb_eval(a, z[j], &q, &dq);
+            if (std::abs(dq) == 0) { z[j] += lzc(1e-3L, 1e-3L); worst = 1; continue; }
+            const lzc nwt = q / dq;
+            lzc rep(0, 0);
+            for (int i = 0; i < K; ++i) if (i != j) rep += 1.0L / (z[j] - z[i]);
+            const lzc step = nwt / (1.0L - nwt * rep);
+            z[j] -= step;
+            worst = std::max(worst, std::abs(step) / std::max<long double>(std::abs(z[j]), 1e-30L));
+        }
+        // the attainable root accuracy is limited by cancellation in q near a root (~1e-15 relative
+        // for K ~ 30): once the steps are below 1e-12 do a few polishing sweeps and let the
+        // factorisation check below decide
+        if (polish < 0 && worst < 1e-12L) polish = it;
+        conv = worst < 1e-17L || (polish >= 0 && it >= polish + 4);
+        if (getenv("LM_DEBUG_PLAN") && (it % 20 == 0 || conv)) fprintf(stderr, "aberth K=%d it=%d worst=%Lg\n", K, it, worst);
+    }
+    if (!conv) { if (getenv("LM_DEBUG_PLAN")) fprintf(stderr, "aberth not converged\n"); return false; }
+    for (int j = 0; j < K; ++j) { lzc q; cheb_eval(a, z[j], &q, nullptr); (void)q; }
+    // Leja ordering (log-domain products)
+    std::vector<int> order; std::vector<char> used(K, 0);
+    std::vector<long double> logp(K, 0.0L);
+    int first = 0; for (int j = 1; j < K; ++j) if (std::abs(z[j]) > std::abs(z[first])) first = j;
+    order.push_back(first); used[first] = 1;
+    for (int n = 1; n < K; ++n) {
+        const int last = order.back(); int best = -1;
+        for (int j = 0; j < K; ++j) if (!used[j]) {
+            logp[j] += logl(std::max<long double>(std::abs(z[j] - z[last]), 1e-300L));
+            if (best < 0 || logp[j] > logp[best]) best = j;
+        }
+        order.push_back(best); used[best] = 1;
+    }
+    lzc q0; cheb_eval(a, lzc(0, 0), &q0, nullptr);
+    if (std::abs(q0) < 1e-3L) return false;
+    // validate the factorisation on [-1, 1]
+    const long double tests[] = {-1.0L, -0.73L, -0.2L, 0.41L, 0.9L, 1.0L};
+    for (long double t : tests) {
+        lzc q; cheb_eval(a, lzc(t, 0), &q, nullptr);
+        lzc prod = q0;
+        for (int n = 0; n < K; ++n) prod *= (1.0L - lzc(t, 0) / z[order[n]]);
+        if (getenv("LM_DEBUG_PLAN")) fprintf(stderr, "validate t=%Lg |prod-q|=%Lg\n", t, std::abs(prod - q));
+        if (std::abs(prod - q) > 2e-14L) return false;
+    }
+    roots_out.resize(K);
+    for (int n = 0; n < K; ++n) roots_out[n] = zc((double)z[order[n]].real(), (double)z[order[n]].imag());
+    *pref_out = zc((double)q0.real(), (double)q0.imag());
+    return true;
+}
+// exp(-i H dt) psi = e^{-i b dt} q_K(0) prod_j (I - Ht / x_j) psi,  Ht = (H - b) / a:
+// every factor is  y = (1 + b/(a x_j)) x - (1/(a x_j)) H x.
+static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u, zc alpha, zc gamma, zc beta, zc delta);
+static int step_cheb_prod(lm_ham* h, long long ld, void** px, void** ps1, double dt, int* nmv) {
+    const double a = std::max(0.5 * (h->emax - h->emin), 1e-300), b = 0.5 * (h->emax + h->emin);
+    const std::vector<zc>& xs = h->plan.croots;
+    const int K = (int)xs.size(), nsub = h->plan.csub;
+    const zc pref = std::exp(zc(0.0, -b * dt / nsub)) * h->plan.cpref;
+    for (int sub = 0; sub < nsub; ++sub)
+        for (int j = 0; j < K; ++j) {
+            zc alpha = -1.0 / (a * xs[j]), gamma = zc(1, 0) + b / (a * xs[j]);
+            if (j == K - 1) { alpha *= pref; gamma *= pref; }
+            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, alpha, gamma, zc(0, 0), zc(0, 0)));
+            std::swap(*px, *ps1);
+            (*nmv)++;
+        }
+    return LM_OK;
+}
+
 struct SymVec { int kind; zc coef; void* buf; };   // 0 zero, 1 coef*psi, 2 buffer
 static int step_cheb(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, int* nmv) {
     const double a = std::max(0.5 * (h->emax - h->emin), 1e-300), b = 0.5 * (h->emax + h->emin);
@@ -1429,22 +1536,40 @@ static int get_plan(lm_ham* h, double dt, double tol, int method) {
     if (p.valid && p.dt == dt && p.tol == tol && p.method_req == method && p.emin == h->emin &&
         p.emax == h->emax && p.norm == h->norm_inf) return LM_OK;
     p.valid = false;
-    int nsub = 1, K = 1; std::vector<zc> coef;
-    const int st_t = (method == LM_METHOD_CHEBYSHEV) ? LM_ERR_UNSUPPORTED : taylor_plan(h->norm_inf * std::fabs(dt), tol, &nsub, &K);
+    REQUIRE(method != LM_METHOD_LANCZOS, "get_plan: Lanczos has no polynomial plan");
+    int nsub = 1, K = 1; std::vector<zc> coef, croots; zc cpref(1, 0);
+    const bool want_t = (method == LM_METHOD_AUTO || method == LM_METHOD_TAYLOR || method == LM_METHOD_TAYLOR_HORNER);
+    const bool want_c = (method == LM_METHOD_AUTO || method == LM_METHOD_CHEBYSHEV || method == LM_METHOD_CHEBYSHEV_CLENSHAW);
+    const int st_t = want_t ? taylor_plan(h->norm_inf * std::fabs(dt), tol, &nsub, &K) : LM_ERR_UNSUPPORTED;
     const double a = std::max(0.5 * (h->emax - h->emin), 1e-300);
-    const int st_c = (method == LM_METHOD_TAYLOR || method == LM_METHOD_TAYLOR_HORNER) ? LM_ERR_UNSUPPORTED : cheb_plan(a * dt, tol, coef);
+    const int st_c = want_c ? cheb_plan(a * dt, tol, coef) : LM_ERR_UNSUPPORTED;
+    static const int cheb_prod_env = env_int("LM_CHEB_PRODUCT", 1);
+    bool prod_ok = false; int csub = 1; double prod_terms = 0;
+    if (st_c == LM_OK && method != LM_METHOD_CHEBYSHEV_CLENSHAW && cheb_prod_env) {
+        // the root finder is reliable up to R ~ 12 (K ~ 35); larger steps are split into equal
+        // sub-steps that share one set of roots (still cheaper than 4-stream Clenshaw)
+        const double R = a * dt;
+        for (csub = std::max(1, (int)std::ceil(std::fabs(R) / 12.0)); csub <= 4096 && !prod_ok; csub = (prod_ok ? csub : csub + 1)) {
+            std::vector<zc> csc;
+            if (cheb_plan(R / csub, tol / csub, csc) != LM_OK) break;
+            prod_ok = cheb_product_plan(csc, R / csub, croots, &cpref);
+            if (prod_ok) { prod_terms = (double)csub * croots.size(); break; }
+            if (csub > (int)std::ceil(std::fabs(R) / 12.0) + 3) break;
+        }
+    }
     int m = method;
     if (method == LM_METHOD_AUTO) {
-        // cost model in HBM streams per term: product-form Taylor 2, Clenshaw-Chebyshev 4
+        // cost model in HBM streams: product forms 2 per term, Clenshaw 4 per term
         if (st_t != LM_OK && st_c != LM_OK) return fail(LM_ERR_NOT_CONVERGED, "lm_step: no propagator plan converged");
-        if (st_t != LM_OK) m = LM_METHOD_CHEBYSHEV;
-        else if (st_c != LM_OK) m = LM_METHOD_TAYLOR;
-        else m = (2.0 * nsub * K <= 4.0 * ((double)coef.size() - 1)) ? LM_METHOD_TAYLOR : LM_METHOD_CHEBYSHEV;
+        const double cost_t = st_t == LM_OK ? 2.0 * nsub * K : 1e300;
+        const double cost_c = st_c == LM_OK ? (prod_ok ? 2.0 * prod_terms : 4.0 * ((double)coef.size() - 1)) : 1e300;
+        m = (cost_c <= cost_t) ? LM_METHOD_CHEBYSHEV : LM_METHOD_TAYLOR;
     } else if (method == LM_METHOD_TAYLOR || method == LM_METHOD_TAYLOR_HORNER) { FWD(st_t); }
-    else if (method == LM_METHOD_CHEBYSHEV) { FWD(st_c); }
-    else return fail(LM_ERR_UNSUPPORTED, "lm_step: method not implemented (use AUTO, CHEBYSHEV or TAYLOR)");
+    else if (method == LM_METHOD_CHEBYSHEV || method == LM_METHOD_CHEBYSHEV_CLENSHAW) { FWD(st_c); }
+    else return fail(LM_ERR_UNSUPPORTED, "lm_step: unknown method");
+    if (m == LM_METHOD_CHEBYSHEV && !prod_ok) m = LM_METHOD_CHEBYSHEV_CLENSHAW;      // robust fallback
     p.dt = dt; p.tol = tol; p.method_req = method; p.emin = h->emin; p.emax = h->emax; p.norm = h->norm_inf;
-    p.method = m; p.nsub = nsub; p.K = K; p.coef.swap(coef); p.valid = true;
+    p.method = m; p.nsub = nsub; p.K = K; p.coef.swap(coef); p.croots.swap(croots); p.cpref = cpref; p.csub = csub; p.valid = true;
     return LM_OK;
 }
 
@@ -1452,6 +1577,7 @@ static int propagate(lm_ham* h, long long ld, void** px, void** ps1, void** ps2,
     if (dt == 0.0) return LM_OK;
     FWD(get_plan(h, dt, tol, method));
     if (h->plan.method == LM_METHOD_TAYLOR) return step_taylor_prod(h, ld, px, ps1, dt, nmv);
+    if (h->plan.method == LM_METHOD_CHEBYSHEV) return step_cheb_prod(h, ld, px, ps1, dt, nmv);
     if (h->plan.method == LM_METHOD_TAYLOR_HORNER) return step_taylor(h, ld, px, ps1, ps2, dt, nmv);
     return step_cheb(h, ld, px, ps1, ps2, dt, nmv);
 }
@@ -1462,7 +1588,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
     REQUIRE(h->N == s->N, "lm_step: dimension mismatch between Hamiltonian and state");
     REQUIRE(std::isfinite(dt), "lm_step: dt is not finite");
     REQUIRE(tol > 0 && tol < 1, "lm_step: tol must be in (0, 1)");
-    REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_TAYLOR_HORNER, "lm_step: unknown method");
+    REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_CHEBYSHEV_CLENSHAW, "lm_step: unknown method");
     lm_ctx* c = h->ctx; FWD(set_dev(c));
     int nmv = 0;
     if (method == LM_METHOD_LANCZOS) {
@@ -1472,11 +1598,12 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
         return LM_OK;
     }
     if (dt != 0.0) FWD(get_plan(h, dt, tol, method));
-    const int nbuf = (dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR) ? 1 : 2;
+    const bool product_form = dt != 0.0 && (h->plan.method == LM_METHOD_TAYLOR || h->plan.method == LM_METHOD_CHEBYSHEV);
+    const int nbuf = product_form ? 1 : 2;
     if (!s->dense) {
         FWD(ensure_scratch(s, nbuf));
         static const int use_graph = env_int("LM_STEP_GRAPH", 1);
-        const bool graphable = use_graph && dt != 0.0 && h->plan.method == LM_METHOD_TAYLOR;
+        const bool graphable = use_graph && product_form;
         if (!graphable) {
             FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
         } else {
@@ -1824,4 +1951,15 @@ extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, 
     c->launches++;
     CK(cudaGetLastError());
     return reduce_and_fetch(c, h->d_oc_J, (size_t)np, J_out);
+}
+
+// host-only hook (tests): the product-form Chebyshev plan for exp(-i R x) on [-1, 1]
+extern "C" int32_t lm_dbg_cheb_product(double R, double tol, int32_t cap, double* roots_ri, double* pref_ri, int32_t* K_out) {
+    std::vector<zc> coef, roots; zc pref;
+    FWD(cheb_plan(R, tol, coef));
+    if (!cheb_product_plan(coef, R, roots, &pref)) return fail(LM_ERR_NOT_CONVERGED, "product-form Chebyshev plan failed");
+    *K_out = (int)roots.size();
+    for (int j = 0; j < (int)roots.size() && j < cap; ++j) { roots_ri[2 * j] = roots[j].real(); roots_ri[2 * j + 1] = roots[j].imag(); }
+    pref_ri[0] = pref.real(); pref_ri[1] = pref.imag();
+    return LM_OK;
 }

@@ -22,7 +22,8 @@ from .hamiltonian import DeviceHam, Hamiltonian
 from .states import DeviceState
 
 _METHODS = {"auto": _lib.METHOD_AUTO, "chebyshev": _lib.METHOD_CHEBYSHEV, "taylor": _lib.METHOD_TAYLOR,
-            "lanczos": _lib.METHOD_LANCZOS, "taylor_horner": _lib.METHOD_TAYLOR_HORNER}
+            "lanczos": _lib.METHOD_LANCZOS, "taylor_horner": _lib.METHOD_TAYLOR_HORNER,
+            "chebyshev_clenshaw": _lib.METHOD_CHEBYSHEV_CLENSHAW}
 
 
 class EvolutionSolver:

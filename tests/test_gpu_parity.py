@@ -118,7 +118,7 @@ def test_all_spmm_kernels_on_plan(ctx, path, model):
         # one propagator step per kernel path (product form, Horner, Chebyshev epilogues)
         X = _rand_block(N, 40, seed=5)
         want = EV.exact_propagator(Ho, 0.3) @ X
-        for method in ("taylor", "taylor_horner", "chebyshev"):
+        for method in ("taylor", "taylor_horner", "chebyshev", "chebyshev_clenshaw"):
             st = lm.DeviceState.from_psi(X, ctx=ctx)
             sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx)
             sol.update_solver(Hd, 0.3)
@@ -207,8 +207,8 @@ def test_field_param_update_path(ctx):
 
 
 # ------------------------------------------------------------------------------ propagator
-@pytest.mark.parametrize("method", ["taylor", "taylor_horner", "chebyshev", "lanczos", "auto"])
-@pytest.mark.parametrize("dt", [0.1, 0.7, 3.0, -0.4])
+@pytest.mark.parametrize("method", ["taylor", "taylor_horner", "chebyshev", "chebyshev_clenshaw", "lanczos", "auto"])
+@pytest.mark.parametrize("dt", [0.1, 0.7, 3.0, -0.4, 12.0])
 def test_step_matches_exact_exponential(ctx, method, dt):
     Ho = OP.qwz(L.square_lattice(6, 5), field=F.LandauGauge(0.1))
     Psi = _rand_block(60, 13)

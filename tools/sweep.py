@@ -74,7 +74,7 @@ def run_case(ctx, kind, n, M, reps, tol=1e-12, what=("spmm", "step", "triad", "o
         out.update(triad_ms=ms, triad_gbs=3.0 * N * M * esz / ms / 1e6)
     if "step" in what:
         nmv = C.c_int32()
-        for method, tag in ((2, "taylor"), (4, "horner"), (1, "cheb")):
+        for method, tag in ((0, "auto"), (2, "taylor"), (1, "cheb"), (5, "clenshaw")):
             ms = timeit(lambda: _lib.check(lib.lm_step(dev.handle, x.handle, 0.1, tol, method, C.byref(nmv))), max(3, reps // 4))
             K = nmv.value
             out.update({tag + "_ms": ms, tag + "_K": K, tag + "_gbs": K * bytes_spmm / ms / 1e6,
