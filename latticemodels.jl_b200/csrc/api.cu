@@ -1139,6 +1139,56 @@ static int apply_sites(lm_ham* h, long long ld, const void* x, void* y, const vo
     return LM_OK;
 }
 
+template <typename T, int CQ, int MODE>
+static int launch_quad_inst(const TiledArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CK(cudaFuncSetAttribute(k_apply_quad<T, CQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_apply_quad<T, CQ, MODE><<<grid, 256, smem, s>>>(a);
+    return LM_OK;
+}
+template <typename T, int CQ>
+static int launch_quad_mode(const TiledArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
+    if (!a.z && !a.u && !g) return launch_quad_inst<T, CQ, 0>(a, grid, smem, s);
+    if (a.z && !a.u && !g) return launch_quad_inst<T, CQ, 1>(a, grid, smem, s);
+    if (!a.z && !a.u && g) return launch_quad_inst<T, CQ, 3>(a, grid, smem, s);
+    return launch_quad_inst<T, CQ, 2>(a, grid, smem, s);
+}
+static int apply_quad(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                      zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    TiledArgs a;
+    a.t_ptr = h->d_t_ptr; a.t_nr = h->d_t_nr; a.t_rows = h->d_t_rows; a.lcols = h->d_lcols;
+    a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    static const int cq_env = env_int("LM_QUAD_CQ", 0);
+    int cq = (ld >= 32) ? 8 : 4;
+    if (cq_env == 4 || cq_env == 8) cq = cq_env;
+    const int CT = 4 * cq;
+    const size_t smem = (size_t)h->tile_max_rows * (CT + 4) * c->esz();
+    REQUIRE(smem <= 200 * 1024, "apply_quad: tile does not fit in shared memory");
+    const long long nchunks = (ld + CT - 1) / CT;
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    long long cps = (long long)(budget / ((double)std::max<long long>(1, h->tile_window_rows) * CT * (double)c->esz()));
+    cps = std::max<long long>(1, std::min<long long>(cps, nchunks));
+    const long long strips = (nchunks + cps - 1) / cps;
+    cps = (nchunks + strips - 1) / strips;
+    REQUIRE((long long)h->ntiles * cps < 2147483647LL && strips <= 65535, "apply_quad: grid too large");
+    a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
+    dim3 grid((unsigned)((long long)h->ntiles * cps), (unsigned)strips);
+    if (c->precision == LM_C128) { if (cq == 8) FWD((launch_quad_mode<double, 8>(a, grid, smem, c->stream))); else FWD((launch_quad_mode<double, 4>(a, grid, smem, c->stream))); }
+    else { if (cq == 8) FWD((launch_quad_mode<float, 8>(a, grid, smem, c->stream))); else FWD((launch_quad_mode<float, 4>(a, grid, smem, c->stream))); }
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
 static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                        zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
@@ -1170,7 +1220,7 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
     return LM_OK;
 }
 
-static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles
+static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad
 // y = alpha H x + gamma x + beta z + delta u
 static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                  zc alpha, zc gamma, zc beta, zc delta) {
@@ -1185,6 +1235,7 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     // default: tile-order register gather whenever the host supplied site coordinates
     if (h->plan_from_coords && ld >= 32 && (tiled_env == 2 || tiled_env < 0)) return apply_rows(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     if (h->tiled && ld >= 16 && tiled_env == 1) return apply_tiled(h, ld, x, y, z, u, alpha, gamma, beta, delta);
+    if (h->plan_from_coords && ld >= 16 && tiled_env == 4) return apply_quad(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     ApplyArgs a;
     a.cols = h->d_cols; a.vals = h->d_vals; a.W = h->W; a.N = h->N; a.ld = ld;
     a.x = x; a.y = y; a.z = z; a.u = u;

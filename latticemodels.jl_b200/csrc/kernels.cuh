@@ -498,6 +498,89 @@ k_apply_tiled(const TiledArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_apply_quad: TMA-staged tiles with a thread <-> (row, column slice) mapping.
+// 64 rows x 4 slices per pass; slice q owns the interleaved columns q, q+4, ... of the CT-column
+// chunk, so ONE load of an H entry (value + uint16 local index) serves CQ = CT/4 elements, and
+// the gathers are 128-bit LDS from the staged rows.  Row stride ST = CT + 4 (== 4 mod 8 in
+// 16-byte units): the 2 rows x 4 slices of a quarter-warp hit 8 distinct bank groups whenever
+// consecutive rows have consecutive neighbours (the stencil case).
+// ------------------------------------------------------------------------------------------
+template <typename T, int CQ, int MODE>
+__global__ void __launch_bounds__(256)
+k_apply_quad(const TiledArgs a) {
+    using T2 = typename cx2<T>::type;
+    constexpr int CT = 4 * CQ, ST = CT + 4;
+    extern __shared__ __align__(128) unsigned char lm_smem[];
+    T2* sx = reinterpret_cast<T2*>(lm_smem);
+    __shared__ __align__(8) unsigned long long bar;
+
+    const unsigned tile = blockIdx.x / a.cps;
+    const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
+    if (chunk >= a.nchunks) return;
+    const long long c0 = (long long)chunk * CT;
+    const int cw = (int)((a.ld - c0) < CT ? (a.ld - c0) : CT);
+    const int p0 = a.t_ptr[tile];
+    const int nrows = a.t_ptr[tile + 1] - p0;
+    const int nr = a.t_nr[tile];
+    const int* __restrict__ rows = a.t_rows + p0;
+    const T2* __restrict__ x = (const T2*)a.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (unsigned)(nrows * cw * (int)sizeof(T2)));
+    }
+    __syncthreads();
+    for (int r = tid; r < nrows; r += 256)
+        tma_bulk_g2s(sx + r * ST, x + (long long)rows[r] * a.ld + c0, (unsigned)(cw * (int)sizeof(T2)), &bar);
+
+    const int q = tid & 3, rl = tid >> 2;
+    const T2 alpha = cmake<T2>(a.alpha[0], a.alpha[1]);
+    const T2 gamma = cmake<T2>(a.gamma[0], a.gamma[1]);
+    const T2 beta  = cmake<T2>(a.beta[0],  a.beta[1]);
+    const T2 delta = cmake<T2>(a.delta[0], a.delta[1]);
+    const bool has_gamma = (a.gamma[0] != 0.0) || (a.gamma[1] != 0.0);
+    const T2* z = (const T2*)a.z;
+    const T2* u = (const T2*)a.u;
+    T2* y = (T2*)a.y;
+    const T2* __restrict__ vals = (const T2*)a.vals;
+    bool ok[CQ];
+#pragma unroll
+    for (int j = 0; j < CQ; ++j) ok[j] = (q + 4 * j) < cw;
+
+    mbar_wait(&bar, 0);
+
+    for (int r = rl; r < nr; r += 64) {
+        const long long g = rows[r];
+        const long long e0 = g * a.ld + c0 + q;
+        T2 acc[CQ];
+#pragma unroll
+        for (int j = 0; j < CQ; ++j) {
+            acc[j].x = 0; acc[j].y = 0;
+            if (MODE == 1 && ok[j]) cfma(acc[j], beta, ld_stream(z + e0 + 4 * j));
+            if (MODE == 3) cfma(acc[j], gamma, sx[r * ST + q + 4 * j]);
+            if (MODE == 2) {
+                if (z && ok[j]) cfma(acc[j], beta, ld_stream(z + e0 + 4 * j));
+                if (u && ok[j]) cfma(acc[j], delta, u[e0 + 4 * j]);
+                if (has_gamma) cfma(acc[j], gamma, sx[r * ST + q + 4 * j]);
+            }
+        }
+        const unsigned short* __restrict__ lcr = a.lcols + g * a.W;
+        const T2* __restrict__ vr = vals + g * a.W;
+#pragma unroll 2
+        for (int k = 0; k < a.W; ++k) {
+            const int l = lcr[k];
+            const T2 v = cmul(alpha, vr[k]);
+            const T2* sr = sx + l * ST + q;
+#pragma unroll
+            for (int j = 0; j < CQ; ++j) cfma(acc[j], v, sr[4 * j]);
+        }
+#pragma unroll
+        for (int j = 0; j < CQ; ++j)
+            if (ok[j]) st_stream(y + e0 + 4 * j, acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Peierls phases regenerated on the device (src/operators/builder.jl:282-285 +
 // src/zoo/magneticfields.jl:15,31,72-104 restated; FP64 always).
 // ------------------------------------------------------------------------------------------

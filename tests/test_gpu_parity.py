@@ -90,7 +90,7 @@ def test_csc_julia_one_based(ctx):
     lib.lm_ham_destroy(h)
 
 
-@pytest.mark.parametrize("path", [0, 1, 2, 3])      # 3 = site-blocked kernel (n_int = 2 models)
+@pytest.mark.parametrize("path", [0, 1, 2, 3, 4])   # 3 = site-blocked (n_int = 2), 4 = TMA quad mapping
 @pytest.mark.parametrize("model", ["square", "qwz_pbc", "haldane"])
 def test_all_spmm_kernels_on_plan(ctx, path, model):
     """Every SpMM kernel generation (consecutive-row gather, TMA-staged tiles, tile-order gather)
