@@ -137,6 +137,10 @@ int32_t lm_ham_dims(lm_ham* ham, int64_t* N, int32_t* n_int, int64_t* nnz, int32
 int32_t lm_ham_get_csc(lm_ham* ham, int64_t* colptr, int64_t* rowval, void* nzval);
 /* Gershgorin bounds [emin, emax] of the spectrum used by the polynomial propagators */
 int32_t lm_ham_spectral_bounds(lm_ham* ham, double* emin, double* emax);
+/* Optional, NOT rigorous: tighten [emin, emax] with `iters` Lanczos steps on one random vector,
+ * widened by margin x width and clamped to the Gershgorin interval (fewer polynomial terms when
+ * phases/signs cancel, e.g. QWZ).  Reset by lm_ham_update_values. */
+int32_t lm_ham_refine_bounds(lm_ham* ham, int32_t iters, double margin);
 int32_t lm_ham_destroy(lm_ham* ham);
 
 /* ------------------------------------------------------------------ states

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "lm_ham_dims": [_vp, _pi64, _pi32, _pi64, _pi32],
     "lm_ham_get_csc": [_vp, _vp, _vp, _vp],
     "lm_ham_spectral_bounds": [_vp, _pf64, _pf64],
+    "lm_ham_refine_bounds": [_vp, _i32, _f64],
     "lm_ham_destroy": [_vp],
     "lm_state_create_psi": [_vp, _i64, _i64, _vp, _vp, C.POINTER(_vp)],
     "lm_state_create_dense": [_vp, _i64, _vp, C.POINTER(_vp)],

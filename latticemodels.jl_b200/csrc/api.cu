@@ -551,27 +551,6 @@ extern "C" int32_t lm_dbg_tile_info(lm_ham* h, int32_t* ntiles, int32_t* max_row
 }
 
 template <typename T>
-static void bounds_from_csc(lm_ham* h, const void* nzval) {
-    // Gershgorin: [min_i (H_ii - R_i), max_i (H_ii + R_i)], R_i = sum_{j != i} |H_ij|
-    const long long N = h->N;
-    std::vector<double> diag(N, 0.0), rad(N, 0.0);
-    const std::complex<T>* v = (const std::complex<T>*)nzval;
-    const int base = h->index_base;
-    for (long long j = 0; j < N; ++j)
-        for (long long q = h->colptr[j] - base; q < h->colptr[j + 1] - base; ++q) {
-            const long long i = h->rowval[q] - base;
-            if (i == j) diag[i] += (double)v[q].real(); else rad[i] += std::abs(std::complex<double>(v[q]));
-        }
-    double lo = 1e300, hi = -1e300, nrm = 0;
-    for (long long i = 0; i < N; ++i) {
-        lo = std::min(lo, diag[i] - rad[i]); hi = std::max(hi, diag[i] + rad[i]);
-        nrm = std::max(nrm, std::fabs(diag[i]) + rad[i]);
-    }
-    if (N == 0) { lo = hi = 0; }
-    h->emin = lo; h->emax = hi; h->norm_inf = nrm;
-}
-
-template <typename T>
 static int upload_nzval(lm_ham* h, const void* nzval) {
     lm_ctx* c = h->ctx;
     using T2 = typename cx2<T>::type;
@@ -643,8 +622,22 @@ extern "C" int32_t lm_ham_update_values(lm_ham* h, const void* nzval) {
     REQUIRE(h && nzval, "lm_ham_update_values: NULL argument");
     REQUIRE(!h->bond_mode, "lm_ham_update_values: Hamiltonian was created from bonds; use lm_ham_set_field_params");
     FWD(set_dev(h->ctx));
-    if (h->ctx->precision == LM_C128) { bounds_from_csc<double>(h, nzval); FWD(upload_nzval<double>(h, nzval)); }
-    else { bounds_from_csc<float>(h, nzval); FWD(upload_nzval<float>(h, nzval)); }
+    lm_ctx* c = h->ctx;
+    if (c->precision == LM_C128) FWD(upload_nzval<double>(h, nzval)); else FWD(upload_nzval<float>(h, nzval));
+    // spectral enclosure on the device (the host loop over nnz used to dominate large updates)
+    const unsigned grid = (unsigned)((h->N + 255) / 256);
+    FWD(ensure_stage(c, sizeof(double) * 3 * (size_t)grid));
+    FWD(ensure_pinned(c, sizeof(double) * 3 * (size_t)grid + 4096));
+    if (c->precision == LM_C128) k_gershgorin<double><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const double2*)h->d_vals, (double*)c->d_stage);
+    else k_gershgorin<float><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const float2*)h->d_vals, (double*)c->d_stage);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_stage, sizeof(double) * 3 * (size_t)grid, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double* pp = (const double*)c->h_pinned;
+    double lo = 1e300, hi = -1e300, nrm = 0;
+    for (unsigned b = 0; b < grid; ++b) { lo = std::min(lo, pp[3 * b]); hi = std::max(hi, pp[3 * b + 1]); nrm = std::max(nrm, pp[3 * b + 2]); }
+    h->emin = lo; h->emax = hi; h->norm_inf = nrm;
     h->version++;
     return LM_OK;
 }
@@ -2012,5 +2005,95 @@ extern "C" int32_t lm_dbg_cheb_product(double R, double tol, int32_t cap, double
     *K_out = (int)roots.size();
     for (int j = 0; j < (int)roots.size() && j < cap; ++j) { roots_ri[2 * j] = roots[j].real(); roots_ri[2 * j + 1] = roots[j].imag(); }
     pref_ri[0] = pref.real(); pref_ri[1] = pref.imag();
+    return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Optional: tighten the spectral enclosure with a short Lanczos run on one random vector.
+// Gershgorin is rigorous but loose when signs/phases cancel (QWZ: [-5, 5] vs the true [-3, 3]);
+// the Ritz extremes converge from inside, so they are widened by `margin` x width and clamped
+// to the Gershgorin interval.  A smaller interval means a smaller R = a dt and fewer terms.
+// NOT rigorous: opt-in (B200Exp(refine_bounds=True)); bounds derived from values are reset by
+// lm_ham_update_values.
+// ------------------------------------------------------------------------------------------
+static int sturm_count(const std::vector<double>& al, const std::vector<double>& be, double x) {
+    int cnt = 0; double d = 1.0;
+    for (size_t j = 0; j < al.size(); ++j) {
+        d = al[j] - x - (j > 0 ? be[j] * be[j] / d : 0.0);
+        if (d == 0.0) d = 1e-300;
+        if (d < 0) cnt++;
+    }
+    return cnt;
+}
+extern "C" int32_t lm_ham_refine_bounds(lm_ham* h, int32_t iters, double margin) {
+    REQUIRE(h, "lm_ham_refine_bounds: NULL");
+    REQUIRE(iters >= 2 && iters <= 500 && margin >= 0 && margin <= 1, "lm_ham_refine_bounds: bad arguments");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    const long long N = h->N;
+    const int m = (int)std::min<long long>(iters, N);
+    // deterministic pseudo-random start vector
+    std::vector<char> host(c->esz() * (size_t)N);
+    unsigned long long sd = 0x9E3779B97F4A7C15ULL;
+    for (long long i = 0; i < 2 * N; ++i) {
+        sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17;
+        const double v = (double)(sd >> 11) / 9007199254740992.0 - 0.5;
+        if (c->precision == LM_C128) ((double*)host.data())[i] = v; else ((float*)host.data())[i] = (float)v;
+    }
+    lm_state *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+    FWD(lm_state_create_psi(c, N, 1, host.data(), nullptr, &v0));
+    int st = state_alloc(c, N, 1, false, &v1); if (st == LM_OK) st = state_alloc(c, N, 1, false, &v2);
+    double2* d_s = nullptr; double* d_b = nullptr;
+    if (st == LM_OK && cudaMalloc(&d_s, sizeof(double2) * 2) != cudaSuccess) st = fail(LM_ERR_CUDA, "refine: alloc");
+    if (st == LM_OK && cudaMalloc(&d_b, sizeof(double) * 2) != cudaSuccess) st = fail(LM_ERR_CUDA, "refine: alloc");
+    std::vector<double> al, be(1, 0.0);
+    auto run = [&]() -> int {
+        const unsigned gb = (unsigned)((N + 255) / 256);
+        auto dot = [&](lm_state* a, lm_state* b2, double2* out) -> int {
+            return (c->precision == LM_C128) ? coldot<double>(a, a->d_x, b2->d_x, out) : coldot<float>(a, a->d_x, b2->d_x, out);
+        };
+        auto scale = [&](lm_state* x, const double* beta) {
+            if (c->precision == LM_C128) k_scale_inv<double2><<<gb, 256, 0, c->stream>>>(N, 1, 1, (const double2*)x->d_x, beta, (double2*)x->d_x);
+            else k_scale_inv<float2><<<gb, 256, 0, c->stream>>>(N, 1, 1, (const float2*)x->d_x, beta, (float2*)x->d_x);
+            c->launches++;
+        };
+        FWD(dot(v0, v0, d_s));
+        k_sqrt_cols<<<1, 32, 0, c->stream>>>(1, d_s, d_b); c->launches++;
+        scale(v0, d_b);
+        lm_state *prev = v2, *cur = v0, *nxt = v1;
+        for (int j = 0; j < m; ++j) {
+            FWD(apply(h, 1, cur->d_x, nxt->d_x, nullptr, nullptr, zc(1, 0), zc(0, 0), zc(0, 0), zc(0, 0)));
+            FWD(dot(cur, nxt, d_s));
+            if (c->precision == LM_C128) k_lanczos_update<double2><<<gb, 256, 0, c->stream>>>(N, 1, 1, (double2*)nxt->d_x, (const double2*)cur->d_x, j > 0 ? (const double2*)prev->d_x : nullptr, d_s, d_b);
+            else k_lanczos_update<float2><<<gb, 256, 0, c->stream>>>(N, 1, 1, (float2*)nxt->d_x, (const float2*)cur->d_x, j > 0 ? (const float2*)prev->d_x : nullptr, d_s, d_b);
+            c->launches++;
+            double2 a_host; CK(cudaMemcpyAsync(&a_host, d_s, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+            FWD(dot(nxt, nxt, d_s + 1));
+            k_sqrt_cols<<<1, 32, 0, c->stream>>>(1, d_s + 1, d_b); c->launches++;
+            double b_host; CK(cudaMemcpyAsync(&b_host, d_b, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            al.push_back(a_host.x);
+            if (!(b_host > 1e-12)) break;                 // invariant subspace
+            be.push_back(b_host);
+            scale(nxt, d_b);
+            lm_state* t = prev; prev = cur; cur = nxt; nxt = t;
+        }
+        return LM_OK;
+    };
+    if (st == LM_OK) st = run();
+    cudaStreamSynchronize(c->stream);
+    if (d_s) cudaFree(d_s); if (d_b) cudaFree(d_b);
+    state_free(v0); state_free(v1); state_free(v2);
+    FWD(st);
+    be.resize(al.size());
+    // extreme Ritz values by Sturm bisection inside the Gershgorin interval
+    auto ritz = [&](int want_index) {
+        double lo = h->emin - 1.0, hi = h->emax + 1.0;
+        for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (sturm_count(al, be, mid) > want_index) hi = mid; else lo = mid; }
+        return 0.5 * (lo + hi);
+    };
+    const double tmin = ritz(0), tmax = ritz((int)al.size() - 1);
+    const double width = tmax - tmin;
+    const double nmin = std::max(h->emin, tmin - margin * width), nmax = std::min(h->emax, tmax + margin * width);
+    if (nmax > nmin) { h->emin = nmin; h->emax = nmax; h->norm_inf = std::min(h->norm_inf, std::max(std::fabs(nmin), std::fabs(nmax))); }
     return LM_OK;
 }

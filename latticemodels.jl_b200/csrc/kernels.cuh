@@ -651,6 +651,37 @@ __global__ void k_assemble(long long E, const double2* __restrict__ stat,
     vals[e] = cmake<typename cx2<T>::type>(v.x, v.y);
 }
 
+// Gershgorin enclosure of the spectrum from the ELL rows: per CTA (min_i H_ii - R_i,
+// max_i H_ii + R_i, max_i |H_ii| + R_i), R_i = sum_{j != i} |H_ij|; the host folds the partials.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gershgorin(long long N, int W, const int* __restrict__ cols, const typename cx2<T>::type* __restrict__ vals,
+             double* __restrict__ partial /* [grid][3] */) {
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    double lo = 1e300, hi = -1e300, nr = 0.0;
+    if (i < N) {
+        double d = 0.0, r = 0.0;
+        for (int k = 0; k < W; ++k) {
+            const double re = (double)vals[i * W + k].x, im = (double)vals[i * W + k].y;
+            if (cols[i * W + k] == i) d += re; else r += sqrt(re * re + im * im);
+        }
+        lo = d - r; hi = d + r; nr = fabs(d) + r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nr = fmax(nr, __shfl_xor_sync(0xffffffffu, nr, o));
+    }
+    __shared__ double s[8][3];
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = lo; s[threadIdx.x >> 5][1] = hi; s[threadIdx.x >> 5][2] = nr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, s[w][0]); hi = fmax(hi, s[w][1]); nr = fmax(nr, s[w][2]); }
+        partial[blockIdx.x * 3 + 0] = lo; partial[blockIdx.x * 3 + 1] = hi; partial[blockIdx.x * 3 + 2] = nr;
+    }
+}
+
 // scatter CSC nzval (host-assembled H) into the ELL value array
 template <typename T>
 __global__ void k_scatter_vals(long long nnz, const typename cx2<T>::type* __restrict__ nz,

@@ -45,13 +45,15 @@ class B200Exp(EvolutionSolver):
     ``tol`` bounds the truncation error of exp(-i H dt) per step (the reference's own test
     pins its solvers to the exact exponential at atol 1e-10, test/test_timedeps.jl:55-67)."""
 
-    def __init__(self, ham=None, tol=1e-12, method="auto", precision="c128", ctx=None, n_int=None, coords=None):
+    def __init__(self, ham=None, tol=1e-12, method="auto", precision="c128", ctx=None, n_int=None, coords=None,
+                 refine_bounds=False):
         self.ctx = ctx or default_context(precision)
         self.tol, self.method = float(tol), _METHODS[method]
         self.dev = None
         self.dt = 0.0
         self.n_int = n_int
         self.coords = coords        # site coordinates for raw-matrix Hamiltonians (tile plan)
+        self.refine_bounds = refine_bounds   # opt-in Lanczos tightening of the spectral enclosure
         self._mat = None            # last raw matrix (identity check, src/evolution.jl:86-88)
         self._csc_dev = None
         self.n_matvec = 0
@@ -62,6 +64,8 @@ class B200Exp(EvolutionSolver):
         self.dt = float(dt)
         if isinstance(mat, Hamiltonian):
             self.dev = mat.device(self.ctx)     # regenerates phases on device if the field changed
+            if self.refine_bounds and not getattr(self.dev, "_refined", False):
+                self.dev.refine_bounds()
             return
         if isinstance(mat, DeviceHam):
             self.dev = mat

@@ -217,6 +217,12 @@ class DeviceHam:
         _lib.check(lib.lm_ham_get_csc(self.handle, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nz)))
         return sp.csc_matrix((nz[:self.nnz], rowval[:self.nnz], colptr), shape=(self.N, self.N))
 
+    def refine_bounds(self, iters=60, margin=0.05):
+        """Opt-in Lanczos tightening of the spectral enclosure (not rigorous; see lm_b200.h)."""
+        _lib.check(_lib.load().lm_ham_refine_bounds(self.handle, int(iters), float(margin)))
+        self._refined = True
+        return self.spectral_bounds()
+
     def spectral_bounds(self):
         lo, hi = C.c_double(), C.c_double()
         _lib.check(_lib.load().lm_ham_spectral_bounds(self.handle, C.byref(lo), C.byref(hi)))

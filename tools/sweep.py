@@ -72,6 +72,9 @@ def run_case(ctx, kind, n, M, reps, tol=1e-12, what=("spmm", "step", "triad", "o
         lib.lm_dbg_triad.argtypes = [C.c_void_p] * 3
         ms = timeit(lambda: _lib.check(lib.lm_dbg_triad(x.handle, z.handle, y.handle)), reps)
         out.update(triad_ms=ms, triad_gbs=3.0 * N * M * esz / ms / 1e6)
+    if "refine" in what:
+        out.update(bounds_gershgorin=dev.spectral_bounds())
+        out.update(bounds_refined=dev.refine_bounds())
     if "step" in what:
         nmv = C.c_int32()
         for method, tag in ((0, "auto"), (2, "taylor"), (1, "cheb"), (5, "clenshaw")):
