@@ -162,6 +162,42 @@ function Currents(curr::DensityCurrents{<:Any,<:DevOp}, solver::B200Exp)
     Currents(l, sparse(vcat(I[keep], J[keep]), vcat(J[keep], I[keep]), vcat(V[keep], -V[keep]), n, n))
 end
 
-export B200Exp, PsiProjector, Context
+# ---- device-resident time-dependent Hamiltonian (AbstractTimeDependentOperator branch) --------
+# Holds the directed bond table once; set_time! only ships the field parameters, the Peierls
+# phases are regenerated on the device (src/evolution.jl:44-47,243; builder.jl:282-309 restated
+# in lm_ham_create_bonds).  `fieldparams(t)` returns the 3-doubles-per-field parameter matrix.
+mutable struct B200Hamiltonian <: QuantumOpticsBase.AbstractTimeDependentOperator
+    dev::DeviceHam
+    kinds::Vector{Int32}
+    fieldparams::Function
+    template::Any                 # a reference Hamiltonian (basis, system) for DensityCurrents(H, P)
+end
+function B200Hamiltonian(ctx::Context, l, n_int::Integer, src::Vector{Int32}, dst::Vector{Int32},
+                         r_src::Matrix{Float64}, r_dst::Matrix{Float64}, amp::Array{ComplexF64,3},
+                         bfac::Vector{ComplexF64}, onsite::Union{Nothing,Array{ComplexF64,3}},
+                         kinds::Vector{Int32}, fieldparams::Function, template)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lm_ham_create_bonds, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int32, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, length(l), n_int, length(src), src, dst, r_src, r_dst, amp, bfac,
+                onsite === nothing ? C_NULL : onsite, 1, h))
+    dev = DeviceHam(h[], Int64[], Int64[])
+    coords = Float64[site.coords[k] for k in 1:2, site in l]
+    check(ccall((:lm_ham_set_site_coords, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), dev.handle, coords))
+    p0 = fieldparams(0.0)
+    check(ccall((:lm_ham_set_fields, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}),
+                dev.handle, length(kinds), kinds, p0))
+    finalizer(x -> ccall((:lm_ham_destroy, LIB), Int32, (Ptr{Cvoid},), x.dev.handle),
+              B200Hamiltonian(dev, kinds, fieldparams, template))
+end
+function QuantumOpticsBase.set_time!(H::B200Hamiltonian, t)
+    check(ccall((:lm_ham_set_field_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), H.dev.handle, H.fieldparams(t)))
+    H
+end
+LatticeModels._data(H::B200Hamiltonian) = H          # update_solver! receives the operator itself
+update_solver!(s::B200Exp, H::B200Hamiltonian, dt, force = false) = (s.dt = dt; s.dev = H.dev; nothing)
+
+export B200Exp, PsiProjector, Context, B200Hamiltonian
 
 end # module

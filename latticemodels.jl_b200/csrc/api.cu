@@ -1062,7 +1062,8 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.gamma[0] = gamma.real(); a.gamma[1] = gamma.imag();
     a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
     static const int cpt_env = env_int("LM_ROWS_CPT", 0);
-    int cpt = (ld >= 128) ? 2 : 1;
+    static const int cpt2_min = env_int("LM_ROWS_CPT2_MIN", 64);
+    int cpt = (ld >= cpt2_min) ? 2 : 1;
     if (cpt_env == 1 || cpt_env == 2 || cpt_env == 4) cpt = cpt_env;
     const int ec = (c->precision == LM_C128) ? 1 : 2;       // complex columns per 128-bit lane element
     const int CT = 32 * cpt * ec;                             // complex columns per chunk

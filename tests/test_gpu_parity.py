@@ -650,3 +650,23 @@ def test_refined_spectral_bounds(ctx):
     sol.update_solver(Hd2, 0.5)
     sol.step(st3)
     assert _relerr(st3.download(), EV.exact_propagator(OP.qwz(lo, field=F.LandauGauge(0.11)), 0.5) @ Psi) < 2e-13
+
+
+def test_timesequence_collects_device_frames(ctx):
+    """TimeSequence(f, ev, times) (src/timesequence.jl:41-43) over a device evolution, then
+    differentiate: d rho/dt matches the continuity equation frame by frame."""
+    l = lm.SquareLattice(6, 6)
+    H = lm.tightbinding_hamiltonian(l, field=lm.LandauGauge(0.1))
+    P0 = lm.densitymatrix(lm.tightbinding_hamiltonian(l), N=9)
+    ev = lm.Evolution(lm.B200Exp(tol=1e-13, ctx=ctx), H, P0)
+    ts = np.arange(0, 21) * 0.01
+    frames = lm.TimeSequence(lambda m: np.concatenate([lm.localdensity(m.state).values,
+                                                       np.asarray(lm.Currents(lm.DensityCurrents(m.H, m.state)).currents.sum(axis=1)).ravel()]),
+                             ev, ts)
+    assert len(frames) == 21 and frames[0.0][:36].sum() == pytest.approx(9.0, abs=1e-12)
+    rho = lm.TimeSequence()
+    for t, v in frames:
+        rho[t] = v[:36]
+    drho = rho.differentiate()
+    mid = 0.5 * (frames[0.1][36:] + frames[0.11][36:])      # sum_j J_ij at the interval midpoint
+    assert np.abs(drho[0.105] - mid).max() < 1e-4 * max(np.abs(mid).max(), 1e-12) + 1e-7
