@@ -670,3 +670,31 @@ def test_timesequence_collects_device_frames(ctx):
     drho = rho.differentiate()
     mid = 0.5 * (frames[0.1][36:] + frames[0.11][36:])      # sum_j J_ij at the interval midpoint
     assert np.abs(drho[0.105] - mid).max() < 1e-4 * max(np.abs(mid).max(), 1e-12) + 1e-7
+
+
+def test_golden_config1_fixture_on_device(ctx):
+    """The CUDA path against the COMMITTED golden vectors of BASELINE config 1
+    (tests/golden/config1_frames.npz): complex128 localdensity and DensityCurrents within 1e-10
+    relative at every stored frame, for the Psi-block and the dense-P state."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_frames.npz"))
+    l = lm.SquareLattice(10, 10)
+    h = lambda t: lm.tightbinding_hamiltonian(l, field=lm.PointFlux(0.2 * min(t, 10.0) / 10.0, (5.5, 5.5)))
+    Psi0, w0 = g["Psi0"], g["w0"]
+    P0 = (Psi0 * w0[None, :]) @ Psi0.conj().T
+    ts = np.arange(0, 201) * 0.1
+    frames = list(g["frames"])
+    ev_b = lm.Evolution(lm.B200Exp(tol=1e-13, ctx=ctx), h, lm.PsiProjector(Psi0, w0))
+    ev_d = lm.Evolution(lm.B200Exp(tol=1e-13, ctx=ctx), h, P0)
+    for k, (mb, md) in enumerate(zip(ev_b(ts), ev_d(ts))):
+        if k not in frames:
+            continue
+        q = frames.index(k)
+        rho_b = lm.localdensity(mb.state).values
+        rho_d = lm.localdensity(md.state).values
+        I, J, V = lm.DensityCurrents(mb.H, mb.state).pair_values()
+        assert [tuple(p) for p in g["pairs"]] == list(zip(I.tolist(), J.tolist()))
+        assert _relerr(rho_b, g["rho"][q]) < 1e-10 and _relerr(rho_d, g["rho"][q]) < 1e-10
+        scale = max(np.abs(g["J"][q]).max(), 1e-300)
+        assert np.abs(V - g["J"][q]).max() < 1e-10 * max(scale, 1e-3)
+        assert mb.t == pytest.approx(g["times"][q])

@@ -357,3 +357,25 @@ def test_operator_currents_and_localexpect_identities(qwz44):
     tot = sum(OB.operator_current(H1, gs, [[1, 0], [0, -1]], site, j, 2) for j in range(1, 17) if j != site)
     assert tot == pytest.approx(spin_dt, abs=1e-13)
     assert np.allclose(OB.localexpect(np.eye(2), P, 2).real, OB.localdensity(P, 2), atol=1e-14)
+
+
+def test_golden_config1_fixture_reproduced_by_oracle():
+    """tests/golden/config1_frames.npz (made by tests/golden/make_golden.py) - the Psi-block
+    reformulation of the oracle reproduces the dense-P golden series from the stored inputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_frames.npz"))
+    lat = L.square_lattice(10, 10)
+    h = lambda t: OP.tightbinding_hamiltonian(lat, field=F.PointFlux(0.2 * min(t, 10.0) / 10.0, (5.5, 5.5)))
+    pairs = [tuple(p) for p in g["pairs"]]
+    assert pairs == OB.site_adjacency(h(0.0), 1)
+    ts = np.arange(0, 201) * 0.1
+    frames = list(g["frames"])
+    for k, (st, H, t) in enumerate(EV.Evolution(h, [g["Psi0"]], solver="exact", block=True)(ts)):
+        if k in frames:
+            q = frames.index(k)
+            ost = OB.State(st[0], g["w0"], block=True)
+            assert np.abs(OB.localdensity(ost, 1) - g["rho"][q]).max() < 1e-12
+            Jq = np.array([OB.density_current(H, ost, i, j, 1) for i, j in pairs])
+            assert np.abs(Jq - g["J"][q]).max() < 1e-12
+        if k >= max(frames):
+            break
