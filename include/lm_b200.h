@@ -86,6 +86,14 @@ int32_t lm_timer_stop(lm_ctx* ctx, double* elapsed_ms_out);
  * any means (torch.distributed, MPI, Julia Distributed), every rank calls lm_ctx_comm_init. */
 int32_t lm_comm_unique_id(void* id128_out);
 int32_t lm_ctx_comm_init(lm_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+/* Optional NVLink peer-memory path for the per-frame reduction (2..8 ranks of ONE node): every
+ * rank allocates a symmetric exchange buffer (slot_doubles >= n_sites + n_pairs of the largest
+ * Hamiltonian) and exports its 64-byte CUDA IPC handle; the host all-gathers the handles (rank
+ * order) and every rank attaches.  Afterwards lm_observables / lm_local_density push their
+ * partial [rho | J] straight into the peers' slots from the finalize kernel and reduce locally;
+ * without it (or if a frame does not fit the slot) the NCCL all-reduce is used. */
+int32_t lm_ctx_peer_handle(lm_ctx* ctx, int64_t slot_doubles, void* handle64_out);
+int32_t lm_ctx_peer_attach(lm_ctx* ctx, const void* all_handles /* nranks x 64 bytes */);
 /* contiguous column range [begin, end) of rank `rank` out of `nranks` for M columns */
 int32_t lm_shard_range(int64_t M, int32_t rank, int32_t nranks, int64_t* begin, int64_t* end);
 

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "lm_timer_stop": [_vp, _pf64],
     "lm_comm_unique_id": [_vp],
     "lm_ctx_comm_init": [_vp, _vp, _i32, _i32],
+    "lm_ctx_peer_handle": [_vp, _i64, _vp],
+    "lm_ctx_peer_attach": [_vp, _vp],
     "lm_shard_range": [_i64, _i32, _i32, _pi64, _pi64],
     "lm_ham_create_csc": [_vp, _i64, _i32, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_update_values": [_vp, _vp],

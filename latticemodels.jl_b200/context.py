@@ -48,6 +48,15 @@ class Context:
         _lib.check(_lib.load().lm_ctx_comm_init(self.handle, buf, rank, nranks))
         self.rank, self.nranks = rank, nranks
 
+    def peer_handle(self, slot_doubles):
+        buf = C.create_string_buffer(64)
+        _lib.check(_lib.load().lm_ctx_peer_handle(self.handle, int(slot_doubles), buf))
+        return buf.raw
+
+    def peer_attach(self, all_handles: bytes):
+        buf = C.create_string_buffer(bytes(all_handles), 64 * self.nranks)
+        _lib.check(_lib.load().lm_ctx_peer_attach(self.handle, buf))
+
     def shard_range(self, M):
         return shard_range(M, self.rank, self.nranks)
 

@@ -90,6 +90,9 @@ struct lm_ctx {
     void* d_stage = nullptr; size_t stage_bytes = 0;      // staging for layout changes
     int l2_bytes = 0;
     struct lm_ham* dens_helper = nullptr;                 // pattern-less ham owning density scratch
+    // NVLink peer-memory exchange for the per-frame [rho | J] reduction
+    void* p2p_local = nullptr; size_t p2p_bytes = 0; long long p2p_cap = 0; bool p2p_ready = false;
+    void* p2p_peer_base[8] = {nullptr}; unsigned int* d_p2p_done = nullptr; unsigned long long p2p_epoch = 0;
     long long le_N = 0; int le_n = 0; int* d_le_a = nullptr; int* d_le_b = nullptr; double2* d_le_G = nullptr; double2* d_le_out = nullptr;   // localexpect tables
     size_t esz() const { return precision == LM_C128 ? 16 : 8; }
 };
@@ -209,6 +212,9 @@ extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->d_stage) cudaFree(c->d_stage);
     { void* q[] = {c->d_le_a, c->d_le_b, c->d_le_G, c->d_le_out}; for (void* p : q) if (p) cudaFree(p); }
+    for (int r = 0; r < 8; ++r) if (c->p2p_peer_base[r] && c->p2p_peer_base[r] != c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer_base[r]);
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    if (c->d_p2p_done) cudaFree(c->d_p2p_done);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -244,6 +250,39 @@ extern "C" int32_t lm_shard_range(int64_t M, int32_t rank, int32_t nranks, int64
     REQUIRE(b && e && nranks >= 1 && rank >= 0 && rank < nranks && M >= 0, "lm_shard_range: bad arguments");
     // contiguous ranges [k*M/G, (k+1)*M/G)   
     *b = (M * (int64_t)rank) / nranks; *e = (M * (int64_t)(rank + 1)) / nranks; return LM_OK;
+}
+
+// Peer-memory exchange buffer: flags[2][nranks] (padded to 4 KiB) followed by slots[2][nranks][cap]
+static size_t p2p_flag_bytes() { return 4096; }
+extern "C" int32_t lm_ctx_peer_handle(lm_ctx* c, int64_t slot_doubles, void* handle64_out) {
+    REQUIRE(c && handle64_out, "lm_ctx_peer_handle: NULL argument");
+    REQUIRE(c->nranks >= 2 && c->nranks <= 8, "lm_ctx_peer_handle: needs an attached communicator with 2..8 ranks");
+    REQUIRE(slot_doubles > 0, "lm_ctx_peer_handle: slot size must be positive");
+    FWD(set_dev(c));
+    if (!c->p2p_local) {
+        c->p2p_cap = slot_doubles;
+        c->p2p_bytes = p2p_flag_bytes() + sizeof(double) * 2 * (size_t)c->nranks * (size_t)slot_doubles;
+        CK(cudaMalloc(&c->p2p_local, c->p2p_bytes));
+        CK(cudaMemset(c->p2p_local, 0, c->p2p_bytes));
+        CK(cudaMalloc(&c->d_p2p_done, sizeof(unsigned int)));
+        CK(cudaMemset(c->d_p2p_done, 0, sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, c->p2p_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64_out, &hnd, 64);
+    return LM_OK;
+}
+extern "C" int32_t lm_ctx_peer_attach(lm_ctx* c, const void* all_handles) {
+    REQUIRE(c && all_handles && c->p2p_local, "lm_ctx_peer_attach: call lm_ctx_peer_handle first");
+    FWD(set_dev(c));
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) { c->p2p_peer_base[r] = c->p2p_local; continue; }
+        cudaIpcMemHandle_t hnd; memcpy(&hnd, (const char*)all_handles + 64 * r, 64);
+        CK(cudaIpcOpenMemHandle(&c->p2p_peer_base[r], hnd, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p_ready = true;
+    return LM_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1787,13 +1826,32 @@ static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, d
     const bool want_j = J_out != nullptr;
     if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
     const long long tot = n_sites + npairs; const int th = 256;
-    if (c->precision == LM_C128)
-        k_finalize_obs<double><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const double2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
-    else
-        k_finalize_obs<float><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const float2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
-    c->launches++;
+    static const int p2p_env = env_int("LM_OBS_P2P", 1);
+    const bool used_p2p = c->nranks > 1 && c->p2p_ready && p2p_env && tot <= c->p2p_cap;
+    if (used_p2p) {
+        // fused finalize + push all-gather over NVLink peer memory, then local acquire + sum
+        PeerPtrs pp;
+        for (int r = 0; r < 8; ++r) {
+            char* base = (char*)(r < c->nranks ? c->p2p_peer_base[r] : c->p2p_local);
+            pp.flags[r] = (unsigned long long*)base; pp.slots[r] = (double*)(base + p2p_flag_bytes());
+        }
+        const unsigned long long epoch = ++c->p2p_epoch; const int parity = (int)(epoch & 1);
+        const unsigned grid = (unsigned)((tot + th - 1) / th);
+        if (c->precision == LM_C128)
+            k_finalize_obs_p2p<double><<<grid, th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const double2*)h->d_vals, h->d_G, want_j ? 1 : 0, pp, c->rank, c->nranks, c->p2p_cap, parity, epoch, c->d_p2p_done);
+        else
+            k_finalize_obs_p2p<float><<<grid, th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const float2*)h->d_vals, h->d_G, want_j ? 1 : 0, pp, c->rank, c->nranks, c->p2p_cap, parity, epoch, c->d_p2p_done);
+        k_obs_p2p_reduce<<<grid, th, 0, c->stream>>>(tot, (const double*)((char*)c->p2p_local + p2p_flag_bytes()), (const unsigned long long*)c->p2p_local, c->nranks, c->p2p_cap, parity, epoch, h->d_obs);
+        c->launches += 2;
+    } else {
+        if (c->precision == LM_C128)
+            k_finalize_obs<double><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const double2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
+        else
+            k_finalize_obs<float><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(n_sites, n_int, h->d_dens, npairs, h->d_pair_ptr, h->d_pair_ent, (const float2*)h->d_vals, h->d_G, h->d_obs, 1, want_j ? 1 : 0);
+        c->launches++;
+    }
     CK(cudaGetLastError());
-    if (c->nranks > 1 && c->comm)
+    if (c->nranks > 1 && c->comm && !used_p2p)
         NCK(g_nccl.AllReduce(h->d_obs, h->d_obs, (size_t)tot, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     FWD(ensure_pinned(c, sizeof(double) * (size_t)tot + 4096));
     CK(cudaMemcpyAsync(c->h_pinned, h->d_obs, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream));
@@ -2098,3 +2156,5 @@ extern "C" int32_t lm_ham_refine_bounds(lm_ham* h, int32_t iters, double margin)
     if (nmax > nmin) { h->emin = nmin; h->emax = nmax; h->norm_inf = std::min(h->norm_inf, std::max(std::fabs(nmin), std::fabs(nmax))); }
     return LM_OK;
 }
+
+extern "C" int32_t lm_dbg_p2p_frames(lm_ctx* c, int64_t* frames) { REQUIRE(c && frames, "lm_dbg_p2p_frames: NULL"); *frames = (int64_t)c->p2p_epoch; return LM_OK; }

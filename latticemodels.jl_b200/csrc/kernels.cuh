@@ -997,6 +997,80 @@ __global__ void k_finalize_obs(long long n_sites, int n_int, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused finalize + all-gather over NVLink peer memory (multi-GPU frames).
+// Every rank owns a symmetric buffer (CUDA IPC-mapped into all peers):
+//     flags[2][nranks] (uint64 epochs) | slots[2][nranks][cap] (double)
+// k_finalize_obs_p2p computes this rank's partial [rho | J] (same arithmetic as k_finalize_obs)
+// and STORES every value directly into slot[parity][rank] of EVERY peer (P2P st.global through
+// NVLink/NVSwitch) - there is no separate collective launch.  The last CTA to finish publishes
+// the epoch with a system-scope release store to each peer's flag.  k_obs_p2p_reduce then
+// acquires all nranks flags of this rank and sums the slots (all local reads).
+// Slots are double-buffered by frame parity: a peer can only be one frame ahead (its next push
+// is stream-ordered after its own reduce, which waited for our flag of the current frame).
+// ------------------------------------------------------------------------------------------
+struct PeerPtrs { double* slots[8]; unsigned long long* flags[8]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+__global__ void k_finalize_obs_p2p(long long n_sites, int n_int, const double* __restrict__ dens,
+                                   long long npairs, const int* __restrict__ pair_ptr, const int* __restrict__ pair_ent,
+                                   const typename cx2<T>::type* __restrict__ vals, const double2* __restrict__ G,
+                                   int want_j, PeerPtrs peers, int rank, int nranks, long long cap, int parity,
+                                   unsigned long long epoch, unsigned int* __restrict__ done_counter) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long tot = n_sites + npairs;
+    if (t < tot) {
+        double v = 0.0;
+        if (t < n_sites) {
+            for (int a = 0; a < n_int; ++a) v += dens[t * n_int + a];
+        } else if (want_j) {
+            const long long p = t - n_sites;
+            for (int q = pair_ptr[p]; q < pair_ptr[p + 1]; ++q) {
+                const int e = pair_ent[q];
+                const double hr = (double)vals[e].x, hi = (double)vals[e].y;
+                const double2 g = G[e];
+                v += 2.0 * (hr * g.y + hi * g.x);
+            }
+        }
+        const long long off = ((long long)parity * nranks + rank) * cap + t;
+        for (int r = 0; r < nranks; ++r) peers.slots[r][off] = v;          // push to every peer (and self)
+    }
+    // publish: all stores of this CTA, then (last CTA only) the epoch flag on every peer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_counter = 0;                                             // re-arm for the next frame
+            __threadfence_system();
+            for (int r = 0; r < nranks; ++r) st_release_sys(peers.flags[r] + (long long)parity * nranks + rank, epoch);
+        }
+    }
+}
+// out[t] = sum_r slot[parity][r][t] after every rank's flag of this frame has arrived
+__global__ void k_obs_p2p_reduce(long long tot, const double* __restrict__ slots, const unsigned long long* __restrict__ flags,
+                                 int nranks, long long cap, int parity, unsigned long long epoch, double* __restrict__ out) {
+    if (threadIdx.x < nranks) {
+        const unsigned long long* f = flags + (long long)parity * nranks + threadIdx.x;
+        while (ld_acquire_sys(f) < epoch) { __nanosleep(64); }
+    }
+    __syncthreads();
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= tot) return;
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r) s += __ldcv(slots + ((long long)parity * nranks + r) * cap + t);
+    out[t] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------
 template <typename T2>

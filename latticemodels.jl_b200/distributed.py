@@ -14,7 +14,7 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def attach_communicator(ctx: Context):
+def attach_communicator(ctx: Context, peer_slot_doubles: int = 4 << 20):
     """Create the library's NCCL communicator over an initialised torch.distributed group."""
     import torch
     import torch.distributed as dist
@@ -26,6 +26,12 @@ def attach_communicator(ctx: Context):
     t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
     dist.broadcast(t, src=0)
     ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
+    if peer_slot_doubles and 2 <= world <= 8 and dist.get_backend() == "nccl":
+        # NVLink peer-memory exchange for the per-frame reduction: all-gather the IPC handles
+        mine = torch.tensor(list(ctx.peer_handle(peer_slot_doubles)), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.peer_attach(b"".join(bytes(h.cpu().tolist()) for h in allh))
     return ctx
 
 
