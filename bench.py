@@ -27,6 +27,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices)
+# write to fd 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON
+# line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
 import numpy as np  # noqa: E402
 
 
@@ -145,7 +156,7 @@ def run_reference(args):
            "cpu_baseline": {"value": 1.0 / t, "unit": "steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
            "e2e": {"value": 1.0 / t, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -305,7 +316,7 @@ def main():
         rate, per_step, info = cpu_reference_rate(wl, args.cpu_cols, 3)
         out["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
