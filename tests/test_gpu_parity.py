@@ -698,3 +698,65 @@ def test_golden_config1_fixture_on_device(ctx):
         scale = max(np.abs(g["J"][q]).max(), 1e-300)
         assert np.abs(V - g["J"][q]).max() < 1e-10 * max(scale, 1e-3)
         assert mb.t == pytest.approx(g["times"][q])
+
+
+def test_edge_cases_ragged_and_degenerate_inputs(ctx):
+    """Edge cases: a 1-D chain (degenerate bounding box for the tile plan), a single site with an
+    EMPTY Hamiltonian, a 3-orbital random-block model (generic ELL width, no site blocking), and a
+    rank that would own no column."""
+    # 1-D chain, wide and narrow blocks
+    lo, l = L.square_lattice(40, 1), lm.SquareLattice(40, 1)
+    Ho = OP.tightbinding_hamiltonian(lo, field=F.LandauGauge(0.1))
+    Hd = lm.tightbinding_hamiltonian(l, field=lm.LandauGauge(0.1))
+    assert abs(Hd.device(ctx).to_csc() - Ho).max() < 5e-15
+    for M in (1, 33, 40):
+        Psi = _rand_block(40, M, seed=M)
+        st = lm.DeviceState.from_psi(Psi, ctx=ctx)
+        sol = lm.B200Exp(tol=1e-14, ctx=ctx)
+        sol.update_solver(Hd, 0.3)
+        sol.step(st)
+        assert _relerr(st.download(), EV.exact_propagator(Ho, 0.3) @ Psi) < 2e-13
+        rho = lm.localdensity(st).values
+        assert rho.sum() == pytest.approx(M, abs=1e-11)
+        assert len(lm.DensityCurrents(Hd, st).pair_values()[2]) == 39
+    # single site: no bonds at all -> empty H, evolution is the identity
+    l1 = lm.SquareLattice(1, 1)
+    H1 = lm.tightbinding_hamiltonian(l1)
+    st = lm.DeviceState.from_psi(np.array([[0.6 + 0.8j]]), ctx=ctx)
+    sol = lm.B200Exp(ctx=ctx)
+    sol.update_solver(H1, 0.1)
+    sol.step(st)
+    assert abs(st.download()[0, 0] - (0.6 + 0.8j)) < 1e-15
+    assert lm.localdensity(st).values[0] == pytest.approx(1.0)
+    assert len(lm.DensityCurrents(H1, st).pair_values()[2]) == 0
+    # 3 internal orbitals, dense random hopping blocks + random on-site blocks
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    B = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    D = rng.standard_normal((3, 3)); D = D + D.T
+    l3, lo3 = lm.SquareLattice(5, 4), L.square_lattice(5, 4)
+    Hd3 = lm.construct_hamiltonian(l3, 3, (D, 1), (A, lm.BravaisTranslation(axis=1)), (B, lm.BravaisTranslation(axis=2)), field=lm.SymmetricGauge(0.1))
+    Ho3 = OP.construct_hamiltonian(lo3, 3, [(D, 1), (A, L.translation(axis=1)), (B, L.translation(axis=2))], field=F.SymmetricGauge(0.1))
+    assert abs(Hd3.device(ctx).to_csc() - Ho3).max() < 5e-15
+    Psi = _rand_block(60, 35, seed=12)
+    w = rng.random(35)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=3)
+    sol = lm.B200Exp(tol=1e-14, ctx=ctx)
+    sol.update_solver(Hd3, 0.2)
+    sol.step(st)
+    want = EV.exact_propagator(Ho3, 0.2) @ Psi
+    assert _relerr(st.download(), want) < 2e-13
+    ost = OB.State(want, w, block=True)
+    assert _relerr(lm.localdensity(st).values, OB.localdensity(ost, 3)) < 1e-12
+    I, J, V = lm.DensityCurrents(Hd3, st).pair_values()
+    Jw = np.array([OB.density_current(Ho3, ost, i, j, 3) for i, j in zip(I, J)])
+    assert np.abs(V - Jw).max() < 1e-12 * max(1.0, np.abs(Jw).max())
+    op = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    assert np.abs(lm.localexpect(op, st).values - OB.localexpect(op, ost, 3)).max() < 1e-12
+    # a rank with no columns is an error, not a silent empty shard
+    class FakeCtx:
+        nranks, rank, precision, handle = 8, 0, ctx.precision, ctx.handle      # rank 0 of 8 gets [0, 0) of 3 columns
+        def shard_range(self, M):
+            return lm.shard_range(M, self.rank, self.nranks)
+    with pytest.raises(lm.ArgumentError, match="owns no column"):
+        lm.DeviceState.from_psi(_rand_block(40, 3), ctx=FakeCtx())
