@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures of the non-headline kernels: fused observables (Haldane),
+site-blocked SpMM (QWZ), dense U P U' on the FP64 tensor cores, device Peierls phase regeneration."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import lm_b200 as lm  # noqa: E402
+
+ctx = lm.Context()
+rng = np.random.default_rng(0)
+which = sys.argv[1]
+if which == "obs":
+    H = lm.haldane(lm.HoneycombLattice(300, 300), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.001))
+    N = H.structure.dim
+    psi = np.asfortranarray((rng.standard_normal((N, 512)) + 1j * rng.standard_normal((N, 512))) / 30)
+    st = lm.DeviceState.from_psi(psi, ctx=ctx)
+    for _ in range(3):
+        lm.localdensity(st)
+        lm.DensityCurrents(H, st).pair_values()
+elif which == "sites":
+    H = lm.qwz(lm.SquareLattice(300, 300), field=lm.LandauGauge(0.01))
+    N = H.structure.dim
+    psi = np.asfortranarray((rng.standard_normal((N, 1024)) + 1j * rng.standard_normal((N, 1024))) / 30)
+    st = lm.DeviceState.from_psi(psi, ctx=ctx)
+    sol = lm.B200Exp(ctx=ctx)
+    for k in range(2):
+        sol.update_solver(lm.qwz(lm.SquareLattice(300, 300), field=lm.LandauGauge(0.01 + 0.001 * k)), 0.1)
+        sol.step(st)
+elif which == "dense":
+    l = lm.SquareLattice(32, 32)
+    H = lm.tightbinding_hamiltonian(l, field=lm.LandauGauge(0.05))
+    P0 = lm.densitymatrix(lm.tightbinding_hamiltonian(l), mu=0.0).dense()
+    st = lm.DeviceState.from_dense(P0, ctx=ctx)
+    sol = lm.B200Exp(ctx=ctx)
+    for _ in range(3):
+        sol.update_solver(H, 0.1)
+        sol.step(st)
+    print("tr P =", lm.localdensity(st).values.sum())
+ctx.synchronize()
