@@ -139,6 +139,15 @@ int32_t lm_ham_set_site_coords(lm_ham* ham, const double* xy);
  * src/lattices/bravais/unitcell.jl:126-132 orders the basis index innermost).  Blocks of 2 rows
  * are processed by the site-blocked kernel. */
 int32_t lm_ham_set_row_block(lm_ham* ham, int32_t rows);
+/* Optional: the Hilbert rows are CELL-MAJOR on an n1 x n2 grid of Bravais unit cells - row =
+ * ((j1 * n2) + j2) * RC + r with RC = N / (n1 n2) rows (basis sites x orbitals) per cell - which
+ * is the reference's own order for an unfiltered lattice (src/lattices/bravais/lattice.jl:101-111:
+ * last lattice axis fastest; src/lattices/bravais/unitcell.jl:126-132: basis index innermost).
+ * If every entry couples cells at most one apart (periodic images included) and the pattern is
+ * covered by a compiled stencil, H x runs on the register-tiled stencil kernel: one thread owns a
+ * block of unit cells of one Psi column and loads every element of the haloed block once.
+ * Anything else keeps the ELL kernels; the call never fails for an unsupported pattern. */
+int32_t lm_ham_set_lattice_dims(lm_ham* ham, int32_t n1, int32_t n2);
 
 int32_t lm_ham_dims(lm_ham* ham, int64_t* N, int32_t* n_int, int64_t* nnz, int32_t* ell_width);
 /* CSC view of the current H (pattern + values), index_base as given at creation */

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "lm_ham_set_field_params": [_vp, _vp],
     "lm_ham_set_site_coords": [_vp, _vp],
     "lm_ham_set_row_block": [_vp, _i32],
+    "lm_ham_set_lattice_dims": [_vp, _i32, _i32],
     "lm_ham_dims": [_vp, _pi64, _pi32, _pi64, _pi32],
     "lm_ham_get_csc": [_vp, _vp, _vp, _vp],
     "lm_ham_spectral_bounds": [_vp, _pf64, _pf64],

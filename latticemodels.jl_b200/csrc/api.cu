@@ -3,6 +3,7 @@
 // returned through this ABI is produced by the CUDA kernels.
 #include "../../include/lm_b200.h"
 #include "kernels.cuh"
+#include "stencil.cuh"
 #include "taylor_roots.h"
 
 #include <algorithm>
@@ -144,6 +145,11 @@ struct lm_ham {
     // LocalOperatorCurrents tables (built on first use): correlator requests of every full
     // n_int x n_int block of the site pairs, and the ELL entry of H[i_k, j_b] (or -1)
     int* d_oc_a = nullptr; int* d_oc_b = nullptr; int* d_oc_ent = nullptr; double2* d_oc_G = nullptr; double* d_oc_J = nullptr;
+    // register-tiled stencil view (stencil.cuh): the host declared the rows to be cell-major on an
+    // n1 x n2 grid of unit cells and the pattern matched a compiled |d| <= 1 stencil
+    int lat_n1 = 0, lat_n2 = 0;
+    int st_id = -1; int st_rc = 0; int st_sw = 0; unsigned long long st_mask = 0;
+    int* d_st_src = nullptr; void* d_svals = nullptr; long long svals_version = -1;
 };
 
 struct lm_state {
@@ -295,7 +301,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -569,6 +575,91 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
         CK(cudaMemcpy(h->d_scols, scols.data(), sizeof(int) * scols.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->d_bsrc, bsrc.data(), sizeof(int) * bsrc.size(), cudaMemcpyHostToDevice));
     }
+    return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stencil view: rows are cell-major on an n1 x n2 grid of unit cells (the reference's site order,
+// src/lattices/bravais/lattice.jl:101-111, last axis fastest, basis / orbital innermost).  If
+// every ELL entry couples cells at most one apart (periodic images included) and the pattern is
+// covered by a compiled stencil (stencil.cu), build the ELL -> stencil-slot gather map.
+// ------------------------------------------------------------------------------------------
+static int ham_build_stencil(lm_ham* h) {
+    lm_ctx* c = h->ctx;
+    FWD(set_dev(c));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h->d_st_src) { cudaFree(h->d_st_src); h->d_st_src = nullptr; }
+    if (h->d_svals) { cudaFree(h->d_svals); h->d_svals = nullptr; }
+    h->st_id = -1; h->svals_version = -1; h->layout_epoch++;
+    const long long n1 = h->lat_n1, n2 = h->lat_n2, N = h->N; const int W = h->W;
+    if (n1 < 3 || n2 < 3 || N % (n1 * n2) != 0) return LM_OK;
+    const int rc = (int)(N / (n1 * n2));
+    if (rc < 1 || rc > 2 || rc % h->n_int != 0) return LM_OK;
+    auto wrapd = [](long long d, long long n) { if (d > n / 2) d -= n; if (d < -(n / 2)) d += n; return d; };
+    // pass 1: pattern mask
+    unsigned long long mask = 0;
+    for (long long i = 0; i < N; ++i) {
+        const long long ci = i / rc; const int a = (int)(i % rc);
+        const long long c1 = ci / n2, c2 = ci % n2;
+        for (int k = 0; k < W; ++k) {
+            const long long j = h->h_cols[i * W + k];
+            const long long cj = j / rc; const int b = (int)(j % rc);
+            const long long d1 = wrapd(cj / n2 - c1, n1), d2 = wrapd(cj % n2 - c2, n2);
+            if (d1 < -1 || d1 > 1 || d2 < -1 || d2 > 1) return LM_OK;        // longer hops: ELL kernels
+            const int o = (int)((d1 + 1) * 3 + (d2 + 1));
+            if (j == i && o != 4) return LM_OK;
+            mask |= 1ull << (o * rc * rc + a * rc + b);
+        }
+    }
+    const int id = stencil_find(rc, mask);
+    if (id < 0) return LM_OK;
+    const StencilDesc& d = stencil_desc(id);
+    const int SW = stencil_stride(id, c->precision != LM_C128);      // slot stride (complex64 rows padded to even)
+    // slot of (o, b) in the list of out row a, same order as st_slot
+    int slot[9][2][2];
+    for (int a = 0; a < rc; ++a) {
+        int s = 0;
+        for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b) {
+            const bool set = (d.mask >> (o * rc * rc + a * rc + b)) & 1ull;
+            slot[o][a][b] = set ? s : -1;
+            if (set) ++s;
+        }
+    }
+    std::vector<int> src((size_t)N * SW, -1);
+    for (long long i = 0; i < N; ++i) {
+        const long long ci = i / rc; const int a = (int)(i % rc);
+        const long long c1 = ci / n2, c2 = ci % n2;
+        for (int k = 0; k < W; ++k) {
+            const long long j = h->h_cols[i * W + k];
+            const long long cj = j / rc; const int b = (int)(j % rc);
+            const long long d1 = wrapd(cj / n2 - c1, n1), d2 = wrapd(cj % n2 - c2, n2);
+            const int o = (int)((d1 + 1) * 3 + (d2 + 1));
+            int& q = src[(size_t)i * SW + slot[o][a][b]];
+            if (q >= 0) {
+                // ELL padding repeats the own row (value 0) after the real entries: keep the first.
+                if (j == i) continue;
+                return LM_OK;                                                 // two hops alias on a tiny torus
+            }
+            q = (int)(i * W + k);
+        }
+    }
+    CK(cudaMalloc(&h->d_st_src, sizeof(int) * src.size()));
+    // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes
+    CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 256));
+    CK(cudaMemset(h->d_svals, 0, c->esz() * src.size() + 256));
+    CK(cudaMemcpy(h->d_st_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
+    h->st_id = id; h->st_rc = rc; h->st_sw = SW; h->st_mask = mask;
+    return LM_OK;
+}
+extern "C" int32_t lm_ham_set_lattice_dims(lm_ham* h, int32_t n1, int32_t n2) {
+    REQUIRE(h, "lm_ham_set_lattice_dims: NULL");
+    REQUIRE(n1 >= 1 && n2 >= 1 && h->N % ((long long)n1 * n2) == 0, "lm_ham_set_lattice_dims: n1 * n2 must divide the Hilbert dimension");
+    h->lat_n1 = n1; h->lat_n2 = n2;
+    return ham_build_stencil(h);
+}
+extern "C" int32_t lm_dbg_stencil_info(lm_ham* h, int32_t* id, int32_t* rc, int32_t* sw, uint64_t* mask) {
+    REQUIRE(h, "lm_dbg_stencil_info: NULL");
+    if (id) *id = h->st_id; if (rc) *rc = h->st_rc; if (sw) *sw = h->st_sw; if (mask) *mask = h->st_mask;
     return LM_OK;
 }
 
@@ -1124,6 +1215,30 @@ static int apply_rows(lm_ham* h, long long ld, const void* x, void* y, const voi
     return LM_OK;
 }
 
+// Re-ordered copies of the ELL values (site blocks for k_apply_sites, stencil slots for
+// k_apply_stencil) follow the value version.  lm_step refreshes them BEFORE it captures or
+// replays a step graph, so a graph never bakes in (or misses) a refresh.
+static int refresh_views(lm_ham* h) {
+    lm_ctx* c = h->ctx;
+    const int th = 256;
+    if (h->d_scols && h->bvals_version != h->version) {
+        const long long nb = h->ngroups * h->Ws * h->grp * h->grp;
+        if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const double2*)h->d_vals, (double2*)h->d_bvals);
+        else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const float2*)h->d_vals, (float2*)h->d_bvals);
+        c->launches++;
+        h->bvals_version = h->version;
+    }
+    if (h->st_id >= 0 && h->svals_version != h->version) {
+        const long long nb = h->N * h->st_sw;
+        if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_st_src, (const double2*)h->d_vals, (double2*)h->d_svals);
+        else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_st_src, (const float2*)h->d_vals, (float2*)h->d_svals);
+        c->launches++;
+        h->svals_version = h->version;
+    }
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
 template <typename T, int CPT>
 static void launch_sites_mode(const SitesArgs& a, dim3 grid, cudaStream_t s) {
     const bool g = a.gamma[0] != 0.0 || a.gamma[1] != 0.0;
@@ -1135,14 +1250,7 @@ static void launch_sites_mode(const SitesArgs& a, dim3 grid, cudaStream_t s) {
 static int apply_sites(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                        zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
-    if (h->bvals_version != h->version) {           // refresh the block copy of the ELL values
-        const long long nb = h->ngroups * h->Ws * h->grp * h->grp;
-        const int th = 256;
-        if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const double2*)h->d_vals, (double2*)h->d_bvals);
-        else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_bsrc, (const float2*)h->d_vals, (float2*)h->d_bvals);
-        c->launches++;
-        h->bvals_version = h->version;
-    }
+    FWD(refresh_views(h));
     SitesArgs a;
     a.t_ptr = h->d_t_ptr; a.t_nr = h->d_t_nr; a.t_rows = h->d_t_rows;
     a.scols = h->d_scols; a.bvals = h->d_bvals; a.Ws = h->Ws; a.N = h->N; a.ld = ld;
@@ -1253,7 +1361,52 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
     return LM_OK;
 }
 
-static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad
+static int g_stencil_variant = -1;       // lm_dbg_set_stencil_variant (sweeps): -1 = default per pattern
+static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
+                         zc alpha, zc gamma, zc beta, zc delta) {
+    lm_ctx* c = h->ctx;
+    FWD(refresh_views(h));
+    static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
+    int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
+    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
+    int P1, P2, cpt, staged;
+    stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
+    StencilArgs a;
+    a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld;
+    a.x = x; a.y = y; a.z = z; a.u = u;
+    const zc g = gamma / alpha;
+    a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.g[0] = g.real(); a.g[1] = g.imag();
+    a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
+    const int ec = (c->precision == LM_C128) ? 1 : 2;
+    const int CT = 32 * cpt * ec;
+    const long long nchunks = (ld + CT - 1) / CT;
+    const long long np1 = (h->lat_n1 + P1 - 1) / P1, np2 = (h->lat_n2 + P2 - 1) / P2;
+    a.np2 = (int)np2;
+    // patches run along the fast lattice axis; the rows a sweep keeps re-reading are two patch
+    // rows with their halo - size the column strips so that this window stays in L2
+    static const int l2_pct = env_int("LM_APPLY_L2PCT", 35);
+    const double budget = 0.01 * l2_pct * (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    const double window_rows = 2.0 * (P1 + 2) * (double)h->lat_n2 * h->st_rc;
+    long long cps = (long long)(budget / (window_rows * CT * (double)c->esz()));
+    cps = std::max<long long>(1, std::min<long long>(cps, nchunks));
+    const long long strips = (nchunks + cps - 1) / cps;
+    cps = (nchunks + strips - 1) / strips;
+    REQUIRE(np1 * np2 * cps < 2147483647LL && strips <= 65535, "apply_stencil: grid too large");
+    REQUIRE(ld % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
+    a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
+    dim3 grid((unsigned)(np1 * np2 * cps), (unsigned)strips);
+    const bool has_g = gamma != zc(0, 0);
+    const int mode = (!z && !u && !has_g) ? 0 : ((z && !u && !has_g) ? 1 : ((!z && !u) ? 3 : 2));
+    const int st = stencil_launch(h->st_id, variant, c->precision != LM_C128, mode, a, grid, c->stream);
+    if (st == -1) return fail(LM_ERR_UNSUPPORTED, "apply_stencil: kernel variant not compiled");
+    if (st != 0) return fail(LM_ERR_CUDA, "apply_stencil: cudaFuncSetAttribute failed");
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+extern "C" int32_t lm_dbg_set_stencil_variant(int32_t v) { g_stencil_variant = v; return LM_OK; }
+
+static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad, 5 register-tiled stencil
 // y = alpha H x + gamma x + beta z + delta u
 static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                  zc alpha, zc gamma, zc beta, zc delta) {
@@ -1264,6 +1417,10 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     //                 2 = register gather over plan tiles (L1 patch reuse)
     // n_int = 2 models: site-blocked gather (3 = force, default on when the block view exists)
     static const int sites_env = env_int("LM_APPLY_SITES", 1);
+    // register-tiled stencil kernel (5 = force): default whenever the lattice matched a compiled stencil
+    static const int stencil_env = env_int("LM_APPLY_STENCIL", 1);
+    if (h->st_id >= 0 && ld >= 32 && alpha != zc(0, 0) && ((tiled_env < 0 && stencil_env) || tiled_env == 5))
+        return apply_stencil(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     if (h->d_scols && ld >= 32 && ((tiled_env < 0 && sites_env) || tiled_env == 3)) return apply_sites(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     // default: tile-order register gather whenever the host supplied site coordinates
     if (h->plan_from_coords && ld >= 32 && (tiled_env == 2 || tiled_env < 0)) return apply_rows(h, ld, x, y, z, u, alpha, gamma, beta, delta);
@@ -1688,6 +1845,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
         FWD(ensure_scratch(s, nbuf));
         static const int use_graph = env_int("LM_STEP_GRAPH", 1);
         const bool graphable = use_graph && product_form;
+        FWD(refresh_views(h));
         if (!graphable) {
             FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
         } else {

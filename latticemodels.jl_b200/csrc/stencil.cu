@@ -1,0 +1,72 @@
+// Registry of the compiled stencil patterns and register-tile variants (kernels: stencil.cuh,
+// instantiated per pattern in stencil_k<id>.cu).
+#include "stencil.cuh"
+
+namespace lm {
+
+// compiled sparsity patterns (|d| <= 1 cell offsets); a detected pattern runs on the smallest
+// compiled superset (missing entries carry the value 0)
+//   id 0  square / rectangular NN + on-site (RC = 1)
+//   id 1  any RC = 1 pattern with |d| <= 1 (NNN square, triangular)
+//   id 2  honeycomb NN + on-site (RC = 2)
+//   id 3  QWZ-type: 2 orbitals, full 2x2 blocks on-site and to the 4 nearest cells
+//   id 4  Haldane: honeycomb NN + NNN + on-site
+
+static const StencilDesc g_desc[] = {
+    {1, LM_ST_MASK0, st_width<1>(LM_ST_MASK0), "square-nn"},
+    {1, LM_ST_MASK1, st_width<1>(LM_ST_MASK1), "rc1-full"},
+    {2, LM_ST_MASK2, st_width<2>(LM_ST_MASK2), "honeycomb-nn"},
+    {2, LM_ST_MASK3, st_width<2>(LM_ST_MASK3), "qwz"},
+    {2, LM_ST_MASK4, st_width<2>(LM_ST_MASK4), "haldane"},
+};
+int stencil_count() { return (int)(sizeof(g_desc) / sizeof(g_desc[0])); }
+const StencilDesc& stencil_desc(int id) { return g_desc[id]; }
+int stencil_find(int rc, st_mask_t mask) {
+    int best = -1;
+    for (int i = 0; i < stencil_count(); ++i) {
+        if (g_desc[i].rc != rc || (mask & ~g_desc[i].mask)) continue;
+        if (best < 0 || g_desc[i].sw < g_desc[best].sw) best = i;
+    }
+    return best;
+}
+
+int stencil_stride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 1) & ~1) : g_desc[id].sw; }
+
+// register-tile variants: T1 x T2 cells per thread, W1 x W2 warps per CTA, CPT lane elements per
+// thread; staged = haloed patch brought into shared memory by TMA bulk copies
+struct Variant { int t1, t2, w1, w2, cpt, staged; };
+static const Variant g_var[] = {
+    {4, 2, 2, 4, 1, 0},   // 0: direct, 8 x 8 cell patch
+    {2, 2, 2, 4, 2, 0},   // 1: direct, 4 x 8, two lane elements per thread
+    {4, 2, 2, 2, 1, 1},   // 2: staged, 8 x 4 patch, 128 threads            (RC = 2 default)
+    {4, 2, 2, 4, 1, 1},   // 3: staged, 8 x 8 patch, 256 threads
+    {2, 2, 2, 2, 2, 1},   // 4: staged, 4 x 4 patch, two lane elements
+    {2, 4, 2, 2, 1, 1},   // 5: staged, 4 x 8 patch
+    {2, 2, 4, 2, 1, 1},   // 6: staged, 8 x 4 patch of 2 x 2 tiles, 256 threads
+    {4, 4, 2, 2, 1, 1},   // 7: staged, 8 x 8 patch, 128 threads              (RC = 1 default)
+    {4, 4, 2, 2, 1, 0},   // 8: direct, 8 x 8 patch                           (RC = 1)
+    {4, 2, 2, 4, 2, 1},   // 9: staged, 8 x 8 patch, two lane elements        (RC = 1)
+};
+int stencil_num_variants() { return (int)(sizeof(g_var) / sizeof(g_var[0])); }
+void stencil_variant_shape(int v, int* P1, int* P2, int* cpt, int* staged) {
+    *P1 = g_var[v].w1 * g_var[v].t1; *P2 = g_var[v].w2 * g_var[v].t2; *cpt = g_var[v].cpt; *staged = g_var[v].staged;
+}
+
+int stencil_launch_0(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_1(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_2(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_3(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_4(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+
+int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+    switch (id) {
+    case 0: return stencil_launch_0(variant, c64, mode, a, grid, s);
+    case 1: return stencil_launch_1(variant, c64, mode, a, grid, s);
+    case 2: return stencil_launch_2(variant, c64, mode, a, grid, s);
+    case 3: return stencil_launch_3(variant, c64, mode, a, grid, s);
+    case 4: return stencil_launch_4(variant, c64, mode, a, grid, s);
+    default: return -1;
+    }
+}
+
+}  // namespace lm

@@ -1,0 +1,71 @@
+// Launch plumbing of the stencil kernels, included by the per-pattern translation units
+// stencil_k<id>.cu (the fully unrolled kernels are large: one pattern per unit, built in parallel).
+#pragma once
+#include "stencil.cuh"
+
+namespace lm {
+
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, bool STAGED>
+static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
+    if constexpr (!STAGED) {
+        k_apply_stencil<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, 0, s>>>(a);
+        return 0;
+    } else {
+    constexpr size_t smem = st_tma_smem<T, RC, MASK, T1, T2, W1, W2, CPT>();
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+        configured = true;
+    }
+    k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
+    return 0;
+    }
+}
+// STAGED is a compile-time family switch so that only the requested family is instantiated
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, bool STAGED>
+static int launch_modes(int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+    switch (mode) {
+    case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, grid, s);
+    case 3: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 3, STAGED>(a, grid, s);
+#ifndef LM_STENCIL_FEWMODES
+    case 1: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 1, STAGED>(a, grid, s);
+    case 2: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 2, STAGED>(a, grid, s);
+#endif
+    default: return -1;
+    }
+}
+template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, bool STAGED>
+static int launch_prec(bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+    if (!c64) return launch_modes<double, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, grid, s);
+#ifndef LM_STENCIL_NOC64
+    return launch_modes<float, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, grid, s);
+#else
+    return -1;
+#endif
+}
+
+#define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MASK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, grid, s);
+template <int RC, st_mask_t MASK>
+static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+    if constexpr (RC == 1) {
+        switch (variant) {
+            LM_ST_V(7, 4, 4, 2, 2, 1, true)
+#ifdef LM_STENCIL_EXPLORE
+            LM_ST_V(8, 4, 4, 2, 2, 1, false) LM_ST_V(9, 4, 2, 2, 4, 2, true) LM_ST_V(3, 4, 2, 2, 4, 1, true)
+#endif
+            default: return -1;
+        }
+    } else {
+        switch (variant) {
+            LM_ST_V(2, 4, 2, 2, 2, 1, true)
+#ifdef LM_STENCIL_EXPLORE
+            LM_ST_V(0, 4, 2, 2, 4, 1, false) LM_ST_V(1, 2, 2, 2, 4, 2, false) LM_ST_V(3, 4, 2, 2, 4, 1, true)
+            LM_ST_V(4, 2, 2, 2, 2, 2, true) LM_ST_V(5, 2, 4, 2, 2, 1, true) LM_ST_V(6, 2, 2, 4, 2, 1, true)
+#endif
+            default: return -1;
+        }
+    }
+}
+
+}  // namespace lm

@@ -164,7 +164,14 @@ class DeviceHam:
         d = cls(ctx, h, st.n_int, True)
         d.field_key = ((), b"")
         d.set_site_coords(st.lat.coords, row_block=_row_block(st.lat, st.n_int))
+        if len(st.lat) == st.lat.sizes[0] * st.lat.sizes[1] * getattr(st.lat, "nb", 1):
+            d.set_lattice_dims(*st.lat.sizes)       # unfiltered Bravais lattice: rows are cell-major
         return d
+
+    def set_lattice_dims(self, n1, n2):
+        """Declare the cell-major row order of an unfiltered n1 x n2 Bravais lattice (enables the
+        register-tiled stencil kernel when the pattern is a compiled |d| <= 1 stencil)."""
+        _lib.check(_lib.load().lm_ham_set_lattice_dims(self.handle, int(n1), int(n2)))
 
     def set_site_coords(self, coords, row_block=None):
         xy = np.ascontiguousarray(np.asarray(coords, float)[:, :2])
@@ -175,7 +182,7 @@ class DeviceHam:
         _lib.check(_lib.load().lm_ham_set_site_coords(self.handle, _lib.ptr(xy)))
 
     @classmethod
-    def from_csc(cls, ctx, mat, n_int=1, coords=None):
+    def from_csc(cls, ctx, mat, n_int=1, coords=None, lattice_dims=None):
         lib = _lib.load()
         m = sp.csc_matrix(mat)
         m.sort_indices()
@@ -189,6 +196,8 @@ class DeviceHam:
         d.pattern = (colptr, rowval)
         if coords is not None:
             d.set_site_coords(coords)
+        if lattice_dims is not None:
+            d.set_lattice_dims(*lattice_dims)
         return d
 
     def update_values(self, nzval):

@@ -90,7 +90,7 @@ def test_csc_julia_one_based(ctx):
     lib.lm_ham_destroy(h)
 
 
-@pytest.mark.parametrize("path", [0, 1, 2, 3, 4])   # 3 = site-blocked (n_int = 2), 4 = TMA quad mapping
+@pytest.mark.parametrize("path", [0, 1, 2, 3, 4, 5])   # 3 = site-blocked (n_int = 2), 4 = TMA quad mapping, 5 = register-tiled stencil
 @pytest.mark.parametrize("model", ["square", "qwz_pbc", "haldane"])
 def test_all_spmm_kernels_on_plan(ctx, path, model):
     """Every SpMM kernel generation (consecutive-row gather, TMA-staged tiles, tile-order gather)
@@ -148,6 +148,128 @@ def test_csc_hamiltonian_with_site_coords(ctx):
     assert np.abs(outs[1] - outs[3]).max() < 1e-13
     with pytest.raises(lm.ArgumentError):
         lm.DeviceHam.from_csc(ctx, Ho, 1, coords=l.coords[:5])
+
+
+# ------------------------------------------------------------------------------ register-tiled stencil kernel
+def _stencil_info(dev):
+    lib = _lib.load()
+    i, rc, sw, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+    lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
+    _lib.check(lib.lm_dbg_stencil_info(dev.handle, C.byref(i), C.byref(rc), C.byref(sw), C.byref(m)))
+    return i.value, rc.value, sw.value, m.value
+
+
+STENCIL_CASES = {
+    # name: (device Hamiltonian, oracle Hamiltonian, expected compiled pattern id)
+    "square_nn": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(23, 17), field=lm.LandauGauge(0.07)),
+                  lambda: OP.tightbinding_hamiltonian(L.square_lattice(23, 17), field=F.LandauGauge(0.07)), 0),
+    "square_nnn": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(9, 21), t1=1, t2=0.3, field=lm.SymmetricGauge(0.05)),
+                   lambda: OP.tightbinding_hamiltonian(L.square_lattice(9, 21), t1=1, t2=0.3, field=F.SymmetricGauge(0.05)), 1),
+    "square_torus": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(8, 8, boundaries=[("axis1", True), ("axis2", True)]), field=lm.LandauGauge(0.125)),
+                     lambda: OP.tightbinding_hamiltonian(L.square_lattice(8, 8, periodic=(1, 2)), field=F.LandauGauge(0.125)), 0),
+    "square_3x3_torus": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(3, 3, boundaries=[("axis1", True), ("axis2", True)])),
+                         lambda: OP.tightbinding_hamiltonian(L.square_lattice(3, 3, periodic=(1, 2))), 0),
+    "honeycomb_nn": (lambda: lm.tightbinding_hamiltonian(lm.HoneycombLattice(7, 12), field=lm.LandauGauge(0.03)),
+                     lambda: OP.tightbinding_hamiltonian(L.honeycomb_lattice(7, 12), field=F.LandauGauge(0.03)), 2),
+    "qwz_pbc": (lambda: lm.qwz(lm.SquareLattice(14, 15, boundaries=[("axis1", True)]), field=lm.LandauGauge(0.5)),
+                lambda: OP.qwz(L.square_lattice(14, 15, periodic=(1,)), field=F.LandauGauge(0.5)), 3),
+    "haldane": (lambda: lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1, field=lm.SymmetricGauge(0.03)),
+                lambda: OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1, field=F.SymmetricGauge(0.03)), 4),
+    "haldane_torus": (lambda: lm.haldane(lm.HoneycombLattice(9, 16, boundaries=[("axis1", True), ("axis2", True)]), 1.0, 0.2, 0.1),
+                      lambda: OP.haldane(L.honeycomb_lattice(9, 16, periodic=(1, 2)), 1.0, 0.2, 0.1), 4),
+}
+
+
+@pytest.mark.parametrize("case", sorted(STENCIL_CASES))
+def test_stencil_kernel_matches_oracle(ctx, case):
+    """The register-tiled stencil kernel (default for unfiltered Bravais lattices, M >= 32) against
+    the oracle matrix: open / periodic boundaries, ragged patch edges, ragged column chunks, every
+    epilogue (plain SpMM, product-form factor, Horner, Clenshaw) through the propagators."""
+    mk_dev, mk_or, want_id = STENCIL_CASES[case]
+    Hd, Ho = mk_dev(), mk_or()
+    dev = Hd.device(ctx)
+    sid, rc, sw, mask = _stencil_info(dev)
+    assert sid == want_id, (case, sid, hex(mask))
+    lib = _lib.load()
+    N = Ho.shape[0]
+    for M in (32, 33, 40, 64, 100, 131):
+        X = _rand_block(N, M, seed=M, orth=False)
+        x = lm.DeviceState.from_psi(X, ctx=ctx)
+        y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+        n0 = ctx.launch_count()
+        _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+        assert ctx.launch_count() - n0 >= 1
+        assert _relerr(y.download(), Ho @ X) < 1e-14, (case, M)
+    X = _rand_block(N, 40, seed=5) if N >= 40 else _rand_block(N, 40, seed=5, orth=False)
+    want = EV.exact_propagator(Ho, 0.3) @ X
+    for method in ("taylor", "taylor_horner", "chebyshev", "chebyshev_clenshaw"):
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx)
+        sol.update_solver(Hd, 0.3)
+        sol.step(st)
+        assert _relerr(st.download(), want) < 2e-13, (case, method)
+
+
+def test_stencil_not_used_for_filtered_or_long_range_lattices(ctx):
+    """Patterns the stencil view cannot express keep the ELL kernels (and stay correct)."""
+    # third-neighbour hops couple cells two apart
+    Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(12, 12), t1=1, t2=0.2, t3=0.1)
+    Ho = OP.tightbinding_hamiltonian(L.square_lattice(12, 12), t1=1, t2=0.2, t3=0.1)
+    dev = Hd.device(ctx)
+    assert _stencil_info(dev)[0] == -1
+    X = _rand_block(144, 48, orth=False)
+    x = lm.DeviceState.from_psi(X, ctx=ctx)
+    y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+    _lib.check(_lib.load().lm_spmm_state(dev.handle, x.handle, y.handle))
+    assert _relerr(y.download(), Ho @ X) < 1e-14
+    # a raw CSC Hamiltonian declared on a lattice it does not live on
+    with pytest.raises(lm.ArgumentError):
+        lm.DeviceHam.from_csc(ctx, Ho, 1, lattice_dims=(7, 5))
+    # a raw CSC Hamiltonian with the right dims gets the stencil view
+    Hn = OP.tightbinding_hamiltonian(L.square_lattice(12, 12), field=F.LandauGauge(0.1))
+    dev2 = lm.DeviceHam.from_csc(ctx, Hn, 1, lattice_dims=(12, 12))
+    assert _stencil_info(dev2)[0] == 0
+    Y = np.zeros((144, 48), complex, order="F")
+    Xf = np.asfortranarray(X)
+    _lib.check(_lib.load().lm_spmm(dev2.handle, _lib.ptr(Xf), _lib.ptr(Y), 144, 48))
+    assert _relerr(Y, Hn @ X) < 1e-14
+
+
+def test_stencil_values_follow_field_updates_under_graph_replay(ctx):
+    """The slot-ordered value copy is refreshed before a step graph is replayed: a time-dependent
+    field must act on every step even when the first step graph was captured with fresh values."""
+    lat, lo = lm.SquareLattice(12, 10), L.square_lattice(12, 10)
+    X = _rand_block(240, 36, seed=9)
+    st = lm.DeviceState.from_psi(X, ctx=ctx, n_int=2)
+    y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx, n_int=2)
+    sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+    want = X.copy()
+    for k in range(4):
+        B = 0.05 + 0.1 * k
+        Hd = lm.qwz(lat, field=lm.LandauGauge(B))
+        sol.update_solver(Hd, 0.2)
+        if k == 0:      # eager SpMM first: the value copy is fresh when the step graph is captured
+            _lib.check(_lib.load().lm_spmm_state(sol.dev.handle, st.handle, y.handle))
+        sol.step(st)
+        want = EV.exact_propagator(OP.qwz(lo, field=F.LandauGauge(B)), 0.2) @ want
+    assert _relerr(st.download(), want) < 1e-12
+
+
+def test_stencil_complex64(ctx64):
+    for mk_dev, mk_or in ((lambda: lm.haldane(lm.HoneycombLattice(9, 10), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.04)),
+                           lambda: OP.haldane(L.honeycomb_lattice(9, 10), 1.0, 0.2, 0.1, field=F.LandauGauge(0.04))),
+                          (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(11, 7), field=lm.LandauGauge(0.04)),
+                           lambda: OP.tightbinding_hamiltonian(L.square_lattice(11, 7), field=F.LandauGauge(0.04)))):
+        Hd, Ho = mk_dev(), mk_or()
+        dev = Hd.device(ctx64)
+        assert _stencil_info(dev)[0] >= 0
+        N = Ho.shape[0]
+        for M in (32, 50, 64, 130):
+            X = _rand_block(N, M, seed=M, orth=False)
+            x = lm.DeviceState.from_psi(X, ctx=ctx64)
+            y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx64)
+            _lib.check(_lib.load().lm_spmm_state(dev.handle, x.handle, y.handle))
+            assert _relerr(y.download(), Ho @ X) < 2e-6
 
 
 # ------------------------------------------------------------------------------ device Peierls phases

@@ -39,4 +39,25 @@ elif which == "dense":
         sol.update_solver(H, 0.1)
         sol.step(st)
     print("tr P =", lm.localdensity(st).values.sum())
+elif which == "stencil":
+    # one plain SpMM launch per register-tile variant of the stencil kernel (Haldane 500 x 500)
+    import ctypes as C
+    from importlib import import_module
+    _lib = import_module("lm_b200._lib")
+    lib = _lib.load()
+    variants = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]
+    M = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    kind = sys.argv[4] if len(sys.argv) > 4 else "haldane"
+    H = lm.haldane(lm.HoneycombLattice(500, 500), 1.0, 0.2, 0.1) if kind == "haldane" else lm.qwz(lm.SquareLattice(300, 300), field=lm.LandauGauge(0.01))
+    dev = H.device(ctx)
+    blk = (rng.standard_normal((dev.N, 32)) + 1j * rng.standard_normal((dev.N, 32))) / 30
+    x = lm.DeviceState.from_psi(np.asfortranarray(np.tile(blk, (1, M // 32))), ctx=ctx, shard=False)
+    y = x.copy()
+    lib.lm_dbg_set_apply_path.argtypes = [C.c_int32]
+    lib.lm_dbg_set_stencil_variant.argtypes = [C.c_int32]
+    for v in variants:
+        lib.lm_dbg_set_apply_path(5 if v >= 0 else 2)
+        lib.lm_dbg_set_stencil_variant(v)
+        _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+    ctx.synchronize()
 ctx.synchronize()
