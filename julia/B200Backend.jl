@@ -45,7 +45,27 @@ mutable struct DeviceHam
     colptr::Vector{Int64}
     rowval::Vector{Int64}
 end
-function DeviceHam(ctx::Context, mat::SparseMatrixCSC{ComplexF64,Int64}, n_int::Integer; coords = nothing)
+# (n1, n2) if `l` is an UNFILTERED 2-D Bravais lattice spanned over n1 x n2 unit cells - its rows
+# are then cell-major (src/lattices/bravais/lattice.jl:101-111: last lattice axis fastest, basis
+# index innermost, unitcell.jl:126-132), which is what lm_ham_set_lattice_dims declares and what
+# the register-tiled stencil kernel needs.  `nothing` for any other lattice (ELL kernels).
+function lattice_dims(l)
+    l = LatticeModels.stripmeta(l)
+    l isa LatticeModels.BravaisLattice || return nothing
+    isempty(l.pointers) && return nothing
+    length(first(l.pointers).latcoords) == 2 || return nothing
+    lo1 = minimum(p -> p.latcoords[1], l.pointers); hi1 = maximum(p -> p.latcoords[1], l.pointers)
+    lo2 = minimum(p -> p.latcoords[2], l.pointers); hi2 = maximum(p -> p.latcoords[2], l.pointers)
+    n1, n2, nb = hi1 - lo1 + 1, hi2 - lo2 + 1, length(l.unitcell)
+    length(l.pointers) == n1 * n2 * nb ? (n1, n2) : nothing
+end
+function set_lattice_dims!(dev, dims)
+    dims === nothing && return dev
+    check(ccall((:lm_ham_set_lattice_dims, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), dev.handle, dims[1], dims[2]))
+    dev
+end
+
+function DeviceHam(ctx::Context, mat::SparseMatrixCSC{ComplexF64,Int64}, n_int::Integer; coords = nothing, dims = nothing)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:lm_ham_create_csc, LIB), Int32,
                 (Ptr{Cvoid}, Int64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Int32, Ref{Ptr{Cvoid}}),
@@ -54,6 +74,7 @@ function DeviceHam(ctx::Context, mat::SparseMatrixCSC{ComplexF64,Int64}, n_int::
     if coords !== nothing       # 2 x n_sites Float64 matrix of site coordinates (site.coords[1:2])
         check(ccall((:lm_ham_set_site_coords, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), dev.handle, coords))
     end
+    set_lattice_dims!(dev, dims)                         # lattice_dims(lattice(H)) of the caller's Hamiltonian
     finalizer(d -> ccall((:lm_ham_destroy, LIB), Int32, (Ptr{Cvoid},), d.handle), dev)
 end
 samepattern(d::DeviceHam, m::SparseMatrixCSC) = d.colptr == m.colptr && d.rowval == m.rowval
@@ -98,15 +119,18 @@ mutable struct B200Exp <: EvolutionSolver
     method::Int32
     n_int::Int
     coords::Any
+    dims::Any                     # (n1, n2) of an unfiltered Bravais lattice, or nothing
 end
 # B200Exp(; kw...) without a Hamiltonian comes for free via IncompleteSolver (src/evolution.jl:219-231)
 function B200Exp(ham; tol = 1e-12, method = 0, precision = :c128, ctx = default_context(), coords = nothing)
     n_int = ham isa LatticeModels.Hamiltonian ? internal_length(ham) : 1
-    if coords === nothing && ham isa LatticeModels.Hamiltonian
+    dims = nothing
+    if ham isa LatticeModels.Hamiltonian
         l = lattice(ham)
-        coords = Float64[site.coords[k] for k in 1:2, site in l]
+        coords === nothing && (coords = Float64[site.coords[k] for k in 1:2, site in l])
+        dims = lattice_dims(l)
     end
-    B200Exp(ctx, nothing, nothing, 0.0, tol, Int32(method), n_int, coords)
+    B200Exp(ctx, nothing, nothing, 0.0, tol, Int32(method), n_int, coords, dims)
 end
 
 function update_solver!(s::B200Exp, mat::SparseMatrixCSC, dt, force = false)      # src/evolution.jl:83-92
@@ -115,7 +139,7 @@ function update_solver!(s::B200Exp, mat::SparseMatrixCSC, dt, force = false)    
     if s.dev !== nothing && samepattern(s.dev, mat)
         check(ccall((:lm_ham_update_values, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}), s.dev.handle, mat.nzval))
     else
-        s.dev = DeviceHam(s.ctx, mat, s.n_int; coords = s.coords)
+        s.dev = DeviceHam(s.ctx, mat, s.n_int; coords = s.coords, dims = s.dims)
     end
     s.mat = mat
     return
@@ -185,6 +209,7 @@ function B200Hamiltonian(ctx::Context, l, n_int::Integer, src::Vector{Int32}, ds
     dev = DeviceHam(h[], Int64[], Int64[])
     coords = Float64[site.coords[k] for k in 1:2, site in l]
     check(ccall((:lm_ham_set_site_coords, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), dev.handle, coords))
+    set_lattice_dims!(dev, lattice_dims(l))
     p0 = fieldparams(0.0)
     check(ccall((:lm_ham_set_fields, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}),
                 dev.handle, length(kinds), kinds, p0))

@@ -90,6 +90,7 @@ struct lm_ctx {
     void* h_pinned = nullptr; size_t pinned_bytes = 0;   // staging for small D2H/H2D
     void* d_stage = nullptr; size_t stage_bytes = 0;      // staging for layout changes
     int l2_bytes = 0;
+    int sm_count = 0;
     struct lm_ham* dens_helper = nullptr;                 // pattern-less ham owning density scratch
     // NVLink peer-memory exchange for the per-frame [rho | J] reduction
     void* p2p_local = nullptr; size_t p2p_bytes = 0; long long p2p_cap = 0; bool p2p_ready = false;
@@ -150,6 +151,7 @@ struct lm_ham {
     int lat_n1 = 0, lat_n2 = 0;
     int st_id = -1; int st_rc = 0; int st_sw = 0; unsigned long long st_mask = 0;
     int* d_st_src = nullptr; void* d_svals = nullptr; long long svals_version = -1;
+    int* d_st_out = nullptr; int st_nf = 0;          // (row, forward slot) -> ELL entry of the pair (k_observe_stencil)
 };
 
 struct lm_state {
@@ -205,6 +207,7 @@ extern "C" int32_t lm_ctx_create(int32_t device, int32_t precision, void* stream
     else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device));
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = c;
     return LM_OK;
 }
@@ -301,7 +304,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_st_out};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -590,6 +593,7 @@ static int ham_build_stencil(lm_ham* h) {
     CK(cudaStreamSynchronize(c->stream));
     if (h->d_st_src) { cudaFree(h->d_st_src); h->d_st_src = nullptr; }
     if (h->d_svals) { cudaFree(h->d_svals); h->d_svals = nullptr; }
+    if (h->d_st_out) { cudaFree(h->d_st_out); h->d_st_out = nullptr; }
     h->st_id = -1; h->svals_version = -1; h->layout_epoch++;
     const long long n1 = h->lat_n1, n2 = h->lat_n2, N = h->N; const int W = h->W;
     if (n1 < 3 || n2 < 3 || N % (n1 * n2) != 0) return LM_OK;
@@ -643,6 +647,34 @@ static int ham_build_stencil(lm_ham* h) {
             q = (int)(i * W + k);
         }
     }
+    // observables: every bond has one forward direction (offset (0,+1), (+1,*), or a later row of the
+    // same cell); map (row, forward slot) to the ELL entry flagged `upper` that carries the pair -
+    // the entry itself, or (encoded -2 - e) the reverse entry when the neighbour wraps around
+    int P1o, P2o, NF;
+    stencil_obs_shape(id, &P1o, &P2o, &NF);
+    std::vector<int> outm((size_t)N * NF, -1);
+    for (long long i = 0; i < N; ++i) {
+        const int a = (int)(i % rc);
+        int f = 0;
+        for (int o = 4; o < 9; ++o) for (int b = 0; b < rc; ++b) {
+            const bool set = (d.mask >> (o * rc * rc + a * rc + b)) & 1ull;
+            if (!set || !(o > 4 || b > a)) continue;
+            const int e = src[(size_t)i * SW + slot[o][a][b]];
+            if (e >= 0) {
+                const long long j = h->h_cols[e];
+                if (h->h_upper[e]) outm[(size_t)i * NF + f] = e;
+                else if (j / h->n_int != i / h->n_int) {
+                    int e2 = -1;
+                    for (int k = 0; k < W; ++k) if (h->h_cols[j * W + k] == i && h->h_upper[j * W + k]) { e2 = (int)(j * W + k); break; }
+                    if (e2 >= 0) outm[(size_t)i * NF + f] = -2 - e2;
+                }
+            }
+            ++f;
+        }
+    }
+    CK(cudaMalloc(&h->d_st_out, sizeof(int) * outm.size()));
+    CK(cudaMemcpy(h->d_st_out, outm.data(), sizeof(int) * outm.size(), cudaMemcpyHostToDevice));
+    h->st_nf = NF;
     CK(cudaMalloc(&h->d_st_src, sizeof(int) * src.size()));
     // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes
     CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 256));
@@ -1962,8 +1994,42 @@ static int observe_tiled(lm_ham* h, lm_state* s) {
     return LM_OK;
 }
 
+// fused observables on the stencil view: CTA = (patch, group of column chunks), two-stage TMA pipeline
+static int observe_stencil(lm_ham* h, lm_state* s) {
+    lm_ctx* c = h->ctx;
+    CK(cudaMemsetAsync(h->d_dens, 0, sizeof(double) * (size_t)h->N, c->stream));
+    CK(cudaMemsetAsync(h->d_G, 0, sizeof(double2) * (size_t)h->N * h->W, c->stream));
+    int P1, P2, NF;
+    stencil_obs_shape(h->st_id, &P1, &P2, &NF);
+    StencilObsArgs a;
+    a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.M = s->M; a.ld = s->ld; a.x = s->d_x; a.w = s->d_w;
+    a.out = h->d_st_out; a.dens = h->d_dens; a.G = h->d_G;
+    const int ec = (c->precision == LM_C128) ? 1 : 2;
+    REQUIRE(s->ld % ec == 0, "observe_stencil: odd leading dimension in complex64 mode");
+    const long long np1 = (h->lat_n1 + P1 - 1) / P1, np2 = (h->lat_n2 + P2 - 1) / P2;
+    a.np2 = (int)np2;
+    const long long nchunks = (s->ld / ec + 31) / 32;
+    // enough CTAs to fill the machine a few times over, groups as long as that allows (the
+    // cross-column reduction and the atomics are paid once per group)
+    static const int cpg_env = env_int("LM_OBS_CPG", 0);
+    const long long want_ctas = 8LL * (c->sm_count > 0 ? c->sm_count : 148);
+    long long ngroups = std::max<long long>(1, std::min<long long>(nchunks, (want_ctas + np1 * np2 - 1) / (np1 * np2)));
+    long long cpg = (nchunks + ngroups - 1) / ngroups;
+    if (cpg_env > 0) cpg = cpg_env;
+    ngroups = (nchunks + cpg - 1) / cpg;
+    REQUIRE(np1 * np2 * ngroups < 2147483647LL, "observe_stencil: grid too large");
+    a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg; a.nchunks = (unsigned)nchunks;
+    const int st = stencil_observe(h->st_id, c->precision != LM_C128, a, (unsigned)(np1 * np2 * ngroups), c->stream);
+    if (st != 0) return fail(LM_ERR_CUDA, "observe_stencil: launch failed");
+    c->launches++;
+    CK(cudaGetLastError());
+    return LM_OK;
+}
+
 template <typename T>
 static int observe(lm_ham* h, lm_state* s, bool want_j) {
+    static const int obs_stencil_env = env_int("LM_OBS_STENCIL", 1);
+    if (h->st_id >= 0 && h->d_st_out && want_j && s->M >= 32 && obs_stencil_env && g_apply_path_override < 0) return observe_stencil(h, s);
     static const int obs_tiled_env = env_int("LM_OBS_TILED", -1);
     if (h->obs_tiled && want_j && s->M >= 16 && obs_tiled_env != 0) return observe_tiled<T>(h, s);
     // ELL slots are processed WB at a time; a density-only pass has no active slot (k0 = W)

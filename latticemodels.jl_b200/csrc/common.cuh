@@ -82,6 +82,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "LM_DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -69,4 +69,28 @@ int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a
     }
 }
 
+
+#define LM_ST_DECL(i) int stencil_observe_##i(bool, const StencilObsArgs&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
+LM_ST_DECL(0) LM_ST_DECL(1) LM_ST_DECL(2) LM_ST_DECL(3) LM_ST_DECL(4)
+#undef LM_ST_DECL
+int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
+    switch (id) {
+    case 0: return stencil_observe_0(c64, a, grid, s);
+    case 1: return stencil_observe_1(c64, a, grid, s);
+    case 2: return stencil_observe_2(c64, a, grid, s);
+    case 3: return stencil_observe_3(c64, a, grid, s);
+    case 4: return stencil_observe_4(c64, a, grid, s);
+    default: return -1;
+    }
+}
+void stencil_obs_shape(int id, int* P1, int* P2, int* nf) {
+    switch (id) {
+    case 0: stencil_obs_shape_0(P1, P2, nf); break;
+    case 1: stencil_obs_shape_1(P1, P2, nf); break;
+    case 2: stencil_obs_shape_2(P1, P2, nf); break;
+    case 3: stencil_obs_shape_3(P1, P2, nf); break;
+    default: stencil_obs_shape_4(P1, P2, nf); break;
+    }
+}
+
 }  // namespace lm

@@ -335,6 +335,223 @@ k_apply_stencil_tma(const StencilArgs a) {
         }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_observe_stencil: fused localdensity + bond correlators on the same cell-major lattices.
+//   dens[i] = sum_c w_c |x[i,c]|^2 ,   G[e] = sum_c w_c x[j,c] conj(x[i,c])  for the upper entry e = (i -> j)
+// Every bond has exactly one FORWARD direction (cell offset (0,+1), (+1,*), or a later row of the
+// same cell), so a thread that owns a T1 x T2 block of cells of ONE column needs the own rows and
+// the forward halo only.  A CTA owns a patch and a GROUP of column chunks: it streams the chunks
+// through a multi-stage TMA pipeline (chunks k+1, k+2 land while chunk k is reduced) and keeps its partial
+// sums in registers over the whole group - the cross-lane (= cross-column) reduction and the
+// atomics run once per group, not once per chunk.  `out` maps (row, forward slot) to the ELL
+// entry that carries the pair: e >= 0 as is, e <= -2 the conjugate goes to entry -2 - e (the
+// forward neighbour sits across a periodic boundary), -1 no such bond on this row.
+// ------------------------------------------------------------------------------------------
+template <int RC> __host__ __device__ constexpr bool st_is_fwd(st_mask_t m, int o, int a, int b) {
+    return st_bit<RC>(m, o, a, b) && (o > 4 || (o == 4 && b > a));
+}
+template <int RC> __host__ __device__ constexpr int st_fslot(st_mask_t m, int o, int a, int b) {
+    int s = 0;
+    for (int oo = 4; oo < 9; ++oo)
+        for (int bb = 0; bb < RC; ++bb) {
+            if (oo == o && bb == b) return s;
+            if (st_is_fwd<RC>(m, oo, a, bb)) ++s;
+        }
+    return s;
+}
+template <int RC> __host__ __device__ constexpr int st_nfwd(st_mask_t m) {
+    int w = 1;
+    for (int a = 0; a < RC; ++a) {
+        int s = 0;
+        for (int o = 4; o < 9; ++o) for (int b = 0; b < RC; ++b) if (st_is_fwd<RC>(m, o, a, b)) ++s;
+        if (s > w) w = s;
+    }
+    return w;
+}
+// is in row b of staged cell (l1, u2) - l1 in [0, T1], u2 in [0, T2 + 2) - a forward neighbour of the tile?
+template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_fwd_needed(st_mask_t m, int l1, int u2, int b) {
+    for (int o = 4; o < 9; ++o)
+        for (int a = 0; a < RC; ++a)
+            if (st_is_fwd<RC>(m, o, a, b)) {
+                const int v1 = l1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
+                if (v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) return true;
+            }
+    return false;
+}
+
+struct StencilObsArgs {
+    int n1, n2, np2;
+    long long M, ld;                // logical columns, leading dimension (complex elements)
+    const void* x; const double* w; // w may be null (all ones)
+    const int* out;                 // [N][NF]
+    double* dens; double2* G;
+    unsigned ngroups, cpg, nchunks; // column groups per patch, chunks per group, chunks in total
+};
+
+template <typename T> struct st_unpack;
+template <> struct st_unpack<double> {
+    static __device__ __forceinline__ void get(const double2& e, int, double& re, double& im) { re = e.x; im = e.y; }
+};
+template <> struct st_unpack<float> {
+    static __device__ __forceinline__ void get(const float4& e, int k, double& re, double& im) {
+        re = k ? (double)e.z : (double)e.x; im = k ? (double)e.w : (double)e.y;
+    }
+};
+__device__ __forceinline__ double st_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int ST_OBS_STAGES = 3;      // TMA pipeline depth: ~2 staged chunks in flight per CTA cover the HBM latency
+template <typename T, int RC, int T1, int T2, int W1, int W2>
+__host__ __device__ constexpr size_t st_obs_smem() { return (size_t)ST_OBS_STAGES * (W1 * T1 + 1) * (W2 * T2 + 2) * RC * 32 * 16; }
+
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
+__global__ void __launch_bounds__(32 * W1 * W2, 65536 / (128 * 32 * W1 * W2) < 1 ? 1 : 65536 / (128 * 32 * W1 * W2))
+k_observe_stencil(const StencilObsArgs a) {
+    constexpr int NS = ST_OBS_STAGES;
+    using E = typename pack<T>::E;
+    constexpr int EC = pack<T>::EC;
+    constexpr int NT = 32 * W1 * W2, P1 = W1 * T1, P2 = W2 * T2;
+    constexpr int L2 = P2 + 2;
+    constexpr int HR = (P1 + 1) * L2 * RC;                  // staged rows: own + forward cell lines
+    constexpr int CE = 32;
+    constexpr int NF = st_nfwd<RC>(MASK);
+    extern __shared__ __align__(128) unsigned char lm_smem[];
+    E* sx = reinterpret_cast<E*>(lm_smem);                  // [NS][HR][CE]
+    __shared__ __align__(8) unsigned long long bar[NS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned patch = blockIdx.x / a.ngroups, group = blockIdx.x - patch * a.ngroups;
+    const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
+    const int o1 = pj1 * P1, o2 = pj2 * P2;
+    const long long lde = a.ld / EC;
+    const E* __restrict__ x = (const E*)a.x;
+    const unsigned ch0 = group * a.cpg;
+    const unsigned ch1 = (ch0 + a.cpg) < a.nchunks ? (ch0 + a.cpg) : a.nchunks;
+    if (ch0 >= ch1) return;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) mbar_init(&bar[q], 1);
+    }
+    __syncthreads();
+    auto issue = [&](unsigned ch, int stage) {              // arm the stage barrier, one bulk copy per staged row
+        const long long c0 = (long long)ch * CE;
+        const int cw = (int)((lde - c0) < CE ? (lde - c0) : CE);
+        if (tid == 0) mbar_arrive_expect_tx(&bar[stage], (unsigned)(HR * cw * (int)sizeof(E)));
+        // rows dealt round-robin over the WARPS (row = warp + NW * lane): every warp issues the same
+        // few copies, none of them reaches the closing barrier late
+        for (int r = warp + (NT / 32) * lane; r < HR; r += NT) {
+            const int l1 = r / (L2 * RC), rem = r - l1 * (L2 * RC), u2 = rem / RC, b = rem - u2 * RC;
+            const long long row = ((long long)st_wrap(o1 + l1, a.n1) * a.n2 + st_wrap(o2 + u2 - 1, a.n2)) * RC + b;
+            tma_bulk_g2s(sx + ((size_t)stage * HR + r) * CE, x + row * lde + c0, (unsigned)(cw * (int)sizeof(E)), &bar[stage]);
+        }
+    };
+
+    const int w1 = warp / W2, w2 = warp % W2;
+    const int q1 = o1 + w1 * T1, q2 = o2 + w2 * T2;
+    const bool active = q1 < a.n1 && q2 < a.n2;
+    double dens[T1][T2][RC];
+    double gr[T1][T2][RC][NF], gi[T1][T2][RC][NF];
+#pragma unroll
+    for (int v1 = 0; v1 < T1; ++v1)
+#pragma unroll
+        for (int v2 = 0; v2 < T2; ++v2)
+#pragma unroll
+            for (int aa = 0; aa < RC; ++aa) {
+                dens[v1][v2][aa] = 0.0;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) { gr[v1][v2][aa][f] = 0.0; gi[v1][v2][aa][f] = 0.0; }
+            }
+
+#pragma unroll
+    for (int q = 0; q < NS - 1; ++q) if (ch0 + q < ch1) issue(ch0 + q, q);
+    for (unsigned ch = ch0; ch < ch1; ++ch) {
+        const int k = (int)(ch - ch0), stage = k % NS;
+        // the stage refilled here was read in iteration k - 1 and released by the barrier below
+        // (a warp-rotating producer with per-stage "empty" mbarriers instead of the CTA barrier was
+        // measured 1.6x slower on Haldane 500 x 500)
+        if (ch + (NS - 1) < ch1) issue(ch + (NS - 1), (k + NS - 1) % NS);
+        const long long c0 = (long long)ch * CE;
+        const bool lane_on = active && (c0 + lane) < lde;
+        double wl[EC];
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            const long long col = (c0 + lane) * EC + e;
+            wl[e] = (col < a.M) ? (a.w ? a.w[col] : 1.0) : 0.0;
+        }
+        mbar_wait(&bar[stage], (unsigned)((k / NS) & 1));
+        if (lane_on) {
+            const E* xb = sx + ((size_t)stage * HR + ((w1 * T1) * L2 + w2 * T2) * RC) * CE + lane;
+            double ar[T1][T2][RC][EC], ai[T1][T2][RC][EC];
+            st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
+                constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
+                const E xe = xb[((v1 * L2 + v2 + 1) * RC + aa) * CE];
+#pragma unroll
+                for (int e = 0; e < EC; ++e) {
+                    double re, im; st_unpack<T>::get(xe, e, re, im);
+                    ar[v1][v2][aa][e] = wl[e] * re; ai[v1][v2][aa][e] = wl[e] * im;
+                    dens[v1][v2][aa] = fma(ar[v1][v2][aa][e], re, dens[v1][v2][aa]);
+                    dens[v1][v2][aa] = fma(ai[v1][v2][aa][e], im, dens[v1][v2][aa]);
+                }
+            }); }); });
+            st_for<T1 + 1>([&](auto LL1) { st_for<T2 + 2>([&](auto U2) { st_for<RC>([&](auto B) {
+                constexpr int l1 = decltype(LL1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
+                if constexpr (st_fwd_needed<RC, T1, T2>(MASK, l1, u2, b)) {
+                    const E xe = xb[((l1 * L2 + u2) * RC + b) * CE];
+                    st_for<5>([&](auto OO) { st_for<RC>([&](auto A) {
+                        constexpr int o = decltype(OO)::value + 4, aa = decltype(A)::value;
+                        constexpr int v1 = l1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
+                        if constexpr (st_is_fwd<RC>(MASK, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
+                            constexpr int f = st_fslot<RC>(MASK, o, aa, b);
+#pragma unroll
+                            for (int e = 0; e < EC; ++e) {
+                                double re, im; st_unpack<T>::get(xe, e, re, im);
+                                // x_j * conj(x_i) * w
+                                gr[v1][v2][aa][f] = fma(re, ar[v1][v2][aa][e], gr[v1][v2][aa][f]);
+                                gr[v1][v2][aa][f] = fma(im, ai[v1][v2][aa][e], gr[v1][v2][aa][f]);
+                                gi[v1][v2][aa][f] = fma(im, ar[v1][v2][aa][e], gi[v1][v2][aa][f]);
+                                gi[v1][v2][aa][f] = fma(-re, ai[v1][v2][aa][e], gi[v1][v2][aa][f]);
+                            }
+                        }
+                    }); });
+                }
+            }); }); });
+        }
+        __syncthreads();                                    // every warp is done with `stage`
+    }
+    if (!active) return;
+    // fold the 32 columns of the lane dimension, one atomic per sum and column group
+    int nacc = 0;
+#pragma unroll
+    for (int v1 = 0; v1 < T1; ++v1)
+#pragma unroll
+        for (int v2 = 0; v2 < T2; ++v2) {
+            const bool valid = (q1 + v1) < a.n1 && (q2 + v2) < a.n2;
+#pragma unroll
+            for (int aa = 0; aa < RC; ++aa) {
+                const long long row = ((long long)(q1 + v1) * a.n2 + (q2 + v2)) * RC + aa;
+                const double d = st_warp_sum(dens[v1][v2][aa]);
+                if (valid && lane == (nacc & 31)) atomicAdd(a.dens + row, d);
+                ++nacc;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double sr = st_warp_sum(gr[v1][v2][aa][f]), si = st_warp_sum(gi[v1][v2][aa][f]);
+                    if (valid && lane == (nacc & 31)) {
+                        const int oe = a.out[row * NF + f];
+                        if (oe != -1) {
+                            double* g = reinterpret_cast<double*>(a.G + (oe >= 0 ? oe : -2 - oe));
+                            atomicAdd(g, sr); atomicAdd(g + 1, oe >= 0 ? si : -si);
+                        }
+                    }
+                    ++nacc;
+                }
+            }
+        }
+}
+
 // ---- compiled patterns (stencil.cu registry; one translation unit per pattern) ----
 #define LM_ST_MASK0 0xbaull
 #define LM_ST_MASK1 0x1ffull
@@ -353,5 +570,8 @@ int stencil_num_variants();
 void stencil_variant_shape(int variant, int* P1, int* P2, int* cpt, int* staged);
 // launches; returns 0 on success, -1 if (id, variant, mode) is not compiled, -2 on a CUDA error
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s);
+// fused observables: patch size / forward-slot count of the compiled kernel, and its launch
+void stencil_obs_shape(int id, int* P1, int* P2, int* nf);
+int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s);
 
 }  // namespace lm

@@ -68,4 +68,38 @@ static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, dim
     }
 }
 
+
+// observables kernel shape per RC: T1 x T2 cells per thread, W1 x W2 warps per CTA
+template <int RC> struct ObsShape;
+template <> struct ObsShape<1> { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };   // 8 x 4 cells, 256 threads
+template <> struct ObsShape<2> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 x 4 cells, 256 threads
+
+template <typename T, int RC, st_mask_t MASK>
+static int launch_obs_t(const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
+    using S = ObsShape<RC>;
+    constexpr size_t smem = st_obs_smem<T, RC, S::T1, S::T2, S::W1, S::W2>();
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+        configured = true;
+    }
+    k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2><<<grid, 32 * S::W1 * S::W2, smem, s>>>(a);
+    return 0;
+}
+template <int RC, st_mask_t MASK>
+static int launch_obs(bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
+    if (!c64) return launch_obs_t<double, RC, MASK>(a, grid, s);
+#ifndef LM_STENCIL_NOC64
+    return launch_obs_t<float, RC, MASK>(a, grid, s);
+#else
+    return -1;
+#endif
+}
+template <int RC, st_mask_t MASK>
+static void obs_shape(int* P1, int* P2, int* nf) {
+    using S = ObsShape<RC>;
+    *P1 = S::W1 * S::T1; *P2 = S::W2 * S::T2; *nf = st_nfwd<RC>(MASK);
+}
+
 }  // namespace lm

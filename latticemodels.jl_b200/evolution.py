@@ -46,13 +46,14 @@ class B200Exp(EvolutionSolver):
     pins its solvers to the exact exponential at atol 1e-10, test/test_timedeps.jl:55-67)."""
 
     def __init__(self, ham=None, tol=1e-12, method="auto", precision="c128", ctx=None, n_int=None, coords=None,
-                 refine_bounds=False):
+                 refine_bounds=False, lattice_dims=None):
         self.ctx = ctx or default_context(precision)
         self.tol, self.method = float(tol), _METHODS[method]
         self.dev = None
         self.dt = 0.0
         self.n_int = n_int
         self.coords = coords        # site coordinates for raw-matrix Hamiltonians (tile plan)
+        self.lattice_dims = lattice_dims   # (n1, n2) of an unfiltered Bravais lattice (stencil kernel)
         self.refine_bounds = refine_bounds   # opt-in Lanczos tightening of the spectral enclosure
         self._mat = None            # last raw matrix (identity check, src/evolution.jl:86-88)
         self._csc_dev = None
@@ -80,7 +81,7 @@ class B200Exp(EvolutionSolver):
                 np.array_equal(d.pattern[0], m.indptr) and np.array_equal(d.pattern[1], m.indices):
             d.update_values(m.data)             # same sparsity pattern: upload nzval only
         else:
-            d = DeviceHam.from_csc(self.ctx, m, self.n_int or 1, coords=self.coords)
+            d = DeviceHam.from_csc(self.ctx, m, self.n_int or 1, coords=self.coords, lattice_dims=self.lattice_dims)
         self._csc_dev, self._mat, self.dev = d, mat, d
 
     def step(self, state, cache=None):

@@ -255,6 +255,38 @@ def test_stencil_values_follow_field_updates_under_graph_replay(ctx):
     assert _relerr(st.download(), want) < 1e-12
 
 
+@pytest.mark.parametrize("case", ["square_torus", "square_nnn", "qwz_pbc", "honeycomb_nn", "haldane", "haldane_torus"])
+def test_stencil_observables_match_oracle(ctx, case):
+    """Fused localdensity + DensityCurrents on the stencil view (streamed column groups, forward
+    halo only, conjugate hand-off across periodic boundaries) against the oracle: every pair."""
+    mk_dev, mk_or, _ = STENCIL_CASES[case]
+    Hd, Ho = mk_dev(), mk_or()
+    n_int = Hd.n_int
+    N = Ho.shape[0]
+    lib = _lib.load()
+    for M in (32, 70, 200):
+        Psi = _rand_block(N, M, seed=M, orth=False) / np.sqrt(N)
+        w = np.random.default_rng(M).random(M)
+        st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, n_int=n_int)
+        I, J, V = lm.DensityCurrents(Hd, st).pair_values()
+        rho = lm.localdensity(st).values
+        P = (Psi * w) @ Psi.conj().T
+        assert _relerr(rho, np.real(np.diag(P)).reshape(-1, n_int).sum(1)) < 1e-13
+        Hdn = Ho.toarray()
+        want = np.zeros(len(I))
+        for q, (i, j) in enumerate(zip(I.tolist(), J.tolist())):       # 1-based site pairs, i < j
+            bi, bj = slice((i - 1) * n_int, i * n_int), slice((j - 1) * n_int, j * n_int)
+            want[q] = 2 * np.imag(np.sum(Hdn[bi, bj] * P[bj, bi].T))
+        assert np.abs(V - want).max() < 1e-13 * max(1.0, np.abs(want).max()), (case, M)
+        # ... and the ELL-plan kernel gives the same numbers
+        try:
+            lib.lm_dbg_set_apply_path(2)
+            V2 = lm.DensityCurrents(Hd, st).pair_values()[2]
+        finally:
+            lib.lm_dbg_set_apply_path(-1)
+        assert np.abs(V - V2).max() < 1e-13 * max(1.0, np.abs(want).max())
+
+
 def test_stencil_complex64(ctx64):
     for mk_dev, mk_or in ((lambda: lm.haldane(lm.HoneycombLattice(9, 10), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.04)),
                            lambda: OP.haldane(L.honeycomb_lattice(9, 10), 1.0, 0.2, 0.1, field=F.LandauGauge(0.04))),
@@ -270,6 +302,14 @@ def test_stencil_complex64(ctx64):
             y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx64)
             _lib.check(_lib.load().lm_spmm_state(dev.handle, x.handle, y.handle))
             assert _relerr(y.download(), Ho @ X) < 2e-6
+        Psi = _rand_block(N, 96, seed=2)
+        st = lm.DeviceState.from_psi(Psi, ctx=ctx64, n_int=Hd.n_int)
+        I, J, V = lm.DensityCurrents(Hd, st).pair_values()
+        P = Psi @ Psi.conj().T
+        Hdn = Ho.toarray()
+        want = np.array([2 * np.imag(Hdn[i - 1, j - 1] * P[j - 1, i - 1]) for i, j in zip(I.tolist(), J.tolist())])
+        assert np.abs(V - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+        assert _relerr(lm.localdensity(st).values, np.real(np.diag(P))) < 1e-5
 
 
 # ------------------------------------------------------------------------------ device Peierls phases

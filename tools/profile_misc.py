@@ -60,4 +60,23 @@ elif which == "stencil":
         lib.lm_dbg_set_stencil_variant(v)
         _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
     ctx.synchronize()
+elif which == "stencil_obs":
+    # fused observables on the stencil view (Haldane 500 x 500)
+    M = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    H = lm.haldane(lm.HoneycombLattice(500, 500), 1.0, 0.2, 0.1)
+    blk = (rng.standard_normal((H.structure.dim, 32)) + 1j * rng.standard_normal((H.structure.dim, 32))) / 30
+    st = lm.DeviceState.from_psi(np.asfortranarray(np.tile(blk, (1, M // 32))), ctx=ctx, shard=False)
+    for _ in range(2):
+        lm.DensityCurrents(H, st).pair_values()
+elif which == "stencil_step":
+    # two propagation steps (K product-form factors each, MODE 3) on the default kernel path
+    kind = sys.argv[2] if len(sys.argv) > 2 else "haldane"
+    M = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    H = lm.haldane(lm.HoneycombLattice(500, 500), 1.0, 0.2, 0.1) if kind == "haldane" else lm.qwz(lm.SquareLattice(300, 300), field=lm.LandauGauge(0.01))
+    blk = (rng.standard_normal((H.structure.dim, 32)) + 1j * rng.standard_normal((H.structure.dim, 32))) / 30
+    st = lm.DeviceState.from_psi(np.asfortranarray(np.tile(blk, (1, M // 32))), ctx=ctx, shard=False)
+    sol = lm.B200Exp(ctx=ctx)
+    for _ in range(2):
+        sol.update_solver(H, 0.1)
+        sol.step(st)
 ctx.synchronize()

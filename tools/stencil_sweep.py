@@ -7,6 +7,7 @@ kernels at the benchmark sizes.  One JSON line per measurement.
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import sys
@@ -120,7 +121,17 @@ def timing(ctx, cases, variants, reps):
                                   step_frac=K * bytes_spmm / ms_step / 1e6 / pk, steps_s=1e3 / ms_step)), flush=True)
         lib.lm_dbg_set_apply_path(-1)
         lib.lm_dbg_set_stencil_variant(-1)
-        del x, y, dev
+        # fused observables: stencil kernel (default) against the ELL-plan kernel
+        rho = np.zeros(N // dev.n_int)
+        J = np.zeros(max(1, len(dev.pairs()[0])))
+        for tag, path in (("obs_stencil", -1), ("obs_ell_plan", 2)):
+            lib.lm_dbg_set_apply_path(path)
+            ms = timeit(lambda: _lib.check(lib.lm_observables(dev.handle, x.handle, _lib.ptr(rho), _lib.ptr(J))), max(3, reps // 2))
+            print(json.dumps(dict(check="timing", kind=kind, n=n, M=M, kernel=tag, obs_ms=ms,
+                                  obs_frac=(N * M * 16.0) / ms / 1e6 / pk, rho_sum=float(rho.sum()), j_abs=float(np.abs(J).sum()))), flush=True)
+        lib.lm_dbg_set_apply_path(-1)
+        del x, y, dev, timeit
+        gc.collect()        # free the big device buffers now, not in the middle of the next case's timing
 
 
 def main():
