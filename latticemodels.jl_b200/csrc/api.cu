@@ -1427,6 +1427,16 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     REQUIRE(ld % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
     a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
     dim3 grid((unsigned)(np1 * np2 * cps), (unsigned)strips);
+    a.ngroups = 1; a.cpg = (unsigned)nchunks; a.npatch = (unsigned)(np1 * np2);
+    if (staged == 2) {
+        // streaming kernel: CTA = (patch, group of consecutive chunks), group-major CTA order
+        static const int cpg_env = env_int("LM_STREAM_CPG", 16);
+        const long long cpg = std::max<long long>(1, std::min<long long>(cpg_env, nchunks));
+        const long long ngroups = (nchunks + cpg - 1) / cpg;
+        REQUIRE(np1 * np2 * ngroups < 2147483647LL, "apply_stencil: grid too large");
+        a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg;
+        grid = dim3((unsigned)(np1 * np2 * ngroups), 1);
+    }
     const bool has_g = gamma != zc(0, 0);
     const int mode = (!z && !u && !has_g) ? 0 : ((z && !u && !has_g) ? 1 : ((!z && !u) ? 3 : 2));
     const int st = stencil_launch(h->st_id, variant, c->precision != LM_C128, mode, a, grid, c->stream);

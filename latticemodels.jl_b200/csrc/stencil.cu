@@ -46,6 +46,9 @@ static const Variant g_var[] = {
     {4, 4, 2, 2, 1, 1},   // 7: staged, 8 x 8 patch, 128 threads              (RC = 1 default)
     {4, 4, 2, 2, 1, 0},   // 8: direct, 8 x 8 patch                           (RC = 1)
     {4, 2, 2, 4, 2, 1},   // 9: staged, 8 x 8 patch, two lane elements        (RC = 1)
+    {2, 2, 4, 2, 1, 2},   // 10: streaming (3-stage TMA pipeline over a column group), 8 x 4 patch, 256 threads
+    {4, 2, 2, 2, 1, 2},   // 11: streaming, 8 x 4 patch, 128 threads
+    {4, 4, 2, 2, 1, 2},   // 12: streaming, 8 x 8 patch, 128 threads          (RC = 1 only)
 };
 int stencil_num_variants() { return (int)(sizeof(g_var) / sizeof(g_var[0])); }
 void stencil_variant_shape(int v, int* P1, int* P2, int* cpt, int* staged) {

@@ -69,6 +69,7 @@ struct StencilArgs {
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], g[2], beta[2], delta[2];   // y = alpha (H x + g x) + beta z + delta u
     unsigned cps, nchunks;
+    unsigned ngroups, cpg, npatch;  // streaming kernel: column groups per patch, chunks per group, patches
 };
 
 __device__ __forceinline__ void pscale(double2& r, const double2 s, const double2 v) { pzero(r); pfma(r, s, v); }
@@ -333,6 +334,134 @@ k_apply_stencil_tma(const StencilArgs a) {
                 }
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_apply_stencil_stream: streaming variant of the staged kernel.  A CTA owns a patch and a GROUP
+// of consecutive column chunks: the value rows of the patch are staged once, the haloed Psi rows
+// of chunk k + 2 are in flight (multi-stage TMA pipeline) while chunk k runs out of shared memory.
+// One CTA per SM; consecutive CTAs take consecutive patches of the SAME group, so the halo rows
+// neighbouring patches share are read by SMs that are at the same chunk at about the same time.
+// MEASURED SLOWER than the single-shot kernel above (Haldane 500 x 500: 0.56-0.60 vs 0.69-0.73 of
+// the roofline, profiles/stencil_variants_r1.jsonl variants 10-12): with one resident CTA the
+// per-chunk CTA barrier is exposed, while three single-shot CTAs per SM overlap each other's copies
+// and FMAs for free.  Built only with LM_STENCIL_EXPLORE.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_STREAM_STAGES = 3;
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
+__host__ __device__ constexpr size_t st_stream_smem() {
+    return (size_t)ST_STREAM_STAGES * (W1 * T1 + 2) * (W2 * T2 + 2) * RC * 32 * 16
+         + (size_t)(W1 * T1) * (W2 * T2) * RC * st_stride<T, RC, MASK>() * (2 * sizeof(T));
+}
+
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int MODE>
+__global__ void __launch_bounds__(32 * W1 * W2, 1)
+k_apply_stencil_stream(const StencilArgs a) {
+    using T2c = typename cx2<T>::type;
+    using E = typename pack<T>::E;
+    constexpr int EC = pack<T>::EC;
+    constexpr int NS = ST_STREAM_STAGES;
+    constexpr int NT = 32 * W1 * W2, P1 = W1 * T1, P2 = W2 * T2;
+    constexpr int HR = (P1 + 2) * (P2 + 2) * RC;
+    constexpr int CE = 32;
+    constexpr int SWP = st_stride<T, RC, MASK>();
+    extern __shared__ __align__(128) unsigned char lm_smem[];
+    E* sx = reinterpret_cast<E*>(lm_smem);                                          // [NS][HR][CE]
+    T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)NS * HR * CE * sizeof(E));    // [P1][P2 * RC * SWP]
+    __shared__ __align__(8) unsigned long long bar[NS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned group = blockIdx.x / a.npatch, patch = blockIdx.x - group * a.npatch;
+    const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
+    const int o1 = pj1 * P1, o2 = pj2 * P2;
+    const long long lde = a.ld / EC;
+    const unsigned ch0 = group * a.cpg;
+    const unsigned ch1 = (ch0 + a.cpg) < a.nchunks ? (ch0 + a.cpg) : a.nchunks;
+    if (ch0 >= ch1) return;
+    const int vl1 = (a.n1 - o1) < P1 ? (a.n1 - o1) : P1;
+    const int vl2 = (a.n2 - o2) < P2 ? (a.n2 - o2) : P2;
+    const unsigned hline = ((unsigned)(vl2 * RC * SWP * (int)sizeof(T2c)) + 15u) & ~15u;
+    const E* __restrict__ x = (const E*)a.x;
+    const T2c* __restrict__ sv = (const T2c*)a.svals;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) mbar_init(&bar[q], 1);
+    }
+    __syncthreads();
+    auto issue = [&](unsigned ch, int stage, bool with_values) {
+        const long long c0 = (long long)ch * CE;
+        const int cw = (int)((lde - c0) < CE ? (lde - c0) : CE);
+        if (tid == 0) mbar_arrive_expect_tx(&bar[stage], (unsigned)(HR * cw * (int)sizeof(E)) + (with_values ? (unsigned)vl1 * hline : 0u));
+        for (int r = warp + (NT / 32) * lane; r < HR; r += NT) {       // rows dealt round-robin over the warps
+            const int u1 = r / ((P2 + 2) * RC), rem = r - u1 * ((P2 + 2) * RC), u2 = rem / RC, b = rem - u2 * RC;
+            const long long row = ((long long)st_wrap(o1 + u1 - 1, a.n1) * a.n2 + st_wrap(o2 + u2 - 1, a.n2)) * RC + b;
+            tma_bulk_g2s(sx + ((size_t)stage * HR + r) * CE, x + row * lde + c0, (unsigned)(cw * (int)sizeof(E)), &bar[stage]);
+        }
+        if (with_values)
+            for (int l = NT - 1 - tid; l < vl1; l += NT)
+                tma_bulk_g2s(sh + l * (P2 * RC * SWP), sv + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWP), hline, &bar[stage]);
+    };
+
+    const int w1 = warp / W2, w2 = warp % W2;
+    const int q1 = o1 + w1 * T1, q2 = o2 + w2 * T2;
+    const bool active = q1 < a.n1 && q2 < a.n2;
+    const T2c* hb = sh + ((w1 * T1) * P2 + w2 * T2) * RC * SWP;
+    const T2c g = cmake<T2c>(a.g[0], a.g[1]);
+    const T2c alpha = cmake<T2c>(a.alpha[0], a.alpha[1]);
+    const T2c beta  = cmake<T2c>(a.beta[0],  a.beta[1]);
+    const T2c delta = cmake<T2c>(a.delta[0], a.delta[1]);
+    E* y = (E*)a.y;
+    const E* z = (const E*)a.z;
+    const E* u = (const E*)a.u;
+
+#pragma unroll
+    for (int q = 0; q < NS - 1; ++q) if (ch0 + q < ch1) issue(ch0 + q, q, q == 0);
+    for (unsigned ch = ch0; ch < ch1; ++ch) {
+        const int k = (int)(ch - ch0), stage = k % NS;
+        // the stage refilled here was read in iteration k - 1 and released by the barrier below
+        if (ch + (NS - 1) < ch1) issue(ch + (NS - 1), (k + NS - 1) % NS, false);
+        const long long cj = (long long)ch * CE + lane;
+        mbar_wait(&bar[stage], (unsigned)((k / NS) & 1));
+        if (active) {
+            const E* xb = sx + ((size_t)stage * HR + ((w1 * T1) * (P2 + 2) + w2 * T2) * RC) * CE + lane;
+            E acc[T1][T2][RC][1];
+#pragma unroll
+            for (int v1 = 0; v1 < T1; ++v1)
+#pragma unroll
+                for (int v2 = 0; v2 < T2; ++v2)
+#pragma unroll
+                    for (int aa = 0; aa < RC; ++aa) pzero(acc[v1][v2][aa][0]);
+            st_tile<T, RC, MASK, T1, T2, 1, (MODE == 2 || MODE == 3)>(acc, g,
+                [&](auto U1, auto U2, auto B, int) {
+                    return xb[((decltype(U1)::value * (P2 + 2) + decltype(U2)::value) * RC + decltype(B)::value) * CE];
+                },
+                [&](auto V1, auto V2, auto A, auto S) {
+                    return hb[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWP + decltype(S)::value];
+                });
+            if (cj < lde) {
+#pragma unroll
+                for (int v1 = 0; v1 < T1; ++v1)
+#pragma unroll
+                    for (int v2 = 0; v2 < T2; ++v2) {
+                        if (q1 + v1 >= a.n1 || q2 + v2 >= a.n2) continue;      // ragged last tile
+#pragma unroll
+                        for (int aa = 0; aa < RC; ++aa) {
+                            const long long e = (((long long)(q1 + v1) * a.n2 + (q2 + v2)) * RC + aa) * lde + cj;
+                            E res;
+                            pscale(res, alpha, acc[v1][v2][aa][0]);
+                            if (MODE == 1) pfma(res, beta, ld_stream(z + e));
+                            if (MODE == 2) {
+                                if (z) pfma(res, beta, ld_stream(z + e));
+                                if (u) pfma(res, delta, u[e]);
+                            }
+                            st_stream(y + e, res);
+                        }
+                    }
+            }
+        }
+        __syncthreads();                                    // every warp is done with `stage`
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -5,9 +5,20 @@
 
 namespace lm {
 
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, bool STAGED>
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, int STAGED>
 static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
-    if constexpr (!STAGED) {
+    if constexpr (STAGED == 2) {
+        static_assert(CPT == 1, "the streaming kernel handles one lane element per thread");
+        constexpr size_t smem = st_stream_smem<T, RC, MASK, T1, T2, W1, W2>();
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(k_apply_stencil_stream<T, RC, MASK, T1, T2, W1, W2, MODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+            configured = true;
+        }
+        k_apply_stencil_stream<T, RC, MASK, T1, T2, W1, W2, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
+        return 0;
+    } else if constexpr (STAGED == 0) {
         k_apply_stencil<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, 0, s>>>(a);
         return 0;
     } else {
@@ -23,7 +34,7 @@ static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
     }
 }
 // STAGED is a compile-time family switch so that only the requested family is instantiated
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, bool STAGED>
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
 static int launch_modes(int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
     switch (mode) {
     case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, grid, s);
@@ -35,7 +46,7 @@ static int launch_modes(int mode, const StencilArgs& a, dim3 grid, cudaStream_t 
     default: return -1;
     }
 }
-template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, bool STAGED>
+template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
 static int launch_prec(bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
     if (!c64) return launch_modes<double, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, grid, s);
 #ifndef LM_STENCIL_NOC64
@@ -50,18 +61,19 @@ template <int RC, st_mask_t MASK>
 static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
     if constexpr (RC == 1) {
         switch (variant) {
-            LM_ST_V(7, 4, 4, 2, 2, 1, true)
+            LM_ST_V(7, 4, 4, 2, 2, 1, 1)
 #ifdef LM_STENCIL_EXPLORE
-            LM_ST_V(8, 4, 4, 2, 2, 1, false) LM_ST_V(9, 4, 2, 2, 4, 2, true) LM_ST_V(3, 4, 2, 2, 4, 1, true)
+            LM_ST_V(8, 4, 4, 2, 2, 1, 0) LM_ST_V(9, 4, 2, 2, 4, 2, 1) LM_ST_V(3, 4, 2, 2, 4, 1, 1) LM_ST_V(10, 2, 2, 4, 2, 1, 2) LM_ST_V(11, 4, 2, 2, 2, 1, 2) LM_ST_V(12, 4, 4, 2, 2, 1, 2)
 #endif
             default: return -1;
         }
     } else {
         switch (variant) {
-            LM_ST_V(2, 4, 2, 2, 2, 1, true)
+            LM_ST_V(2, 4, 2, 2, 2, 1, 1)
 #ifdef LM_STENCIL_EXPLORE
-            LM_ST_V(0, 4, 2, 2, 4, 1, false) LM_ST_V(1, 2, 2, 2, 4, 2, false) LM_ST_V(3, 4, 2, 2, 4, 1, true)
-            LM_ST_V(4, 2, 2, 2, 2, 2, true) LM_ST_V(5, 2, 4, 2, 2, 1, true) LM_ST_V(6, 2, 2, 4, 2, 1, true)
+            LM_ST_V(0, 4, 2, 2, 4, 1, 0) LM_ST_V(1, 2, 2, 2, 4, 2, 0) LM_ST_V(3, 4, 2, 2, 4, 1, 1)
+            LM_ST_V(4, 2, 2, 2, 2, 2, 1) LM_ST_V(5, 2, 4, 2, 2, 1, 1) LM_ST_V(6, 2, 2, 4, 2, 1, 1)
+            LM_ST_V(10, 2, 2, 4, 2, 1, 2) LM_ST_V(11, 4, 2, 2, 2, 1, 2)
 #endif
             default: return -1;
         }

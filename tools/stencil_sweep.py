@@ -138,7 +138,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--M", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9")
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10,11,12")
     ap.add_argument("--cases", default="haldane:500,qwz:300,square:100")
     ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
