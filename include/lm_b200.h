@@ -200,6 +200,24 @@ int32_t lm_currents_npairs(lm_ham* ham, int64_t* npairs);
 int32_t lm_currents_pairs(lm_ham* ham, int32_t* I, int32_t* J);
 /* fused pass: density (nullable) and all pair currents (nullable) from ONE read of Psi */
 int32_t lm_observables(lm_ham* ham, lm_state* state, double* rho_out, double* J_out);
+/* Asynchronous frame sink (TimeSequence collection, src/timesequence.jl:41-43, without a host
+ * stall per frame): lm_observables_async enqueues the fused reductions of the CURRENT state and
+ * the device->host copy of the frame [rho | J] into slot 0 or 1 and returns at once - the copy
+ * runs on a second stream, so the following lm_step calls overlap it.  lm_frame_wait blocks until
+ * that slot's frame has landed and copies it out (either pointer may be NULL).  A slot must be
+ * waited for before it is enqueued again.  Multi-GPU: the frame is the rank-reduced one. */
+int32_t lm_observables_async(lm_ham* ham, lm_state* state, int32_t slot, int32_t want_currents);
+int32_t lm_frame_wait(lm_ctx* ctx, int32_t slot, double* rho_out, double* J_out);
+/* Region sums on the device (src/currents.jl:85-109) so that only one number / one LatticeValue
+ * crosses PCIe: masks are n_sites bytes (non-zero = in the region); dst_mask NULL = every site
+ * outside src.  reuse_frame != 0 sums over the most recent currents frame of `ham`
+ * (lm_observables / lm_observables_async with currents) instead of recomputing it - the caller
+ * guarantees the state has not changed; `state` may then be NULL.
+ *   lm_currents_fromto: sum_{i in src, j in dst} curr[i, j]
+ *   lm_currents_from  : out[j] = (j in src) ? 0 : sum_{i in src} curr[i, j]   (n_sites doubles) */
+int32_t lm_currents_fromto(lm_ham* ham, lm_state* state, const uint8_t* src_mask, const uint8_t* dst_mask,
+                           int32_t reuse_frame, double* out);
+int32_t lm_currents_from(lm_ham* ham, lm_state* state, const uint8_t* src_mask, int32_t reuse_frame, double* out);
 /* Currents(curr, bonds) (src/currents.jl:238-255) on a host-given bond list */
 int32_t lm_bond_currents(lm_ham* ham, lm_state* state, int64_t nb, const int32_t* I,
                          const int32_t* J, double* J_out);

@@ -186,6 +186,50 @@ function Currents(curr::DensityCurrents{<:Any,<:DevOp}, solver::B200Exp)
     Currents(l, sparse(vcat(I[keep], J[keep]), vcat(J[keep], I[keep]), vcat(V[keep], -V[keep]), n, n))
 end
 
+# currentsfromto / currentsfrom (src/currents.jl:85-109) summed on the device: only one number / one
+# LatticeValue crosses PCIe.  Regions go through the reference's own `to_inds`.
+function region_mask(l, region)
+    m = zeros(UInt8, length(l)); m[LatticeModels.to_inds(l, region)] .= 1; m
+end
+function currentsfromto(curr::DensityCurrents{<:Any,<:DevOp}, solver::B200Exp, src, dst = nothing)
+    l = lattice(curr); out = Ref{Float64}(0.0)
+    ms = region_mask(l, src)
+    md = dst === nothing ? C_NULL : region_mask(l, dst)
+    check(ccall((:lm_currents_fromto, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}, Int32, Ref{Float64}),
+                solver.dev.handle, curr.state.data.handle, ms, md, 0, out))
+    out[]
+end
+function currentsfrom(curr::DensityCurrents{<:Any,<:DevOp}, solver::B200Exp, src)
+    l = lattice(curr); out = Vector{Float64}(undef, length(l))
+    check(ccall((:lm_currents_from, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int32, Ptr{Float64}),
+                solver.dev.handle, curr.state.data.handle, region_mask(l, src), 0, out))
+    LatticeValue(l, out)
+end
+
+# Asynchronous frame sink for TimeSequence-style collection (src/timesequence.jl:41-43): frame k is
+# reduced and copied to the host on a second stream while step k + 1 runs; two slots alternate.
+# push!(sink, solver, state, t) after every step, then finish!(sink) -> (times, rho frames, J frames).
+mutable struct FrameSink
+    ctx::Context; pending::Vector{Tuple{Int32,Float64,Int,Int}}; next::Int32
+    times::Vector{Float64}; rho::Vector{Vector{Float64}}; J::Vector{Vector{Float64}}
+end
+FrameSink(ctx::Context = default_context()) = FrameSink(ctx, Tuple{Int32,Float64,Int,Int}[], Int32(0), Float64[], Vector{Float64}[], Vector{Float64}[])
+function collect_frame!(k::FrameSink)
+    slot, t, ns, np = popfirst!(k.pending)
+    rho = Vector{Float64}(undef, ns); J = Vector{Float64}(undef, np)
+    check(ccall((:lm_frame_wait, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), k.ctx.handle, slot, rho, J))
+    push!(k.times, t); push!(k.rho, rho); push!(k.J, J); k
+end
+function Base.push!(k::FrameSink, solver::B200Exp, state::DevOp, t)
+    length(k.pending) == 2 && collect_frame!(k)
+    np = Ref{Int64}(0)
+    check(ccall((:lm_currents_npairs, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), solver.dev.handle, np))
+    check(ccall((:lm_observables_async, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32),
+                solver.dev.handle, state.data.handle, k.next, 1))
+    push!(k.pending, (k.next, Float64(t), length(lattice(state)), Int(np[]))); k.next = xor(k.next, Int32(1)); k
+end
+finish!(k::FrameSink) = (while !isempty(k.pending) collect_frame!(k) end; (k.times, k.rho, k.J))
+
 # ---- device-resident time-dependent Hamiltonian (AbstractTimeDependentOperator branch) --------
 # Holds the directed bond table once; set_time! only ships the field parameters, the Peierls
 # phases are regenerated on the device (src/evolution.jl:44-47,243; builder.jl:282-309 restated

@@ -18,4 +18,4 @@ from .states import DeviceState, PsiProjector, densitymatrix, diagonalize, groun
 from .evolution import B200Exp, Evolution, EvolutionSolver, EvolutionTimestamp  # noqa: F401
 from .observables import (Currents, DensityCurrents, LatticeValue, LocalOperatorCurrents,  # noqa: F401
                           currentsfrom, currentsfromto, findnz, localdensity, localexpect)
-from .timesequence import TimeSequence  # noqa: F401
+from .timesequence import AsyncFrameSink, TimeSequence  # noqa: F401

@@ -71,6 +71,10 @@ PROTOTYPES = {
     "lm_currents_npairs": [_vp, _pi64],
     "lm_currents_pairs": [_vp, _vp, _vp],
     "lm_observables": [_vp, _vp, _vp, _vp],
+    "lm_observables_async": [_vp, _vp, _i32, _i32],
+    "lm_frame_wait": [_vp, _i32, _vp, _vp],
+    "lm_currents_fromto": [_vp, _vp, _vp, _vp, _i32, _pf64],
+    "lm_currents_from": [_vp, _vp, _vp, _i32, _vp],
     "lm_bond_currents": [_vp, _vp, _i64, _vp, _vp, _vp],
     "lm_local_expect": [_vp, _i32, _vp, _vp],
     "lm_operator_currents": [_vp, _vp, _vp, _vp],

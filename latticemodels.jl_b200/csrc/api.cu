@@ -96,6 +96,13 @@ struct lm_ctx {
     void* p2p_local = nullptr; size_t p2p_bytes = 0; long long p2p_cap = 0; bool p2p_ready = false;
     void* p2p_peer_base[8] = {nullptr}; unsigned int* d_p2p_done = nullptr; unsigned long long p2p_epoch = 0;
     long long le_N = 0; int le_n = 0; int* d_le_a = nullptr; int* d_le_b = nullptr; double2* d_le_G = nullptr; double2* d_le_out = nullptr;   // localexpect tables
+    // asynchronous frame sink (lm_observables_async / lm_frame_wait): two slots, a copy stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t fr_ready[2] = {nullptr, nullptr}, fr_done[2] = {nullptr, nullptr};
+    double* d_frame[2] = {nullptr, nullptr}; double* h_frame[2] = {nullptr, nullptr}; size_t frame_cap[2] = {0, 0};
+    long long frame_nsites[2] = {0, 0}, frame_npairs[2] = {0, 0}; bool frame_pending[2] = {false, false};
+    double* d_region = nullptr;                            // region-sum scratch (lm_currents_fromto / lm_currents_from)
+    unsigned char* d_mask = nullptr; size_t mask_cap = 0;
     size_t esz() const { return precision == LM_C128 ? 16 : 8; }
 };
 
@@ -120,6 +127,7 @@ struct lm_ham {
     std::vector<long long> colptr, rowval; int* d_csc2ell = nullptr; void* d_nz = nullptr;
     // site pairs (I < J) in findnz order and the ELL entries of every pair
     long long npairs = 0; std::vector<int> pairI, pairJ; int* d_pair_ptr = nullptr; int* d_pair_ent = nullptr;
+    int* d_pairI = nullptr; int* d_pairJ = nullptr;          // device copy of the pair list (region sums, uploaded on first use)
     // bond mode
     bool bond_mode = false; long long nb = 0;
     double* d_r = nullptr; double2* d_bfac = nullptr; double2* d_phase = nullptr;
@@ -225,6 +233,15 @@ extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (c->d_p2p_done) cudaFree(c->d_p2p_done);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int q = 0; q < 2; ++q) {
+        if (c->fr_ready[q]) cudaEventDestroy(c->fr_ready[q]);
+        if (c->fr_done[q]) cudaEventDestroy(c->fr_done[q]);
+        if (c->d_frame[q]) cudaFree(c->d_frame[q]);
+        if (c->h_frame[q]) cudaFreeHost(c->h_frame[q]);
+    }
+    if (c->d_region) cudaFree(c->d_region);
+    if (c->d_mask) cudaFree(c->d_mask);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return LM_OK;
@@ -304,7 +321,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_st_out};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_st_out, h->d_pairI, h->d_pairJ};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -2052,12 +2069,13 @@ static int observe(lm_ham* h, lm_state* s, bool want_j) {
     return LM_OK;
 }
 
-static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, double* J_out) {
+// Enqueue the fused reductions of the current state: on return (stream order) h->d_obs holds the
+// rank-reduced frame [rho (n_sites) | J (npairs, only if want_j)].  No host synchronisation.
+static int enqueue_observables(lm_ham* h, lm_state* s, int n_int, bool want_j) {
     lm_ctx* c = s->ctx; FWD(set_dev(c));
     REQUIRE(!s->dense, "observables of a dense state: download it with lm_state_download_dense (diagonal) instead");
     const long long n_sites = s->N / n_int;
-    const long long npairs = (h && J_out) ? h->npairs : 0;
-    const bool want_j = J_out != nullptr;
+    const long long npairs = (h && want_j) ? h->npairs : 0;
     if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
     const long long tot = n_sites + npairs; const int th = 256;
     static const int p2p_env = env_int("LM_OBS_P2P", 1);
@@ -2087,6 +2105,15 @@ static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, d
     CK(cudaGetLastError());
     if (c->nranks > 1 && c->comm && !used_p2p)
         NCK(g_nccl.AllReduce(h->d_obs, h->d_obs, (size_t)tot, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    return LM_OK;
+}
+
+static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, double* J_out) {
+    lm_ctx* c = s->ctx;
+    FWD(enqueue_observables(h, s, n_int, J_out != nullptr));
+    const long long n_sites = s->N / n_int;
+    const long long npairs = (h && J_out) ? h->npairs : 0;
+    const long long tot = n_sites + npairs;
     FWD(ensure_pinned(c, sizeof(double) * (size_t)tot + 4096));
     CK(cudaMemcpyAsync(c->h_pinned, h->d_obs, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -2107,6 +2134,122 @@ extern "C" int32_t lm_observables(lm_ham* h, lm_state* s, double* rho_out, doubl
     REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_observables: Hamiltonian/state mismatch");
     return run_observables(h, s, h->n_int, rho_out, J_out);
 }
+// ------------------------------------------------------------------------------------------
+// N4: asynchronous frame sink and on-device region sums
+// ------------------------------------------------------------------------------------------
+static int frame_slot_setup(lm_ctx* c, int slot, size_t ndoubles) {
+    if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->fr_ready[slot]) { CK(cudaEventCreateWithFlags(&c->fr_ready[slot], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->fr_done[slot], cudaEventDisableTiming)); }
+    if (c->frame_cap[slot] < ndoubles) {
+        if (c->d_frame[slot]) CK(cudaFree(c->d_frame[slot]));
+        if (c->h_frame[slot]) CK(cudaFreeHost(c->h_frame[slot]));
+        c->d_frame[slot] = nullptr; c->h_frame[slot] = nullptr; c->frame_cap[slot] = 0;
+        CK(cudaMalloc(&c->d_frame[slot], sizeof(double) * ndoubles));
+        CK(cudaMallocHost(&c->h_frame[slot], sizeof(double) * ndoubles));
+        c->frame_cap[slot] = ndoubles;
+    }
+    return LM_OK;
+}
+extern "C" int32_t lm_observables_async(lm_ham* h, lm_state* s, int32_t slot, int32_t want_currents) {
+    REQUIRE(h && s, "lm_observables_async: NULL argument");
+    REQUIRE(slot == 0 || slot == 1, "lm_observables_async: slot must be 0 or 1");
+    REQUIRE(h->ctx == s->ctx, "lm_observables_async: Hamiltonian and state belong to different contexts");
+    REQUIRE(h->N == s->N, "lm_observables_async: dimension mismatch");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    REQUIRE(!c->frame_pending[slot], "lm_observables_async: slot still holds an unread frame (call lm_frame_wait first)");
+    const long long n_sites = s->N / h->n_int, npairs = want_currents ? h->npairs : 0, tot = n_sites + npairs;
+    FWD(frame_slot_setup(c, slot, (size_t)std::max<long long>(1, tot)));
+    FWD(enqueue_observables(h, s, h->n_int, want_currents != 0));
+    // snapshot the frame (the next frame reuses d_obs), then ship it on the copy stream while the
+    // main stream runs the following steps
+    CK(cudaMemcpyAsync(c->d_frame[slot], h->d_obs, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaEventRecord(c->fr_ready[slot], c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->fr_ready[slot], 0));
+    CK(cudaMemcpyAsync(c->h_frame[slot], c->d_frame[slot], sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->fr_done[slot], c->copy_stream));
+    c->frame_nsites[slot] = n_sites; c->frame_npairs[slot] = npairs; c->frame_pending[slot] = true;
+    return LM_OK;
+}
+extern "C" int32_t lm_frame_wait(lm_ctx* c, int32_t slot, double* rho_out, double* J_out) {
+    REQUIRE(c, "lm_frame_wait: NULL context");
+    REQUIRE(slot == 0 || slot == 1, "lm_frame_wait: slot must be 0 or 1");
+    REQUIRE(c->frame_pending[slot], "lm_frame_wait: no frame was enqueued in this slot");
+    FWD(set_dev(c));
+    CK(cudaEventSynchronize(c->fr_done[slot]));
+    const double* src = c->h_frame[slot];
+    if (rho_out) memcpy(rho_out, src, sizeof(double) * (size_t)c->frame_nsites[slot]);
+    if (J_out) {
+        memcpy(J_out, src + c->frame_nsites[slot], sizeof(double) * (size_t)c->frame_npairs[slot]);
+    }
+    c->frame_pending[slot] = false;
+    return LM_OK;
+}
+
+// currentsfromto / currentsfrom (src/currents.jl:85-109) over H's pair list, on the device:
+// curr[i, j] = +J_p for the stored pair p = (i < j), -J_p for (j, i).
+static int region_prepare(lm_ham* h, lm_state* s, const uint8_t* src_mask, const uint8_t* dst_mask, int32_t reuse_frame) {
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    const size_t ns = (size_t)h->n_sites;
+    if (c->mask_cap < 2 * ns) {
+        if (c->d_mask) CK(cudaFree(c->d_mask));
+        c->d_mask = nullptr; c->mask_cap = 0;
+        CK(cudaMalloc(&c->d_mask, 2 * ns)); c->mask_cap = 2 * ns;
+    }
+    if (!c->d_region) CK(cudaMalloc(&c->d_region, sizeof(double)));
+    if (!h->d_pairI && h->npairs > 0) {
+        CK(cudaMalloc(&h->d_pairI, sizeof(int) * (size_t)h->npairs)); CK(cudaMalloc(&h->d_pairJ, sizeof(int) * (size_t)h->npairs));
+        CK(cudaMemcpy(h->d_pairI, h->pairI.data(), sizeof(int) * (size_t)h->npairs, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_pairJ, h->pairJ.data(), sizeof(int) * (size_t)h->npairs, cudaMemcpyHostToDevice));
+    }
+    FWD(ensure_pinned(c, 2 * ns + 4096));
+    unsigned char* hm = (unsigned char*)c->h_pinned;
+    for (size_t i = 0; i < ns; ++i) {
+        hm[i] = src_mask[i] ? 1 : 0;
+        hm[ns + i] = dst_mask ? (dst_mask[i] ? 1 : 0) : (src_mask[i] ? 0 : 1);   // default: everything else
+    }
+    CK(cudaMemcpyAsync(c->d_mask, hm, 2 * ns, cudaMemcpyHostToDevice, c->stream));
+    if (!reuse_frame) FWD(enqueue_observables(h, s, h->n_int, true));
+    return LM_OK;
+}
+extern "C" int32_t lm_currents_fromto(lm_ham* h, lm_state* s, const uint8_t* src_mask, const uint8_t* dst_mask,
+                                      int32_t reuse_frame, double* out) {
+    REQUIRE(h && src_mask && out, "lm_currents_fromto: NULL argument");
+    REQUIRE(reuse_frame || s, "lm_currents_fromto: a state is required unless the last frame is reused");
+    REQUIRE(!s || (h->ctx == s->ctx && h->N == s->N), "lm_currents_fromto: Hamiltonian / state mismatch");
+    lm_ctx* c = h->ctx;
+    FWD(region_prepare(h, s, src_mask, dst_mask, reuse_frame));
+    CK(cudaMemsetAsync(c->d_region, 0, sizeof(double), c->stream));
+    if (h->npairs > 0) {
+        const unsigned grid = (unsigned)std::min<long long>((h->npairs + 255) / 256, 4096);
+        k_region_flux<<<grid, 256, 0, c->stream>>>(h->npairs, h->d_pairI, h->d_pairJ, h->d_obs + h->n_sites, c->d_mask, c->d_mask + h->n_sites, c->d_region);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_region, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = *(const double*)c->h_pinned;
+    return LM_OK;
+}
+extern "C" int32_t lm_currents_from(lm_ham* h, lm_state* s, const uint8_t* src_mask, int32_t reuse_frame, double* out) {
+    REQUIRE(h && src_mask && out, "lm_currents_from: NULL argument");
+    REQUIRE(reuse_frame || s, "lm_currents_from: a state is required unless the last frame is reused");
+    REQUIRE(!s || (h->ctx == s->ctx && h->N == s->N), "lm_currents_from: Hamiltonian / state mismatch");
+    lm_ctx* c = h->ctx;
+    FWD(region_prepare(h, s, src_mask, nullptr, reuse_frame));
+    // per-site accumulator: the density scratch is free once the frame sits in d_obs
+    CK(cudaMemsetAsync(h->d_dens, 0, sizeof(double) * (size_t)h->n_sites, c->stream));
+    if (h->npairs > 0) {
+        k_region_from<<<(unsigned)((h->npairs + 255) / 256), 256, 0, c->stream>>>(h->npairs, h->d_pairI, h->d_pairJ, h->d_obs + h->n_sites, c->d_mask, h->d_dens);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    FWD(ensure_pinned(c, sizeof(double) * (size_t)h->n_sites + 4096));
+    CK(cudaMemcpyAsync(c->h_pinned, h->d_dens, sizeof(double) * (size_t)h->n_sites, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_pinned, sizeof(double) * (size_t)h->n_sites);
+    return LM_OK;
+}
+
 extern "C" int32_t lm_bond_currents(lm_ham* h, lm_state* s, int64_t nb, const int32_t* I, const int32_t* J, double* out) {
     REQUIRE(h && s && out && (nb == 0 || (I && J)), "lm_bond_currents: NULL argument");
     REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_bond_currents: Hamiltonian/state mismatch");

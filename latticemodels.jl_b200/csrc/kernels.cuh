@@ -821,6 +821,42 @@ k_observe_tiled(const ObsTiledArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Region sums over the pair currents of one frame (src/currents.jl:85-109): the stored pair
+// p = (I < J) carries curr[I, J] = +J_p and curr[J, I] = -J_p.
+//   k_region_flux: sum_{i in A, j in B} curr[i, j]  -> one double
+//   k_region_from: out[j] = (j in A) ? 0 : sum_{i in A} curr[i, j]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_region_flux(long long npairs, const int* __restrict__ I, const int* __restrict__ J, const double* __restrict__ Jv,
+              const unsigned char* __restrict__ A, const unsigned char* __restrict__ B, double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long p = blockIdx.x * 256LL + threadIdx.x; p < npairs; p += (long long)gridDim.x * 256LL) {
+        const int i = I[p], j = J[p];
+        const int sgn = (int)(A[i] && B[j]) - (int)(A[j] && B[i]);
+        acc += sgn * Jv[p];
+    }
+    acc = warp_sum(acc);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        atomicAdd(out, t);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_region_from(long long npairs, const int* __restrict__ I, const int* __restrict__ J, const double* __restrict__ Jv,
+              const unsigned char* __restrict__ A, double* __restrict__ out) {
+    const long long p = blockIdx.x * 256LL + threadIdx.x;
+    if (p >= npairs) return;
+    const int i = I[p], j = J[p];
+    if (A[i] && !A[j]) atomicAdd(out + j, Jv[p]);
+    else if (A[j] && !A[i]) atomicAdd(out + i, -Jv[p]);
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic correlators for localexpect / LocalOperatorCurrents:
 //   out[q] = P[rowB_q, rowA_q] = sum_c w_c x[rowB_q, c] conj(x[rowA_q, c])
 // one warp per requested pair, lanes stride over the columns, warp-shuffle reduction.

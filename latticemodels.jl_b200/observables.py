@@ -217,8 +217,26 @@ class Currents:
         return self.currents.toarray()
 
 
+def _site_mask(ns, region):
+    """Region given as 1-based site indices or a boolean per-site mask -> uint8 mask."""
+    r = np.asarray(region)
+    if r.dtype == bool:
+        if r.shape != (ns,):
+            raise _lib.ArgumentError("region mask must have one entry per site")
+        return np.ascontiguousarray(r, np.uint8)
+    m = np.zeros(ns, np.uint8)
+    m[np.atleast_1d(r.astype(int)) - 1] = 1
+    return m
+
+
 def currentsfrom(curr, src):
     """LatticeValue of the currents from region ``src`` (1-based site indices) to every other site."""
+    if type(curr) is DensityCurrents:        # summed on the device: one LatticeValue crosses PCIe
+        dev = curr._ham()
+        ns = curr.state.N // curr.n_int
+        out = np.zeros(ns)
+        _lib.check(_lib.load().lm_currents_from(dev.handle, curr.state.handle, _lib.ptr(_site_mask(ns, src)), 0, _lib.ptr(out)))
+        return LatticeValue(curr.lattice, out)
     c = curr if isinstance(curr, Currents) else Currents(curr)
     src = np.atleast_1d(np.asarray(src, int)) - 1
     m = c.currents.tocsr()
@@ -228,6 +246,15 @@ def currentsfrom(curr, src):
 
 
 def currentsfromto(curr, src, dst=None):
+    """Total current from region ``src`` to region ``dst`` (default: every other site),
+    src/currents.jl:103-109.  Device currents are summed on the device (one double comes back)."""
+    if type(curr) is DensityCurrents:
+        dev = curr._ham()
+        ns = curr.state.N // curr.n_int
+        out = C.c_double()
+        _lib.check(_lib.load().lm_currents_fromto(dev.handle, curr.state.handle, _lib.ptr(_site_mask(ns, src)),
+                                                  None if dst is None else _lib.ptr(_site_mask(ns, dst)), 0, C.byref(out)))
+        return float(out.value)
     c = curr if isinstance(curr, Currents) else Currents(curr)
     ns = c.currents.shape[0]
     src = np.atleast_1d(np.asarray(src, int)) - 1

@@ -312,6 +312,85 @@ def test_stencil_complex64(ctx64):
         assert _relerr(lm.localdensity(st).values, np.real(np.diag(P))) < 1e-5
 
 
+# ------------------------------------------------------------------------------ N4: async frame sink, region sums
+def test_async_frame_sink_matches_synchronous_frames(ctx):
+    """lm_observables_async / lm_frame_wait (double-buffered D2H on a second stream) deliver the
+    same frames as the synchronous lm_observables while the evolution keeps stepping."""
+    lat = lm.HoneycombLattice(9, 8)
+
+    def ham(t):
+        return lm.haldane(lat, 1.0, 0.2, 0.1, field=lm.LandauGauge(0.02 * t))
+    Psi = _rand_block(144, 40, seed=11)
+    w = np.random.default_rng(5).random(40)
+    ts = [0.1 * k for k in range(1, 8)]
+    frames = []
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx)
+    sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+    for t in ts:
+        sol.update_solver(ham(t), 0.1)
+        sol.step(st)
+        frames.append((lm.localdensity(st).values.copy(), lm.DensityCurrents(ham(t), st).pair_values()[2].copy()))
+    st2 = lm.DeviceState.from_psi(Psi, w, ctx=ctx)
+    sink = lm.AsyncFrameSink()
+    for t in ts:
+        sol.update_solver(ham(t), 0.1)
+        sol.step(st2)
+        sink.push(sol.dev, st2, t)
+    rho_seq, cur_seq = sink.finish()
+    assert len(rho_seq) == len(ts) and len(cur_seq) == len(ts)
+    for t, (rho, J) in zip(ts, frames):
+        assert np.abs(rho_seq[t] - rho).max() < 1e-14
+        assert np.abs(cur_seq[t] - J).max() < 1e-14
+    # slot discipline
+    lib = _lib.load()
+    _lib.check(lib.lm_observables_async(sol.dev.handle, st2.handle, 0, 1))
+    with pytest.raises(lm.ArgumentError):
+        _lib.check(lib.lm_observables_async(sol.dev.handle, st2.handle, 0, 1))     # slot 0 not read yet
+    with pytest.raises(lm.ArgumentError):
+        _lib.check(lib.lm_frame_wait(ctx.handle, 1, None, None))                   # nothing enqueued in slot 1
+    with pytest.raises(lm.ArgumentError):
+        _lib.check(lib.lm_observables_async(sol.dev.handle, st2.handle, 2, 1))
+    _lib.check(lib.lm_frame_wait(ctx.handle, 0, None, None))
+
+
+def test_region_sums_on_device(ctx):
+    """currentsfromto / currentsfrom (src/currents.jl:85-109) summed on the device against the
+    host sums over the materialised Currents matrix; mask and index-list regions; QWZ (n_int=2)."""
+    l = lm.SquareLattice(7, 6)
+    Hd = lm.qwz(l, field=lm.LandauGauge(0.1))
+    Psi = _rand_block(84, 36, seed=3)
+    st = lm.DeviceState.from_psi(Psi, ctx=ctx, n_int=2)
+    dc = lm.DensityCurrents(Hd, st)
+    full = lm.Currents(dc).currents.toarray()
+    rng = np.random.default_rng(1)
+    src = np.sort(rng.choice(42, 11, replace=False)) + 1
+    dst = np.setdiff1d(np.arange(1, 43), src)[::2]
+    want = full[np.ix_(src - 1, dst - 1)].sum()
+    assert lm.currentsfromto(dc, src, dst) == pytest.approx(want, abs=1e-13)
+    rest = np.setdiff1d(np.arange(1, 43), src)
+    assert lm.currentsfromto(dc, src) == pytest.approx(full[np.ix_(src - 1, rest - 1)].sum(), abs=1e-13)
+    mask = np.zeros(42, bool)
+    mask[src - 1] = True
+    assert lm.currentsfromto(dc, mask) == pytest.approx(lm.currentsfromto(dc, src), abs=1e-14)
+    got = lm.currentsfrom(dc, src).values
+    wantv = full[src - 1, :].sum(0)
+    wantv[src - 1] = 0
+    assert np.abs(got - wantv).max() < 1e-13
+    # overlapping regions: i in src and j in dst counted per ordered pair, like the reference's double sum
+    both = np.arange(1, 20)
+    assert lm.currentsfromto(dc, both, both) == pytest.approx(full[np.ix_(both - 1, both - 1)].sum(), abs=1e-13)
+    # reuse of the most recent frame: no state needed
+    lib = _lib.load()
+    dev = Hd.device(ctx)
+    J = np.zeros(len(dev.pairs()[0]))
+    _lib.check(lib.lm_observables(dev.handle, st.handle, None, _lib.ptr(J)))
+    out = C.c_double()
+    m = np.zeros(42, np.uint8)
+    m[src - 1] = 1
+    _lib.check(lib.lm_currents_fromto(dev.handle, None, _lib.ptr(m), None, 1, C.byref(out)))
+    assert out.value == pytest.approx(full[np.ix_(src - 1, rest - 1)].sum(), abs=1e-13)
+
+
 # ------------------------------------------------------------------------------ device Peierls phases
 FIELD_CASES = {
     "nofield": (lambda: lm.NoField(), lambda: F.NoField()),
