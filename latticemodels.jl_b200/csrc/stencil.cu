@@ -30,6 +30,16 @@ int stencil_find(int rc, st_mask_t mask) {
     return best;
 }
 
+int stencil_diag_slot(int id, int a) {
+    const int rc = g_desc[id].rc;
+    int s = 0;
+    for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b) {
+        const bool set = (g_desc[id].mask >> (o * rc * rc + a * rc + b)) & 1ull;
+        if (o == 4 && b == a) return set ? s : -1;
+        if (set) ++s;
+    }
+    return -1;
+}
 int stencil_stride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 1) & ~1) : g_desc[id].sw; }
 
 // register-tile variants: T1 x T2 cells per thread, W1 x W2 warps per CTA, CPT lane elements per

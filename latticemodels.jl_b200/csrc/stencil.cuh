@@ -324,7 +324,8 @@ k_apply_stencil_tma(const StencilArgs a) {
                     if (cj >= lde) continue;
                     const long long e = row * lde + cj;
                     E res;
-                    pscale(res, alpha, acc[v1][v2][aa][j]);
+                    if (MODE == 4) res = acc[v1][v2][aa][j];             // values pre-scaled: y = (alpha H + gamma I) x
+                    else pscale(res, alpha, acc[v1][v2][aa][j]);
                     if (MODE == 1) pfma(res, beta, ld_stream(z + e));
                     if (MODE == 2) {
                         if (z) pfma(res, beta, ld_stream(z + e));
@@ -334,6 +335,26 @@ k_apply_stencil_tma(const StencilArgs a) {
                 }
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_fold_svals: slot-ordered values of the WHOLE factor  alpha H + gamma I  (one factor of the
+// product-form propagator) gathered straight from the ELL values: out[i][s] = alpha * H-value of
+// slot s (+ gamma on the diagonal slot of the row).  nnz-sized, runs once per factor; the stencil
+// kernel then stores its accumulators as they are (MODE 4): 40 instead of 48 DFMA per element.
+// ------------------------------------------------------------------------------------------
+template <typename T2>
+__global__ void k_fold_svals(long long n, int sw, int rc, int dslot0, int dslot1, const int* __restrict__ src,
+                             const T2* __restrict__ vals, T2 alpha, T2 gamma, T2* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long row = i / sw; const int slot = (int)(i - row * sw);
+    T2 v; v.x = 0; v.y = 0;
+    const int e = src[i];
+    if (e >= 0) v = cmul(alpha, vals[e]);
+    const int dslot = (rc == 2 && (row & 1)) ? dslot1 : dslot0;
+    if (slot == dslot) { v.x += gamma.x; v.y += gamma.y; }
+    out[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -694,6 +715,7 @@ int stencil_count();
 const StencilDesc& stencil_desc(int id);
 int stencil_find(int rc, st_mask_t mask);                  // smallest compiled superset, -1 if none
 int stencil_stride(int id, bool c64);                      // value-slot stride (complex64 rows are padded to even)
+int stencil_diag_slot(int id, int a);                      // slot of the diagonal entry of in-cell row a
 int stencil_num_variants();
 // patch size in cells, lane elements per thread and kernel family (staged = TMA) of a variant
 void stencil_variant_shape(int variant, int* P1, int* P2, int* cpt, int* staged);

@@ -39,6 +39,7 @@ static int launch_modes(int mode, const StencilArgs& a, dim3 grid, cudaStream_t 
     switch (mode) {
     case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, grid, s);
     case 3: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 3, STAGED>(a, grid, s);
+    case 4: if constexpr (STAGED == 1) return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 4, STAGED>(a, grid, s); else return -1;
 #ifndef LM_STENCIL_FEWMODES
     case 1: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 1, STAGED>(a, grid, s);
     case 2: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 2, STAGED>(a, grid, s);
