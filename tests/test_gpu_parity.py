@@ -190,6 +190,8 @@ def test_stencil_kernel_matches_oracle(ctx, case):
     dev = Hd.device(ctx)
     sid, rc, sw, mask = _stencil_info(dev)
     assert sid == want_id, (case, sid, hex(mask))
+    from oracle import stencil as ST
+    assert (rc, mask) == ST.stencil_mask(Ho, *Hd.lattice.sizes)      # device detection == oracle restatement
     lib = _lib.load()
     N = Ho.shape[0]
     for M in (32, 33, 40, 64, 100, 131):

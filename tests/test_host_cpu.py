@@ -176,3 +176,37 @@ def test_column_sharding_allreduce_gloo_world2(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_compiled_stencil_masks_cover_reference_models():
+    """The sparsity masks compiled into the register-tiled stencil kernels (LM_ST_MASK* in
+    csrc/stencil.cuh) cover the stencils of the reference's own models, derived
+    here from the oracle's Hamiltonians; periodic wrapping and field phases do not change them."""
+    import re
+    from oracle import fields as F, lattice as L, operators as OP, stencil as ST
+    src = open(os.path.join(ROOT, "latticemodels.jl_b200", "csrc", "stencil.cuh")).read()
+    masks = {int(k): int(v, 16) for k, v in re.findall(r"#define LM_ST_MASK(\d) (0x[0-9a-f]+)ull", src)}
+    assert sorted(masks) == [0, 1, 2, 3, 4]
+    cases = [
+        (OP.tightbinding_hamiltonian(L.square_lattice(6, 7)), 6, 7, 1, 0),
+        (OP.tightbinding_hamiltonian(L.square_lattice(6, 7, periodic=(1, 2)), field=F.LandauGauge(0.1)), 6, 7, 1, 0),
+        (OP.tightbinding_hamiltonian(L.square_lattice(6, 7), t1=1, t2=0.3), 6, 7, 1, 1),
+        (OP.tightbinding_hamiltonian(L.honeycomb_lattice(5, 6)), 5, 6, 2, 2),
+        (OP.qwz(L.square_lattice(5, 6), field=F.LandauGauge(0.2)), 5, 6, 2, 3),
+        (OP.haldane(L.honeycomb_lattice(5, 6), 1.0, 0.2, 0.1), 5, 6, 2, 4),
+        (OP.haldane(L.honeycomb_lattice(5, 6, periodic=(1, 2)), 1.0, 0.2, 0.1), 5, 6, 2, 4),
+    ]
+    for H, n1, n2, rc_want, mid in cases:
+        rc, m = ST.stencil_mask(H, n1, n2)
+        assert rc == rc_want and m is not None
+        assert m & ~masks[mid] == 0, (mid, hex(m), hex(masks[mid]))
+        # tight: the compiled mask adds nothing but the on-site (same-cell) block to the model's own pattern
+        extra = masks[mid] & ~m
+        assert mid == 1 or extra & ~(((1 << (rc * rc)) - 1) << (4 * rc * rc)) == 0
+    # third-neighbour hops couple cells two apart: no |d| <= 1 mask
+    assert ST.stencil_mask(OP.tightbinding_hamiltonian(L.square_lattice(8, 8), t1=1, t3=0.1), 8, 8)[1] is None
+    # Haldane: 4 forward bonds from the A row, 5 from the B row (one correlator per bond)
+    fw = ST.forward_entries(2, masks[4])
+    assert [sum(1 for a, _, _ in fw if a == r) for r in (0, 1)] == [4, 5]
+    # QWZ: 2 forward cells x 2 x 2 orbital pairs + the same-site orbital pair (never a current: mapped to -1)
+    assert len(ST.forward_entries(1, masks[0])) == 2 and len(ST.forward_entries(2, masks[3])) == 9
