@@ -113,6 +113,9 @@ struct Plan {          // cached propagator plan (host-side Bessel / Taylor book
 };
 
 static unsigned long long g_ham_uid = 0;
+// bumped by the lm_dbg_set_* switches that change which kernels a step launches: captured step
+// graphs of an older epoch are not replayed
+static unsigned long long g_sched_epoch = 0;
 struct lm_ham {
     lm_ctx* ctx = nullptr;
     unsigned long long uid = ++g_ham_uid;   // identity for cached step graphs (addresses get recycled)
@@ -170,7 +173,8 @@ struct lm_state {
     void* d_s1 = nullptr; void* d_s2 = nullptr;               // propagator scratch
     // CUDA graphs of one propagation step (the K term launches), keyed by plan + buffer roles
     struct StepGraph { cudaGraphExec_t exec = nullptr; lm_ham* h = nullptr; unsigned long long uid = 0, epoch = 0; void* x = nullptr; void* s1 = nullptr;
-                       double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false; };
+                       double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false;
+                       unsigned long long sched = 0; };      // sched: g_sched_epoch the graph was captured under
     StepGraph graphs[4]; int graph_next = 0;
     // block-Lanczos workspace (LM_METHOD_LANCZOS): Krylov basis + per-column scalars
     std::vector<void*> kry; double2* d_alpha = nullptr; double* d_beta = nullptr; double2* d_coef = nullptr;
@@ -1415,24 +1419,27 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
 }
 
 static int g_stencil_variant = -1;       // lm_dbg_set_stencil_variant (sweeps): -1 = default per pattern
+// nc = columns processed starting at the pointers (ld = the whole block; fewer for an L2-resident
+// column strip, see step_strips), keep = plain instead of evict-first stores of y
 static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
-                         zc alpha, zc gamma, zc beta, zc delta) {
+                         zc alpha, zc gamma, zc beta, zc delta, long long nc = -1, bool keep = false) {
     lm_ctx* c = h->ctx;
     FWD(refresh_views(h));
+    if (nc < 0) nc = ld;
     static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
     int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
     if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
     int P1, P2, cpt, staged;
     stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
     StencilArgs a;
-    a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld;
+    a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld; a.nc = nc; a.keep = keep ? 1 : 0;
     a.x = x; a.y = y; a.z = z; a.u = u;
     const zc g = gamma / alpha;
     a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.g[0] = g.real(); a.g[1] = g.imag();
     a.beta[0] = beta.real(); a.beta[1] = beta.imag(); a.delta[0] = delta.real(); a.delta[1] = delta.imag();
     const int ec = (c->precision == LM_C128) ? 1 : 2;
     const int CT = 32 * cpt * ec;
-    const long long nchunks = (ld + CT - 1) / CT;
+    const long long nchunks = (nc + CT - 1) / CT;
     const long long np1 = (h->lat_n1 + P1 - 1) / P1, np2 = (h->lat_n2 + P2 - 1) / P2;
     a.np2 = (int)np2;
     // patches run along the fast lattice axis; the rows a sweep keeps re-reading are two patch
@@ -1445,7 +1452,7 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     const long long strips = (nchunks + cps - 1) / cps;
     cps = (nchunks + strips - 1) / strips;
     REQUIRE(np1 * np2 * cps < 2147483647LL && strips <= 65535, "apply_stencil: grid too large");
-    REQUIRE(ld % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
+    REQUIRE(ld % ec == 0 && nc % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
     a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
     dim3 grid((unsigned)(np1 * np2 * cps), (unsigned)strips);
     a.ngroups = 1; a.cpg = (unsigned)nchunks; a.npatch = (unsigned)(np1 * np2);
@@ -1485,9 +1492,16 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     CK(cudaGetLastError());
     return LM_OK;
 }
-extern "C" int32_t lm_dbg_set_stencil_variant(int32_t v) { g_stencil_variant = v; return LM_OK; }
+extern "C" int32_t lm_dbg_set_stencil_variant(int32_t v) { g_stencil_variant = v; ++g_sched_epoch; return LM_OK; }
 
 static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad, 5 register-tiled stencil
+// register-tiled stencil kernel (path 5 = force): default whenever the lattice matched a compiled stencil
+static bool stencil_path(const lm_ham* h, long long ld) {
+    static const int tiled_env0 = env_int("LM_APPLY_TILED", -1);
+    static const int stencil_env = env_int("LM_APPLY_STENCIL", 1);
+    const int tiled_env = g_apply_path_override >= 0 ? g_apply_path_override : tiled_env0;
+    return h->st_id >= 0 && ld >= 32 && ((tiled_env < 0 && stencil_env) || tiled_env == 5);
+}
 // y = alpha H x + gamma x + beta z + delta u
 static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
                  zc alpha, zc gamma, zc beta, zc delta) {
@@ -1498,9 +1512,7 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     //                 2 = register gather over plan tiles (L1 patch reuse)
     // n_int = 2 models: site-blocked gather (3 = force, default on when the block view exists)
     static const int sites_env = env_int("LM_APPLY_SITES", 1);
-    // register-tiled stencil kernel (5 = force): default whenever the lattice matched a compiled stencil
-    static const int stencil_env = env_int("LM_APPLY_STENCIL", 1);
-    if (h->st_id >= 0 && ld >= 32 && alpha != zc(0, 0) && ((tiled_env < 0 && stencil_env) || tiled_env == 5))
+    if (stencil_path(h, ld) && alpha != zc(0, 0))
         return apply_stencil(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     if (h->d_scols && ld >= 32 && ((tiled_env < 0 && sites_env) || tiled_env == 3)) return apply_sites(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     // default: tile-order register gather whenever the host supplied site coordinates
@@ -1565,6 +1577,62 @@ static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
     *nsub = s; *K = k;
     return LM_OK;
 }
+// ------------------------------------------------------------------------------------------
+// A product-form step is a chain of factors  x <- (alpha_j H + gamma_j I) x  ping-ponging between
+// the state and ONE scratch buffer.  Plain schedule: factor by factor over the whole block - every
+// factor streams the block through HBM (2 N M s bytes each).
+// L2-resident schedule (LM_STEP_L2_MB > 0, register-tiled stencil path only): columns are
+// independent, so the chain can run strip by strip instead - for a strip of `ms` columns all
+// factors are applied back to back while its two buffers (2 N ms s bytes <= the budget) stay in
+// the 126 MB L2: HBM sees the block once per STEP (first read + last write) instead of once per
+// factor, the remaining factors run at L2 bandwidth.  The intermediate factors store y with the
+// default policy (keep), the last one evict-first.  Pays for N small enough that a strip of >= 64
+// columns fits (C2: N = 1e4 -> 224 columns in 72 MB); for larger N the plain schedule is used.
+// The result lands in the same buffer for every strip (parity of the factor count).
+// ------------------------------------------------------------------------------------------
+struct Factor { zc alpha, gamma; };
+static long long g_step_l2_kb = -1;      // lm_dbg_set_step_l2_kb (tests / sweeps): -1 = LM_STEP_L2_MB
+static long long strip_columns(const lm_ham* h, long long ld) {
+    static const int mb_env = env_int("LM_STEP_L2_MB", 0);
+    const long long kb = g_step_l2_kb >= 0 ? g_step_l2_kb : 1024LL * mb_env;
+    if (kb <= 0 || !stencil_path(h, ld)) return 0;
+    const lm_ctx* c = h->ctx;
+    const long long unit = 32 * (c->precision == LM_C128 ? 1 : 2);      // one staged chunk of the kernel
+    long long ms = (long long)((double)kb * 1024.0 / (2.0 * (double)h->N * (double)c->esz()));
+    ms = (ms / unit) * unit;
+    if (ms < 2 * unit || ms >= ld) return 0;                             // too narrow to pay / nothing to split
+    // even strips (no short last strip), still a multiple of the chunk
+    const long long nstrips = (ld + ms - 1) / ms;
+    ms = (((ld + nstrips - 1) / nstrips) + unit - 1) / unit * unit;
+    return ms;
+}
+static int run_factors(lm_ham* h, long long ld, void** px, void** ps1, const std::vector<Factor>& fac, int* nmv) {
+    const long long ms = strip_columns(h, ld);
+    const int nf = (int)fac.size();
+    if (ms <= 0) {
+        for (int j = 0; j < nf; ++j) {
+            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, fac[j].alpha, fac[j].gamma, zc(0, 0), zc(0, 0)));
+            std::swap(*px, *ps1);
+        }
+        *nmv += nf;
+        return LM_OK;
+    }
+    const size_t esz = h->ctx->esz();
+    for (long long c0 = 0; c0 < ld; c0 += ms) {
+        const long long nc = std::min(ms, ld - c0);
+        char* a = (char*)*px + (size_t)c0 * esz;
+        char* b = (char*)*ps1 + (size_t)c0 * esz;
+        for (int j = 0; j < nf; ++j) {
+            FWD(apply_stencil(h, ld, a, b, nullptr, nullptr, fac[j].alpha, fac[j].gamma, zc(0, 0), zc(0, 0), nc, j + 1 < nf));
+            std::swap(a, b);
+        }
+    }
+    if (nf & 1) std::swap(*px, *ps1);
+    *nmv += nf;
+    return LM_OK;
+}
+extern "C" int32_t lm_dbg_set_step_l2_kb(int64_t kb) { g_step_l2_kb = kb; ++g_sched_epoch; return LM_OK; }
+
 // Product-form Taylor: exp(A) ~ p_K(A) = prod_j (I - A / r_j), r_j the roots of the truncated
 // exponential (taylor_roots.h), A = -i H dt / nsub.  Each factor is ONE pass
 //     y = x + (i dt / (nsub r_j)) H x
@@ -1575,14 +1643,13 @@ static int step_taylor_prod(lm_ham* h, long long ld, void** px, void** ps1, doub
     const int nsub = h->plan.nsub, K = h->plan.K;
     const zc f(0.0, -dt / nsub);
     const int off = kTaylorRootOffset[K];
+    std::vector<Factor> fac;
     for (int sub = 0; sub < nsub; ++sub)
         for (int j = 0; j < K; ++j) {
             const zc r(kTaylorRoots[off + j][0], kTaylorRoots[off + j][1]);
-            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, -f / r, zc(1, 0), zc(0, 0), zc(0, 0)));
-            std::swap(*px, *ps1);
-            (*nmv)++;
+            fac.push_back(Factor{-f / r, zc(1, 0)});
         }
-    return LM_OK;
+    return run_factors(h, ld, px, ps1, fac, nmv);
 }
 
 static int step_taylor(lm_ham* h, long long ld, void** px, void** ps1, void** ps2, double dt, int* nmv) {
@@ -1720,15 +1787,14 @@ static int step_cheb_prod(lm_ham* h, long long ld, void** px, void** ps1, double
     const std::vector<zc>& xs = h->plan.croots;
     const int K = (int)xs.size(), nsub = h->plan.csub;
     const zc pref = std::exp(zc(0.0, -b * dt / nsub)) * h->plan.cpref;
+    std::vector<Factor> fac;
     for (int sub = 0; sub < nsub; ++sub)
         for (int j = 0; j < K; ++j) {
             zc alpha = -1.0 / (a * xs[j]), gamma = zc(1, 0) + b / (a * xs[j]);
             if (j == K - 1) { alpha *= pref; gamma *= pref; }
-            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, alpha, gamma, zc(0, 0), zc(0, 0)));
-            std::swap(*px, *ps1);
-            (*nmv)++;
+            fac.push_back(Factor{alpha, gamma});
         }
-    return LM_OK;
+    return run_factors(h, ld, px, ps1, fac, nmv);
 }
 
 struct SymVec { int kind; zc coef; void* buf; };   // 0 zero, 1 coef*psi, 2 buffer
@@ -1936,7 +2002,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
             lm_state::StepGraph* g = nullptr;
             for (auto& c2 : s->graphs)
                 if (c2.exec && c2.h == h && c2.uid == h->uid && c2.epoch == h->layout_epoch && c2.x == s->d_x && c2.s1 == s->d_s1 && c2.dt == dt && c2.tol == tol && c2.method == method &&
-                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf) { g = &c2; break; }
+                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf && c2.sched == g_sched_epoch) { g = &c2; break; }
             if (!g) {
                 g = &s->graphs[s->graph_next]; s->graph_next = (s->graph_next + 1) % 4;
                 if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
@@ -1952,7 +2018,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g->exec = nullptr; s->d_x = x0; s->d_s1 = s10; return fail(LM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
                 g->h = h; g->uid = h->uid; g->epoch = h->layout_epoch; g->x = x0; g->s1 = s10; g->dt = dt; g->tol = tol; g->method = method;
-                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv;
+                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv; g->sched = g_sched_epoch;
                 g->launches = c->launches - l0; g->swap = (s->d_x != x0);
                 c->launches = l0;                       // counted at replay
                 s->d_x = x0; s->d_s1 = s10;             // capture did not execute anything
@@ -2345,7 +2411,7 @@ extern "C" int32_t lm_dbg_triad(lm_state* x, lm_state* z, lm_state* y) {
     return LM_OK;
 }
 
-extern "C" int32_t lm_dbg_set_apply_path(int32_t path) { g_apply_path_override = path; return LM_OK; }
+extern "C" int32_t lm_dbg_set_apply_path(int32_t path) { g_apply_path_override = path; ++g_sched_epoch; return LM_OK; }
 
 // ------------------------------------------------------------------------------------------
 // N3: localexpect and LocalOperatorCurrents

@@ -63,7 +63,17 @@ __device__ __forceinline__ void pfma(float4& acc, const float2 v, const float4 x
     acc.w = fmaf(v.x, x.w, acc.w); acc.w = fmaf(v.y, x.z, acc.w);
 }
 
+// ---- shared-memory declarations of the staged kernels ----
+// (macros so that the CPU execution harness, tests/cpu_emul/, can substitute host storage;
+//  under nvcc they expand to exactly the usual CUDA declarations)
+#ifndef LM_CPU_EMUL
+#define LM_SMEM_DYN(name) extern __shared__ __align__(128) unsigned char name[]
+#define LM_SMEM_STATIC __shared__
+#endif
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----
+// (the CPU execution harness restates these five primitives in tests/cpu_emul/shim/cuda_runtime.h)
+#ifndef LM_CPU_EMUL
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
@@ -90,5 +100,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#endif  // LM_CPU_EMUL
 
 }  // namespace lm

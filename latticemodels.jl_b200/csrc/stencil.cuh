@@ -65,7 +65,10 @@ struct StencilArgs {
     const void* svals;              // [N][SW] complex, stencil-slot order
     int n1, n2;                     // unit cells along the slow / fast lattice axis
     int np2;                        // CTA patches along the fast axis
-    long long ld;
+    long long ld;                   // row stride of x / y / z / u (complex elements)
+    long long nc;                   // columns processed, starting at the pointers (== ld for the whole block;
+                                    // fewer for an L2-resident column strip of the propagator, api.cu step_*_prod)
+    int keep;                       // 1: plain stores (y is re-read out of L2 by the next factor), 0: evict-first
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], g[2], beta[2], delta[2];   // y = alpha (H x + g x) + beta z + delta u
     unsigned cps, nchunks;
@@ -148,7 +151,7 @@ k_apply_stencil(const StencilArgs a) {
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = (pj1 * W1 + warp / W2) * T1, o2 = (pj2 * W2 + warp % W2) * T2;
     if (o1 >= a.n1 || o2 >= a.n2) return;
-    const long long lde = a.ld / EC;
+    const long long lde = a.ld / EC, nce = a.nc / EC;
     const E* __restrict__ x = (const E*)a.x;
     const T2c* __restrict__ sv = (const T2c*)a.svals;
     long long cidx[CPT];
@@ -156,8 +159,8 @@ k_apply_stencil(const StencilArgs a) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const long long c = (long long)chunk * (32 * CPT) + lane + 32 * j;
-        ok[j] = c < lde;
-        cidx[j] = ok[j] ? c : (lde - 1);
+        ok[j] = c < nce;
+        cidx[j] = ok[j] ? c : (nce - 1);
     }
     // wrapped cell coordinates of the haloed tile (periodic images; open-boundary entries are 0)
     int r1[T1 + 2], r2[T2 + 2];
@@ -246,10 +249,10 @@ k_apply_stencil_tma(const StencilArgs a) {
     constexpr int HR = (P1 + 2) * (P2 + 2) * RC;            // haloed rows of the patch
     constexpr int CE = 32 * CPT;                            // lane elements per staged row
     constexpr int SWP = st_stride<T, RC, MASK>();
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                                   // [HR][CE]
     T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)HR * CE * sizeof(E));  // [P1][P2 * RC * SWP]
-    __shared__ __align__(8) unsigned long long bar;
+    LM_SMEM_STATIC __align__(8) unsigned long long bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned patch = blockIdx.x / a.cps;
@@ -257,9 +260,9 @@ k_apply_stencil_tma(const StencilArgs a) {
     if (chunk >= a.nchunks) return;
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = pj1 * P1, o2 = pj2 * P2;                 // patch origin (always inside the lattice)
-    const long long lde = a.ld / EC;
+    const long long lde = a.ld / EC, nce = a.nc / EC;
     const long long c0 = (long long)chunk * CE;
-    const int cw = (int)((lde - c0) < CE ? (lde - c0) : CE);
+    const int cw = (int)((nce - c0) < CE ? (nce - c0) : CE);
     const int vl1 = (a.n1 - o1) < P1 ? (a.n1 - o1) : P1;    // own cells inside the lattice
     const int vl2 = (a.n2 - o2) < P2 ? (a.n2 - o2) : P2;
     const unsigned hline = ((unsigned)(vl2 * RC * SWP * (int)sizeof(T2c)) + 15u) & ~15u;
@@ -321,7 +324,7 @@ k_apply_stencil_tma(const StencilArgs a) {
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     const long long cj = c0 + lane + 32 * j;
-                    if (cj >= lde) continue;
+                    if (cj >= nce) continue;
                     const long long e = row * lde + cj;
                     E res;
                     if (MODE == 4) res = acc[v1][v2][aa][j];             // values pre-scaled: y = (alpha H + gamma I) x
@@ -331,7 +334,7 @@ k_apply_stencil_tma(const StencilArgs a) {
                         if (z) pfma(res, beta, ld_stream(z + e));
                         if (u) pfma(res, delta, u[e]);
                     }
-                    st_stream(y + e, res);
+                    if (a.keep) y[e] = res; else st_stream(y + e, res);
                 }
             }
         }
@@ -386,16 +389,16 @@ k_apply_stencil_stream(const StencilArgs a) {
     constexpr int HR = (P1 + 2) * (P2 + 2) * RC;
     constexpr int CE = 32;
     constexpr int SWP = st_stride<T, RC, MASK>();
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                                          // [NS][HR][CE]
     T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)NS * HR * CE * sizeof(E));    // [P1][P2 * RC * SWP]
-    __shared__ __align__(8) unsigned long long bar[NS];
+    LM_SMEM_STATIC __align__(8) unsigned long long bar[NS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned group = blockIdx.x / a.npatch, patch = blockIdx.x - group * a.npatch;
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = pj1 * P1, o2 = pj2 * P2;
-    const long long lde = a.ld / EC;
+    const long long lde = a.ld / EC, nce = a.nc / EC;
     const unsigned ch0 = group * a.cpg;
     const unsigned ch1 = (ch0 + a.cpg) < a.nchunks ? (ch0 + a.cpg) : a.nchunks;
     if (ch0 >= ch1) return;
@@ -412,7 +415,7 @@ k_apply_stencil_stream(const StencilArgs a) {
     __syncthreads();
     auto issue = [&](unsigned ch, int stage, bool with_values) {
         const long long c0 = (long long)ch * CE;
-        const int cw = (int)((lde - c0) < CE ? (lde - c0) : CE);
+        const int cw = (int)((nce - c0) < CE ? (nce - c0) : CE);
         if (tid == 0) mbar_arrive_expect_tx(&bar[stage], (unsigned)(HR * cw * (int)sizeof(E)) + (with_values ? (unsigned)vl1 * hline : 0u));
         for (int r = warp + (NT / 32) * lane; r < HR; r += NT) {       // rows dealt round-robin over the warps
             const int u1 = r / ((P2 + 2) * RC), rem = r - u1 * ((P2 + 2) * RC), u2 = rem / RC, b = rem - u2 * RC;
@@ -460,7 +463,7 @@ k_apply_stencil_stream(const StencilArgs a) {
                 [&](auto V1, auto V2, auto A, auto S) {
                     return hb[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWP + decltype(S)::value];
                 });
-            if (cj < lde) {
+            if (cj < nce) {
 #pragma unroll
                 for (int v1 = 0; v1 < T1; ++v1)
 #pragma unroll
@@ -568,9 +571,9 @@ k_observe_stencil(const StencilObsArgs a) {
     constexpr int HR = (P1 + 1) * L2 * RC;                  // staged rows: own + forward cell lines
     constexpr int CE = 32;
     constexpr int NF = st_nfwd<RC>(MASK);
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                  // [NS][HR][CE]
-    __shared__ __align__(8) unsigned long long bar[NS];
+    LM_SMEM_STATIC __align__(8) unsigned long long bar[NS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned patch = blockIdx.x / a.ngroups, group = blockIdx.x - patch * a.ngroups;

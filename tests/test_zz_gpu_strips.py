@@ -1,0 +1,97 @@
+"""GPU tests of the L2-resident strip schedule of the product-form propagators (csrc/api.cu
+run_factors; opt-in through LM_STEP_L2_MB / lm_dbg_set_step_l2_kb).  The schedule only re-orders
+independent column strips, so its results must equal the plain factor-by-factor schedule BIT FOR
+BIT, and both must match the exact exponential.  Kept in its own file, sorted after the parity
+suite: written in a session without GPU time, first run is the driver's."""
+import ctypes as C
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+import lm_b200 as lm
+from oracle import evolution as EV
+from oracle import fields as F
+from oracle import lattice as L
+from oracle import operators as OP
+
+pytestmark = pytest.mark.gpu
+_lib = import_module("lm_b200._lib")
+
+
+def _set_l2_kb(kb):
+    lib = _lib.load()
+    lib.lm_dbg_set_step_l2_kb.argtypes = [C.c_int64]
+    lib.lm_dbg_set_step_l2_kb.restype = C.c_int32
+    _lib.check(lib.lm_dbg_set_step_l2_kb(kb))
+
+
+def _rand_block(n, m, seed):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m)))
+
+
+def _relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+CASES = {
+    "square": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(23, 17), field=lm.LandauGauge(0.07)),
+               lambda: OP.tightbinding_hamiltonian(L.square_lattice(23, 17), field=F.LandauGauge(0.07))),
+    "qwz_pbc": (lambda: lm.qwz(lm.SquareLattice(14, 15, boundaries=[("axis1", True)]), field=lm.LandauGauge(0.5)),
+                lambda: OP.qwz(L.square_lattice(14, 15, periodic=(1,)), field=F.LandauGauge(0.5))),
+    "haldane": (lambda: lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1, field=lm.SymmetricGauge(0.03)),
+                lambda: OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1, field=F.SymmetricGauge(0.03))),
+}
+
+
+@pytest.mark.parametrize("precision", ["c128", "c64"])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_strip_schedule_is_bitwise_equal_to_plain_schedule(case, precision):
+    ctx = lm.default_context(precision)
+    mk_dev, mk_or = CASES[case]
+    Hd, Ho = mk_dev(), mk_or()
+    N = Ho.shape[0]
+    tol = 1e-13 if precision == "c128" else 1e-6
+    try:
+        for M, method, dt in ((200, "chebyshev", 0.3), (333, "taylor", 0.2), (131, "chebyshev", -0.7)):
+            X = _rand_block(N, M, seed=M)
+            outs, launches = [], []
+            for kb in (0, 2 * N * 16 * 64 // 1024 + 1):      # plain, then strips of 64 columns
+                _set_l2_kb(kb)
+                st = lm.DeviceState.from_psi(X, ctx=ctx)
+                sol = lm.B200Exp(tol=tol, method=method, ctx=ctx)
+                sol.update_solver(Hd, dt)
+                n0 = ctx.launch_count()
+                for _ in range(3):                            # odd factor counts swap buffers: several steps
+                    sol.step(st)
+                launches.append(ctx.launch_count() - n0)
+                outs.append(st.download())
+            assert launches[1] > launches[0], (case, M, launches)      # the strip schedule really ran
+            assert np.array_equal(outs[0], outs[1]), (case, M, method, _relerr(outs[1], outs[0]))
+            U = EV.exact_propagator(Ho, dt)
+            want = U @ (U @ (U @ X))
+            assert _relerr(outs[1], want) < (5e-13 if precision == "c128" else 2e-4), (case, M, method)
+    finally:
+        _set_l2_kb(-1)
+
+
+def test_strip_schedule_keeps_graph_cache_consistent():
+    """Switching the schedule between steps of the SAME state must not replay a stale step graph."""
+    ctx = lm.default_context("c128")
+    Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(20, 20), field=lm.LandauGauge(0.1))
+    Ho = OP.tightbinding_hamiltonian(L.square_lattice(20, 20), field=F.LandauGauge(0.1))
+    X = _rand_block(400, 256, seed=3)
+    st = lm.DeviceState.from_psi(X, ctx=ctx)
+    sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+    sol.update_solver(Hd, 0.1)
+    want = X
+    U = EV.exact_propagator(Ho, 0.1)
+    try:
+        for k in range(6):
+            _set_l2_kb(0 if k % 2 == 0 else 2 * 400 * 16 * 64 // 1024 + 1)
+            sol.step(st)
+            want = U @ want
+        assert _relerr(st.download(), want) < 1e-12
+    finally:
+        _set_l2_kb(-1)
