@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(256)
 k_apply_tiled(const TiledArgs a) {
     using T2 = typename cx2<T>::type;
     constexpr int CT = 16 * CPT;
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     T2* sx = reinterpret_cast<T2*>(lm_smem);
-    __shared__ __align__(8) unsigned long long bar;
+    LM_SMEM_STATIC __align__(8) unsigned long long bar;
 
     const unsigned tile = blockIdx.x / a.cps;
     const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
@@ -430,9 +430,9 @@ __global__ void __launch_bounds__(256)
 k_apply_quad(const TiledArgs a) {
     using T2 = typename cx2<T>::type;
     constexpr int CT = 4 * CQ, ST = CT + 4;
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     T2* sx = reinterpret_cast<T2*>(lm_smem);
-    __shared__ __align__(8) unsigned long long bar;
+    LM_SMEM_STATIC __align__(8) unsigned long long bar;
 
     const unsigned tile = blockIdx.x / a.cps;
     const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - tile * a.cps);
@@ -593,7 +593,7 @@ k_gershgorin(long long N, int W, const int* __restrict__ cols, const typename cx
         hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         nr = fmax(nr, __shfl_xor_sync(0xffffffffu, nr, o));
     }
-    __shared__ double s[8][3];
+    LM_SMEM_STATIC double s[8][3];
     if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = lo; s[threadIdx.x >> 5][1] = hi; s[threadIdx.x >> 5][2] = nr; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -623,7 +623,7 @@ __global__ void k_gather_vals(long long nnz, typename cx2<T>::type* __restrict__
 template <typename T2>
 __global__ void k_col2row(long long N, long long Mc, const T2* __restrict__ src,
                           T2* __restrict__ dst, long long ld, long long c0) {
-    __shared__ T2 tile[32][33];
+    LM_SMEM_STATIC T2 tile[32][33];
     const long long i0 = blockIdx.x * 32LL, m0 = blockIdx.y * 32LL;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {           // r: column (orbital) in tile
         long long m = m0 + r, i = i0 + threadIdx.x;
@@ -638,7 +638,7 @@ __global__ void k_col2row(long long N, long long Mc, const T2* __restrict__ src,
 template <typename T2>
 __global__ void k_row2col(long long N, long long Mc, T2* __restrict__ dst,
                           const T2* __restrict__ src, long long ld, long long c0) {
-    __shared__ T2 tile[32][33];
+    LM_SMEM_STATIC T2 tile[32][33];
     const long long i0 = blockIdx.x * 32LL, m0 = blockIdx.y * 32LL;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         long long i = i0 + r, m = m0 + threadIdx.x;
@@ -720,7 +720,7 @@ k_observe(long long N, long long M, long long ld, const typename cx2<T>::type* _
             for (int k = 0; k < WB; ++k) if (act[k]) G[row * W + k0 + k] = make_double2(gr[k], gi[k]);
         }
     } else {
-        __shared__ double sm[8][2 * WB + 1];
+        LM_SMEM_STATIC double sm[8][2 * WB + 1];
         if (lane == 0) {
             sm[warp][0] = d;
 #pragma unroll
@@ -768,10 +768,10 @@ __global__ void __launch_bounds__(256)
 k_observe_tiled(const ObsTiledArgs a) {
     using T2 = typename cx2<T>::type;
     constexpr int CT = 32, ST = (sizeof(T2) == 16) ? 33 : 34;   // padded, 16-byte aligned row stride
-    extern __shared__ __align__(128) unsigned char lm_smem[];
+    LM_SMEM_DYN(lm_smem);
     T2* sx = reinterpret_cast<T2*>(lm_smem);
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ double sw[CT];
+    LM_SMEM_STATIC __align__(8) unsigned long long bar;
+    LM_SMEM_STATIC double sw[CT];
 
     const unsigned tile = blockIdx.x / a.nchunks;
     const unsigned chunk = blockIdx.x - tile * a.nchunks;
@@ -836,7 +836,7 @@ k_region_flux(long long npairs, const int* __restrict__ I, const int* __restrict
         acc += sgn * Jv[p];
     }
     acc = warp_sum(acc);
-    __shared__ double sm[8];
+    LM_SMEM_STATIC double sm[8];
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -966,6 +966,7 @@ __global__ void k_finalize_obs(long long n_sites, int n_int, const double* __res
 // ------------------------------------------------------------------------------------------
 struct PeerPtrs { double* slots[8]; unsigned long long* flags[8]; };
 
+#ifndef LM_CPU_EMUL      // (the CPU execution harness supplies atomics for these two, tests/cpu_emul/shim)
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
@@ -974,6 +975,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 template <typename T>
 __global__ void k_finalize_obs_p2p(long long n_sites, int n_int, const double* __restrict__ dens,
@@ -1069,8 +1071,8 @@ template <bool CONJ_B>
 __global__ void __launch_bounds__(128)
 k_zgemm_dmma(int Mr, int Nc, int K, const double2* __restrict__ A, long long lda,
              const double2* __restrict__ B, long long ldb, double2* __restrict__ C, long long ldc) {
-    __shared__ double sAr[32][17], sAi[32][17];     // [m][k]
-    __shared__ double sBr[16][33], sBi[16][33];     // [k][n]
+    LM_SMEM_STATIC double sAr[32][17], sAi[32][17];     // [m][k]
+    LM_SMEM_STATIC double sBr[16][33], sBi[16][33];     // [k][n]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
@@ -1137,7 +1139,7 @@ template <bool CONJ_B>
 __global__ void __launch_bounds__(256)
 k_cgemm_simple(int Mr, int Nc, int K, const float2* __restrict__ A, long long lda,
                const float2* __restrict__ B, long long ldb, float2* __restrict__ C, long long ldc) {
-    __shared__ float2 sA[16][17], sB[16][17];
+    LM_SMEM_STATIC float2 sA[16][17], sB[16][17];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
     float2 acc = make_float2(0, 0);

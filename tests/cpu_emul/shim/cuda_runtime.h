@@ -60,7 +60,6 @@ struct Cta {
 };
 inline Cta*& cta() { static Cta* c = nullptr; return c; }
 inline unsigned char* dyn_smem() { alignas(128) static unsigned char buf[232448]; return buf; }
-static thread_local bool t_exited_barrier = false;
 
 struct MBar { long long tx = 0; int pending = 0, count = 0; unsigned phase = 0; };
 inline std::mutex& mbar_mutex() { static std::mutex m; return m; }
@@ -104,12 +103,28 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     return r;
 }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+    std::atomic_ref<unsigned long long> a(*p);
+    unsigned long long o = a.load();
+    while (o < v && !a.compare_exchange_weak(o, v)) {}
+    return o;
+}
+inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, sizeof r); return r; }
+inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+template <typename T> inline T __ldcv(const T* p) { return *(const volatile T*)p; }
+using std::fmax; using std::fmin; using std::fabs; using std::sqrt; using std::acos; using std::ceil;
 
 // dynamic / static shared memory of the kernels (csrc/common.cuh defines the CUDA forms)
 #define LM_SMEM_DYN(name) unsigned char* name = lm_emul::dyn_smem()
 #define LM_SMEM_STATIC static
 
 namespace lm {
+inline void st_release_sys(unsigned long long* p, unsigned long long v) { std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release); }
+inline unsigned long long ld_acquire_sys(const unsigned long long* p) { return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_acquire); }
 inline unsigned smem_u32(const void* p) { return (unsigned)(size_t)p; }
 inline void mbar_init(unsigned long long* bar, unsigned count) {
     std::lock_guard<std::mutex> g(lm_emul::mbar_mutex());
