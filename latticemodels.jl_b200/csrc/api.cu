@@ -1433,6 +1433,9 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
     StencilArgs a;
     a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld; a.nc = nc; a.keep = keep ? 1 : 0;
+    // LM_STEP_PDL=1 (opt-in): chains of factors are launched with programmatic dependent launch
+    static const int pdl_env = env_int("LM_STEP_PDL", 0);
+    a.pdl = (pdl_env && staged == 1 && !z && !u) ? 1 : 0;
     a.x = x; a.y = y; a.z = z; a.u = u;
     const zc g = gamma / alpha;
     a.alpha[0] = alpha.real(); a.alpha[1] = alpha.imag(); a.g[0] = g.real(); a.g[1] = g.imag();

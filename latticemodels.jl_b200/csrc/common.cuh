@@ -100,6 +100,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// programmatic dependent launch (griddepcontrol): no-ops for a grid launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif  // LM_CPU_EMUL
 
 }  // namespace lm

@@ -69,6 +69,9 @@ struct StencilArgs {
     long long nc;                   // columns processed, starting at the pointers (== ld for the whole block;
                                     // fewer for an L2-resident column strip of the propagator, api.cu step_*_prod)
     int keep;                       // 1: plain stores (y is re-read out of L2 by the next factor), 0: evict-first
+    int pdl;                        // 1: launched with programmatic stream serialization (k_apply_stencil_tma only):
+                                    //    let the next launch of the chain start its CTAs while this grid drains,
+                                    //    and wait for the previous grid before touching global memory
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], g[2], beta[2], delta[2];   // y = alpha (H x + g x) + beta z + delta u
     unsigned cps, nchunks;
@@ -272,6 +275,10 @@ k_apply_stencil_tma(const StencilArgs a) {
         mbar_init(&bar, 1);
         mbar_arrive_expect_tx(&bar, (unsigned)(HR * cw * (int)sizeof(E)) + (unsigned)vl1 * hline);
     }
+    // a chain of factors (x <- y of the previous launch): with programmatic dependent launch the
+    // CTAs of this grid are scheduled while the previous grid drains; nothing of global memory is
+    // touched before the previous grid has completed and flushed
+    if (a.pdl) { pdl_launch_dependents(); pdl_wait(); }
     __syncthreads();
     for (int r = tid; r < HR; r += NT) {
         const int u1 = r / ((P2 + 2) * RC), rem = r - u1 * ((P2 + 2) * RC), u2 = rem / RC, b = rem - u2 * RC;

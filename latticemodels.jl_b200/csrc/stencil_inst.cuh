@@ -29,6 +29,17 @@ static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         configured = true;
     }
+    if (a.pdl) {
+        // programmatic stream serialization: this grid may start while the previous one of the
+        // stream drains (the kernel waits with griddepcontrol.wait before touching memory)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(32 * W1 * W2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, a) == cudaSuccess ? 0 : -2;
+    }
     k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
     return 0;
     }

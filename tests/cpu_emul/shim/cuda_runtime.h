@@ -125,6 +125,8 @@ using std::fmax; using std::fmin; using std::fabs; using std::sqrt; using std::a
 namespace lm {
 inline void st_release_sys(unsigned long long* p, unsigned long long v) { std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release); }
 inline unsigned long long ld_acquire_sys(const unsigned long long* p) { return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_acquire); }
+inline void pdl_wait() {}
+inline void pdl_launch_dependents() {}
 inline unsigned smem_u32(const void* p) { return (unsigned)(size_t)p; }
 inline void mbar_init(unsigned long long* bar, unsigned count) {
     std::lock_guard<std::mutex> g(lm_emul::mbar_mutex());

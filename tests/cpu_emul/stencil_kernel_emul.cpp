@@ -73,7 +73,7 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
 
     const zc alpha(rnd(), rnd()), g(rnd(), rnd()), beta(rnd(), rnd()), delta(rnd(), rnd());
     StencilArgs a;
-    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.nc = nc; a.keep = keep;
+    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.nc = nc; a.keep = keep; a.pdl = 0;
     a.x = x.data() + c_off / EC; a.y = y.data() + c_off / EC;
     a.z = (MODE == 1 || MODE == 2) ? z.data() + c_off / EC : nullptr;
     a.u = (MODE == 2) ? u.data() + c_off / EC : nullptr;
