@@ -11,6 +11,7 @@ namespace lm {
 //   id 2  honeycomb NN + on-site (RC = 2)
 //   id 3  QWZ-type: 2 orbitals, full 2x2 blocks on-site and to the 4 nearest cells
 //   id 4  Haldane: honeycomb NN + NNN + on-site
+//   id 5  any RC = 2 pattern with |d| <= 1 (honeycomb with third neighbours, 2-orbital models with diagonal hops)
 
 static const StencilDesc g_desc[] = {
     {1, LM_ST_MASK0, st_width<1>(LM_ST_MASK0), "square-nn"},
@@ -18,6 +19,7 @@ static const StencilDesc g_desc[] = {
     {2, LM_ST_MASK2, st_width<2>(LM_ST_MASK2), "honeycomb-nn"},
     {2, LM_ST_MASK3, st_width<2>(LM_ST_MASK3), "qwz"},
     {2, LM_ST_MASK4, st_width<2>(LM_ST_MASK4), "haldane"},
+    {2, LM_ST_MASK5, st_width<2>(LM_ST_MASK5), "rc2-full"},
 };
 int stencil_count() { return (int)(sizeof(g_desc) / sizeof(g_desc[0])); }
 const StencilDesc& stencil_desc(int id) { return g_desc[id]; }
@@ -70,6 +72,7 @@ int stencil_launch_1(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 int stencil_launch_2(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 int stencil_launch_3(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 int stencil_launch_4(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_5(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
     switch (id) {
@@ -78,13 +81,14 @@ int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a
     case 2: return stencil_launch_2(variant, c64, mode, a, grid, s);
     case 3: return stencil_launch_3(variant, c64, mode, a, grid, s);
     case 4: return stencil_launch_4(variant, c64, mode, a, grid, s);
+    case 5: return stencil_launch_5(variant, c64, mode, a, grid, s);
     default: return -1;
     }
 }
 
 
 #define LM_ST_DECL(i) int stencil_observe_##i(bool, const StencilObsArgs&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
-LM_ST_DECL(0) LM_ST_DECL(1) LM_ST_DECL(2) LM_ST_DECL(3) LM_ST_DECL(4)
+LM_ST_DECL(0) LM_ST_DECL(1) LM_ST_DECL(2) LM_ST_DECL(3) LM_ST_DECL(4) LM_ST_DECL(5)
 #undef LM_ST_DECL
 int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
     switch (id) {
@@ -93,6 +97,7 @@ int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cu
     case 2: return stencil_observe_2(c64, a, grid, s);
     case 3: return stencil_observe_3(c64, a, grid, s);
     case 4: return stencil_observe_4(c64, a, grid, s);
+    case 5: return stencil_observe_5(c64, a, grid, s);
     default: return -1;
     }
 }
@@ -102,7 +107,8 @@ void stencil_obs_shape(int id, int* P1, int* P2, int* nf) {
     case 1: stencil_obs_shape_1(P1, P2, nf); break;
     case 2: stencil_obs_shape_2(P1, P2, nf); break;
     case 3: stencil_obs_shape_3(P1, P2, nf); break;
-    default: stencil_obs_shape_4(P1, P2, nf); break;
+    case 4: stencil_obs_shape_4(P1, P2, nf); break;
+    default: stencil_obs_shape_5(P1, P2, nf); break;
     }
 }
 

@@ -718,6 +718,7 @@ k_observe_stencil(const StencilObsArgs a) {
 #define LM_ST_MASK2 0x404f2020ull
 #define LM_ST_MASK3 0xf0fff0f0ull
 #define LM_ST_MASK4 0xd9dfb9b0ull
+#define LM_ST_MASK5 0xfffffffffull
 
 // ---- host-visible registry (stencil.cu) ----
 struct StencilDesc { int rc; st_mask_t mask; int sw; const char* name; };

@@ -94,13 +94,16 @@ static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, dim
 
 
 // observables kernel shape per RC: T1 x T2 cells per thread, W1 x W2 warps per CTA
-template <int RC> struct ObsShape;
-template <> struct ObsShape<1> { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };   // 8 x 4 cells, 256 threads
-template <> struct ObsShape<2> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 x 4 cells, 256 threads
+// (WIDE = more than 6 forward entries per row: one cell per thread keeps the partial sums in registers)
+template <int RC, bool WIDE> struct ObsShape;
+template <> struct ObsShape<1, false> { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };   // 8 x 4 cells, 256 threads
+template <> struct ObsShape<1, true>  { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };
+template <> struct ObsShape<2, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 x 4 cells, 256 threads
+template <> struct ObsShape<2, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };   // 4 x 2 cells, 256 threads
 
 template <typename T, int RC, st_mask_t MASK>
 static int launch_obs_t(const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
-    using S = ObsShape<RC>;
+    using S = ObsShape<RC, (st_nfwd<RC>(MASK) > 6)>;
     constexpr size_t smem = st_obs_smem<T, RC, S::T1, S::T2, S::W1, S::W2>();
     static bool configured = false;
     if (!configured) {
@@ -122,7 +125,7 @@ static int launch_obs(bool c64, const StencilObsArgs& a, unsigned grid, cudaStre
 }
 template <int RC, st_mask_t MASK>
 static void obs_shape(int* P1, int* P2, int* nf) {
-    using S = ObsShape<RC>;
+    using S = ObsShape<RC, (st_nfwd<RC>(MASK) > 6)>;
     *P1 = S::W1 * S::T1; *P2 = S::W2 * S::T2; *nf = st_nfwd<RC>(MASK);
 }
 

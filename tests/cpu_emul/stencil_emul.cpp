@@ -32,7 +32,7 @@ static bool check_tile(const char* name) {
     using T2c = typename cx2<T>::type;
     constexpr int EC = pack<T>::EC;
     constexpr int SW = st_width<RC>(MASK);
-    static zc x[T1 + 2][T2 + 2][RC][2], h[T1][T2][RC][16];
+    static zc x[T1 + 2][T2 + 2][RC][2], h[T1][T2][RC][20];
     for (auto& p : x) for (auto& q : p) for (auto& r : q) for (auto& v : r) v = zc(rnd(), rnd());
     for (auto& p : h) for (auto& q : p) for (auto& r : q) for (auto& v : r) v = zc(rnd(), rnd());
     const zc g(rnd(), rnd());
@@ -112,6 +112,7 @@ int main() {
     ok = ok && check_pattern<2, LM_ST_MASK2>("honeycomb-nn");
     ok = ok && check_pattern<2, LM_ST_MASK3>("qwz");
     ok = ok && check_pattern<2, LM_ST_MASK4>("haldane");
+    ok = ok && check_pattern<2, LM_ST_MASK5>("rc2-full");
     if (!ok) return 1;
     printf("OK %d checks\n", nchecks);
     return 0;

@@ -95,3 +95,54 @@ def test_strip_schedule_keeps_graph_cache_consistent():
         assert _relerr(st.download(), want) < 1e-12
     finally:
         _set_l2_kb(-1)
+
+
+# ------------------------------------------------------------------------------ catch-all RC = 2 stencil (pattern 5)
+def _stencil_id(dev):
+    lib = _lib.load()
+    i, rc, sw, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+    lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
+    _lib.check(lib.lm_dbg_stencil_info(dev.handle, C.byref(i), C.byref(rc), C.byref(sw), C.byref(m)))
+    return i.value
+
+
+@pytest.mark.parametrize("case", ["honeycomb_t123", "honeycomb_t123_torus"])
+def test_catch_all_two_row_stencil_matches_oracle(case):
+    """A two-rows-per-cell pattern outside the model-specific masks (honeycomb with third-neighbour
+    hops) runs on the catch-all RC = 2 stencil kernel (pattern 5, 18 slots per row, one cell per
+    thread in the observables kernel): SpMM, propagator, localdensity and DensityCurrents vs the oracle."""
+    ctx = lm.default_context("c128")
+    if case == "honeycomb_t123":
+        Hd = lm.tightbinding_hamiltonian(lm.HoneycombLattice(9, 11), t1=1, t2=0.2, t3=0.1, field=lm.LandauGauge(0.04))
+        Ho = OP.tightbinding_hamiltonian(L.honeycomb_lattice(9, 11), t1=1, t2=0.2, t3=0.1, field=F.LandauGauge(0.04))
+    else:
+        Hd = lm.tightbinding_hamiltonian(lm.HoneycombLattice(8, 7, boundaries=[("axis1", True), ("axis2", True)]), t1=1, t2=0.2, t3=0.1)
+        Ho = OP.tightbinding_hamiltonian(L.honeycomb_lattice(8, 7, periodic=(1, 2)), t1=1, t2=0.2, t3=0.1)
+    dev = Hd.device(ctx)
+    assert _stencil_id(dev) == 5
+    lib = _lib.load()
+    N = Ho.shape[0]
+    for M in (32, 45, 100):
+        X = _rand_block(N, M, seed=M)
+        x = lm.DeviceState.from_psi(X, ctx=ctx)
+        y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+        _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+        assert _relerr(y.download(), Ho @ X) < 1e-14, (case, M)
+    X = _rand_block(N, 40, seed=5)
+    want = EV.exact_propagator(Ho, 0.3) @ X
+    for method in ("taylor", "chebyshev", "chebyshev_clenshaw"):
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx)
+        sol.update_solver(Hd, 0.3)
+        sol.step(st)
+        assert _relerr(st.download(), want) < 2e-13, (case, method)
+    Hdn = Ho.toarray()
+    for M in (32, 70):
+        Psi = _rand_block(N, M, seed=M) / np.sqrt(N)
+        w = np.random.default_rng(M).random(M)
+        st = lm.DeviceState.from_psi(Psi, w, ctx=ctx)
+        I, J, V = lm.DensityCurrents(Hd, st).pair_values()
+        P = (Psi * w) @ Psi.conj().T
+        assert _relerr(lm.localdensity(st).values, np.real(np.diag(P))) < 1e-13
+        want_j = np.array([2 * np.imag(Hdn[i - 1, j - 1] * P[j - 1, i - 1]) for i, j in zip(I.tolist(), J.tolist())])
+        assert np.abs(V - want_j).max() < 1e-13 * max(1.0, np.abs(want_j).max()), (case, M)
