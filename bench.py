@@ -329,6 +329,7 @@ def main():
            "scaling": "strong", "vs_baseline": None, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
            "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
                       "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
+                      "schedule": {"l2_strip_mb": int(os.environ.get("LM_STEP_L2_MB", "0") or 0), "pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0)},
                       "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 
