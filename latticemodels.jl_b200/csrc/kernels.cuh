@@ -1062,10 +1062,12 @@ __global__ void k_scale_cols(long long N, long long M, long long ld, const T2* _
 // K staged through shared memory in slabs of 16.  (FP32 mode falls back to the same kernel
 // instantiated on float with FFMA - the dense path is only used for N <~ 4096.)
 // ------------------------------------------------------------------------------------------
+#ifndef LM_CPU_EMUL      // (the CPU execution harness restates the fragment layout, tests/cpu_emul/shim)
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+#endif
 
 template <bool CONJ_B>
 __global__ void __launch_bounds__(128)
