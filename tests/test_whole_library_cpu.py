@@ -19,7 +19,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_gpu_parity_suite_on_the_cpu_build_of_the_library(tmp_path):
+@pytest.fixture(scope="module")
+def emul_lib(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_emul"))
@@ -27,7 +28,20 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(tmp_path):
         import build_emul_lib
     finally:
         sys.path.pop(0)
-    so = build_emul_lib.build(str(tmp_path / "emul"))
+    return build_emul_lib.build(str(tmp_path_factory.mktemp("emul")))
+
+
+def test_randomised_parity_sweep_on_the_cpu_build(emul_lib):
+    """tools/fuzz_parity.py: 80 random (lattice, boundaries, model, field, width, precision, method,
+    step, schedule) cases through the C ABI against the oracle - device-assembled H, H X, evolution
+    steps vs the exact exponential, localdensity and DensityCurrents."""
+    env = dict(os.environ, LM_EMUL_LIB=emul_lib, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "1000", "80"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert res.returncode == 0 and "80 cases, 0 failures" in res.stdout, (res.stdout + res.stderr)[-3000:]
+
+
+def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
+    so = emul_lib
     # the emulated kernels are single-threaded per process: xdist workers, BLAS kept to two threads each
     env = dict(os.environ, LM_EMUL_LIB=so, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
     for k in ("LM_STEP_L2_MB", "LM_STEP_PDL", "LM_APPLY_TILED", "LM_APPLY_STENCIL", "LM_STENCIL_VARIANT"):
