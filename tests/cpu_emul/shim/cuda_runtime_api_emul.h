@@ -4,6 +4,7 @@
 // cudaGraphLaunch - kernel arguments are evaluated when the launch is recorded, as on the device.
 // TEST INFRASTRUCTURE ONLY.
 #pragma once
+#include <sys/mman.h>
 
 enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 inline const char* cudaGetErrorString(cudaError_t e) {
@@ -49,14 +50,32 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
     *v = (a == cudaDevAttrMultiProcessorCount) ? 148 : (a == cudaDevAttrL2CacheSize ? 126 * 1024 * 1024 : 0);
     return cudaSuccess;
 }
+// Device allocations END at a PROT_NONE guard page (16-byte granularity): a kernel or copy that runs
+// past a buffer - silently tolerated by a real GPU more often than not - faults here.
+namespace lm_emul {
+struct Alloc { void* map; size_t map_bytes; size_t bytes; };
+inline std::map<void*, Alloc>& allocs() { static std::map<void*, Alloc> m; return m; }
+}
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
-    void* q = nullptr;
-    if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) return cudaErrorMemoryAllocation;
-    std::memset(q, 0xA5, bytes);                    // device memory is not zeroed: make reliance on it visible
+    const size_t page = 4096, need = (bytes + 15) & ~(size_t)15;
+    const size_t body = (need + page - 1) / page * page;
+    void* map = mmap(nullptr, body + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (map == MAP_FAILED) return cudaErrorMemoryAllocation;
+    mprotect((char*)map + body, page, PROT_NONE);
+    char* q = (char*)map + body - need;
+    std::memset(map, 0xA5, body);                   // device memory is not zeroed: make reliance on it visible
+    lm_emul::allocs()[q] = lm_emul::Alloc{map, body + page, bytes};
     *p = (T*)q; ++lm_emul::live_allocs();
     return cudaSuccess;
 }
-inline cudaError_t cudaFree(void* p) { if (p) { std::free(p); --lm_emul::live_allocs(); } return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    auto it = lm_emul::allocs().find(p);
+    if (it == lm_emul::allocs().end()) { fprintf(stderr, "EMUL FAULT: cudaFree of a pointer cudaMalloc did not return (%p)\n", p); std::abort(); }
+    munmap(it->second.map, it->second.map_bytes);
+    lm_emul::allocs().erase(it); --lm_emul::live_allocs();
+    return cudaSuccess;
+}
 template <typename T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { *p = (T*)std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
