@@ -255,6 +255,10 @@ def main():
     l0 = ctx.launch_count()
     ms, t0, t1 = timed(dev_step, args.steps)
     launches = ctx.launch_count() - l0
+    # schedule of the timed steps: strip width in columns (0 = plain, -1 = fixed by LM_STEP_L2_MB)
+    lib.lm_dbg_step_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    sched_cols, sched_cal = C.c_int64(0), C.c_int32(0)
+    lib.lm_dbg_step_schedule(state.handle, C.byref(sched_cols), C.byref(sched_cal))
     clocks = sampler.stop(t0, t1)
     K = sol.n_matvec
     ms_per_step = ms / args.steps
@@ -274,7 +278,8 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf):
+    plain_schedule = launches <= args.steps * (K + 2)
+    if os.path.exists(tf) and plain_schedule:        # the stored ncu traffic is that of the plain schedule
         traffic = json.load(open(tf)).get("%s_n%d" % (args.workload, world))
     roofline = {"bound": "hbm", "kernel": "lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -329,7 +334,8 @@ def main():
            "scaling": "strong", "vs_baseline": None, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
            "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
                       "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
-                      "schedule": {"l2_strip_mb": int(os.environ.get("LM_STEP_L2_MB", "0") or 0), "pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0)},
+                      "schedule": {"LM_STEP_L2_MB": os.environ.get("LM_STEP_L2_MB", "unset (plain)"), "online_choice_strip_cols": int(sched_cols.value),
+                                   "pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(args.steps, 1)},
                       "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 

@@ -174,8 +174,14 @@ struct lm_state {
     // CUDA graphs of one propagation step (the K term launches), keyed by plan + buffer roles
     struct StepGraph { cudaGraphExec_t exec = nullptr; lm_ham* h = nullptr; unsigned long long uid = 0, epoch = 0; void* x = nullptr; void* s1 = nullptr;
                        double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false;
-                       unsigned long long sched = 0; };      // sched: g_sched_epoch the graph was captured under
-    StepGraph graphs[4]; int graph_next = 0;
+                       unsigned long long sched = 0; long long kb = 0; };   // sched: g_sched_epoch at capture; kb: schedule (strip width in columns, 0 = plain)
+    StepGraph graphs[8]; int graph_next = 0;
+    // online choice of the step schedule (plain vs L2-resident strips): the first steps of a
+    // (Hamiltonian, dt, tol, method) run one candidate each, timed with events; all candidates give
+    // bit-identical results, so these are ordinary steps
+    struct Tune { bool valid = false; unsigned long long uid = 0, epoch = 0, sched = 0; double dt = 0, tol = 0; int method = -1; long long ld = 0;
+                  int ncand = 0, phase = 0, choice = -1; long long cand[3] = {0, 0, 0}; float ms[3] = {0, 0, 0}; };
+    Tune tune; cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
     // block-Lanczos workspace (LM_METHOD_LANCZOS): Krylov basis + per-column scalars
     std::vector<void*> kry; double2* d_alpha = nullptr; double* d_beta = nullptr; double2* d_coef = nullptr;
     double* d_err = nullptr; unsigned long long* d_max = nullptr; double2* d_dot = nullptr;
@@ -1022,6 +1028,8 @@ static void state_free(lm_state* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (s->tune_ev0) cudaEventDestroy(s->tune_ev0);
+    if (s->tune_ev1) cudaEventDestroy(s->tune_ev1);
     for (void* p : s->kry) if (p) cudaFree(p);
     { void* q[] = {s->d_alpha, s->d_beta, s->d_coef, s->d_err, s->d_max, s->d_dot}; for (void* p : q) if (p) cudaFree(p); }
     void* ptrs[] = {s->d_x, s->d_w, s->d_s1, s->d_s2, s->d_U};
@@ -1419,6 +1427,12 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
 }
 
 static int g_stencil_variant = -1;       // lm_dbg_set_stencil_variant (sweeps): -1 = default per pattern
+static int stencil_variant_of(const lm_ham* h) {
+    static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
+    int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
+    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
+    return variant;
+}
 // nc = columns processed starting at the pointers (ld = the whole block; fewer for an L2-resident
 // column strip, see step_strips), keep = plain instead of evict-first stores of y
 static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
@@ -1426,9 +1440,7 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     lm_ctx* c = h->ctx;
     FWD(refresh_views(h));
     if (nc < 0) nc = ld;
-    static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
-    int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
-    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
+    const int variant = stencil_variant_of(h);
     int P1, P2, cpt, staged;
     stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
     StencilArgs a;
@@ -1594,10 +1606,23 @@ static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
 // The result lands in the same buffer for every strip (parity of the factor count).
 // ------------------------------------------------------------------------------------------
 struct Factor { zc alpha, gamma; };
-static long long g_step_l2_kb = -1;      // lm_dbg_set_step_l2_kb (tests / sweeps): -1 = LM_STEP_L2_MB
-static long long strip_columns(const lm_ham* h, long long ld) {
-    static const int mb_env = env_int("LM_STEP_L2_MB", 0);
-    const long long kb = g_step_l2_kb >= 0 ? g_step_l2_kb : 1024LL * mb_env;
+static const long long kSchedAuto = -1;
+static long long g_step_l2_kb = -1;      // lm_dbg_set_step_l2_kb (tests / sweeps): >= 0 fixed budget (0 = plain), -1 = LM_STEP_L2_MB
+static long long g_tune_kb[2] = {0, 0};  // lm_dbg_set_autotune_kb: fixed candidate budgets of the online choice (0, 0 = wave-aware default)
+static long long g_cur_ms = 0;           // schedule of the step being enqueued: strip width in columns, 0 = plain (set by lm_step, read by run_factors)
+// LM_STEP_L2_MB: unset = plain schedule, "auto" = online choice between plain and two strip budgets,
+// <MB> = fixed strip budget
+static long long sched_request() {
+    if (g_step_l2_kb >= 0) return g_step_l2_kb;
+    static const long long env_kb = [] {
+        const char* v = getenv("LM_STEP_L2_MB");
+        if (!v || !*v) return 0LL;
+        if (!strcmp(v, "auto")) return kSchedAuto;
+        return 1024LL * std::max(0, atoi(v));
+    }();
+    return g_step_l2_kb == -2 ? kSchedAuto : env_kb;
+}
+static long long strip_columns(const lm_ham* h, long long ld, long long kb) {
     if (kb <= 0 || !stencil_path(h, ld)) return 0;
     const lm_ctx* c = h->ctx;
     const long long unit = 32 * (c->precision == LM_C128 ? 1 : 2);      // one staged chunk of the kernel
@@ -1609,8 +1634,42 @@ static long long strip_columns(const lm_ham* h, long long ld) {
     ms = (((ld + nstrips - 1) / nstrips) + unit - 1) / unit * unit;
     return ms;
 }
+// Candidate strip widths of the online choice: every width (a multiple of the kernel's chunk) whose
+// two strip buffers stay under 60 % of the L2, ranked by how evenly its CTAs fill the machine
+// (patches x chunks against the resident CTAs of all SMs); the best two, wider first on near-ties.
+static int strip_candidates(const lm_ham* h, long long ld, long long out[2]) {
+    const lm_ctx* c = h->ctx;
+    if (!stencil_path(h, ld)) return 0;
+    if (g_tune_kb[0] > 0 || g_tune_kb[1] > 0) {
+        int n = 0;
+        for (long long kb : g_tune_kb) { const long long ms = strip_columns(h, ld, kb); if (ms > 0 && (n == 0 || out[0] != ms)) out[n++] = ms; }
+        return n;
+    }
+    // a block whose two buffers (nearly) fit the L2 is L2-resident under the plain schedule already
+    const double l2 = (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
+    if (2.0 * (double)h->N * (double)ld * (double)c->esz() <= 1.5 * l2) return 0;
+    const int variant = stencil_variant_of(h);
+    int P1, P2, cpt, staged;
+    stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
+    if (staged != 1) return 0;
+    const long long unit = 32LL * cpt * (c->precision == LM_C128 ? 1 : 2);
+    const double cap = 0.6 * l2;
+    const long long npatch = ((h->lat_n1 + P1 - 1) / P1) * ((h->lat_n2 + P2 - 1) / P2);
+    const long long resident = (long long)stencil_resident_ctas(h->st_id, variant, c->precision != LM_C128) * (c->sm_count > 0 ? c->sm_count : 148);
+    double best[2] = {0, 0}; int n = 0;
+    for (long long nch = 2; ; ++nch) {
+        const long long ms = nch * unit;
+        if (ms >= ld || 2.0 * (double)h->N * (double)ms * (double)c->esz() > cap) break;
+        const long long ctas = npatch * nch, waves = (ctas + resident - 1) / resident;
+        const double eff = (double)ctas / (double)(waves * resident) + 1e-4 * (double)nch;   // near-ties: the wider strip
+        if (n < 2) { out[n] = ms; best[n] = eff; ++n; if (n == 2 && best[1] > best[0]) { std::swap(best[0], best[1]); std::swap(out[0], out[1]); } }
+        else if (eff > best[0]) { best[1] = best[0]; out[1] = out[0]; best[0] = eff; out[0] = ms; }
+        else if (eff > best[1]) { best[1] = eff; out[1] = ms; }
+    }
+    return n;
+}
 static int run_factors(lm_ham* h, long long ld, void** px, void** ps1, const std::vector<Factor>& fac, int* nmv) {
-    const long long ms = strip_columns(h, ld);
+    const long long ms = (g_cur_ms > 0 && g_cur_ms < ld && stencil_path(h, ld)) ? g_cur_ms : 0;
     const int nf = (int)fac.size();
     if (ms <= 0) {
         for (int j = 0; j < nf; ++j) {
@@ -1634,7 +1693,57 @@ static int run_factors(lm_ham* h, long long ld, void** px, void** ps1, const std
     *nmv += nf;
     return LM_OK;
 }
+// kb >= 0: fixed strip budget in KiB (0 = plain schedule); -1: what LM_STEP_L2_MB says; -2: online choice
 extern "C" int32_t lm_dbg_set_step_l2_kb(int64_t kb) { g_step_l2_kb = kb; ++g_sched_epoch; return LM_OK; }
+extern "C" int32_t lm_dbg_set_autotune_kb(int64_t kb_a, int64_t kb_b) { g_tune_kb[0] = kb_a; g_tune_kb[1] = kb_b; ++g_sched_epoch; return LM_OK; }
+// Schedule of the next product-form step of `s` under `h`.  *timed: this step is a calibration
+// sample (the caller brackets it with events and reports back through tune_record).
+static long long pick_schedule(lm_ham* h, lm_state* s, double dt, double tol, int method, bool* timed) {
+    *timed = false;
+    const long long req = sched_request();
+    if (req != kSchedAuto) return strip_columns(h, s->ld, req);
+    lm_state::Tune& t = s->tune;
+    if (!t.valid || t.uid != h->uid || t.epoch != h->layout_epoch || t.sched != g_sched_epoch || t.dt != dt || t.tol != tol || t.method != method || t.ld != s->ld) {
+        t = lm_state::Tune();
+        t.valid = true; t.uid = h->uid; t.epoch = h->layout_epoch; t.sched = g_sched_epoch; t.dt = dt; t.tol = tol; t.method = method; t.ld = s->ld;
+        t.cand[t.ncand++] = 0;
+        long long ms2[2];
+        const int nc = strip_candidates(h, s->ld, ms2);
+        for (int k = 0; k < nc; ++k) t.cand[t.ncand++] = ms2[k];
+        if (t.ncand == 1) t.choice = 0;             // strips do not apply (N too large, narrow block, no stencil view)
+    }
+    if (t.choice >= 0) return t.cand[t.choice];
+    *timed = true;
+    return t.cand[t.phase];
+}
+static void tune_record(lm_state* s, float ms) {
+    lm_state::Tune& t = s->tune;
+    t.ms[t.phase++] = ms;
+    if (t.phase < t.ncand) return;
+    t.choice = 0;
+    for (int k = 1; k < t.ncand; ++k) if (t.ms[k] < t.ms[t.choice]) t.choice = k;
+    if (getenv("LM_DEBUG_PLAN")) fprintf(stderr, "step schedule: plain %.3f ms, strips(%lld columns) %.3f ms, strips(%lld columns) %.3f ms -> %lld\n",
+                                         t.ms[0], t.cand[1], t.ms[1], t.cand[2], t.ms[2], t.cand[t.choice]);
+}
+// candidate strip widths the online choice would sample for a block of leading dimension ld
+extern "C" int32_t lm_dbg_strip_candidates(lm_ham* h, int64_t ld, int64_t* out2, int32_t* n) {
+    REQUIRE(h && out2 && n, "lm_dbg_strip_candidates: NULL");
+    FWD(refresh_views(h));
+    long long ms[2] = {0, 0};
+    *n = strip_candidates(h, ld, ms);
+    out2[0] = ms[0]; out2[1] = ms[1];
+    return LM_OK;
+}
+// schedule the online choice settled on for the state: *strip_cols = strip width in columns
+// (0 = plain), *calibrating = 1 while it is still sampling; (-1, 0) when the schedule is fixed by
+// LM_STEP_L2_MB / lm_dbg_set_step_l2_kb
+extern "C" int32_t lm_dbg_step_schedule(lm_state* s, int64_t* strip_cols, int32_t* calibrating) {
+    REQUIRE(s && strip_cols && calibrating, "lm_dbg_step_schedule: NULL");
+    if (sched_request() != kSchedAuto) { *strip_cols = -1; *calibrating = 0; return LM_OK; }
+    *calibrating = (s->tune.valid && s->tune.choice < 0) ? 1 : 0;
+    *strip_cols = (s->tune.valid && s->tune.choice >= 0) ? s->tune.cand[s->tune.choice] : 0;
+    return LM_OK;
+}
 
 // Product-form Taylor: exp(A) ~ p_K(A) = prod_j (I - A / r_j), r_j the roots of the truncated
 // exponential (taylor_roots.h), A = -i H dt / nsub.  Each factor is ONE pass
@@ -1996,7 +2105,12 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
         static const int use_graph = env_int("LM_STEP_GRAPH", 1);
         const bool graphable = use_graph && product_form;
         FWD(refresh_views(h));
+        bool timed = false;
+        g_cur_ms = product_form ? pick_schedule(h, s, dt, tol, method, &timed) : 0;
+        struct Restore { ~Restore() { g_cur_ms = 0; } } restore_schedule;
+        if (timed && !s->tune_ev0) { CK(cudaEventCreate(&s->tune_ev0)); CK(cudaEventCreate(&s->tune_ev1)); }
         if (!graphable) {
+            if (timed) CK(cudaEventRecord(s->tune_ev0, c->stream));
             FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
         } else {
             // The step is K back-to-back launches with fixed arguments: replay it as one graph
@@ -2005,9 +2119,9 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
             lm_state::StepGraph* g = nullptr;
             for (auto& c2 : s->graphs)
                 if (c2.exec && c2.h == h && c2.uid == h->uid && c2.epoch == h->layout_epoch && c2.x == s->d_x && c2.s1 == s->d_s1 && c2.dt == dt && c2.tol == tol && c2.method == method &&
-                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf && c2.sched == g_sched_epoch) { g = &c2; break; }
+                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf && c2.sched == g_sched_epoch && c2.kb == g_cur_ms) { g = &c2; break; }
             if (!g) {
-                g = &s->graphs[s->graph_next]; s->graph_next = (s->graph_next + 1) % 4;
+                g = &s->graphs[s->graph_next]; s->graph_next = (s->graph_next + 1) % 8;
                 if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
                 void *x0 = s->d_x, *s10 = s->d_s1;
                 const long long l0 = c->launches;
@@ -2021,15 +2135,23 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g->exec = nullptr; s->d_x = x0; s->d_s1 = s10; return fail(LM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
                 g->h = h; g->uid = h->uid; g->epoch = h->layout_epoch; g->x = x0; g->s1 = s10; g->dt = dt; g->tol = tol; g->method = method;
-                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv; g->sched = g_sched_epoch;
+                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv; g->sched = g_sched_epoch; g->kb = g_cur_ms;
                 g->launches = c->launches - l0; g->swap = (s->d_x != x0);
                 c->launches = l0;                       // counted at replay
                 s->d_x = x0; s->d_s1 = s10;             // capture did not execute anything
             }
+            if (timed) CK(cudaEventRecord(s->tune_ev0, c->stream));     // device time of the replay only (capture is host work)
             CK(cudaGraphLaunch(g->exec, c->stream));
             c->launches += g->launches;
             nmv = g->nmv;
             if (g->swap) std::swap(s->d_x, s->d_s1);
+        }
+        if (timed) {
+            float ms = 0.f;
+            CK(cudaEventRecord(s->tune_ev1, c->stream));
+            CK(cudaEventSynchronize(s->tune_ev1));
+            CK(cudaEventElapsedTime(&ms, s->tune_ev0, s->tune_ev1));
+            tune_record(s, ms);
         }
     } else {
         // P <- U P U^H with U = exp(-i H dt) built by applying the propagator to the identity

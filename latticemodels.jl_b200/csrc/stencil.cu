@@ -67,6 +67,18 @@ void stencil_variant_shape(int v, int* P1, int* P2, int* cpt, int* staged) {
     *P1 = g_var[v].w1 * g_var[v].t1; *P2 = g_var[v].w2 * g_var[v].t2; *cpt = g_var[v].cpt; *staged = g_var[v].staged;
 }
 
+// CTAs of k_apply_stencil_tma resident per SM (host restatement of st_tma_smem / st_tma_blocks)
+int stencil_resident_ctas(int id, int v, bool c64) {
+    const Variant& q = g_var[v];
+    const int rc = g_desc[id].rc, sw = stencil_stride(id, c64);
+    const int P1 = q.w1 * q.t1, P2 = q.w2 * q.t2;
+    const size_t smem = (size_t)(P1 + 2) * (P2 + 2) * rc * 32 * q.cpt * 16 + (size_t)P1 * P2 * rc * sw * (c64 ? 8 : 16);
+    const int by_smem = (int)((227 * 1024) / (smem + 1024 + 64));
+    const int by_regs = st_min_blocks(q.t1 * q.t2 * rc * q.cpt * 4, 32 * q.w1 * q.w2);
+    const int m = by_smem < by_regs ? by_smem : by_regs;
+    return m < 1 ? 1 : m;
+}
+
 int stencil_launch_0(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 int stencil_launch_1(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
 int stencil_launch_2(int, bool, int, const StencilArgs&, dim3, cudaStream_t);

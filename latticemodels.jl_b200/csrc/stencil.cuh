@@ -730,6 +730,7 @@ int stencil_diag_slot(int id, int a);                      // slot of the diagon
 int stencil_num_variants();
 // patch size in cells, lane elements per thread and kernel family (staged = TMA) of a variant
 void stencil_variant_shape(int variant, int* P1, int* P2, int* cpt, int* staged);
+int stencil_resident_ctas(int id, int variant, bool c64);  // CTAs of the staged kernel resident per SM
 // launches; returns 0 on success, -1 if (id, variant, mode) is not compiled, -2 on a CUDA error
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s);
 // fused observables: patch size / forward-slot count of the compiled kernel, and its launch

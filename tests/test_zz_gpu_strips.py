@@ -146,3 +146,84 @@ def test_catch_all_two_row_stencil_matches_oracle(case):
         assert _relerr(lm.localdensity(st).values, np.real(np.diag(P))) < 1e-13
         want_j = np.array([2 * np.imag(Hdn[i - 1, j - 1] * P[j - 1, i - 1]) for i, j in zip(I.tolist(), J.tolist())])
         assert np.abs(V - want_j).max() < 1e-13 * max(1.0, np.abs(want_j).max()), (case, M)
+
+
+# ------------------------------------------------------------------------------ online choice of the schedule
+def test_online_schedule_choice_samples_every_candidate_and_settles():
+    """LM_STEP_L2_MB=auto (here: lm_dbg_set_step_l2_kb(-2)): the first steps of a (Hamiltonian, dt,
+    tol, method) run one candidate schedule each - plain, strips of two budgets - timed with events;
+    afterwards the fastest is used.  All candidates are bit-identical, so the sampled steps are
+    ordinary steps: the trajectory must equal the plain one bit for bit."""
+    ctx = lm.default_context("c128")
+    lib = _lib.load()
+    lib.lm_dbg_set_autotune_kb.argtypes = [C.c_int64, C.c_int64]
+    lib.lm_dbg_step_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    Hd = lm.haldane(lm.HoneycombLattice(9, 8), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.05))
+    Ho = OP.haldane(L.honeycomb_lattice(9, 8), 1.0, 0.2, 0.1, field=F.LandauGauge(0.05))
+    N = Ho.shape[0]
+    X = _rand_block(N, 300, seed=11)
+    kb64, kb128 = 2 * N * 16 * 64 // 1024 + 1, 2 * N * 16 * 128 // 1024 + 1
+    try:
+        _set_l2_kb(0)
+        ref = lm.DeviceState.from_psi(X, ctx=ctx)
+        sol0 = lm.B200Exp(tol=1e-13, ctx=ctx)
+        sol0.update_solver(Hd, 0.2)
+        for _ in range(6):
+            sol0.step(ref)
+        _lib.check(lib.lm_dbg_set_autotune_kb(kb64, kb128))
+        _set_l2_kb(-2)
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        sol = lm.B200Exp(tol=1e-13, ctx=ctx)
+        sol.update_solver(Hd, 0.2)
+        kb, cal = C.c_int64(), C.c_int32()
+        per_step = []
+        for k in range(6):
+            n0 = ctx.launch_count()
+            sol.step(st)
+            per_step.append(ctx.launch_count() - n0)
+            _lib.check(lib.lm_dbg_step_schedule(st.handle, C.byref(kb), C.byref(cal)))
+            assert cal.value == (1 if k < 2 else 0), (k, cal.value)
+        # step 0 plain (K launches), step 1 strips of 64 columns (5 strips), step 2 strips of 128 (3 strips)
+        assert per_step[1] == 5 * per_step[0] and per_step[2] == 3 * per_step[0], per_step
+        assert kb.value in (0, 64, 128)          # the strip width the choice settled on (0 = plain)
+        assert len(set(per_step[3:])) == 1 and per_step[3] in per_step[:3]
+        assert np.array_equal(st.download(), ref.download())
+        U = EV.exact_propagator(Ho, 0.2)
+        want = X
+        for _ in range(6):
+            want = U @ want
+        assert _relerr(st.download(), want) < 1e-12
+        # a new dt is a new calibration; a block too narrow for strips settles at once on the plain schedule
+        sol.update_solver(Hd, 0.1)
+        sol.step(st)
+        _lib.check(lib.lm_dbg_step_schedule(st.handle, C.byref(kb), C.byref(cal)))
+        assert cal.value == 1
+        narrow = lm.DeviceState.from_psi(X[:, :40].copy(), ctx=ctx)
+        sol.step(narrow)
+        _lib.check(lib.lm_dbg_step_schedule(narrow.handle, C.byref(kb), C.byref(cal)))
+        assert cal.value == 0 and kb.value == 0
+    finally:
+        _set_l2_kb(-1)
+        lib.lm_dbg_set_autotune_kb(0, 0)
+
+
+def test_strip_candidates_fill_the_machine_evenly():
+    """The widths the online choice samples: multiples of the kernel's 32-column chunk whose two strip
+    buffers stay under 60 % of the L2, ranked by wave efficiency (patches x chunks against the CTAs
+    resident on all SMs).  C2 (square 100 x 100, 5000 columns): 13 x 13 patches of 8 x 8 cells, 4
+    CTAs per SM -> 592 resident; 7 chunks = 1183 CTAs fill two waves (1184) almost exactly, 6 chunks =
+    1014 CTAs are next (0.86).  C4-sized lattices have no candidate (the plain schedule)."""
+    ctx = lm.default_context("c128")
+    lib = _lib.load()
+    lib.lm_dbg_strip_candidates.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    out, n = (C.c_int64 * 2)(), C.c_int32()
+    dev = lm.tightbinding_hamiltonian(lm.SquareLattice(100, 100)).device(ctx)
+    _lib.check(lib.lm_dbg_strip_candidates(dev.handle, 5000, out, C.byref(n)))
+    assert n.value == 2 and list(out) == [224, 192], (n.value, list(out))
+    for ms in out:
+        assert ms % 32 == 0 and 2 * 10**4 * ms * 16 <= 0.6 * 126 * 2**20
+    _lib.check(lib.lm_dbg_strip_candidates(dev.handle, 96, out, C.byref(n)))      # 31 MB of buffers: L2-resident as it is
+    assert n.value == 0
+    big = lm.haldane(lm.HoneycombLattice(200, 200), 1.0, 0.2, 0.1).device(ctx)     # N = 8e4: a 64-column strip pair is 164 MB
+    _lib.check(lib.lm_dbg_strip_candidates(big.handle, 4096, out, C.byref(n)))
+    assert n.value == 0
