@@ -3,8 +3,8 @@
 // reductions with their finalisation, the Gershgorin enclosure, the per-column Lanczos
 // exponential coefficients) behind a plain C interface, so that tests/test_device_code_cpu.py can
 // feed them numpy arrays and compare with the oracle - on the CPU, no GPU needed.  The kernels are
-// the product's own source, compiled by g++ through shim/cuda_runtime.h (threads of a CTA are OS
-// threads).  TEST INFRASTRUCTURE ONLY - never linked into the product.
+// the product's own source, compiled by g++ through shim/cuda_runtime.h (threads of a CTA are
+// fibers).  TEST INFRASTRUCTURE ONLY - never linked into the product.
 #include "kernels.cuh"
 
 using namespace lm;
@@ -103,6 +103,36 @@ double emul_lanczos_coef(long long M, int m, long long ldc, double dt, const dou
     lm_emul::launch(run_max, dim3(grid), th, MaxArgs{M, err, &bits});
     double v; std::memcpy(&v, &bits, sizeof v);
     return v;
+}
+
+// Fused finalize + peer-memory all-gather of the per-frame [rho | J] (k_finalize_obs_p2p /
+// k_obs_p2p_reduce), `nranks` ranks played in ONE address space: every rank owns a symmetric buffer
+// flags[2][nranks] | slots[2][nranks][cap] laid out as api.cu does (4096 flag bytes), pushes its
+// partial into its slot on EVERY peer and publishes the frame epoch; then every rank acquires all
+// flags and sums.  Inputs per rank r: dens_r [N], G_r [N*W]; output per rank: obs_r [tot].
+// Returns the number of ranks whose `done` counter was re-armed (must be nranks).
+int emul_p2p_frame(int nranks, long long cap, unsigned long long epoch, long long n_sites, int n_int, long long npairs,
+                   const int* pair_ptr, const int* pair_ent, const double* vals, const double* const* dens, const double* const* G,
+                   void* const* bufs /* nranks symmetric buffers */, unsigned* const* done, double* const* obs) {
+    const size_t flag_bytes = 4096;
+    const int parity = (int)(epoch & 1);
+    const long long tot = n_sites + npairs;
+    const int th = 256; const unsigned grid = (unsigned)((tot + th - 1) / th);
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) {
+        char* base = (char*)bufs[r < nranks ? r : 0];
+        pp.flags[r] = (unsigned long long*)base; pp.slots[r] = (double*)(base + flag_bytes);
+    }
+    for (int r = 0; r < nranks; ++r)
+        lm_emul::enqueue(grid, th, [](auto... a_) { k_finalize_obs_p2p<double>(a_...); }, n_sites, n_int, dens[r], npairs, pair_ptr, pair_ent,
+                         (const double2*)vals, (const double2*)G[r], 1, pp, r, nranks, cap, parity, epoch, done[r]);
+    int rearmed = 0;
+    for (int r = 0; r < nranks; ++r) {
+        rearmed += (*done[r] == 0);
+        lm_emul::enqueue(grid, th, [](auto... a_) { k_obs_p2p_reduce(a_...); }, tot, (const double*)((char*)bufs[r] + flag_bytes),
+                         (const unsigned long long*)bufs[r], nranks, cap, parity, epoch, obs[r]);
+    }
+    return rearmed;
 }
 
 }  // extern "C"
