@@ -39,8 +39,8 @@ for mb in 24 40 56 72 96; do
     run c2_l2_${mb}         LM_STEP_L2_MB=$mb LM_STEP_PDL=0 -- --steps 40 --warmup 5
     run c2_l2_${mb}_pdl     LM_STEP_L2_MB=$mb LM_STEP_PDL=1 -- --steps 40 --warmup 5
 done
-run c2_auto             LM_STEP_L2_MB=auto LM_STEP_PDL=0 -- --steps 40 --warmup 5
-run c2_auto_pdl         LM_STEP_L2_MB=auto LM_STEP_PDL=1 -- --steps 40 --warmup 5
+run c2_auto             LM_STEP_L2_MB=auto LM_STEP_PDL=0 LM_DEBUG_PLAN=1 -- --steps 40 --warmup 5
+run c2_auto_pdl         LM_STEP_L2_MB=auto LM_STEP_PDL=1 LM_DEBUG_PLAN=1 -- --steps 40 --warmup 5
 run c2_c64_plain        LM_STEP_L2_MB=0  LM_STEP_PDL=0 -- --steps 40 --warmup 5 --precision c64
 run c2_c64_l2_56_pdl    LM_STEP_L2_MB=56 LM_STEP_PDL=1 -- --steps 40 --warmup 5 --precision c64
 
@@ -48,7 +48,7 @@ echo "== 3. narrow shards (one of 8 GPUs' share): launch-bound regime"
 run c2_m625_plain       LM_STEP_L2_MB=0  LM_STEP_PDL=0 -- --steps 100 --warmup 10 --M 625
 run c2_m625_pdl         LM_STEP_L2_MB=0  LM_STEP_PDL=1 -- --steps 100 --warmup 10 --M 625
 run c2_m625_l2_56_pdl   LM_STEP_L2_MB=56 LM_STEP_PDL=1 -- --steps 100 --warmup 10 --M 625
-run c2_m625_auto_pdl    LM_STEP_L2_MB=auto LM_STEP_PDL=1 -- --steps 100 --warmup 10 --M 625
+run c2_m625_auto_pdl    LM_STEP_L2_MB=auto LM_STEP_PDL=1 LM_DEBUG_PLAN=1 -- --steps 100 --warmup 10 --M 625
 
 echo "== 4. C3 / C4: PDL only (N too large for strips)"
 run c3_plain            LM_STEP_PDL=0 -- --workload c3 --steps 10 --warmup 3
