@@ -40,6 +40,15 @@ def test_randomised_parity_sweep_on_the_cpu_build(emul_lib):
     assert res.returncode == 0 and "80 cases, 0 failures" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 
+def test_smoke_entry_point_on_the_cpu_build(emul_lib):
+    """__graft_entry__.smoke() - the README-style Psi-block evolution with localdensity and
+    DensityCurrents checked against the oracle - on the CPU build of the library."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import conftest; assert conftest._emulated_library(); "
+            "import __graft_entry__ as g; g.smoke()" % (ROOT, os.path.join(ROOT, "tests")))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LM_EMUL_LIB=emul_lib), timeout=600)
+    assert res.returncode == 0 and "smoke ok" in res.stdout, (res.stdout + res.stderr)[-3000:]
+
+
 def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     so = emul_lib
     # the emulated kernels are single-threaded per process: xdist workers, BLAS kept to two threads each
