@@ -1182,14 +1182,26 @@ extern "C" int32_t lm_state_download_dense(lm_state* s, void* out) {
 // ------------------------------------------------------------------------------------------
 // the polynomial propagators
 // ------------------------------------------------------------------------------------------
+// launch with programmatic stream serialization: the grid may be scheduled while the previous one of
+// the stream drains (the kernel waits with griddepcontrol.wait before touching global memory)
+template <typename K, typename A>
+static void launch_pdl(K kernel, const A& a, dim3 grid, unsigned threads, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
 template <typename T, int CPT, int MODE>
 static void launch_apply_w(const ApplyArgs& a, dim3 grid, cudaStream_t s) {
     static const int generic_only = getenv("LM_APPLY_GENERIC") ? atoi(getenv("LM_APPLY_GENERIC")) : 0;
     switch (generic_only ? 0 : a.W) {
-#define LM_CASE(w) case w: k_apply<T, CPT, w, MODE><<<grid, 256, 0, s>>>(a); break;
+#define LM_CASE(w) case w: if (a.pdl) launch_pdl(k_apply<T, CPT, w, MODE>, a, grid, 256, s); else k_apply<T, CPT, w, MODE><<<grid, 256, 0, s>>>(a); break;
         LM_CASE(4) LM_CASE(5) LM_CASE(9) LM_CASE(10)
 #undef LM_CASE
-        default: k_apply<T, CPT, 0, MODE><<<grid, 256, 0, s>>>(a); break;
+        default: if (a.pdl) launch_pdl(k_apply<T, CPT, 0, MODE>, a, grid, 256, s); else k_apply<T, CPT, 0, MODE><<<grid, 256, 0, s>>>(a); break;
     }
 }
 template <typename T, int CPT>
@@ -1557,6 +1569,8 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     tps = (tiles_c + strips - 1) / strips;                 // even strips
     REQUIRE(tiles_r * tps < 2147483647LL && strips <= 65535, "apply: grid too large");
     a.tiles_c = (unsigned)tiles_c; a.tps = (unsigned)tps;
+    static const int pdl_env = env_int("LM_STEP_PDL", 0);
+    a.pdl = (pdl_env && !z && !u) ? 1 : 0;
     dim3 grid((unsigned)(tiles_r * tps), (unsigned)strips);
     if (c->precision == LM_C128) launch_apply_cpt<double>(a, cpt, grid, c->stream);
     else launch_apply_cpt<float>(a, cpt, grid, c->stream);

@@ -34,6 +34,7 @@ struct ApplyArgs {
     int lc_log2;            // log2(LC)
     unsigned tiles_c;       // column tiles in total
     unsigned tps;           // column tiles per strip (grid.x = tps * row tiles, grid.y = strips)
+    int pdl;                // 1: launched with programmatic stream serialization (chains of factors, LM_STEP_PDL)
 };
 
 // WX = exact ELL width (fully unrolled), 0 = generic loop (unrolled by 4).
@@ -46,6 +47,9 @@ k_apply(const ApplyArgs a) {
     using T2 = typename cx2<T>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int LC = 1 << a.lc_log2, LR = 32 >> a.lc_log2;
+    // chain of factors: let the next launch schedule its CTAs while this grid drains; nothing of
+    // global memory is touched before the previous grid has completed
+    if (a.pdl) { pdl_launch_dependents(); pdl_wait(); }
     // CTA order (x fastest, then y): column tiles of one strip, next row tile, ..., next strip
     const unsigned rt = blockIdx.x / a.tps;
     const unsigned ct = blockIdx.y * a.tps + (blockIdx.x - rt * a.tps);

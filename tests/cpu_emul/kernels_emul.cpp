@@ -60,6 +60,7 @@ int emul_apply_ell(long long N, int W, const int* cols, const double* vals, long
     ApplyArgs a;
     a.cols = cols; a.vals = vals; a.W = W; a.N = N; a.ld = ld;
     a.x = x; a.y = y; a.z = z; a.u = u;
+    a.pdl = 0;
     a.alpha[0] = abgd[0]; a.alpha[1] = abgd[1]; a.gamma[0] = abgd[2]; a.gamma[1] = abgd[3];
     a.beta[0] = abgd[4]; a.beta[1] = abgd[5]; a.delta[0] = abgd[6]; a.delta[1] = abgd[7];
     int lc = 0; while ((1LL << lc) < ld && lc < 5) lc++;

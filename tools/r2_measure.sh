@@ -50,6 +50,12 @@ run c2_m625_pdl         LM_STEP_L2_MB=0  LM_STEP_PDL=1 -- --steps 100 --warmup 1
 run c2_m625_l2_56_pdl   LM_STEP_L2_MB=56 LM_STEP_PDL=1 -- --steps 100 --warmup 10 --M 625
 run c2_m625_auto_pdl    LM_STEP_L2_MB=auto LM_STEP_PDL=1 LM_DEBUG_PLAN=1 -- --steps 100 --warmup 10 --M 625
 
+echo "== 3b. single ket / narrow blocks (ELL kernel, launch-bound): PDL"
+run c2_m1_plain         LM_STEP_PDL=0 -- --steps 400 --warmup 20 --M 1
+run c2_m1_pdl           LM_STEP_PDL=1 -- --steps 400 --warmup 20 --M 1
+run c2_m8_plain         LM_STEP_PDL=0 -- --steps 400 --warmup 20 --M 8
+run c2_m8_pdl           LM_STEP_PDL=1 -- --steps 400 --warmup 20 --M 8
+
 echo "== 4. C3 / C4: PDL only (N too large for strips)"
 run c3_plain            LM_STEP_PDL=0 -- --workload c3 --steps 10 --warmup 3
 run c3_pdl              LM_STEP_PDL=1 -- --workload c3 --steps 10 --warmup 3
