@@ -10,7 +10,7 @@ boundaries), a model (tight binding with t1 / t2 / t3, QWZ, Haldane), a field (L
 axial and singular point fluxes, sums), a block width 1..150, a precision, a propagator method, a
 step and the schedule (plain or L2-resident strips) and checks, through the C ABI: the device
 assembled H, H X, a few evolution steps against the exact exponential, localdensity and
-DensityCurrents against the dense formulas.  Test infrastructure (imports oracle/).
+DensityCurrents against the dense formulas, and (small N) the dense-P path U P U'.  Test infrastructure (imports oracle/).
 
 Tolerances: the axial point flux is ill-conditioned by construction when the flux point is nearly
 collinear with a bond (acos(c / (1 + 1e-11)) near c = 1, src/zoo/magneticfields.jl:80-84: one ulp of c
@@ -111,6 +111,18 @@ for case in range(seed0, seed0 + ncases):
         wantj = np.array([2 * np.imag(np.sum(Hdn[(i - 1) * n:i * n, (j - 1) * n:j * n] * P[(j - 1) * n:j * n, (i - 1) * n:i * n].T)) for i, j in zip(I.tolist(), J.tolist())])
         e4 = np.abs(V - wantj).max() / max(1.0, np.abs(wantj).max()) if len(V) else 0.0
         assert e3 < 1e-13 * eps and e4 < 1e-13 * eps, ("observables", e3, e4)
+        if N <= 160 and prec == "c128" and case % 3 == 0:
+            # dense density matrix: P <- U P U' (FP64 DMMA path, CachedExp semantics) and the Psi W Psi' escape hatch
+            Pd = (Xn * w) @ Xn.conj().T
+            sd = lm.DeviceState.from_dense(Pd, ctx=ctx, n_int=n)
+            sol2 = lm.B200Exp(tol=1e-13, ctx=ctx, n_int=n)
+            sol2.update_solver(Hd, dt)
+            sol2.step(sd); sol2.step(sd)
+            wantd = U @ (U @ Pd @ U.conj().T) @ U.conj().T
+            e5 = relerr(sd.download(), wantd)
+            e6 = relerr(so.dense(), Pd)
+            e7 = relerr(lm.localdensity(sd).values, np.real(np.diag(wantd)).reshape(-1, n).sum(1))
+            assert e5 < 1e-12 and e6 < 1e-13 and e7 < 1e-12, ("dense", e5, e6, e7)
     except Exception as e:
         nfail += 1
         lib.lm_dbg_set_step_l2_kb(-1)
