@@ -379,3 +379,26 @@ def test_golden_config1_fixture_reproduced_by_oracle():
             assert np.abs(Jq - g["J"][q]).max() < 1e-12
         if k >= max(frames):
             break
+
+
+@pytest.mark.parametrize("name", ["config3s", "config4s"])
+def test_golden_reduced_config_fixtures_reproduced_by_dense_oracle(name):
+    """tests/golden/config3s_frames.npz / config4s_frames.npz (made by make_golden_small.py from the
+    Psi-block form) are reproduced by the oracle's dense-P form P <- U P U' from the stored inputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + "_frames.npz"))
+    if name == "config3s":
+        h, n = (lambda t: OP.qwz(L.square_lattice(12, 10), field=F.LandauGauge(0.1 * min(t, 1.0)))), 2
+    else:
+        h, n = (lambda t: OP.haldane(L.honeycomb_lattice(9, 8, periodic=(1,)), 1.0, 0.2, 0.1, field=F.LandauGauge(0.03))), 1
+    pairs = [tuple(p) for p in g["pairs"]]
+    assert pairs == OB.site_adjacency(h(0.0), n)
+    P0 = (g["Psi0"] * g["w0"][None, :]) @ g["Psi0"].conj().T
+    frames = list(g["frames"])
+    ts = np.arange(0, 21) * 0.1
+    for k, (st, H, t) in enumerate(EV.Evolution(h, [P0], solver="exact")(ts)):
+        if k in frames:
+            q = frames.index(k)
+            assert np.abs(OB.localdensity(st[0], n) - g["rho"][q]).max() < 1e-12
+            Jq = np.array([OB.density_current(H, st[0], i, j, n) for i, j in pairs])
+            assert np.abs(Jq - g["J"][q]).max() < 1e-12

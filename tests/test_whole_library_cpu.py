@@ -66,5 +66,5 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     tail = (res.stdout + res.stderr)[-4000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
-    assert m and int(m.group(1)) >= 128, tail
+    assert m and int(m.group(1)) >= 132, tail
     assert "failed" not in res.stdout.splitlines()[-1] and "skipped" not in res.stdout.splitlines()[-1], tail

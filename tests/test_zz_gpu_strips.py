@@ -227,3 +227,35 @@ def test_strip_candidates_fill_the_machine_evenly():
     big = lm.haldane(lm.HoneycombLattice(200, 200), 1.0, 0.2, 0.1).device(ctx)     # N = 8e4: a 64-column strip pair is 164 MB
     _lib.check(lib.lm_dbg_strip_candidates(big.handle, 4096, out, C.byref(n)))
     assert n.value == 0
+
+
+# ------------------------------------------------------------------------------ golden fixtures of reduced configs 3 / 4
+@pytest.mark.parametrize("method", ["auto", "lanczos"])
+@pytest.mark.parametrize("name", ["config3s", "config4s"])
+def test_golden_reduced_config_fixtures_on_device(name, method):
+    """The CUDA path against the COMMITTED golden vectors of the reduced BASELINE configs 3 (QWZ,
+    Landau field ramped and regenerated on the device every step) and 4 (Haldane on a honeycomb
+    cylinder): complex128 localdensity and DensityCurrents within 1e-10 relative at every stored frame."""
+    import os
+    ctx = lm.default_context("c128")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + "_frames.npz"))
+    if name == "config3s":
+        l, n_int = lm.SquareLattice(12, 10), 2
+        h = lambda t: lm.qwz(l, field=lm.LandauGauge(0.1 * min(t, 1.0)))
+    else:
+        l, n_int = lm.HoneycombLattice(9, 8, boundaries=[("axis1", True)]), 1
+        h = lambda t: lm.haldane(l, 1.0, 0.2, 0.1, field=lm.LandauGauge(0.03))
+    frames = list(g["frames"])
+    ev = lm.Evolution(lm.B200Exp(tol=1e-13, method=method, ctx=ctx), h, lm.PsiProjector(g["Psi0"], g["w0"], lattice=l, n_int=n_int))
+    seen = 0
+    for k, m in enumerate(ev(np.arange(0, 21) * 0.1)):
+        if k not in frames:
+            continue
+        q = frames.index(k)
+        I, J, V = lm.DensityCurrents(m.H, m.state).pair_values()
+        assert [tuple(p) for p in g["pairs"]] == list(zip(I.tolist(), J.tolist()))
+        assert _relerr(lm.localdensity(m.state).values, g["rho"][q]) < 1e-10
+        assert np.abs(V - g["J"][q]).max() < 1e-10 * max(np.abs(g["J"][q]).max(), 1e-3)
+        assert m.t == pytest.approx(g["times"][q])
+        seen += 1
+    assert seen == len(frames)
