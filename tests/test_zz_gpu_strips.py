@@ -259,3 +259,26 @@ def test_golden_reduced_config_fixtures_on_device(name, method):
         assert m.t == pytest.approx(g["times"][q])
         seen += 1
     assert seen == len(frames)
+
+
+@pytest.mark.parametrize("name", ["config3s", "config4s"])
+def test_golden_reduced_config_fixtures_complex64_mode(name):
+    """The optional complex64 mode against the same golden vectors at the stated 1e-5 relative."""
+    import os
+    ctx = lm.default_context("c64")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + "_frames.npz"))
+    if name == "config3s":
+        l, n_int = lm.SquareLattice(12, 10), 2
+        h = lambda t: lm.qwz(l, field=lm.LandauGauge(0.1 * min(t, 1.0)))
+    else:
+        l, n_int = lm.HoneycombLattice(9, 8, boundaries=[("axis1", True)]), 1
+        h = lambda t: lm.haldane(l, 1.0, 0.2, 0.1, field=lm.LandauGauge(0.03))
+    frames = list(g["frames"])
+    ev = lm.Evolution(lm.B200Exp(tol=1e-7, ctx=ctx), h, lm.PsiProjector(g["Psi0"], g["w0"], lattice=l, n_int=n_int))     # the states live on the solver's context
+    for k, m in enumerate(ev(np.arange(0, 21) * 0.1)):
+        if k not in frames:
+            continue
+        q = frames.index(k)
+        V = lm.DensityCurrents(m.H, m.state).pair_values()[2]
+        assert _relerr(lm.localdensity(m.state).values, g["rho"][q]) < 1e-5
+        assert np.abs(V - g["J"][q]).max() < 1e-5 * max(np.abs(g["J"][q]).max(), 1e-3)
