@@ -49,6 +49,24 @@ def test_smoke_entry_point_on_the_cpu_build(emul_lib):
     assert res.returncode == 0 and "smoke ok" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 
+def test_bench_harness_dry_run_on_the_cpu_build(emul_lib):
+    """bench.py's GPU arm (device-resident `value` leg, host-buffer `e2e` leg, roofline and
+    cpu_baseline objects) executed end to end on the `tiny` workload: tools/bench_dryrun_cpu.py
+    stands host objects in for torch.cuda and checks the JSON line against the contract's keys.
+    The reference arm (`--impl reference`) needs no device and is run as is."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun_cpu.py")], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(os.environ, LM_EMUL_LIB=emul_lib), timeout=600)
+    assert res.returncode == 0 and "bench dry run ok" in res.stderr, (res.stdout + res.stderr)[-3000:]
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "2", "--warmup", "3", "--ref-cols", "16"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert res.returncode == 0 and len(lines) == 1, (res.stdout + res.stderr)[-3000:]
+    import json
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["value"] > 0 and out["gpu_launches"] == 0
+    assert out["cpu_baseline"]["kind"] == "port" and out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0
+
+
 def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     so = emul_lib
     # the emulated kernels are single-threaded per process: xdist workers, BLAS kept to two threads each
