@@ -2,8 +2,8 @@
 """Randomised parity sweep of the library against the oracle, on the CPU build of the library
 (tests/cpu_emul/build_emul_lib.py) or on a real device.
 
-    LM_EMUL_LIB=<liblm_b200_emul.so> python tools/fuzz_parity.py [first_seed] [n_cases]     # no GPU
-    python tools/fuzz_parity.py 0 200                                                         # on a B200
+    LM_EMUL_LIB=<liblm_b200_emul.so> python tests/fuzz_parity.py [first_seed] [n_cases]     # no GPU
+    python tests/fuzz_parity.py 0 200                                                         # on a B200
 
 Every case draws a lattice (square / honeycomb, 3..18 cells per axis, open / periodic / twisted
 boundaries), a model (tight binding with t1 / t2 / t3, QWZ, Haldane), a field (Landau, symmetric,

@@ -32,11 +32,11 @@ def emul_lib(tmp_path_factory):
 
 
 def test_randomised_parity_sweep_on_the_cpu_build(emul_lib):
-    """tools/fuzz_parity.py: 80 random (lattice, boundaries, model, field, width, precision, method,
+    """tests/fuzz_parity.py: 80 random (lattice, boundaries, model, field, width, precision, method,
     step, schedule) cases through the C ABI against the oracle - device-assembled H, H X, evolution
     steps vs the exact exponential, localdensity and DensityCurrents."""
     env = dict(os.environ, LM_EMUL_LIB=emul_lib, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "1000", "80"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_parity.py"), "1000", "80"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
     assert res.returncode == 0 and "80 cases, 0 failures" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 

@@ -14,7 +14,7 @@ echo "== 1. GPU parity suite (new tests sort last: tests/test_zz_gpu_strips.py)"
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee "$OUT/pytest_gpu.txt"
 
 echo "== 1b. randomised parity sweep against the oracle ON THE DEVICE (300 cases; the same sweep runs on the CPU build in the CPU suite)"
-python tools/fuzz_parity.py 0 300 2>&1 | tail -4 | tee "$OUT/fuzz_device.txt"
+python tests/fuzz_parity.py 0 300 2>&1 | tail -4 | tee "$OUT/fuzz_device.txt"
 
 run() {  # name, env..., -- bench args
     local name=$1; shift
