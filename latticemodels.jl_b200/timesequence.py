@@ -7,28 +7,108 @@ import math
 import numpy as np
 
 
+_ATOL = math.sqrt(np.finfo(float).eps)        # the reference's key tolerance: isapprox(t, atol = sqrt(eps()))
+
+
+def _in(t, rng):
+    lo, hi = rng
+    return lo <= t <= hi
+
+
+def _same(a, b):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        return np.shape(a) == np.shape(b) and bool(np.all(np.asarray(a) == np.asarray(b)))
+    return bool(a == b)
+
+
 class TimeSequence:
+    """Time-ordered ``t => value`` dictionary (src/timesequence.jl:6-61).
+
+    ``TimeSequence()`` is empty, ``TimeSequence(times, values)`` wraps two equally long sequences
+    (``ValueError`` otherwise, the reference's ``ArgumentError``, :9-12), and
+    ``TimeSequence(f, evol[, times])`` is ``[f(moment) for moment in evol(times)]`` (:41-43).
+    Keys match within ``sqrt(eps)`` (:85-88); new keys are inserted in time order (:89-99).
+    A closed interval ``(lo, hi)`` stands for the reference's ``t = lo .. hi``."""
+
     def __init__(self, f=None, evol=None, times=None):
         self.times, self.snapshots = [], []
-        if f is not None:
+        if f is None:
+            return
+        if callable(f):
             it = evol(times) if times is not None else evol
-            for moment in it:                       # [f(moment) for moment in evol]
+            for moment in it:
                 self[moment.t] = f(moment)
+            return
+        ts, vs = list(f), list(evol if evol is not None else [])
+        if len(ts) != len(vs):
+            raise ValueError("Keys/values length mismatch:\n%d timestamps, %d snapshots" % (len(ts), len(vs)))
+        self.times = [float(t) for t in ts]
+        self.snapshots = [self._own(v) for v in vs]
+
+    @staticmethod
+    def _own(v):
+        return v if np.isscalar(v) else np.array(v, copy=True)
+
+    # ---- dictionary interface (:54-58, 85-137) ----
+    def timestamps(self):
+        return self.times
+
+    def timerange(self):
+        return (self.times[0], self.times[-1])
+
+    def values(self):
+        return self.snapshots
+
+    def _find(self, t):
+        for k, tk in enumerate(self.times):
+            if abs(tk - t) <= _ATOL:
+                return k
+        return None
+
+    def get(self, t, default=None):
+        k = self._find(t)
+        return default if k is None else self.snapshots[k]
 
     def __setitem__(self, t, value):
-        v = np.array(value, copy=True) if not np.isscalar(value) else value
-        for k, tk in enumerate(self.times):
-            if abs(tk - t) < math.sqrt(np.finfo(float).eps):
-                self.snapshots[k] = v
-                return
-        self.times.append(float(t))
-        self.snapshots.append(v)
+        v = self._own(value)
+        k = self._find(t)
+        if k is None:
+            k = int(np.searchsorted(np.asarray(self.times, dtype=float), float(t), side="left"))   # searchsortedfirst
+            self.times.insert(k, float(t))
+            self.snapshots.insert(k, v)
+        else:
+            self.snapshots[k] = v
 
     def __getitem__(self, t):
-        for tk, v in zip(self.times, self.snapshots):
-            if abs(tk - t) < math.sqrt(np.finfo(float).eps):   # tolerant lookup
-                return v
-        raise KeyError(t)
+        if isinstance(t, tuple) and len(t) == 2:            # tseq[t = lo .. hi]
+            return self.slice(t)
+        k = self._find(t)
+        if k is None:
+            raise KeyError(t)
+        return self.snapshots[k]
+
+    def slice(self, t=(-math.inf, math.inf), index=None):
+        """``tseq[args...; t = lo .. hi]`` (:106-120): the entries inside the closed interval, each value
+        optionally indexed by ``index`` (a site number, a mask, ...)."""
+        pick = (lambda v: v) if index is None else (lambda v: np.asarray(v)[index])
+        keep = [k for k, tk in enumerate(self.times) if _in(tk, t)]
+        return TimeSequence([self.times[k] for k in keep], [pick(self.snapshots[k]) for k in keep])
+
+    def delete(self, t):
+        """``delete!(tseq, t)`` for a number (:100-106, a missing key is ignored) or
+        ``delete!(tseq; t = lo .. hi)`` for an interval ``(lo, hi)`` (:121-126)."""
+        if isinstance(t, tuple):
+            drop = [k for k, tk in enumerate(self.times) if _in(tk, t)]
+        else:
+            k = self._find(t)
+            drop = [] if k is None else [k]
+        for k in reversed(drop):
+            del self.times[k]
+            del self.snapshots[k]
+        return self
+
+    def __contains__(self, t):
+        return self._find(t) is not None
 
     def __len__(self):
         return len(self.times)
@@ -36,22 +116,63 @@ class TimeSequence:
     def __iter__(self):
         return iter(zip(self.times, self.snapshots))
 
+    def __eq__(self, other):
+        if not isinstance(other, TimeSequence):
+            return NotImplemented
+        return self.times == other.times and len(self.snapshots) == len(other.snapshots) and \
+            all(_same(a, b) for a, b in zip(self.snapshots, other.snapshots))
+
+    __hash__ = None
+
+    def copy(self):
+        return TimeSequence(list(self.times), self.snapshots)
+
+    def empty(self):
+        return TimeSequence()
+
+    def map(self, f):
+        return TimeSequence(list(self.times), [f(v) for v in self.snapshots])
+
+    def __repr__(self):
+        head = "TimeSequence with %d entr%s" % (len(self), "y" if len(self) == 1 else "ies")
+        if len(self) >= 2:
+            head += ", timestamps in range %g .. %g" % self.timerange()
+        return head
+
+    # ---- calculus (:193-265) ----
+    def differentiate_(self):
+        """``differentiate!``: symmetric differences, keys moved to the interval midpoints (:193-207)."""
+        if len(self) < 2:
+            raise RuntimeError("Cannot differentiate TimeSequence of length %d" % len(self))
+        td, vs = self.times, self.snapshots
+        for i in range(1, len(td)):
+            dt = td[i] - td[i - 1]
+            vs[i - 1] = (1 / dt) * np.asarray(vs[i]) + (-1 / dt) * np.asarray(vs[i - 1]) if not np.isscalar(vs[i]) else \
+                (1 / dt) * vs[i] + (-1 / dt) * vs[i - 1]
+            td[i - 1] += dt / 2
+        td.pop()
+        vs.pop()
+        return self
+
     def differentiate(self):
-        out = TimeSequence()
-        for k in range(len(self.times) - 1):
-            dt = self.times[k + 1] - self.times[k]
-            out[(self.times[k + 1] + self.times[k]) / 2] = (np.asarray(self.snapshots[k + 1]) - np.asarray(self.snapshots[k])) / dt
-        return out
+        return self.copy().differentiate_()
+
+    def integrate_(self):
+        """``integrate!``: trapezoidal rule, first value zero, keys kept (:251-264)."""
+        if len(self) < 2:
+            raise RuntimeError("Cannot integrate TimeSequence of length %d" % len(self))
+        td, vs = self.times, self.snapshots
+        for i in range(1, len(td)):
+            dt = td[i] - td[i - 1]
+            vs[i - 1] = (dt / 2) * (np.asarray(vs[i]) if not np.isscalar(vs[i]) else vs[i]) + (dt / 2) * (np.asarray(vs[i - 1]) if not np.isscalar(vs[i - 1]) else vs[i - 1])
+        last = vs.pop()
+        vs.insert(0, 0 * last)
+        for i in range(1, len(td)):
+            vs[i] = vs[i - 1] + vs[i]
+        return self
 
     def integrate(self):
-        out = TimeSequence()
-        acc = np.zeros_like(np.asarray(self.snapshots[0], dtype=float))
-        out[self.times[0]] = acc.copy()
-        for k in range(1, len(self.times)):
-            dt = self.times[k] - self.times[k - 1]
-            acc = acc + (np.asarray(self.snapshots[k]) + np.asarray(self.snapshots[k - 1])) / 2 * dt
-            out[self.times[k]] = acc.copy()
-        return out
+        return self.copy().integrate_()
 
 
 class AsyncFrameSink:

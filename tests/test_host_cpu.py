@@ -133,6 +133,60 @@ def test_timesequence_semantics():
         ts[0.35]
 
 
+def test_timesequence_reference_testset():
+    """test/test_timedeps.jl:2-40 re-expressed on the host mirror (src/timesequence.jl:6-137,193-265):
+    length-mismatch error, site / mask indexing under a time interval, iteration, differentiate,
+    tolerant keys, interval slicing, integrate, KeyError, empty / delete! by key and by interval;
+    plus the two doctest series (:162-191, :218-247)."""
+    TS = lm.TimeSequence
+    l = lm.SquareLattice(3, 3)
+    c = np.asarray(l.coords)
+    x, y = c[:, 0], c[:, 1]
+    xy, xly, site = x * y, x < y, 4                      # l[5] in 1-based Julia
+    with pytest.raises(ValueError):
+        TS([0.5], [xy, xy])
+    rec = TS()
+    rec[0] = xy
+    rec[1] = xy
+    rec[2] = xy
+    assert rec.slice((0, np.inf), index=site) == TS(rec.timestamps(), [xy[site]] * 3)
+    assert rec.slice((0, np.inf), index=xly) == TS(range(3), [xy[xly]] * 3)
+    assert [(t, v.tolist()) for t, v in rec] == [(0, xy.tolist()), (1, xy.tolist()), (2, xy.tolist())]
+    z = np.zeros(9)
+    assert rec.differentiate() == TS([0.5, 1.5], [z, z])
+    assert rec.slice((0, np.inf), index=site).differentiate() == TS([0.5, 1.5], [0, 0])
+    rec2 = TS()
+    rec2[0] = xy * 0
+    rec2[1] = xy * 1
+    rec2[2] = xy * 2
+    assert (rec2[1e-9] == z).all() and (rec2[1 + 1e-9] == xy).all()
+    assert rec2[(0.9, 2.1)] == TS([1, 2], [xy, xy * 2])
+    assert rec.integrate() == rec2
+    with pytest.raises(KeyError):
+        rec2[0.5]
+    g = np.arange(0, 101) / 10
+    ts = TS(g, g ** 2)
+    ts2 = ts.empty()
+    assert isinstance(ts2, TS) and len(ts2) == 0
+    for t in np.arange(70, 101) / 10:
+        ts.delete(t)
+    ts.delete((5, 7))
+    for t in np.arange(0, 50) / 10:
+        ts2[t] = t ** 2
+    assert ts == ts2
+    d = TS(g, g).differentiate()                          # f(t) = t -> f'(t) = 1 at the midpoints
+    assert len(d) == 100 and abs(d.times[0] - 0.05) < 1e-15 and abs(d.times[-1] - 9.95) < 1e-12 and np.allclose(d.values(), 1.0)
+    i = TS(g, g).integrate()                              # F(t) = t^2 / 2, first value zero
+    assert len(i) == 101 and i.values()[0] == 0 and np.allclose(i.values(), g ** 2 / 2)
+    u = TS()                                              # keys are kept in time order (searchsortedfirst)
+    u[2] = 1.0
+    u[0] = 2.0
+    u[1] = 3.0
+    assert u.times == [0.0, 1.0, 2.0] and u.values() == [2.0, 3.0, 1.0]
+    with pytest.raises(RuntimeError):
+        TS([0.0], [1.0]).differentiate()
+
+
 GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)
