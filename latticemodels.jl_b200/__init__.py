@@ -16,6 +16,6 @@ from .hamiltonian import (DeviceHam, Hamiltonian, construct_hamiltonian, constru
                           haldane, qwz, tightbinding_hamiltonian)
 from .states import DeviceState, PsiProjector, densitymatrix, diagonalize, groundstate  # noqa: F401
 from .evolution import B200Exp, Evolution, EvolutionSolver, EvolutionTimestamp  # noqa: F401
-from .observables import (Currents, DensityCurrents, LatticeValue, LocalOperatorCurrents,  # noqa: F401
+from .observables import (Currents, DensityCurrents, LatticeValue, LocalOperatorCurrents, SubCurrents, SubLattice,  # noqa: F401
                           currentsfrom, currentsfromto, findnz, localdensity, localexpect)
 from .timesequence import AsyncFrameSink, TimeSequence  # noqa: F401

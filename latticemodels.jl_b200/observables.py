@@ -6,13 +6,17 @@ Same names and semantics as the reference (paths relative to the reference repos
   Currents(curr[, bonds])      src/currents.jl:223-255   (|J| < 1e-10 dropped, :4)
   findnz                       src/currents.jl:159-177
   currentsfrom / currentsfromto  src/currents.jl:85-109
+  SubCurrents, curr[region]    src/currents.jl:48-66,154-157
+  Currents arithmetic / iteration / setindex!  src/currents.jl:30-47,122-152,179-190
 """
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import numpy as np
 import scipy.sparse as sp
+from scipy.sparse.linalg import norm as spla_norm
 
 from . import _lib
 from .hamiltonian import DeviceHam, Hamiltonian
@@ -115,6 +119,8 @@ class DensityCurrents:
         return self._values
 
     def __getitem__(self, ij):
+        if not isinstance(ij, tuple):                # curr[region]: lazy SubCurrents (src/currents.jl:63-66)
+            return SubCurrents(self, ij)
         i, j = ij
         out = np.zeros(1)
         I = np.array([i - 1], np.int32)
@@ -151,6 +157,8 @@ class LocalOperatorCurrents(DensityCurrents):
         return self._values
 
     def __getitem__(self, ij):
+        if not isinstance(ij, tuple):
+            return SubCurrents(self, ij)
         i, j = ij
         I, J, V = self.pair_values()
         if i == j:
@@ -173,36 +181,189 @@ def findnz(curr):
     return I[keep], J[keep], V[keep]
 
 
+def _to_inds(ns, region):
+    """0-based site indices of a region: a boolean per-site mask or 1-based site numbers (``to_inds``)."""
+    r = np.asarray(region)
+    if r.dtype == bool:
+        if r.shape != (ns,):
+            raise _lib.ArgumentError("region mask must have one entry per site")
+        return np.flatnonzero(r)
+    return np.atleast_1d(r.astype(int)) - 1
+
+
+class SubLattice:
+    """``lat[indices]``: the sites of ``parent`` picked by 0-based ``indices`` (kept in that order)."""
+
+    def __init__(self, parent, indices):
+        self.parent, self.indices = parent, np.asarray(indices, int)
+
+    def __len__(self):
+        return len(self.indices)
+
+    @property
+    def coords(self):
+        return np.asarray(self.parent.coords)[self.indices]
+
+    def __eq__(self, o):
+        return isinstance(o, SubLattice) and (o.parent is self.parent or o.parent == self.parent) and np.array_equal(o.indices, self.indices)
+
+    __hash__ = None
+
+
+def _sublattice(lat, inds):
+    if isinstance(lat, SubLattice):
+        return SubLattice(lat.parent, lat.indices[inds])
+    return SubLattice(lat, inds)
+
+
+class SubCurrents:
+    """Lazy view of a currents object on a subset of its sites (``SubCurrents``,
+    src/currents.jl:48-66): ``sub[i, j] = parent[indices[i], indices[j]]`` (1-based)."""
+
+    def __init__(self, parent, region):
+        ns = parent.state.N // parent.n_int if isinstance(parent, DensityCurrents) else len(parent.lattice)
+        self.parent, self._nparent = parent, ns
+        self.indices = _to_inds(ns, region)
+        self.lattice = _sublattice(parent.lattice, self.indices)
+
+    def __getitem__(self, ij):
+        if not isinstance(ij, tuple):
+            return SubCurrents(self, ij)
+        i, j = ij
+        return self.parent[int(self.indices[i - 1]) + 1, int(self.indices[j - 1]) + 1]
+
+    def __len__(self):
+        n = len(self.indices)
+        return n * (n - 1) // 2
+
+    def pair_values(self):
+        """The parent's (I, J, V) restricted to pairs inside the subset, renumbered (I < J, 1-based)."""
+        I, J, V = self.parent.pair_values()
+        pos = np.zeros(self._nparent + 1, int)
+        pos[self.indices + 1] = np.arange(1, len(self.indices) + 1)
+        a, b = pos[I], pos[J]
+        keep = (a > 0) & (b > 0)
+        a, b, v = a[keep], b[keep], V[keep]
+        flip = a > b
+        return np.where(flip, b, a), np.where(flip, a, b), np.where(flip, -v, v)
+
+
 class Currents:
-    """Materialised antisymmetric site-current matrix ``Currents(lat, mat)``."""
+    """Materialised antisymmetric site-current matrix ``Currents(lat, mat)`` (src/currents.jl:110-190).
+
+    ``Currents(curr[, bonds])`` materialises a lazy currents object over H's own sparsity, dropping
+    ``|J| < 1e-10`` (:223-255); ``Currents(lattice)`` is the empty matrix on a lattice (:122);
+    ``Currents(matrix, lattice=...)`` wraps a matrix."""
 
     def __init__(self, curr, bonds=None, lattice=None):
-        if isinstance(curr, DensityCurrents):       # incl. LocalOperatorCurrents
+        if isinstance(curr, (DensityCurrents, SubCurrents)):       # incl. LocalOperatorCurrents
             I, J, V = curr.pair_values()
             if bonds is not None:
-                # Currents(curr, bonds): only the listed (i, j) pairs (1-based), either order
+                # Currents(curr, bonds): only the listed (i, j) pairs (1-based, numbered on the lattice
+                # the bonds were made for - the parent's for a SubCurrents), either order
                 want = {(min(a, b), max(a, b)) for a, b in bonds}
-                sel = np.array([(a, b) in want for a, b in zip(I.tolist(), J.tolist())], bool)
+                if isinstance(curr, SubCurrents):
+                    root, idx = curr, np.arange(len(curr.indices))
+                    while isinstance(root, SubCurrents):
+                        idx = root.indices[idx]
+                        root = root.parent
+                    gi, gj = idx[I - 1] + 1, idx[J - 1] + 1
+                else:
+                    gi, gj = I, J
+                sel = np.array([(min(a, b), max(a, b)) in want for a, b in zip(gi.tolist(), gj.tolist())], bool)
                 I, J, V = I[sel], J[sel], V[sel]
             keep = np.abs(V) >= CURRENTS_EPS
             I, J, V = I[keep], J[keep], V[keep]
-            ns = curr.state.N // curr.n_int
+            ns = len(curr.indices) if isinstance(curr, SubCurrents) else curr.state.N // curr.n_int
             self.lattice = curr.lattice
             self.currents = sp.coo_matrix((np.concatenate([V, -V]),
                                            (np.concatenate([I, J]) - 1, np.concatenate([J, I]) - 1)),
                                           shape=(ns, ns)).tocsc()
+        elif hasattr(curr, "coords") and not hasattr(curr, "shape"):   # Currents(lattice)
+            self.lattice = curr
+            self.currents = sp.csc_matrix((len(curr), len(curr)))
         else:
             self.lattice = lattice
             self.currents = sp.csc_matrix(curr)
+            if self.currents.shape[0] != self.currents.shape[1]:
+                raise _lib.ArgumentError("currents matrix must be square")
+            if lattice is not None and len(lattice) != self.currents.shape[0]:
+                raise _lib.ArgumentError("currents matrix size does not match the lattice")
 
     def __getitem__(self, ij):
+        if not isinstance(ij, tuple):                # Currents on the sub-lattice (:154-157)
+            inds = _to_inds(self.currents.shape[0], ij)
+            lat = _sublattice(self.lattice, inds) if self.lattice is not None else None
+            return Currents(self.currents[inds, :][:, inds], lattice=lat)
         i, j = ij
         return float(self.currents[i - 1, j - 1])
 
+    def __setitem__(self, ij, rhs):
+        """``curr[site1, site2] = rhs`` also stores ``-rhs`` at ``[site2, site1]``; a nonzero current
+        from a site to itself is refused with a warning (:138-152)."""
+        i, j = ij
+        if i == j and abs(rhs) > CURRENTS_EPS:
+            import warnings
+            warnings.warn("Attempt to assign nonzero current from site to self")
+            return
+        m = self.currents.tolil()
+        m[i - 1, j - 1] = rhs
+        m[j - 1, i - 1] = -rhs
+        self.currents = m.tocsc()
+
+    def __len__(self):
+        n = self.currents.shape[0]
+        return n * (n - 1) // 2
+
+    def __iter__(self):
+        """Every pair once, oriented along the flow: ``((a, b), c)`` with ``c >= 0`` (:36-47; sites as
+        1-based indices)."""
+        dense = self.currents.toarray()
+        n = dense.shape[0]
+        for i in range(n):
+            for j in range(i + 1, n):
+                c = dense[i, j]
+                yield ((i + 1, j + 1), c) if c > 0 else ((j + 1, i + 1), -c)
+
+    def _same_sites(self, o):
+        if self.currents.shape != o.currents.shape:
+            return False
+        if self.lattice is None or o.lattice is None or self.lattice is o.lattice:
+            return True
+        eq = self.lattice == o.lattice
+        return bool(eq) if isinstance(eq, (bool, np.bool_)) else self.lattice is o.lattice
+
+    def __eq__(self, o):
+        if not isinstance(o, Currents):
+            return NotImplemented
+        return self._same_sites(o) and (self.currents != o.currents).nnz == 0
+
+    __hash__ = None
+
+    def isapprox(self, o, rtol=None, atol=0.0):
+        """``isapprox`` of the matrices in the Frobenius norm, Julia's default ``rtol = sqrt(eps)`` (:128-129)."""
+        if not self._same_sites(o):
+            return False
+        rtol = math.sqrt(np.finfo(float).eps) if rtol is None else rtol
+        na, nb = spla_norm(self.currents), spla_norm(o.currents)
+        return spla_norm(self.currents - o.currents) <= max(atol, rtol * max(na, nb))
+
+    def copy(self):
+        return Currents(self.currents.copy(), lattice=self.lattice)
+
+    def zero(self):
+        return Currents(sp.csc_matrix(self.currents.shape), lattice=self.lattice)
+
+    def _check(self, o):
+        if not self._same_sites(o):
+            raise _lib.ArgumentError("currents are defined on different sites")
+
     def __add__(self, o):
+        self._check(o)
         return Currents(self.currents + o.currents, lattice=self.lattice)
 
     def __sub__(self, o):
+        self._check(o)
         return Currents(self.currents - o.currents, lattice=self.lattice)
 
     def __mul__(self, k):

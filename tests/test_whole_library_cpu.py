@@ -73,7 +73,7 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     env = dict(os.environ, LM_EMUL_LIB=so, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
     for k in ("LM_STEP_L2_MB", "LM_STEP_PDL", "LM_APPLY_TILED", "LM_APPLY_STENCIL", "LM_STENCIL_VARIANT"):
         env.pop(k, None)
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_gpu_strips.py"),
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_gpu_strips.py"), os.path.join(ROOT, "tests", "test_zz_gpu_currents_api.py"),
            "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not full_size and not readme_workflow"]
     try:
         import xdist  # noqa: F401
@@ -84,5 +84,5 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     tail = (res.stdout + res.stderr)[-4000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
-    assert m and int(m.group(1)) >= 132, tail
+    assert m and int(m.group(1)) >= 134, tail
     assert "failed" not in res.stdout.splitlines()[-1] and "skipped" not in res.stdout.splitlines()[-1], tail
