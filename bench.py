@@ -2,7 +2,10 @@
 """Benchmark of the Psi-block unitary-evolution hot path (BASELINE.json metric:
 "evolution steps/sec (N x Nocc Psi block)"; SpMM HBM GB/s vs peak).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c4|c3|c2] [--impl reference]
+
+The default workload is the north-star headline: config 4, the Haldane model on a 500 x 500
+honeycomb lattice (N = 5e5), a 4096-column Psi block, complex128.
 
 One rank per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE); rank 0 prints ONE JSON line.
 A "step" is one application of exp(-i H dt) to the whole Psi block (all ranks' column shards).
@@ -11,8 +14,12 @@ Strong scaling: the block is fixed, its columns are sharded over the ranks, H is
   e2e       : steps/s through the C ABI with HOST buffers every step: H values uploaded from
               pinned host memory (host-assembled time-dependent H path), step, fused
               localdensity + bond currents reduced (all-reduced for N > 1) and copied back
-  roofline  : the dominant kernel (k_apply = fused ELL SpMM + polynomial term): algorithmic
-              bytes per launch / average launch duration vs the measured HBM copy bandwidth
+  roofline  : the dominant kernel (k_apply_stencil_tma = lattice-stencil SpMM fused with one
+              product-form propagator factor): algorithmic bytes per launch / average launch
+              duration vs the measured HBM copy bandwidth
+  parity_check : in-run self-checks on the bench's own state - trace identity on the reduced frame,
+              sharded (all ranks) vs unsharded (rank 0 alone) evolution + observables of a check
+              block, and 8 columns against a host Taylor series of exp(-i H dt)
   cpu_baseline / --impl reference : the reference's CPU algorithm (one KrylovKit-style Lanczos
               exponentiate per ket, oracle/cpu_ref.c) on the host cores, bounded column sample
 """
@@ -125,9 +132,9 @@ def cpu_reference_rate(wl, n_sample_cols, n_steps, seed=99):
     H = wl["ham"](0.0).data
     ham = cpu_ref.CsrHam(H)
     N, M = H.shape[0], wl["M"]
-    ns = min(n_sample_cols, M)
-    psi = synth_block(N, ns, seed)
     cores = cpu_ref.max_threads()
+    ns = min(n_sample_cols if n_sample_cols > 0 else (-n_sample_cols or 4) * cores, M)
+    psi = synth_block(N, ns, seed)
     cpu_ref.krylov_block_step(ham, psi[:, :min(ns, 2 * cores)].copy(order="F"), wl["dt"])    # warm-up
     per_step = []
     for _ in range(n_steps):
@@ -136,7 +143,7 @@ def cpu_reference_rate(wl, n_sample_cols, n_steps, seed=99):
         cpu_ref.localdensity(psi)
         per_step.append(time.perf_counter() - t0)
     t = float(np.median(per_step)) * (M / ns)           # scale the sample to the full block
-    return 1.0 / t, per_step, dict(cores=cores, sample="%d of %d columns x %d steps (Lanczos krylovdim=30 tol=1e-12 per ket + localdensity), scaled by M/sample" % (ns, M, n_steps))
+    return 1.0 / t, per_step, dict(cores=cores, ns=ns, sample="%d of %d columns x %d steps (Lanczos krylovdim=30 tol=1e-12 per ket + localdensity), scaled by M/sample" % (ns, M, n_steps))
 
 
 def run_reference(args):
@@ -144,19 +151,94 @@ def run_reference(args):
     if rank != 0:
         return
     wl = workload(args.workload)
-    ns = args.ref_cols
-    rate, per_step, info = cpu_reference_rate(wl, ns, args.steps + args.warmup)
+    if args.M:
+        wl["M"] = args.M
+    rate, per_step, info = cpu_reference_rate(wl, args.ref_cols, args.steps + args.warmup)
     per_step = per_step[args.warmup:] or per_step
     M = wl["M"]
-    t = float(np.median(per_step)) * (M / min(ns, M))
+    t_sample = float(np.median(per_step))
+    t = t_sample * (M / info["ns"])
     out = {"impl": "reference", "metric": "evolution steps/sec (N x Nocc Psi block)", "value": 1.0 / t, "unit": "steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
-           "config": {"workload": wl["label"], "note": "reference CPU algorithm restated in C (oracle/cpu_ref.c, kind=port): Julia is not installed, the reference itself cannot run"},
+           "config": {"workload": wl["label"], "M_total": M, "sample_columns": info["ns"], "ms_per_step_sample": 1e3 * t_sample,
+                      "note": "reference CPU algorithm restated in C (oracle/cpu_ref.c, kind=port): Julia is not installed, the reference itself cannot run; "
+                              "each timed step evolves a bounded column sample (+ localdensity) and value / ms_per_step are scaled by M / sample_columns"},
            "cpu_baseline": {"value": 1.0 / t, "unit": "steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
            "e2e": {"value": 1.0 / t, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
+
+
+# ------------------------------------------------------------------------------------ in-run parity checks
+def parity_check(lm, _lib, lib, torch, dist, ctx, dev, state, Hmat, H0, rho_frame, N, M, dt, args, rank, world, local, cdt):
+    """Self-checks of THIS run's state (complex128 tolerances; none of it touches oracle/):
+    (a) trace identity on the last reduced frame of the timed e2e leg:  sum_i rho_i == sum_c ||psi_c||^2
+        (column norms from an independent kernel, summed over the ranks through torch.distributed);
+    (b) N > 1: a check block of 32 columns per rank, sharded over all ranks, evolved 2 steps and reduced
+        through the same exchange as the timed frames, against the SAME block evolved unsharded by rank 0
+        alone on a second context without a communicator - rho and J;
+    (c) 8 columns of that block after 2 steps against a host Taylor series of exp(-i H dt) (scipy sparse
+        matrix-vector products on the host-assembled H)."""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import synth_block as synth_host
+    out = {}
+    n2 = float(state.column_norms2().sum())
+    if world > 1:
+        t = torch.tensor([n2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        n2 = float(t.item())
+    out["trace_rel"] = abs(float(rho_frame.sum()) - n2) / n2
+    nmv = C.c_int32()
+    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4, "chebyshev_clenshaw": 5}[args.method]
+    Mc = 32 * world
+    n_sites, npairs = N // H0.n_int, len(dev.pairs()[0])
+    chk = lm.DeviceState.synthetic(N, Mc, ctx=ctx, seed=4321, lattice=H0.lattice, n_int=H0.n_int)
+    for _ in range(2):
+        _lib.check(lib.lm_step(dev.handle, chk.handle, dt, args.tol, method, C.byref(nmv)))
+    rho, J = np.empty(n_sites), np.empty(max(npairs, 1))
+    _lib.check(lib.lm_observables(dev.handle, chk.handle, _lib.ptr(rho), _lib.ptr(J)))
+    if rank == 0:
+        lat = H0.lattice
+        dims = lat.sizes if len(lat) == lat.sizes[0] * lat.sizes[1] * lat.nb else None
+        if world > 1:
+            solo = lm.Context(device=local, precision=args.precision)          # no communicator: nothing is reduced
+            dev1 = lm.DeviceHam.from_csc(solo, Hmat, H0.n_int, coords=lat.coords, lattice_dims=dims)
+            full = lm.DeviceState.synthetic(N, Mc, ctx=solo, seed=4321, lattice=lat, n_int=H0.n_int)
+            for _ in range(2):
+                _lib.check(lib.lm_step(dev1.handle, full.handle, dt, args.tol, method, C.byref(nmv)))
+            rho1, J1 = np.empty(n_sites), np.empty(max(npairs, 1))
+            _lib.check(lib.lm_observables(dev1.handle, full.handle, _lib.ptr(rho1), _lib.ptr(J1)))
+            out["sharded_vs_unsharded_rho_rel"] = float(np.abs(rho - rho1).max() / np.abs(rho1).max())
+            out["sharded_vs_unsharded_J_rel"] = float(np.abs(J - J1).max() / max(np.abs(J1).max(), 1e-300)) if npairs else 0.0
+            small_ctx, small_dev = solo, dev1
+        else:
+            small_ctx, small_dev = ctx, dev
+        # (c) host Taylor series on 8 columns (first 8 of a 32-column device block: the stencil kernels need >= 32)
+        s8 = lm.DeviceState.synthetic(N, 32, ctx=small_ctx, seed=4321, lattice=lat, n_int=H0.n_int, shard=False)
+        for _ in range(2):
+            _lib.check(lib.lm_step(small_dev.handle, s8.handle, dt, args.tol, method, C.byref(nmv)))
+        got = s8.download()[:, :8].astype(np.complex128)
+        X = synth_host(N, 8, 0, seed=4321).astype(cdt).astype(np.complex128)
+        A = (-1j * dt) * Hmat.tocsr()
+        for _ in range(2):
+            term, acc, k = X.copy(), X.copy(), 0
+            while k < 200:
+                k += 1
+                term = (A @ term) / k
+                acc += term
+                if np.abs(term).max() <= 1e-18 * max(np.abs(acc).max(), 1e-300):
+                    break
+            X = acc
+        out["psi_vs_host_taylor_rel"] = float(np.abs(got - X).max() / np.abs(X).max())
+        out["checked"] = "trace identity on the timed frame; %d-column check block, 2 steps%s; 8 columns vs host Taylor series at N = %d" % (
+            Mc, ", sharded over %d ranks vs unsharded on rank 0 (rho, J)" % world if world > 1 else "", N)
+        out["max_rel"] = max(v for k, v in out.items() if k.endswith("_rel"))
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -165,13 +247,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c4")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tol", type=float, default=1e-12)
     ap.add_argument("--method", default="auto")
     ap.add_argument("--precision", default="c128")
-    ap.add_argument("--ref-cols", type=int, default=512)
-    ap.add_argument("--cpu-cols", type=int, default=1024)
+    ap.add_argument("--ref-cols", type=int, default=0, help="columns of the reference arm's sample (0 = 4 per host thread)")
+    ap.add_argument("--cpu-cols", type=int, default=0, help="columns of the cpu_baseline sample (0 = 8 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--M", type=int, default=0, help="override the block width")
     args = ap.parse_args()
@@ -211,9 +293,10 @@ def main():
     Ml = e - b
     esz = 16 if args.precision == "c128" else 8
     cdt = np.complex128 if args.precision == "c128" else np.complex64
-    psi = synth_block(N, Ml, 1234 + rank).astype(cdt, order="F")
-    state = lm.DeviceState.from_psi(psi, None, ctx=ctx, lattice=H0.lattice, n_int=H0.n_int, shard=False)
-    del psi
+    # the block is generated on the device (a 32.8 GB host block would take minutes): this rank's
+    # column shard [b, e) of the seeded N x M block (tests/synth.py restates the generator)
+    state = lm.DeviceState.synthetic(N, M, ctx=ctx, seed=1234, lattice=H0.lattice, n_int=H0.n_int)
+    assert state.col_range == (b, e) and state.M == Ml
     sol = lm.B200Exp(tol=args.tol, method=args.method, precision=args.precision, ctx=ctx)
     lib = _lib.load()
 
@@ -255,10 +338,6 @@ def main():
     l0 = ctx.launch_count()
     ms, t0, t1 = timed(dev_step, args.steps)
     launches = ctx.launch_count() - l0
-    # schedule of the timed steps: strip width in columns (0 = plain, -1 = fixed by LM_STEP_L2_MB)
-    lib.lm_dbg_step_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
-    sched_cols, sched_cal = C.c_int64(0), C.c_int32(0)
-    lib.lm_dbg_step_schedule(state.handle, C.byref(sched_cols), C.byref(sched_cal))
     clocks = sampler.stop(t0, t1)
     K = sol.n_matvec
     ms_per_step = ms / args.steps
@@ -276,12 +355,13 @@ def main():
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "traffic.json")
-    plain_schedule = launches <= args.steps * (K + 2)
-    if os.path.exists(tf) and plain_schedule:        # the stored ncu traffic is that of the plain schedule
-        traffic = json.load(open(tf)).get("%s_n%d" % (args.workload, world))
-    roofline = {"bound": "hbm", "kernel": "lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells)", "achieved": achieved, "peak": peak,
+    traffic = None                                   # DRAM bytes are not measured inside this run (ncu captures: profiles/)
+    sid = C.c_int32(-1)
+    lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
+    lib.lm_dbg_stencil_info(dev.handle, C.byref(sid), None, None, None)
+    kernel = ("lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells, shared value loads for Hermitian H)"
+              if (sid.value >= 0 and state.M >= 32) else "lm::k_apply / k_apply_rows (ELL gather SpMM fused with one product-form propagator factor)")
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmm, "launches_timed": n_apply, "avg_launch_ms": avg_launch_ms,
                 "K_matvec_per_step": K}
@@ -314,7 +394,7 @@ def main():
     slot = [0]
 
     def e2e_step(k):
-        _lib.check(lib.lm_ham_update_values(csc_dev.handle, _lib.ptr(nz_np)))                  # H2D
+        _lib.check(lib.lm_ham_update_values_async(csc_dev.handle, _lib.ptr(nz_np)))            # H2D (pinned buffer; enclosure checked on the device)
         _lib.check(lib.lm_step(csc_dev.handle, state.handle, dt, args.tol, method, C.byref(nmv)))
         if len(pending) == 2:
             _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))   # D2H of frame k - 2 lands
@@ -327,20 +407,21 @@ def main():
     ms_e2e, _, _ = timed(e2e_step, args.steps, tail=drain)
     e2e = {"value": 1e3 / (ms_e2e / args.steps), "unit": "steps/s", "h2d_bytes_per_step": int(nnz * esz),
            "d2h_bytes_per_step": int(8 * (n_sites + npairs)),
-           "what": "lm_ham_update_values(pinned nzval) + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
+           "what": "lm_ham_update_values_async(pinned nzval) + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
+    parity = parity_check(lm, _lib, lib, torch, dist, ctx, csc_dev, state, Hmat, H0, rho_np.copy(), N, M, dt, args, rank, world, local, cdt)
 
     out = {"metric": "evolution steps/sec (N x Nocc Psi block)", "value": value, "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
            "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
                       "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
-                      "schedule": {"LM_STEP_L2_MB": os.environ.get("LM_STEP_L2_MB", "unset (plain)"), "online_choice_strip_cols": int(sched_cols.value),
-                                   "pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(args.steps, 1)},
+                      "schedule": {"pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(args.steps, 1),
+                                   "stencil_shared_value_loads": int(os.environ.get("LM_STENCIL_HERM", "1") or 0), "stencil_tensor_map_boxes": int(os.environ.get("LM_STENCIL_TMAP", "1") or 0)},
                       "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": parity}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, per_step, info = cpu_reference_rate(wl, args.cpu_cols, 3)
+        rate, per_step, info = cpu_reference_rate(wl, args.cpu_cols if args.cpu_cols > 0 else -8, 3)
         out["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
     if rank == 0:
         emit(out)

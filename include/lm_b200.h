@@ -106,8 +106,20 @@ int32_t lm_ham_create_csc(lm_ctx* ctx, int64_t N, int32_t n_int,
                           const int64_t* colptr, const int64_t* rowval, const void* nzval,
                           int32_t index_base, lm_ham** out);
 /* same sparsity pattern, new values (time-dependent H assembled on the host: the parity
- * fallback for arbitrary closures t -> H(t), src/evolution.jl:43) */
+ * fallback for arbitrary closures t -> H(t), src/evolution.jl:43).  The values need not be
+ * Hermitian for lm_spmm, but lm_step and the currents refuse a non-Hermitian operator
+ * (max |H_ij - conj(H_ji)| > 1e-13 ||H||; 1e-6 in LM_C64): the propagators assume H = H'. */
 int32_t lm_ham_update_values(lm_ham* ham, const void* nzval);
+/* Same update without a host synchronisation (update_solver! inside a frame loop whose closure only
+ * moves Peierls phases, src/evolution.jl:83-92,243): the copy, the scatter and a device-side check
+ * are enqueued on the context's stream and the call returns.  `nzval` must stay valid and unchanged
+ * until the next synchronising call on the context (lm_frame_wait, lm_ctx_synchronize,
+ * lm_observables, a download).  The propagator keeps the spectral enclosure of the last
+ * lm_ham_update_values; if the new values leave it, or are not Hermitian, a sticky error is raised
+ * by that next synchronising call (LM_ERR_NOT_CONVERGED / LM_ERR_INVALID): re-do the frame with
+ * lm_ham_update_values.  Peierls phases never change the Gershgorin bounds, so a gauge-field ramp
+ * never trips it. */
+int32_t lm_ham_update_values_async(lm_ham* ham, const void* nzval);
 
 /* Device-resident time-dependent Hamiltonian (the AbstractTimeDependentOperator branch,
  * src/evolution.jl:44-47,243).  Restates OperatorBuilder.setindex! + expand_bond
@@ -167,9 +179,22 @@ int32_t lm_ham_destroy(lm_ham* ham);
  * each rank passes ITS shard of the columns (lm_shard_range). */
 int32_t lm_state_create_psi(lm_ctx* ctx, int64_t N, int64_t M, const void* psi_colmajor,
                             const double* weights, lm_state** out);
+/* Synthetic block generated on the device (SURVEY.md section 8d inputs: uniform complex in
+ * [-1, 1]^2, columns scaled to norm ~ 1): element (i, col0 + c) is a SplitMix64 hash of (seed, i,
+ * col0 + c), so a column shard [col0, col0 + M) equals the same columns of the unsharded block.
+ * Replaces nothing in the reference; bench.py and the full-size tests use it instead of a
+ * multi-GB host upload. */
+int32_t lm_state_create_psi_synth(lm_ctx* ctx, int64_t N, int64_t M, int64_t col0, uint64_t seed, lm_state** out);
+/* squared norms of the local columns, M doubles (norm(ket)^2; for P = Psi diag(w) Psi':
+ * tr P = sum_c w_c out[c] = sum_i localdensity_i) */
+int32_t lm_state_column_norms2(lm_state* state, double* out);
 /* dense density matrix P (N x N column-major): stepped as U P U' (src/evolution.jl:73-78) */
 int32_t lm_state_create_dense(lm_ctx* ctx, int64_t N, const void* P_colmajor, lm_state** out);
 int32_t lm_state_copy(lm_state* state, lm_state** out);           /* copy(state), src/evolution.jl:193 */
+/* Multi-GPU: mark a state whose columns are the SAME on every rank (a single Ket evolved by
+ * Evolution(solver, H, psi), an unsharded block): its densities / currents are complete on each
+ * rank and are NOT summed across ranks.  Default 0 = the columns are this rank's shard. */
+int32_t lm_state_set_replicated(lm_state* state, int32_t replicated);
 int32_t lm_state_dims(lm_state* state, int64_t* N, int64_t* M, int32_t* is_dense);
 int32_t lm_state_download_psi(lm_state* state, void* psi_colmajor_out);
 /* dense P (N x N column-major); for a Psi state materialises Psi diag(w) Psi' (local columns

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "lm_shard_range": [_i64, _i32, _i32, _pi64, _pi64],
     "lm_ham_create_csc": [_vp, _i64, _i32, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_update_values": [_vp, _vp],
+    "lm_ham_update_values_async": [_vp, _vp],
     "lm_ham_create_bonds": [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_set_fields": [_vp, _i32, _vp, _vp],
     "lm_ham_set_field_params": [_vp, _vp],
@@ -58,8 +59,11 @@ PROTOTYPES = {
     "lm_ham_refine_bounds": [_vp, _i32, _f64],
     "lm_ham_destroy": [_vp],
     "lm_state_create_psi": [_vp, _i64, _i64, _vp, _vp, C.POINTER(_vp)],
+    "lm_state_create_psi_synth": [_vp, _i64, _i64, _i64, C.c_uint64, C.POINTER(_vp)],
+    "lm_state_column_norms2": [_vp, _vp],
     "lm_state_create_dense": [_vp, _i64, _vp, C.POINTER(_vp)],
     "lm_state_copy": [_vp, C.POINTER(_vp)],
+    "lm_state_set_replicated": [_vp, _i32],
     "lm_state_dims": [_vp, _pi64, _pi64, _pi32],
     "lm_state_download_psi": [_vp, _vp],
     "lm_state_download_dense": [_vp, _vp],

@@ -101,6 +101,7 @@ struct lm_ctx {
     cudaEvent_t fr_ready[2] = {nullptr, nullptr}, fr_done[2] = {nullptr, nullptr};
     double* d_frame[2] = {nullptr, nullptr}; double* h_frame[2] = {nullptr, nullptr}; size_t frame_cap[2] = {0, 0};
     long long frame_nsites[2] = {0, 0}, frame_npairs[2] = {0, 0}; bool frame_pending[2] = {false, false};
+    unsigned* h_async_flag = nullptr; unsigned* d_async_flag = nullptr;   // sticky status of lm_ham_update_values_async
     double* d_region = nullptr;                            // region-sum scratch (lm_currents_fromto / lm_currents_from)
     unsigned char* d_mask = nullptr; size_t mask_cap = 0;
     size_t esz() const { return precision == LM_C128 ? 16 : 8; }
@@ -138,6 +139,8 @@ struct lm_ham {
     int nfields = 0; int* d_kinds = nullptr; double* d_params = nullptr;
     // spectral enclosure
     double emin = 0, emax = 0, norm_inf = 0;
+    double herm_defect = 0;
+    bool hermitian = true;                                      // max |H_ij - conj(H_ji)| <= eps * norm (k_gershgorin; bond mode: by construction)
     long long version = 0;
     // observable scratch
     double* d_dens = nullptr; double2* d_G = nullptr; double* d_obs = nullptr;
@@ -162,26 +165,20 @@ struct lm_ham {
     int lat_n1 = 0, lat_n2 = 0;
     int st_id = -1; int st_rc = 0; int st_sw = 0; unsigned long long st_mask = 0;
     int* d_st_src = nullptr; void* d_svals = nullptr; long long svals_version = -1;
-    void* d_svals_f = nullptr;                       // values of one folded factor alpha H + gamma I (k_fold_svals)
     int* d_st_out = nullptr; int st_nf = 0;          // (row, forward slot) -> ELL entry of the pair (k_observe_stencil)
 };
 
 struct lm_state {
     lm_ctx* ctx = nullptr;
     long long N = 0, M = 0, ld = 0; bool dense = false;
+    bool replicated = false;                                  // every rank holds the SAME columns (a ket, an unsharded block): no cross-rank sum
     void* d_x = nullptr; double* d_w = nullptr;
     void* d_s1 = nullptr; void* d_s2 = nullptr;               // propagator scratch
     // CUDA graphs of one propagation step (the K term launches), keyed by plan + buffer roles
     struct StepGraph { cudaGraphExec_t exec = nullptr; lm_ham* h = nullptr; unsigned long long uid = 0, epoch = 0; void* x = nullptr; void* s1 = nullptr;
                        double dt = 0, tol = 0, emin = 0, emax = 0, norm = 0; int method = -1, nmv = 0; long long launches = 0; bool swap = false;
-                       unsigned long long sched = 0; long long kb = 0; };   // sched: g_sched_epoch at capture; kb: schedule (strip width in columns, 0 = plain)
+                       unsigned long long sched = 0; };   // sched: g_sched_epoch at capture
     StepGraph graphs[8]; int graph_next = 0;
-    // online choice of the step schedule (plain vs L2-resident strips): the first steps of a
-    // (Hamiltonian, dt, tol, method) run one candidate each, timed with events; all candidates give
-    // bit-identical results, so these are ordinary steps
-    struct Tune { bool valid = false; unsigned long long uid = 0, epoch = 0, sched = 0; double dt = 0, tol = 0; int method = -1; long long ld = 0;
-                  int ncand = 0, phase = 0, choice = -1; long long cand[3] = {0, 0, 0}; float ms[3] = {0, 0, 0}; };
-    Tune tune; cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
     // block-Lanczos workspace (LM_METHOD_LANCZOS): Krylov basis + per-column scalars
     std::vector<void*> kry; double2* d_alpha = nullptr; double* d_beta = nullptr; double2* d_coef = nullptr;
     double* d_err = nullptr; unsigned long long* d_max = nullptr; double2* d_dot = nullptr;
@@ -190,6 +187,7 @@ struct lm_state {
 };
 
 static int set_dev(lm_ctx* c) { CK(cudaSetDevice(c->device)); return LM_OK; }
+static int check_async_status(lm_ctx* c);
 static int ensure_pinned(lm_ctx* c, size_t bytes) {
     if (c->pinned_bytes >= bytes) return LM_OK;
     if (c->h_pinned) CK(cudaFreeHost(c->h_pinned));
@@ -253,13 +251,15 @@ extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
     }
     if (c->d_region) cudaFree(c->d_region);
     if (c->d_mask) cudaFree(c->d_mask);
+    if (c->h_async_flag) cudaFreeHost(c->h_async_flag);
+    if (c->d_async_flag) cudaFree(c->d_async_flag);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return LM_OK;
 }
 extern "C" int32_t lm_ctx_synchronize(lm_ctx* c) {
     REQUIRE(c, "lm_ctx_synchronize: ctx is NULL");
-    FWD(set_dev(c)); CK(cudaStreamSynchronize(c->stream)); return LM_OK;
+    FWD(set_dev(c)); CK(cudaStreamSynchronize(c->stream)); return check_async_status(c);
 }
 extern "C" int32_t lm_ctx_stream(lm_ctx* c, void** s) { REQUIRE(c && s, "lm_ctx_stream: NULL"); *s = (void*)c->stream; return LM_OK; }
 extern "C" int32_t lm_ctx_launch_count(lm_ctx* c, int64_t* n) { REQUIRE(c && n, "lm_ctx_launch_count: NULL"); *n = c->launches; return LM_OK; }
@@ -332,7 +332,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_svals_f, h->d_st_out, h->d_pairI, h->d_pairJ};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_st_out, h->d_pairI, h->d_pairJ};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -621,7 +621,6 @@ static int ham_build_stencil(lm_ham* h) {
     CK(cudaStreamSynchronize(c->stream));
     if (h->d_st_src) { cudaFree(h->d_st_src); h->d_st_src = nullptr; }
     if (h->d_svals) { cudaFree(h->d_svals); h->d_svals = nullptr; }
-    if (h->d_svals_f) { cudaFree(h->d_svals_f); h->d_svals_f = nullptr; }
     if (h->d_st_out) { cudaFree(h->d_st_out); h->d_st_out = nullptr; }
     h->st_id = -1; h->svals_version = -1; h->layout_epoch++;
     const long long n1 = h->lat_n1, n2 = h->lat_n2, N = h->N; const int W = h->W;
@@ -708,8 +707,6 @@ static int ham_build_stencil(lm_ham* h) {
     // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes
     CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 256));
     CK(cudaMemset(h->d_svals, 0, c->esz() * src.size() + 256));
-    CK(cudaMalloc(&h->d_svals_f, c->esz() * src.size() + 256));
-    CK(cudaMemset(h->d_svals_f, 0, c->esz() * src.size() + 256));
     CK(cudaMemcpy(h->d_st_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
     h->st_id = id; h->st_rc = rc; h->st_sw = SW; h->st_mask = mask;
     return LM_OK;
@@ -754,9 +751,30 @@ static int upload_nzval(lm_ham* h, const void* nzval) {
     k_scatter_vals<T><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const T2*)h->d_nz, h->d_csc2ell, (T2*)h->d_vals);
     c->launches++;
     CK(cudaGetLastError());
-    // the host buffer is borrowed only for the duration of the call
-    CK(cudaStreamSynchronize(c->stream));
     return LM_OK;
+}
+// Gershgorin partials [grid][4] of the current ELL values into c->d_stage (k_gershgorin)
+static int enqueue_gershgorin(lm_ham* h, unsigned* grid_out) {
+    lm_ctx* c = h->ctx;
+    const unsigned grid = (unsigned)((h->N + 255) / 256);
+    FWD(ensure_stage(c, sizeof(double) * 4 * (size_t)grid));
+    if (c->precision == LM_C128) k_gershgorin<double><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const double2*)h->d_vals, (double*)c->d_stage);
+    else k_gershgorin<float><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const float2*)h->d_vals, (double*)c->d_stage);
+    c->launches++;
+    CK(cudaGetLastError());
+    *grid_out = grid;
+    return LM_OK;
+}
+static double herm_tol(const lm_ctx* c) { return c->precision == LM_C128 ? 1e-13 : 1e-6; }
+// sticky status of the asynchronous value updates, read at the synchronising calls
+static int check_async_status(lm_ctx* c) {
+    if (!c->h_async_flag || !*c->h_async_flag) return LM_OK;
+    const unsigned bits = *c->h_async_flag;
+    *c->h_async_flag = 0;
+    if (c->d_async_flag) cudaMemsetAsync(c->d_async_flag, 0, sizeof(unsigned), c->stream);
+    if (bits & 2u) return fail(LM_ERR_INVALID, "lm_ham_update_values_async: the new values are not Hermitian; the steps taken since are invalid");
+    return fail(LM_ERR_NOT_CONVERGED, "lm_ham_update_values_async: the new values left the spectral enclosure the propagator was planned for; "
+                                      "the steps taken since are invalid (use lm_ham_update_values, which re-plans)");
 }
 
 extern "C" int32_t lm_ham_create_csc(lm_ctx* c, int64_t N, int32_t n_int, const int64_t* colptr,
@@ -817,20 +835,48 @@ extern "C" int32_t lm_ham_update_values(lm_ham* h, const void* nzval) {
     FWD(set_dev(h->ctx));
     lm_ctx* c = h->ctx;
     if (c->precision == LM_C128) FWD(upload_nzval<double>(h, nzval)); else FWD(upload_nzval<float>(h, nzval));
-    // spectral enclosure on the device (the host loop over nnz used to dominate large updates)
-    const unsigned grid = (unsigned)((h->N + 255) / 256);
-    FWD(ensure_stage(c, sizeof(double) * 3 * (size_t)grid));
-    FWD(ensure_pinned(c, sizeof(double) * 3 * (size_t)grid + 4096));
-    if (c->precision == LM_C128) k_gershgorin<double><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const double2*)h->d_vals, (double*)c->d_stage);
-    else k_gershgorin<float><<<grid, 256, 0, c->stream>>>(h->N, h->W, h->d_cols, (const float2*)h->d_vals, (double*)c->d_stage);
+    // spectral enclosure + Hermiticity defect on the device (the host loop over nnz used to dominate large updates)
+    unsigned grid = 0;
+    FWD(enqueue_gershgorin(h, &grid));
+    FWD(ensure_pinned(c, sizeof(double) * 4 * (size_t)grid + 4096));
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_stage, sizeof(double) * 4 * (size_t)grid, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));           // also: the host buffer is borrowed only for the duration of the call
+    const double* pp = (const double*)c->h_pinned;
+    double lo = 1e300, hi = -1e300, nrm = 0, as = 0;
+    for (unsigned b = 0; b < grid; ++b) { lo = std::min(lo, pp[4 * b]); hi = std::max(hi, pp[4 * b + 1]); nrm = std::max(nrm, pp[4 * b + 2]); as = std::max(as, pp[4 * b + 3]); }
+    // Hysteresis: values that only move the bounds by rounding noise (Peierls phases change, |H_ij| do not)
+    // keep the enclosure - and with it the propagator plan and the captured step graph - as they are.
+    const double w = std::max(h->emax - h->emin, 0.0), slack = 1e-9 * std::max(w, h->norm_inf);
+    const bool keep = h->version > 0 && lo >= h->emin - slack && hi <= h->emax + slack && nrm <= h->norm_inf + slack &&
+                      (hi - lo) >= w * (1.0 - 1e-6) && nrm >= h->norm_inf * (1.0 - 1e-6);
+    if (!keep) { h->emin = lo; h->emax = hi; h->norm_inf = nrm; }
+    h->hermitian = as <= herm_tol(c) * std::max(nrm, 1e-300);
+    h->herm_defect = as;
+    h->version++;
+    return LM_OK;
+}
+// Same, without a host synchronisation: copy, scatter, and a device-side check that the new values
+// stay inside the enclosure of the last synchronous update (sticky flag, reported by the next
+// lm_frame_wait / lm_ctx_synchronize / lm_observables on the context).
+extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
+    REQUIRE(h && nzval, "lm_ham_update_values_async: NULL argument");
+    REQUIRE(!h->bond_mode, "lm_ham_update_values_async: Hamiltonian was created from bonds; use lm_ham_set_field_params");
+    REQUIRE(h->version > 0, "lm_ham_update_values_async: no synchronous update yet");
+    FWD(set_dev(h->ctx));
+    lm_ctx* c = h->ctx;
+    if (!c->h_async_flag) {
+        CK(cudaMallocHost(&c->h_async_flag, sizeof(unsigned))); *c->h_async_flag = 0;
+        CK(cudaMalloc(&c->d_async_flag, sizeof(unsigned)));
+        CK(cudaMemsetAsync(c->d_async_flag, 0, sizeof(unsigned), c->stream));
+    }
+    if (c->precision == LM_C128) FWD(upload_nzval<double>(h, nzval)); else FWD(upload_nzval<float>(h, nzval));
+    unsigned grid = 0;
+    FWD(enqueue_gershgorin(h, &grid));
+    const double slack = 1e-9 * std::max(std::max(h->emax - h->emin, 0.0), h->norm_inf);
+    k_enclosure_check<<<1, 256, 0, c->stream>>>((const double*)c->d_stage, grid, h->emin, h->emax, h->norm_inf, slack, herm_tol(c), c->d_async_flag);
     c->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_pinned, c->d_stage, sizeof(double) * 3 * (size_t)grid, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const double* pp = (const double*)c->h_pinned;
-    double lo = 1e300, hi = -1e300, nrm = 0;
-    for (unsigned b = 0; b < grid; ++b) { lo = std::min(lo, pp[3 * b]); hi = std::max(hi, pp[3 * b + 1]); nrm = std::max(nrm, pp[3 * b + 2]); }
-    h->emin = lo; h->emax = hi; h->norm_inf = nrm;
+    CK(cudaMemcpyAsync(c->h_async_flag, c->d_async_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     h->version++;
     return LM_OK;
 }
@@ -1028,8 +1074,6 @@ static void state_free(lm_state* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (s->tune_ev0) cudaEventDestroy(s->tune_ev0);
-    if (s->tune_ev1) cudaEventDestroy(s->tune_ev1);
     for (void* p : s->kry) if (p) cudaFree(p);
     { void* q[] = {s->d_alpha, s->d_beta, s->d_coef, s->d_err, s->d_max, s->d_dot}; for (void* p : q) if (p) cudaFree(p); }
     void* ptrs[] = {s->d_x, s->d_w, s->d_s1, s->d_s2, s->d_U};
@@ -1098,6 +1142,42 @@ extern "C" int32_t lm_state_create_psi(lm_ctx* c, int64_t N, int64_t M, const vo
     *out = s;
     return LM_OK;
 }
+// Synthetic block generated on the device (bench / sweep inputs: a 32.8 GB host block would take minutes)
+extern "C" int32_t lm_state_create_psi_synth(lm_ctx* c, int64_t N, int64_t M, int64_t col0, uint64_t seed, lm_state** out) {
+    REQUIRE(c && out, "lm_state_create_psi_synth: NULL argument");
+    REQUIRE(N > 0 && M > 0 && col0 >= 0, "lm_state_create_psi_synth: N and M must be positive, col0 non-negative");
+    FWD(set_dev(c));
+    lm_state* s = nullptr;
+    FWD(state_alloc(c, N, M, false, &s));
+    const long long tot = N * s->ld; const int th = 256;
+    const double scale = std::sqrt(1.5 / (double)N);
+    if (c->precision == LM_C128) k_synth_block<double2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, M, s->ld, col0, seed, scale, (double2*)s->d_x);
+    else k_synth_block<float2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(N, M, s->ld, col0, seed, scale, (float2*)s->d_x);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { state_free(s); return fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = s;
+    return LM_OK;
+}
+// ||psi_c||^2 of the local columns (norm(ket)^2 of the reference, QuantumOpticsBase `norm`)
+extern "C" int32_t lm_state_column_norms2(lm_state* s, double* out) {
+    REQUIRE(s && out, "lm_state_column_norms2: NULL argument");
+    REQUIRE(!s->dense, "lm_state_column_norms2: Psi states only");
+    lm_ctx* c = s->ctx; FWD(set_dev(c));
+    FWD(ensure_stage(c, sizeof(double) * (size_t)s->M));
+    FWD(ensure_pinned(c, sizeof(double) * (size_t)s->M + 4096));
+    CK(cudaMemsetAsync(c->d_stage, 0, sizeof(double) * (size_t)s->M, c->stream));
+    const long long rpc = std::max<long long>(256, (s->N + 1023) / 1024);
+    dim3 grid((unsigned)((s->M + 31) / 32), (unsigned)((s->N + rpc - 1) / rpc));
+    if (c->precision == LM_C128) k_colnorm2<double2><<<grid, 256, 0, c->stream>>>(s->N, s->M, s->ld, rpc, (const double2*)s->d_x, (double*)c->d_stage);
+    else k_colnorm2<float2><<<grid, 256, 0, c->stream>>>(s->N, s->M, s->ld, rpc, (const float2*)s->d_x, (double*)c->d_stage);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_stage, sizeof(double) * (size_t)s->M, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_pinned, sizeof(double) * (size_t)s->M);
+    return LM_OK;
+}
 extern "C" int32_t lm_state_create_dense(lm_ctx* c, int64_t N, const void* P, lm_state** out) {
     REQUIRE(c && out && P, "lm_state_create_dense: NULL argument");
     REQUIRE(N > 0 && N <= 16384, "lm_state_create_dense: N must be in 1..16384 (dense path)");
@@ -1121,7 +1201,13 @@ extern "C" int32_t lm_state_copy(lm_state* s, lm_state** out) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_w, s->d_w, sizeof(double) * (size_t)s->ld, cudaMemcpyDeviceToDevice, c->stream);
     }
     if (e != cudaSuccess) { state_free(t); return fail(LM_ERR_CUDA, cudaGetErrorString(e)); }
+    t->replicated = s->replicated;
     *out = t;
+    return LM_OK;
+}
+extern "C" int32_t lm_state_set_replicated(lm_state* s, int32_t replicated) {
+    REQUIRE(s, "lm_state_set_replicated: NULL");
+    s->replicated = replicated != 0;
     return LM_OK;
 }
 extern "C" int32_t lm_state_dims(lm_state* s, int64_t* N, int64_t* M, int32_t* dense) {
@@ -1438,25 +1524,53 @@ static int apply_tiled(lm_ham* h, long long ld, const void* x, void* y, const vo
     return LM_OK;
 }
 
+// 3-D tiled tensor map over FLOAT64 units (cuTensorMapEncodeTiled through the runtime's driver entry
+// point: no link dependency on libcuda).  Returns 0 on success.
+#ifndef LM_CPU_EMUL
+static int make_tmap3d(CUtensorMap* out, const void* base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                       unsigned long long stride1_bytes, unsigned long long stride2_bytes, unsigned b0, unsigned b1, unsigned b2) {
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = [] {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (encode_t)fn;
+    }();
+    if (!encode || b0 > 256 || b1 > 256 || b2 > 256 || ((uintptr_t)base & 15) || (stride1_bytes & 15) || (stride2_bytes & 15) || stride2_bytes >= (1ull << 40)) return -1;
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    const cuuint32_t box[3] = {b0, b1, b2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+#else
+static int make_tmap3d(CUtensorMap* out, const void* base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                       unsigned long long stride1_bytes, unsigned long long stride2_bytes, unsigned b0, unsigned b1, unsigned b2) {
+    if (b0 > 256 || b1 > 256 || b2 > 256 || ((uintptr_t)base & 15) || (stride1_bytes & 15) || (stride2_bytes & 15)) return -1;
+    *out = CUtensorMap{base, {d0, d1, d2}, {stride1_bytes, stride2_bytes}, {b0, b1, b2}, 1};
+    return 0;
+}
+#endif
+
 static int g_stencil_variant = -1;       // lm_dbg_set_stencil_variant (sweeps): -1 = default per pattern
+static int g_stencil_herm = -1, g_stencil_tmap = -1;   // lm_dbg_set_stencil_flags (tests / sweeps): -1 = LM_STENCIL_HERM / LM_STENCIL_TMAP (default on)
 static int stencil_variant_of(const lm_ham* h) {
     static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
     int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
     if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
     return variant;
 }
-// nc = columns processed starting at the pointers (ld = the whole block; fewer for an L2-resident
-// column strip, see step_strips), keep = plain instead of evict-first stores of y
 static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
-                         zc alpha, zc gamma, zc beta, zc delta, long long nc = -1, bool keep = false) {
+                         zc alpha, zc gamma, zc beta, zc delta) {
     lm_ctx* c = h->ctx;
     FWD(refresh_views(h));
-    if (nc < 0) nc = ld;
+    const long long nc = ld;
     const int variant = stencil_variant_of(h);
     int P1, P2, cpt, staged;
     stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
     StencilArgs a;
-    a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld; a.nc = nc; a.keep = keep ? 1 : 0;
+    a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld;
     // LM_STEP_PDL=1 (opt-in): chains of factors are launched with programmatic dependent launch
     static const int pdl_env = env_int("LM_STEP_PDL", 0);
     a.pdl = (pdl_env && staged == 1 && !z && !u) ? 1 : 0;
@@ -1479,7 +1593,7 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     const long long strips = (nchunks + cps - 1) / cps;
     cps = (nchunks + strips - 1) / strips;
     REQUIRE(np1 * np2 * cps < 2147483647LL && strips <= 65535, "apply_stencil: grid too large");
-    REQUIRE(ld % ec == 0 && nc % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
+    REQUIRE(ld % ec == 0, "apply_stencil: odd leading dimension in complex64 mode");
     a.cps = (unsigned)cps; a.nchunks = (unsigned)nchunks;
     dim3 grid((unsigned)(np1 * np2 * cps), (unsigned)strips);
     a.ngroups = 1; a.cpg = (unsigned)nchunks; a.npatch = (unsigned)(np1 * np2);
@@ -1493,26 +1607,24 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
         grid = dim3((unsigned)(np1 * np2 * ngroups), 1);
     }
     const bool has_g = gamma != zc(0, 0);
-    int mode = (!z && !u && !has_g) ? 0 : ((z && !u && !has_g) ? 1 : ((!z && !u) ? 3 : 2));
-    // product-form factor y = (alpha H + gamma I) x: optionally fold alpha and gamma into a per-factor
-    // copy of the slot-ordered values (nnz-sized gather) so that the kernel stores its accumulators as
-    // is (40 instead of 48 DFMA per element).  Measured NEUTRAL on C2/C3/C4 (the FP64 pipe is not what
-    // bounds the kernel) at the price of one more launch per factor: opt-in, LM_STENCIL_FOLD=1.
-    static const int fold_env = env_int("LM_STENCIL_FOLD", 0);
-    const int ds0 = stencil_diag_slot(h->st_id, 0), ds1 = h->st_rc == 2 ? stencil_diag_slot(h->st_id, 1) : -1;
-    if (mode == 3 && staged == 1 && fold_env && ds0 >= 0 && (h->st_rc == 1 || ds1 >= 0)) {
-        const long long nb = h->N * h->st_sw; const int th = 256;
-        if (c->precision == LM_C128)
-            k_fold_svals<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->st_sw, h->st_rc, ds0, ds1, h->d_st_src, (const double2*)h->d_vals,
-                make_double2(alpha.real(), alpha.imag()), make_double2(gamma.real(), gamma.imag()), (double2*)h->d_svals_f);
-        else
-            k_fold_svals<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->st_sw, h->st_rc, ds0, ds1, h->d_st_src, (const float2*)h->d_vals,
-                make_float2((float)alpha.real(), (float)alpha.imag()), make_float2((float)gamma.real(), (float)gamma.imag()), (float2*)h->d_svals_f);
-        c->launches++;
-        a.svals = h->d_svals_f;
-        mode = 4;
+    const int mode = (!z && !u && !has_g) ? 0 : ((z && !u && !has_g) ? 1 : ((!z && !u) ? 3 : 2));
+    // haloed block of an interior patch as ONE tensor-map box of the [n1][n2 RC][columns] view of x
+    // (FLOAT64 units: 2 per complex128, 1 per complex64; columns beyond nc are zero-filled)
+    CUtensorMap tmx;
+    memset(&tmx, 0, sizeof(tmx));
+    static const int tmap_env = env_int("LM_STENCIL_TMAP", 1);
+    a.tmap = 0;
+    if (staged == 1 && (g_stencil_tmap >= 0 ? g_stencil_tmap : tmap_env)) {
+        const unsigned long long u8 = (unsigned long long)(c->esz() / 8);
+        const int st_t = make_tmap3d(&tmx, x, (unsigned long long)nc * u8, (unsigned long long)h->lat_n2 * h->st_rc, (unsigned long long)h->lat_n1,
+                                     (unsigned long long)ld * c->esz(), (unsigned long long)h->lat_n2 * h->st_rc * (unsigned long long)ld * c->esz(),
+                                     (unsigned)(32 * cpt * 2), (unsigned)((P2 + 2) * h->st_rc), (unsigned)(P1 + 2));
+        a.tmap = (st_t == 0) ? 1 : 0;
     }
-    const int st = stencil_launch(h->st_id, variant, c->precision != LM_C128, mode, a, grid, c->stream);
+    // Hermitian operator (verified on the device at every value change): in-tile bonds share one value load
+    static const int herm_env = env_int("LM_STENCIL_HERM", 1);
+    a.herm = ((g_stencil_herm >= 0 ? g_stencil_herm : herm_env) && h->hermitian) ? 1 : 0;
+    const int st = stencil_launch(h->st_id, variant, c->precision != LM_C128, mode, a, tmx, grid, c->stream);
     if (st == -1) return fail(LM_ERR_UNSUPPORTED, "apply_stencil: kernel variant not compiled");
     if (st != 0) return fail(LM_ERR_CUDA, "apply_stencil: cudaFuncSetAttribute failed");
     c->launches++;
@@ -1520,6 +1632,8 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     return LM_OK;
 }
 extern "C" int32_t lm_dbg_set_stencil_variant(int32_t v) { g_stencil_variant = v; ++g_sched_epoch; return LM_OK; }
+// herm: shared value loads for Hermitian operators; tmap: tensor-map boxes for interior patches (-1 = default)
+extern "C" int32_t lm_dbg_set_stencil_flags(int32_t herm, int32_t tmap) { g_stencil_herm = herm; g_stencil_tmap = tmap; ++g_sched_epoch; return LM_OK; }
 
 static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad, 5 register-tiled stencil
 // register-tiled stencil kernel (path 5 = force): default whenever the lattice matched a compiled stencil
@@ -1608,154 +1722,19 @@ static int taylor_plan(double theta_total, double tol, int* nsub, int* K) {
 }
 // ------------------------------------------------------------------------------------------
 // A product-form step is a chain of factors  x <- (alpha_j H + gamma_j I) x  ping-ponging between
-// the state and ONE scratch buffer.  Plain schedule: factor by factor over the whole block - every
-// factor streams the block through HBM (2 N M s bytes each).
-// L2-resident schedule (LM_STEP_L2_MB > 0, register-tiled stencil path only): columns are
-// independent, so the chain can run strip by strip instead - for a strip of `ms` columns all
-// factors are applied back to back while its two buffers (2 N ms s bytes <= the budget) stay in
-// the 126 MB L2: HBM sees the block once per STEP (first read + last write) instead of once per
-// factor, the remaining factors run at L2 bandwidth.  The intermediate factors store y with the
-// default policy (keep), the last one evict-first.  Pays for N small enough that a strip of >= 64
-// columns fits (C2: N = 1e4 -> 224 columns in 72 MB); for larger N the plain schedule is used.
-// The result lands in the same buffer for every strip (parity of the factor count).
+// the state and ONE scratch buffer, factor by factor over the whole block (2 N M s bytes of HBM
+// traffic each).  (Round 1 also carried an L2-resident column-strip schedule of the same chain; on
+// the device it lost on every configuration - C2 0.56-0.79 of the roofline against 0.85 plain, the
+// 625-column shard 0.65 against 0.76, profiles/r2/strips_pdl_grid_r2.md - and was removed.)
 // ------------------------------------------------------------------------------------------
 struct Factor { zc alpha, gamma; };
-static const long long kSchedAuto = -1;
-static long long g_step_l2_kb = -1;      // lm_dbg_set_step_l2_kb (tests / sweeps): >= 0 fixed budget (0 = plain), -1 = LM_STEP_L2_MB
-static long long g_tune_kb[2] = {0, 0};  // lm_dbg_set_autotune_kb: fixed candidate budgets of the online choice (0, 0 = wave-aware default)
-static long long g_cur_ms = 0;           // schedule of the step being enqueued: strip width in columns, 0 = plain (set by lm_step, read by run_factors)
-// LM_STEP_L2_MB: unset = plain schedule, "auto" = online choice between plain and two strip budgets,
-// <MB> = fixed strip budget
-static long long sched_request() {
-    if (g_step_l2_kb >= 0) return g_step_l2_kb;
-    static const long long env_kb = [] {
-        const char* v = getenv("LM_STEP_L2_MB");
-        if (!v || !*v) return 0LL;
-        if (!strcmp(v, "auto")) return kSchedAuto;
-        return 1024LL * std::max(0, atoi(v));
-    }();
-    return g_step_l2_kb == -2 ? kSchedAuto : env_kb;
-}
-static long long strip_columns(const lm_ham* h, long long ld, long long kb) {
-    if (kb <= 0 || !stencil_path(h, ld)) return 0;
-    const lm_ctx* c = h->ctx;
-    const long long unit = 32 * (c->precision == LM_C128 ? 1 : 2);      // one staged chunk of the kernel
-    long long ms = (long long)((double)kb * 1024.0 / (2.0 * (double)h->N * (double)c->esz()));
-    ms = (ms / unit) * unit;
-    if (ms < 2 * unit || ms >= ld) return 0;                             // too narrow to pay / nothing to split
-    // even strips (no short last strip), still a multiple of the chunk
-    const long long nstrips = (ld + ms - 1) / ms;
-    ms = (((ld + nstrips - 1) / nstrips) + unit - 1) / unit * unit;
-    return ms;
-}
-// Candidate strip widths of the online choice: every width (a multiple of the kernel's chunk) whose
-// two strip buffers stay under 60 % of the L2, ranked by how evenly its CTAs fill the machine
-// (patches x chunks against the resident CTAs of all SMs); the best two, wider first on near-ties.
-static int strip_candidates(const lm_ham* h, long long ld, long long out[2]) {
-    const lm_ctx* c = h->ctx;
-    if (!stencil_path(h, ld)) return 0;
-    if (g_tune_kb[0] > 0 || g_tune_kb[1] > 0) {
-        int n = 0;
-        for (long long kb : g_tune_kb) { const long long ms = strip_columns(h, ld, kb); if (ms > 0 && (n == 0 || out[0] != ms)) out[n++] = ms; }
-        return n;
-    }
-    // a block whose two buffers (nearly) fit the L2 is L2-resident under the plain schedule already
-    const double l2 = (double)(c->l2_bytes > 0 ? c->l2_bytes : (64 << 20));
-    if (2.0 * (double)h->N * (double)ld * (double)c->esz() <= 1.5 * l2) return 0;
-    const int variant = stencil_variant_of(h);
-    int P1, P2, cpt, staged;
-    stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
-    if (staged != 1) return 0;
-    const long long unit = 32LL * cpt * (c->precision == LM_C128 ? 1 : 2);
-    const double cap = 0.6 * l2;
-    const long long npatch = ((h->lat_n1 + P1 - 1) / P1) * ((h->lat_n2 + P2 - 1) / P2);
-    const long long resident = (long long)stencil_resident_ctas(h->st_id, variant, c->precision != LM_C128) * (c->sm_count > 0 ? c->sm_count : 148);
-    double best[2] = {0, 0}; int n = 0;
-    for (long long nch = 2; ; ++nch) {
-        const long long ms = nch * unit;
-        if (ms >= ld || 2.0 * (double)h->N * (double)ms * (double)c->esz() > cap) break;
-        const long long ctas = npatch * nch, waves = (ctas + resident - 1) / resident;
-        const double eff = (double)ctas / (double)(waves * resident) + 1e-4 * (double)nch;   // near-ties: the wider strip
-        if (n < 2) { out[n] = ms; best[n] = eff; ++n; if (n == 2 && best[1] > best[0]) { std::swap(best[0], best[1]); std::swap(out[0], out[1]); } }
-        else if (eff > best[0]) { best[1] = best[0]; out[1] = out[0]; best[0] = eff; out[0] = ms; }
-        else if (eff > best[1]) { best[1] = eff; out[1] = ms; }
-    }
-    return n;
-}
 static int run_factors(lm_ham* h, long long ld, void** px, void** ps1, const std::vector<Factor>& fac, int* nmv) {
-    const long long ms = (g_cur_ms > 0 && g_cur_ms < ld && stencil_path(h, ld)) ? g_cur_ms : 0;
     const int nf = (int)fac.size();
-    if (ms <= 0) {
-        for (int j = 0; j < nf; ++j) {
-            FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, fac[j].alpha, fac[j].gamma, zc(0, 0), zc(0, 0)));
-            std::swap(*px, *ps1);
-        }
-        *nmv += nf;
-        return LM_OK;
+    for (int j = 0; j < nf; ++j) {
+        FWD(apply(h, ld, *px, *ps1, nullptr, nullptr, fac[j].alpha, fac[j].gamma, zc(0, 0), zc(0, 0)));
+        std::swap(*px, *ps1);
     }
-    const size_t esz = h->ctx->esz();
-    for (long long c0 = 0; c0 < ld; c0 += ms) {
-        const long long nc = std::min(ms, ld - c0);
-        char* a = (char*)*px + (size_t)c0 * esz;
-        char* b = (char*)*ps1 + (size_t)c0 * esz;
-        for (int j = 0; j < nf; ++j) {
-            FWD(apply_stencil(h, ld, a, b, nullptr, nullptr, fac[j].alpha, fac[j].gamma, zc(0, 0), zc(0, 0), nc, j + 1 < nf));
-            std::swap(a, b);
-        }
-    }
-    if (nf & 1) std::swap(*px, *ps1);
     *nmv += nf;
-    return LM_OK;
-}
-// kb >= 0: fixed strip budget in KiB (0 = plain schedule); -1: what LM_STEP_L2_MB says; -2: online choice
-extern "C" int32_t lm_dbg_set_step_l2_kb(int64_t kb) { g_step_l2_kb = kb; ++g_sched_epoch; return LM_OK; }
-extern "C" int32_t lm_dbg_set_autotune_kb(int64_t kb_a, int64_t kb_b) { g_tune_kb[0] = kb_a; g_tune_kb[1] = kb_b; ++g_sched_epoch; return LM_OK; }
-// Schedule of the next product-form step of `s` under `h`.  *timed: this step is a calibration
-// sample (the caller brackets it with events and reports back through tune_record).
-static long long pick_schedule(lm_ham* h, lm_state* s, double dt, double tol, int method, bool* timed) {
-    *timed = false;
-    const long long req = sched_request();
-    if (req != kSchedAuto) return strip_columns(h, s->ld, req);
-    lm_state::Tune& t = s->tune;
-    if (!t.valid || t.uid != h->uid || t.epoch != h->layout_epoch || t.sched != g_sched_epoch || t.dt != dt || t.tol != tol || t.method != method || t.ld != s->ld) {
-        t = lm_state::Tune();
-        t.valid = true; t.uid = h->uid; t.epoch = h->layout_epoch; t.sched = g_sched_epoch; t.dt = dt; t.tol = tol; t.method = method; t.ld = s->ld;
-        t.cand[t.ncand++] = 0;
-        long long ms2[2];
-        const int nc = strip_candidates(h, s->ld, ms2);
-        for (int k = 0; k < nc; ++k) t.cand[t.ncand++] = ms2[k];
-        if (t.ncand == 1) t.choice = 0;             // strips do not apply (N too large, narrow block, no stencil view)
-    }
-    if (t.choice >= 0) return t.cand[t.choice];
-    *timed = true;
-    return t.cand[t.phase];
-}
-static void tune_record(lm_state* s, float ms) {
-    lm_state::Tune& t = s->tune;
-    t.ms[t.phase++] = ms;
-    if (t.phase < t.ncand) return;
-    t.choice = 0;
-    for (int k = 1; k < t.ncand; ++k) if (t.ms[k] < t.ms[t.choice]) t.choice = k;
-    if (getenv("LM_DEBUG_PLAN")) fprintf(stderr, "step schedule: plain %.3f ms, strips(%lld columns) %.3f ms, strips(%lld columns) %.3f ms -> %lld\n",
-                                         t.ms[0], t.cand[1], t.ms[1], t.cand[2], t.ms[2], t.cand[t.choice]);
-}
-// candidate strip widths the online choice would sample for a block of leading dimension ld
-extern "C" int32_t lm_dbg_strip_candidates(lm_ham* h, int64_t ld, int64_t* out2, int32_t* n) {
-    REQUIRE(h && out2 && n, "lm_dbg_strip_candidates: NULL");
-    FWD(refresh_views(h));
-    long long ms[2] = {0, 0};
-    *n = strip_candidates(h, ld, ms);
-    out2[0] = ms[0]; out2[1] = ms[1];
-    return LM_OK;
-}
-// schedule the online choice settled on for the state: *strip_cols = strip width in columns
-// (0 = plain), *calibrating = 1 while it is still sampling; (-1, 0) when the schedule is fixed by
-// LM_STEP_L2_MB / lm_dbg_set_step_l2_kb
-extern "C" int32_t lm_dbg_step_schedule(lm_state* s, int64_t* strip_cols, int32_t* calibrating) {
-    REQUIRE(s && strip_cols && calibrating, "lm_dbg_step_schedule: NULL");
-    if (sched_request() != kSchedAuto) { *strip_cols = -1; *calibrating = 0; return LM_OK; }
-    *calibrating = (s->tune.valid && s->tune.choice < 0) ? 1 : 0;
-    *strip_cols = (s->tune.valid && s->tune.choice >= 0) ? s->tune.cand[s->tune.choice] : 0;
     return LM_OK;
 }
 
@@ -2103,6 +2082,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
     REQUIRE(std::isfinite(dt), "lm_step: dt is not finite");
     REQUIRE(tol > 0 && tol < 1, "lm_step: tol must be in (0, 1)");
     REQUIRE(method >= LM_METHOD_AUTO && method <= LM_METHOD_CHEBYSHEV_CLENSHAW, "lm_step: unknown method");
+    REQUIRE(h->hermitian, "lm_step: H is not Hermitian (max |H_ij - conj(H_ji)| = " + std::to_string(h->herm_defect) + "): the propagators assume a Hermitian operator");
     lm_ctx* c = h->ctx; FWD(set_dev(c));
     int nmv = 0;
     if (method == LM_METHOD_LANCZOS) {
@@ -2119,12 +2099,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
         static const int use_graph = env_int("LM_STEP_GRAPH", 1);
         const bool graphable = use_graph && product_form;
         FWD(refresh_views(h));
-        bool timed = false;
-        g_cur_ms = product_form ? pick_schedule(h, s, dt, tol, method, &timed) : 0;
-        struct Restore { ~Restore() { g_cur_ms = 0; } } restore_schedule;
-        if (timed && !s->tune_ev0) { CK(cudaEventCreate(&s->tune_ev0)); CK(cudaEventCreate(&s->tune_ev1)); }
         if (!graphable) {
-            if (timed) CK(cudaEventRecord(s->tune_ev0, c->stream));
             FWD(propagate(h, s->ld, &s->d_x, &s->d_s1, &s->d_s2, dt, tol, method, &nmv));
         } else {
             // The step is K back-to-back launches with fixed arguments: replay it as one graph
@@ -2133,7 +2108,7 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
             lm_state::StepGraph* g = nullptr;
             for (auto& c2 : s->graphs)
                 if (c2.exec && c2.h == h && c2.uid == h->uid && c2.epoch == h->layout_epoch && c2.x == s->d_x && c2.s1 == s->d_s1 && c2.dt == dt && c2.tol == tol && c2.method == method &&
-                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf && c2.sched == g_sched_epoch && c2.kb == g_cur_ms) { g = &c2; break; }
+                    c2.emin == h->emin && c2.emax == h->emax && c2.norm == h->norm_inf && c2.sched == g_sched_epoch) { g = &c2; break; }
             if (!g) {
                 g = &s->graphs[s->graph_next]; s->graph_next = (s->graph_next + 1) % 8;
                 if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
@@ -2149,23 +2124,15 @@ extern "C" int32_t lm_step(lm_ham* h, lm_state* s, double dt, double tol, int32_
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g->exec = nullptr; s->d_x = x0; s->d_s1 = s10; return fail(LM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
                 g->h = h; g->uid = h->uid; g->epoch = h->layout_epoch; g->x = x0; g->s1 = s10; g->dt = dt; g->tol = tol; g->method = method;
-                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv; g->sched = g_sched_epoch; g->kb = g_cur_ms;
+                g->emin = h->emin; g->emax = h->emax; g->norm = h->norm_inf; g->nmv = nmv; g->sched = g_sched_epoch;
                 g->launches = c->launches - l0; g->swap = (s->d_x != x0);
                 c->launches = l0;                       // counted at replay
                 s->d_x = x0; s->d_s1 = s10;             // capture did not execute anything
             }
-            if (timed) CK(cudaEventRecord(s->tune_ev0, c->stream));     // device time of the replay only (capture is host work)
             CK(cudaGraphLaunch(g->exec, c->stream));
             c->launches += g->launches;
             nmv = g->nmv;
             if (g->swap) std::swap(s->d_x, s->d_s1);
-        }
-        if (timed) {
-            float ms = 0.f;
-            CK(cudaEventRecord(s->tune_ev1, c->stream));
-            CK(cudaEventSynchronize(s->tune_ev1));
-            CK(cudaEventElapsedTime(&ms, s->tune_ev0, s->tune_ev1));
-            tune_record(s, ms);
         }
     } else {
         // P <- U P U^H with U = exp(-i H dt) built by applying the propagator to the identity
@@ -2301,12 +2268,15 @@ static int observe(lm_ham* h, lm_state* s, bool want_j) {
 static int enqueue_observables(lm_ham* h, lm_state* s, int n_int, bool want_j) {
     lm_ctx* c = s->ctx; FWD(set_dev(c));
     REQUIRE(!s->dense, "observables of a dense state: download it with lm_state_download_dense (diagonal) instead");
+    REQUIRE(!want_j || !h || h->hermitian, "DensityCurrents: H is not Hermitian");
     const long long n_sites = s->N / n_int;
     const long long npairs = (h && want_j) ? h->npairs : 0;
     if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
     const long long tot = n_sites + npairs; const int th = 256;
     static const int p2p_env = env_int("LM_OBS_P2P", 1);
-    const bool used_p2p = c->nranks > 1 && c->p2p_ready && p2p_env && tot <= c->p2p_cap;
+    // a replicated state (every rank holds the same columns) is already the whole sum on every rank
+    const bool reduce = c->nranks > 1 && !s->replicated;
+    const bool used_p2p = reduce && c->p2p_ready && p2p_env && tot <= c->p2p_cap;
     if (used_p2p) {
         // fused finalize + push all-gather over NVLink peer memory, then local acquire + sum
         PeerPtrs pp;
@@ -2330,7 +2300,7 @@ static int enqueue_observables(lm_ham* h, lm_state* s, int n_int, bool want_j) {
         c->launches++;
     }
     CK(cudaGetLastError());
-    if (c->nranks > 1 && c->comm && !used_p2p)
+    if (reduce && c->comm && !used_p2p)
         NCK(g_nccl.AllReduce(h->d_obs, h->d_obs, (size_t)tot, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     return LM_OK;
 }
@@ -2344,6 +2314,7 @@ static int run_observables(lm_ham* h, lm_state* s, int n_int, double* rho_out, d
     FWD(ensure_pinned(c, sizeof(double) * (size_t)tot + 4096));
     CK(cudaMemcpyAsync(c->h_pinned, h->d_obs, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    FWD(check_async_status(c));
     const double* src = (const double*)c->h_pinned;
     if (rho_out) memcpy(rho_out, src, sizeof(double) * (size_t)n_sites);
     if (J_out) memcpy(J_out, src + n_sites, sizeof(double) * (size_t)npairs);
@@ -2403,6 +2374,8 @@ extern "C" int32_t lm_frame_wait(lm_ctx* c, int32_t slot, double* rho_out, doubl
     REQUIRE(c->frame_pending[slot], "lm_frame_wait: no frame was enqueued in this slot");
     FWD(set_dev(c));
     CK(cudaEventSynchronize(c->fr_done[slot]));
+    c->frame_pending[slot] = false;
+    FWD(check_async_status(c));
     const double* src = c->h_frame[slot];
     if (rho_out) memcpy(rho_out, src, sizeof(double) * (size_t)c->frame_nsites[slot]);
     if (J_out) {

@@ -3,6 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifndef LM_CPU_EMUL
+#include <cuda.h>               // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 namespace lm {
 
@@ -63,10 +66,23 @@ __device__ __forceinline__ void pfma(float4& acc, const float2 v, const float4 x
     acc.w = fmaf(v.x, x.w, acc.w); acc.w = fmaf(v.y, x.z, acc.w);
 }
 
+// acc += conj(v) * x  (the Hermitian partner of a bond shares the value load, stencil.cuh st_tile_herm)
+__device__ __forceinline__ void pfma_conj(double2& acc, const double2 v, const double2 x) {
+    acc.x = fma(v.x, x.x, acc.x); acc.x = fma(v.y, x.y, acc.x);
+    acc.y = fma(v.x, x.y, acc.y); acc.y = fma(-v.y, x.x, acc.y);
+}
+__device__ __forceinline__ void pfma_conj(float4& acc, const float2 v, const float4 x) {
+    acc.x = fmaf(v.x, x.x, acc.x); acc.x = fmaf(v.y, x.y, acc.x);
+    acc.y = fmaf(v.x, x.y, acc.y); acc.y = fmaf(-v.y, x.x, acc.y);
+    acc.z = fmaf(v.x, x.z, acc.z); acc.z = fmaf(v.y, x.w, acc.z);
+    acc.w = fmaf(v.x, x.w, acc.w); acc.w = fmaf(-v.y, x.z, acc.w);
+}
+
 // ---- shared-memory declarations of the staged kernels ----
 // (macros so that the CPU execution harness, tests/cpu_emul/, can substitute host storage;
 //  under nvcc they expand to exactly the usual CUDA declarations)
 #ifndef LM_CPU_EMUL
+#define LM_GRID_CONSTANT __grid_constant__
 #define LM_SMEM_DYN(name) extern __shared__ __align__(128) unsigned char name[]
 #define LM_SMEM_STATIC __shared__
 #endif
@@ -99,6 +115,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 3-D tiled tensor-map copy global -> shared (TMA, SASS UTMALDG): one instruction moves the whole
+// box; coordinates are element indices, innermost first; out-of-range elements are zero-filled and
+// still counted in the transaction bytes
+__device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const void* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 // programmatic dependent launch (griddepcontrol): no-ops for a grid launched without the attribute
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -576,18 +576,30 @@ __global__ void k_assemble(long long E, const double2* __restrict__ stat,
 }
 
 // Gershgorin enclosure of the spectrum from the ELL rows: per CTA (min_i H_ii - R_i,
-// max_i H_ii + R_i, max_i |H_ii| + R_i), R_i = sum_{j != i} |H_ij|; the host folds the partials.
+// max_i H_ii + R_i, max_i |H_ii| + R_i, max_ij |H_ij - conj(H_ji)|), R_i = sum_{j != i} |H_ij|; the
+// partials are folded by the host (lm_ham_update_values) or by k_enclosure_check (asynchronous updates).
+// The last entry is the Hermiticity defect: the mirror entry of (i, j) is looked up in row j (W
+// columns); a missing mirror counts with |H_ij|.  The polynomial propagators, the real Lanczos
+// recurrence, the pair currents and the shared value loads of st_tile_herm all assume H = H'.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_gershgorin(long long N, int W, const int* __restrict__ cols, const typename cx2<T>::type* __restrict__ vals,
-             double* __restrict__ partial /* [grid][3] */) {
+             double* __restrict__ partial /* [grid][4] */) {
     const long long i = blockIdx.x * 256LL + threadIdx.x;
-    double lo = 1e300, hi = -1e300, nr = 0.0;
+    double lo = 1e300, hi = -1e300, nr = 0.0, as = 0.0;
     if (i < N) {
         double d = 0.0, r = 0.0;
         for (int k = 0; k < W; ++k) {
             const double re = (double)vals[i * W + k].x, im = (double)vals[i * W + k].y;
-            if (cols[i * W + k] == i) d += re; else r += sqrt(re * re + im * im);
+            const long long j = cols[i * W + k];
+            if (j == i) { d += re; as = fmax(as, 2.0 * fabs(im)); }
+            else {
+                r += sqrt(re * re + im * im);
+                double mr = 0.0, mi = 0.0;                       // mirror entry H_ji (0 if not stored)
+                for (int q = 0; q < W; ++q)
+                    if (cols[j * W + q] == i) { mr = (double)vals[j * W + q].x; mi = (double)vals[j * W + q].y; break; }
+                as = fmax(as, fmax(fabs(re - mr), fabs(im + mi)));
+            }
         }
         lo = d - r; hi = d + r; nr = fabs(d) + r;
     }
@@ -596,13 +608,42 @@ k_gershgorin(long long N, int W, const int* __restrict__ cols, const typename cx
         lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         nr = fmax(nr, __shfl_xor_sync(0xffffffffu, nr, o));
+        as = fmax(as, __shfl_xor_sync(0xffffffffu, as, o));
     }
-    LM_SMEM_STATIC double s[8][3];
-    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = lo; s[threadIdx.x >> 5][1] = hi; s[threadIdx.x >> 5][2] = nr; }
+    LM_SMEM_STATIC double s[8][4];
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = lo; s[threadIdx.x >> 5][1] = hi; s[threadIdx.x >> 5][2] = nr; s[threadIdx.x >> 5][3] = as; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) { lo = fmin(lo, s[w][0]); hi = fmax(hi, s[w][1]); nr = fmax(nr, s[w][2]); }
-        partial[blockIdx.x * 3 + 0] = lo; partial[blockIdx.x * 3 + 1] = hi; partial[blockIdx.x * 3 + 2] = nr;
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, s[w][0]); hi = fmax(hi, s[w][1]); nr = fmax(nr, s[w][2]); as = fmax(as, s[w][3]); }
+        partial[blockIdx.x * 4 + 0] = lo; partial[blockIdx.x * 4 + 1] = hi; partial[blockIdx.x * 4 + 2] = nr; partial[blockIdx.x * 4 + 3] = as;
+    }
+}
+// Asynchronous value updates (lm_ham_update_values_async): fold the k_gershgorin partials on the device
+// and raise sticky bits in *flag when the new values leave the enclosure the propagator plan was built
+// for (bit 0) or are not Hermitian (bit 1).  The host reads the word at its next synchronising call.
+__global__ void __launch_bounds__(256)
+k_enclosure_check(const double* __restrict__ partial, unsigned nparts, double emin, double emax, double norm,
+                  double slack, double herm_tol, unsigned* __restrict__ flag) {
+    double lo = 1e300, hi = -1e300, nr = 0.0, as = 0.0;
+    for (unsigned b = threadIdx.x; b < nparts; b += 256) {
+        lo = fmin(lo, partial[4 * b]); hi = fmax(hi, partial[4 * b + 1]); nr = fmax(nr, partial[4 * b + 2]); as = fmax(as, partial[4 * b + 3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nr = fmax(nr, __shfl_xor_sync(0xffffffffu, nr, o));
+        as = fmax(as, __shfl_xor_sync(0xffffffffu, as, o));
+    }
+    LM_SMEM_STATIC double s[8][4];
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = lo; s[threadIdx.x >> 5][1] = hi; s[threadIdx.x >> 5][2] = nr; s[threadIdx.x >> 5][3] = as; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, s[w][0]); hi = fmax(hi, s[w][1]); nr = fmax(nr, s[w][2]); as = fmax(as, s[w][3]); }
+        unsigned bits = 0;
+        if (lo < emin - slack || hi > emax + slack || nr > norm + slack) bits |= 1u;
+        if (as > herm_tol * fmax(nr, 1e-300)) bits |= 2u;
+        if (bits) atomicOr(flag, bits);
     }
 }
 
@@ -618,6 +659,56 @@ __global__ void k_gather_vals(long long nnz, typename cx2<T>::type* __restrict__
                               const int* __restrict__ pos, const typename cx2<T>::type* __restrict__ vals) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e < nnz) nz[e] = vals[pos[e]];
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic Psi block generated on the device (SURVEY.md section 8d, C5 inputs: uniform complex in
+// [-1, 1]^2): element (i, c) is a pure function of (seed, i, global column c) - a SplitMix64 hash,
+// restated in numpy by tests/ and bench.py - so that a column shard of a block equals the same
+// columns of the unsharded block.  Scaled by sqrt(3 / (2 N)): columns have norm ~ 1.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline unsigned long long lm_splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <typename T2>
+__global__ void k_synth_block(long long N, long long M, long long ld, long long col0, unsigned long long seed, double scale, T2* __restrict__ x) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld) return;
+    const long long i = e / ld, c = e - i * ld;
+    T2 v; v.x = 0; v.y = 0;
+    if (c < M) {
+        const unsigned long long k = (unsigned long long)i * 4294967311ull + (unsigned long long)(col0 + c);
+        const unsigned long long h1 = lm_splitmix64(k ^ (seed * 0x9E3779B97F4A7C15ull)), h2 = lm_splitmix64(h1);
+        const double re = (double)(h1 >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        const double im = (double)(h2 >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        v.x = (decltype(v.x))(re * scale); v.y = (decltype(v.y))(im * scale);
+    }
+    x[e] = v;
+}
+// squared column norms of a row-major [N][ld] block: out[c] += sum_i |x[i, c]|^2   (out zeroed by the caller)
+template <typename T2>
+__global__ void __launch_bounds__(256)
+k_colnorm2(long long N, long long M, long long ld, long long rows_per_cta, const T2* __restrict__ x, double* __restrict__ out) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long c = blockIdx.x * 32LL + tx;
+    const long long r0 = blockIdx.y * rows_per_cta, r1 = (r0 + rows_per_cta) < N ? (r0 + rows_per_cta) : N;
+    double acc = 0.0;
+    if (c < M)
+        for (long long i = r0 + ty; i < r1; i += 8) {
+            const T2 v = x[i * ld + c];
+            acc = fma((double)v.x, (double)v.x, acc); acc = fma((double)v.y, (double)v.y, acc);
+        }
+    LM_SMEM_STATIC double s[8][33];
+    s[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < M) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += s[q][tx];
+        atomicAdd(out + c, t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -79,21 +79,21 @@ int stencil_resident_ctas(int id, int v, bool c64) {
     return m < 1 ? 1 : m;
 }
 
-int stencil_launch_0(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
-int stencil_launch_1(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
-int stencil_launch_2(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
-int stencil_launch_3(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
-int stencil_launch_4(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
-int stencil_launch_5(int, bool, int, const StencilArgs&, dim3, cudaStream_t);
+int stencil_launch_0(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+int stencil_launch_1(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+int stencil_launch_2(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+int stencil_launch_3(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+int stencil_launch_4(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+int stencil_launch_5(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
 
-int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     switch (id) {
-    case 0: return stencil_launch_0(variant, c64, mode, a, grid, s);
-    case 1: return stencil_launch_1(variant, c64, mode, a, grid, s);
-    case 2: return stencil_launch_2(variant, c64, mode, a, grid, s);
-    case 3: return stencil_launch_3(variant, c64, mode, a, grid, s);
-    case 4: return stencil_launch_4(variant, c64, mode, a, grid, s);
-    case 5: return stencil_launch_5(variant, c64, mode, a, grid, s);
+    case 0: return stencil_launch_0(variant, c64, mode, a, tmx, grid, s);
+    case 1: return stencil_launch_1(variant, c64, mode, a, tmx, grid, s);
+    case 2: return stencil_launch_2(variant, c64, mode, a, tmx, grid, s);
+    case 3: return stencil_launch_3(variant, c64, mode, a, tmx, grid, s);
+    case 4: return stencil_launch_4(variant, c64, mode, a, tmx, grid, s);
+    case 5: return stencil_launch_5(variant, c64, mode, a, tmx, grid, s);
     default: return -1;
     }
 }

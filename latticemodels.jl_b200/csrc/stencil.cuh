@@ -66,12 +66,11 @@ struct StencilArgs {
     int n1, n2;                     // unit cells along the slow / fast lattice axis
     int np2;                        // CTA patches along the fast axis
     long long ld;                   // row stride of x / y / z / u (complex elements)
-    long long nc;                   // columns processed, starting at the pointers (== ld for the whole block;
-                                    // fewer for an L2-resident column strip of the propagator, api.cu step_*_prod)
-    int keep;                       // 1: plain stores (y is re-read out of L2 by the next factor), 0: evict-first
     int pdl;                        // 1: launched with programmatic stream serialization (k_apply_stencil_tma only):
                                     //    let the next launch of the chain start its CTAs while this grid drains,
                                     //    and wait for the previous grid before touching global memory
+    int herm;                       // 1: H is Hermitian (checked on the device): in-tile bonds share one value load (st_tile_herm)
+    int tmap;                       // 1: interior patches stage their haloed block with ONE 3-D tensor-map copy (k_apply_stencil_tma)
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], g[2], beta[2], delta[2];   // y = alpha (H x + g x) + beta z + delta u
     unsigned cps, nchunks;
@@ -135,6 +134,89 @@ __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][C
     });
 }
 
+// Is the pattern structurally symmetric (entry (a <- b at offset d) present iff (b <- a at -d) is)?
+template <int RC> __host__ __device__ constexpr bool st_symmetric(st_mask_t m) {
+    for (int o = 0; o < 9; ++o)
+        for (int a = 0; a < RC; ++a)
+            for (int b = 0; b < RC; ++b)
+                if (st_bit<RC>(m, o, a, b) != st_bit<RC>(m, 8 - o, b, a)) return false;
+    return true;
+}
+// forward half of a symmetric pattern: offset (+1, *), (0, +1), or a later row of the same cell
+template <int RC> __host__ __device__ constexpr bool st_fwd_bit(st_mask_t m, int o, int a, int b) {
+    return st_bit<RC>(m, o, a, b) && (o > 4 || (o == 4 && b > a));
+}
+
+// Register-tile body for a HERMITIAN operator (H[q,p] = conj(H[p,q]); checked on the device whenever
+// the values change, api.cu).  The uniform 128-bit value loads are the largest share of the kernel's
+// shared-memory wavefronts (each costs two; profiles/r1_stencil_kernels.md), so a bond whose two rows
+// both live in the thread's tile loads its value ONCE and feeds both directions:
+//     acc[p] += h x[q] ,   acc[q] += conj(h) x[p]        (Haldane 4 x 2 tile: 116 value loads instead of 160).
+// The own rows of the tile are held in registers; halo rows are loaded one at a time and feed the
+// own rows they couple to, as in st_tile.  `g` is folded into the diagonal value (2 additions per
+// row and thread instead of 4 FMAs per element).  Only valid for a tile that lies completely
+// inside the lattice (the value rows of cells beyond the edge are not staged): the kernels fall
+// back to st_tile for ragged tiles.
+template <typename T, int RC, st_mask_t MASK, int T1, int T2, int CPT, bool SELF, typename LX, typename LH>
+__device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][RC][CPT], const typename cx2<T>::type g,
+                                             LX&& load_x, LH&& load_h) {
+    using T2c = typename cx2<T>::type;
+    using E = typename pack<T>::E;
+    static_assert(st_symmetric<RC>(MASK), "st_tile_herm needs a structurally symmetric pattern");
+    E xo[T1][T2][RC][CPT];
+    st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
+        constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            xo[v1][v2][aa][j] = load_x(std::integral_constant<int, v1 + 1>{}, std::integral_constant<int, v2 + 1>{}, A, j);
+    }); }); });
+    // diagonal entries (+ g) and the bonds inside the tile, one value load per bond
+    st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
+        constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
+        if constexpr (st_bit<RC>(MASK, 4, aa, aa)) {
+            T2c hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MASK, 4, aa, aa)>{});
+            if constexpr (SELF) { hv.x += g.x; hv.y += g.y; }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xo[v1][v2][aa][j]);
+        } else if constexpr (SELF) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], g, xo[v1][v2][aa][j]);
+        }
+        st_for<5>([&](auto OO) { st_for<RC>([&](auto B) {
+            constexpr int o = decltype(OO)::value + 4, b = decltype(B)::value;
+            constexpr int w1 = v1 + (o / 3 - 1), w2 = v2 + (o % 3 - 1);
+            if constexpr (st_fwd_bit<RC>(MASK, o, aa, b) && w1 >= 0 && w1 < T1 && w2 >= 0 && w2 < T2) {
+                const T2c hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MASK, o, aa, b)>{});
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    pfma(acc[v1][v2][aa][j], hv, xo[w1][w2][b][j]);
+                    pfma_conj(acc[w1][w2][b][j], hv, xo[v1][v2][aa][j]);
+                }
+            }
+        }); });
+    }); }); });
+    // halo rows: loaded once, feed every own row they couple to
+    st_for<T1 + 2>([&](auto U1) { st_for<T2 + 2>([&](auto U2) { st_for<RC>([&](auto B) {
+        constexpr int u1 = decltype(U1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
+        constexpr bool own = u1 >= 1 && u1 <= T1 && u2 >= 1 && u2 <= T2;
+        if constexpr (!own && st_needed<RC, T1, T2>(MASK, u1, u2, b)) {
+            E xv[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) xv[j] = load_x(U1, U2, B, j);
+            st_for<9>([&](auto O) { st_for<RC>([&](auto A) {
+                constexpr int o = decltype(O)::value, aa = decltype(A)::value;
+                constexpr int v1 = u1 - 1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
+                if constexpr (st_bit<RC>(MASK, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
+                    const T2c hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
+                                          A, std::integral_constant<int, st_slot<RC>(MASK, o, aa, b)>{});
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xv[j]);
+                }
+            }); });
+        }
+    }); }); });
+}
+
 // ------------------------------------------------------------------------------------------
 // k_apply_stencil: direct variant - the haloed block is read with ld.global.nc (L1 shares the halo
 // rows between the W1 x W2 register tiles of a CTA).  Latency-bound in practice: the loads in
@@ -154,7 +236,7 @@ k_apply_stencil(const StencilArgs a) {
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = (pj1 * W1 + warp / W2) * T1, o2 = (pj2 * W2 + warp % W2) * T2;
     if (o1 >= a.n1 || o2 >= a.n2) return;
-    const long long lde = a.ld / EC, nce = a.nc / EC;
+    const long long lde = a.ld / EC, nce = lde;
     const E* __restrict__ x = (const E*)a.x;
     const T2c* __restrict__ sv = (const T2c*)a.svals;
     long long cidx[CPT];
@@ -244,7 +326,7 @@ __host__ __device__ constexpr int st_tma_blocks() {
 
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE>
 __global__ void __launch_bounds__(32 * W1 * W2, st_tma_blocks<T, RC, MASK, T1, T2, W1, W2, CPT>())
-k_apply_stencil_tma(const StencilArgs a) {
+k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx) {
     using T2c = typename cx2<T>::type;
     using E = typename pack<T>::E;
     constexpr int EC = pack<T>::EC;
@@ -263,7 +345,7 @@ k_apply_stencil_tma(const StencilArgs a) {
     if (chunk >= a.nchunks) return;
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = pj1 * P1, o2 = pj2 * P2;                 // patch origin (always inside the lattice)
-    const long long lde = a.ld / EC, nce = a.nc / EC;
+    const long long lde = a.ld / EC, nce = lde;
     const long long c0 = (long long)chunk * CE;
     const int cw = (int)((nce - c0) < CE ? (nce - c0) : CE);
     const int vl1 = (a.n1 - o1) < P1 ? (a.n1 - o1) : P1;    // own cells inside the lattice
@@ -271,19 +353,27 @@ k_apply_stencil_tma(const StencilArgs a) {
     const unsigned hline = ((unsigned)(vl2 * RC * SWP * (int)sizeof(T2c)) + 15u) & ~15u;
     const E* __restrict__ x = (const E*)a.x;
     const T2c* __restrict__ sv = (const T2c*)a.svals;
+    // a patch whose haloed block lies inside the lattice is one dense box of the [n1][n2 RC][columns]
+    // view of x: ONE tensor-map copy (SASS UTMALDG; columns beyond the block are zero-filled and
+    // counted) instead of HR row copies.  Patches on the rim keep the row copies (periodic images).
+    const bool boxed = a.tmap && o1 >= 1 && o1 + P1 + 1 <= a.n1 && o2 >= 1 && o2 + P2 + 1 <= a.n2;
     if (tid == 0) {
         mbar_init(&bar, 1);
-        mbar_arrive_expect_tx(&bar, (unsigned)(HR * cw * (int)sizeof(E)) + (unsigned)vl1 * hline);
+        mbar_arrive_expect_tx(&bar, (unsigned)(HR * (boxed ? CE : cw) * (int)sizeof(E)) + (unsigned)vl1 * hline);
     }
     // a chain of factors (x <- y of the previous launch): with programmatic dependent launch the
     // CTAs of this grid are scheduled while the previous grid drains; nothing of global memory is
     // touched before the previous grid has completed and flushed
     if (a.pdl) { pdl_launch_dependents(); pdl_wait(); }
     __syncthreads();
-    for (int r = tid; r < HR; r += NT) {
-        const int u1 = r / ((P2 + 2) * RC), rem = r - u1 * ((P2 + 2) * RC), u2 = rem / RC, b = rem - u2 * RC;
-        const long long row = ((long long)st_wrap(o1 + u1 - 1, a.n1) * a.n2 + st_wrap(o2 + u2 - 1, a.n2)) * RC + b;
-        tma_bulk_g2s(sx + r * CE, x + row * lde + c0, (unsigned)(cw * (int)sizeof(E)), &bar);
+    if (boxed) {
+        if (tid == 0) tma_tensor3d_g2s(sx, &tmx, (int)(c0 * (long long)(sizeof(E) / 8)), (o2 - 1) * RC, o1 - 1, &bar);
+    } else {
+        for (int r = tid; r < HR; r += NT) {
+            const int u1 = r / ((P2 + 2) * RC), rem = r - u1 * ((P2 + 2) * RC), u2 = rem / RC, b = rem - u2 * RC;
+            const long long row = ((long long)st_wrap(o1 + u1 - 1, a.n1) * a.n2 + st_wrap(o2 + u2 - 1, a.n2)) * RC + b;
+            tma_bulk_g2s(sx + r * CE, x + row * lde + c0, (unsigned)(cw * (int)sizeof(E)), &bar);
+        }
     }
     for (int l = NT - 1 - tid; l < vl1; l += NT)
         tma_bulk_g2s(sh + l * (P2 * RC * SWP), sv + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWP), hline, &bar);
@@ -306,13 +396,20 @@ k_apply_stencil_tma(const StencilArgs a) {
     mbar_wait(&bar, 0);
     if (q1 >= a.n1 || q2 >= a.n2) return;
 
-    st_tile<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g,
-        [&](auto U1, auto U2, auto B, int j) {
-            return xb[((decltype(U1)::value * (P2 + 2) + decltype(U2)::value) * RC + decltype(B)::value) * CE + 32 * j];
-        },
-        [&](auto V1, auto V2, auto A, auto S) {
-            return hb[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWP + decltype(S)::value];
-        });
+    auto lx = [&](auto U1, auto U2, auto B, int j) {
+        return xb[((decltype(U1)::value * (P2 + 2) + decltype(U2)::value) * RC + decltype(B)::value) * CE + 32 * j];
+    };
+    auto lh = [&](auto V1, auto V2, auto A, auto S) {
+        return hb[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWP + decltype(S)::value];
+    };
+    bool shared_bonds = false;
+    if constexpr (st_symmetric<RC>(MASK))
+        shared_bonds = a.herm && q1 + T1 <= a.n1 && q2 + T2 <= a.n2;      // warp-uniform
+    if (shared_bonds) {
+        if constexpr (st_symmetric<RC>(MASK)) st_tile_herm<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g, lx, lh);
+    } else {
+        st_tile<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g, lx, lh);
+    }
 
     const T2c alpha = cmake<T2c>(a.alpha[0], a.alpha[1]);
     const T2c beta  = cmake<T2c>(a.beta[0],  a.beta[1]);
@@ -334,37 +431,16 @@ k_apply_stencil_tma(const StencilArgs a) {
                     if (cj >= nce) continue;
                     const long long e = row * lde + cj;
                     E res;
-                    if (MODE == 4) res = acc[v1][v2][aa][j];             // values pre-scaled: y = (alpha H + gamma I) x
-                    else pscale(res, alpha, acc[v1][v2][aa][j]);
+                    pscale(res, alpha, acc[v1][v2][aa][j]);
                     if (MODE == 1) pfma(res, beta, ld_stream(z + e));
                     if (MODE == 2) {
                         if (z) pfma(res, beta, ld_stream(z + e));
                         if (u) pfma(res, delta, u[e]);
                     }
-                    if (a.keep) y[e] = res; else st_stream(y + e, res);
+                    st_stream(y + e, res);
                 }
             }
         }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_fold_svals: slot-ordered values of the WHOLE factor  alpha H + gamma I  (one factor of the
-// product-form propagator) gathered straight from the ELL values: out[i][s] = alpha * H-value of
-// slot s (+ gamma on the diagonal slot of the row).  nnz-sized, runs once per factor; the stencil
-// kernel then stores its accumulators as they are (MODE 4): 40 instead of 48 DFMA per element.
-// ------------------------------------------------------------------------------------------
-template <typename T2>
-__global__ void k_fold_svals(long long n, int sw, int rc, int dslot0, int dslot1, const int* __restrict__ src,
-                             const T2* __restrict__ vals, T2 alpha, T2 gamma, T2* __restrict__ out) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const long long row = i / sw; const int slot = (int)(i - row * sw);
-    T2 v; v.x = 0; v.y = 0;
-    const int e = src[i];
-    if (e >= 0) v = cmul(alpha, vals[e]);
-    const int dslot = (rc == 2 && (row & 1)) ? dslot1 : dslot0;
-    if (slot == dslot) { v.x += gamma.x; v.y += gamma.y; }
-    out[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,7 +481,7 @@ k_apply_stencil_stream(const StencilArgs a) {
     const unsigned group = blockIdx.x / a.npatch, patch = blockIdx.x - group * a.npatch;
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = pj1 * P1, o2 = pj2 * P2;
-    const long long lde = a.ld / EC, nce = a.nc / EC;
+    const long long lde = a.ld / EC, nce = lde;
     const unsigned ch0 = group * a.cpg;
     const unsigned ch1 = (ch0 + a.cpg) < a.nchunks ? (ch0 + a.cpg) : a.nchunks;
     if (ch0 >= ch1) return;
@@ -732,7 +808,7 @@ int stencil_num_variants();
 void stencil_variant_shape(int variant, int* P1, int* P2, int* cpt, int* staged);
 int stencil_resident_ctas(int id, int variant, bool c64);  // CTAs of the staged kernel resident per SM
 // launches; returns 0 on success, -1 if (id, variant, mode) is not compiled, -2 on a CUDA error
-int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s);
+int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s);
 // fused observables: patch size / forward-slot count of the compiled kernel, and its launch
 void stencil_obs_shape(int id, int* P1, int* P2, int* nf);
 int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s);

@@ -6,7 +6,7 @@
 namespace lm {
 
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, int STAGED>
-static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_one(const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if constexpr (STAGED == 2) {
         static_assert(CPT == 1, "the streaming kernel handles one lane element per thread");
         constexpr size_t smem = st_stream_smem<T, RC, MASK, T1, T2, W1, W2>();
@@ -38,39 +38,38 @@ static int launch_one(const StencilArgs& a, dim3 grid, cudaStream_t s) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, a) == cudaSuccess ? 0 : -2;
+        return cudaLaunchKernelEx(&cfg, k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, a, tmx) == cudaSuccess ? 0 : -2;
     }
-    k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
+    k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a, tmx);
     return 0;
     }
 }
 // STAGED is a compile-time family switch so that only the requested family is instantiated
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
-static int launch_modes(int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_modes(int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     switch (mode) {
-    case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, grid, s);
-    case 3: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 3, STAGED>(a, grid, s);
-    case 4: if constexpr (STAGED == 1) return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 4, STAGED>(a, grid, s); else return -1;
+    case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, tmx, grid, s);
+    case 3: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 3, STAGED>(a, tmx, grid, s);
 #ifndef LM_STENCIL_FEWMODES
-    case 1: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 1, STAGED>(a, grid, s);
-    case 2: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 2, STAGED>(a, grid, s);
+    case 1: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 1, STAGED>(a, tmx, grid, s);
+    case 2: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 2, STAGED>(a, tmx, grid, s);
 #endif
     default: return -1;
     }
 }
 template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
-static int launch_prec(bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
-    if (!c64) return launch_modes<double, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, grid, s);
+static int launch_prec(bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
+    if (!c64) return launch_modes<double, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
 #ifndef LM_STENCIL_NOC64
-    return launch_modes<float, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, grid, s);
+    return launch_modes<float, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
 #else
     return -1;
 #endif
 }
 
-#define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MASK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, grid, s);
+#define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MASK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, tmx, grid, s);
 template <int RC, st_mask_t MASK>
-static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if constexpr (RC == 1) {
         switch (variant) {
             LM_ST_V(7, 4, 4, 2, 2, 1, 1)

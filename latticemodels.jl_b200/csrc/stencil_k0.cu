@@ -2,11 +2,11 @@
 #include "stencil_inst.cuh"
 
 namespace lm {
-int stencil_launch_0(int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+int stencil_launch_0(int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
 #if defined(LM_STENCIL_EXPLORE) && (0 == 1 || 0 == 2)
     return -1;      // exploration builds skip the catch-all / honeycomb-NN patterns
 #else
-    return launch_var<1, LM_ST_MASK0>(variant, c64, mode, a, grid, s);
+    return launch_var<1, LM_ST_MASK0>(variant, c64, mode, a, tmx, grid, s);
 #endif
 }
 int stencil_observe_0(bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {

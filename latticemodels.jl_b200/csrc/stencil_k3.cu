@@ -2,11 +2,11 @@
 #include "stencil_inst.cuh"
 
 namespace lm {
-int stencil_launch_3(int variant, bool c64, int mode, const StencilArgs& a, dim3 grid, cudaStream_t s) {
+int stencil_launch_3(int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
 #if defined(LM_STENCIL_EXPLORE) && (3 == 1 || 3 == 2)
     return -1;      // exploration builds skip the catch-all / honeycomb-NN patterns
 #else
-    return launch_var<2, LM_ST_MASK3>(variant, c64, mode, a, grid, s);
+    return launch_var<2, LM_ST_MASK3>(variant, c64, mode, a, tmx, grid, s);
 #endif
 }
 int stencil_observe_3(bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {

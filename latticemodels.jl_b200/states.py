@@ -81,6 +81,11 @@ class DeviceState:
         self.N, self.M, self.is_dense = N.value, M.value, bool(d.value)
         self.full_M = full_M if full_M is not None else self.M
         self.col_range = col_range if col_range is not None else (0, self.M)
+        # every rank holds the whole block (a ket, shard=False, a one-rank job): its observables are
+        # complete on each rank and must not be summed across ranks (lm_state_set_replicated)
+        self.replicated = (not self.is_dense) and ctx.nranks > 1 and self.col_range == (0, self.full_M)
+        if self.replicated:
+            _lib.check(_lib.load().lm_state_set_replicated(handle, 1))
 
     # ---- constructors ---------------------------------------------------------------
     @classmethod
@@ -98,6 +103,24 @@ class DeviceState:
         h = C.c_void_p()
         _lib.check(_lib.load().lm_state_create_psi(ctx.handle, N, e - b, _lib.ptr(local), _lib.ptr(w), C.byref(h)))
         return cls(ctx, h, lattice, n_int, M, (b, e))
+
+    @classmethod
+    def synthetic(cls, N, M, ctx=None, seed=1234, lattice=None, n_int=1, shard=True):
+        """Device-generated block (lm_state_create_psi_synth): uniform complex in [-1, 1]^2, columns
+        of norm ~ 1; a rank's shard holds the same values as those columns of the unsharded block."""
+        ctx = ctx or default_context()
+        b, e = ctx.shard_range(M) if (shard and ctx.nranks > 1) else (0, M)
+        if e <= b:
+            raise _lib.ArgumentError("rank %d owns no column of the %d-column block" % (ctx.rank, M))
+        h = C.c_void_p()
+        _lib.check(_lib.load().lm_state_create_psi_synth(ctx.handle, N, e - b, b, seed, C.byref(h)))
+        return cls(ctx, h, lattice, n_int, M, (b, e))
+
+    def column_norms2(self):
+        """||psi_c||^2 of the local columns."""
+        out = np.empty(self.M)
+        _lib.check(_lib.load().lm_state_column_norms2(self.handle, _lib.ptr(out)))
+        return out
 
     @classmethod
     def from_dense(cls, P, ctx=None, lattice=None, n_int=1):

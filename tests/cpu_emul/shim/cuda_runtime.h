@@ -206,6 +206,7 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
 }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_or(v); }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
     std::atomic_ref<unsigned long long> a(*p);
     unsigned long long o = a.load();
@@ -222,6 +223,9 @@ using std::fmax; using std::fmin; using std::fabs; using std::sqrt; using std::a
 // dynamic / static shared memory of the kernels (csrc/common.cuh defines the CUDA forms)
 #define LM_SMEM_DYN(name) unsigned char* name = lm_emul::dyn_smem()
 #define LM_SMEM_STATIC static
+#define LM_GRID_CONSTANT
+// tensor map of the emulated TMA: what cuTensorMapEncodeTiled is given (FLOAT64 units)
+struct CUtensorMap { const void* base; unsigned long long dims[3]; unsigned long long strides[2]; unsigned box[3]; int valid; };
 
 namespace lm {
 inline void st_release_sys(unsigned long long* p, unsigned long long v) { std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release); }
@@ -253,6 +257,24 @@ inline void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned lo
         std::abort();
     }
     std::memcpy(dst, src, bytes);
+    lm_emul::MBar& b = lm_emul::mbars().at(bar);
+    b.tx -= bytes; lm_emul::bulk_bytes() += bytes; lm_emul::mbar_settle(b);
+    lm_emul::cta().progress = true;
+}
+// cp.async.bulk.tensor.3d (tile mode, FLOAT64 elements): the whole box lands densely in shared memory,
+// innermost dimension first; elements outside the tensor are zero-filled and counted in the bytes
+inline void tma_tensor3d_g2s(void* dst, const void* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+    const CUtensorMap& t = *(const CUtensorMap*)tmap;
+    if (!t.valid || (size_t)dst % 128) { fprintf(stderr, "EMUL FAULT: tensor copy with an invalid map / misaligned destination\n"); std::abort(); }
+    double* d = (double*)dst;
+    for (unsigned k2 = 0; k2 < t.box[2]; ++k2)
+        for (unsigned k1 = 0; k1 < t.box[1]; ++k1)
+            for (unsigned k0 = 0; k0 < t.box[0]; ++k0) {
+                const long long i0 = (long long)c0 + k0, i1 = (long long)c1 + k1, i2 = (long long)c2 + k2;
+                const bool in = i0 >= 0 && i1 >= 0 && i2 >= 0 && i0 < (long long)t.dims[0] && i1 < (long long)t.dims[1] && i2 < (long long)t.dims[2];
+                *d++ = in ? *(const double*)((const char*)t.base + (size_t)i2 * t.strides[1] + (size_t)i1 * t.strides[0] + (size_t)i0 * 8) : 0.0;
+            }
+    const long long bytes = 8LL * t.box[0] * t.box[1] * t.box[2];
     lm_emul::MBar& b = lm_emul::mbars().at(bar);
     b.tx -= bytes; lm_emul::bulk_bytes() += bytes; lm_emul::mbar_settle(b);
     lm_emul::cta().progress = true;

@@ -121,8 +121,8 @@ enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization 
 struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
 struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
 struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute* attrs; unsigned numAttrs; };
-template <typename K, typename A> inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, K kernel, A arg) {
-    lm_emul::enqueue(cfg->gridDim, cfg->blockDim, kernel, arg);
+template <typename K, typename... A> inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, K kernel, A... arg) {
+    lm_emul::enqueue(cfg->gridDim, cfg->blockDim, kernel, arg...);
     return cudaSuccess;
 }
 // multi-GPU plumbing: not available in the single-process harness

@@ -3,8 +3,8 @@
 // localdensity + bond correlators) - against independently written reference loops.  Every CUDA
 // thread of a CTA is a real OS thread (shim/cuda_runtime.h: real __syncthreads, warp-shuffle
 // mailboxes, atomics, the mbarrier phase rule and 16-byte checked bulk copies), so the staging
-// index math, the ragged patch / chunk handling, the column window of the L2-resident strip
-// schedule and the periodic wrap are exercised exactly as written for the device.
+// index math, the ragged patch / chunk handling, the tensor-map box of interior patches, the shared
+// value loads of Hermitian operators and the periodic wrap are exercised exactly as written for the device.
 // TEST INFRASTRUCTURE ONLY.  Prints "OK <n checks>" or the first mismatch; exit code 0 / 1.
 #include <complex>
 #include <cstdio>
@@ -36,11 +36,14 @@ template <typename T> static void set_el(typename pack<T>::E* p, long long lde, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// y[:, c_off : c_off + nc] = alpha (H x + g x) + beta z + delta u   on an n1 x n2 lattice
+// y = alpha (H x + g x) + beta z + delta u   on an n1 x n2 lattice
 // STAGED: 1 = k_apply_stencil_tma, 0 = k_apply_stencil
+// flags: bit 0 = Hermitian values + shared value loads (StencilArgs.herm), bit 1 = tensor-map boxes (StencilArgs.tmap)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, int STAGED>
-static bool check_apply(const char* name, int n1, int n2, bool periodic, long long ld, long long c_off, long long nc, unsigned cps, int keep) {
+static bool check_apply(const char* name, int n1, int n2, bool periodic, long long ld, unsigned cps, int flags) {
+    const long long c_off = 0, nc = ld;
+    const bool herm = flags & 1, tmap = flags & 2;
     using E = typename pack<T>::E;
     using T2c = typename cx2<T>::type;
     constexpr int EC = pack<T>::EC;
@@ -69,11 +72,28 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
             ++s;
         }
     }
+    if (herm) {
+        // H[q, p] = conj(H[p, q]): the mirror of slot (o, a, b) of row p is slot (8 - o, b, a) of the neighbour row
+        for (int j1 = 0; j1 < n1; ++j1) for (int j2 = 0; j2 < n2; ++j2) for (int a = 0; a < RC; ++a) {
+            const long long row = ((long long)j1 * n2 + j2) * RC + a;
+            for (int o = 0; o < 9; ++o) for (int b = 0; b < RC; ++b) {
+                if (!((MASK >> (o * RC * RC + a * RC + b)) & 1ull)) continue;
+                const int k1 = j1 + o / 3 - 1, k2 = j2 + o % 3 - 1;
+                const bool inside = k1 >= 0 && k1 < n1 && k2 >= 0 && k2 < n2;
+                zc& v = svz[row * SWP + st_slot<RC>(MASK, o, a, b)];
+                if (o == 4 && a == b) { v = zc(v.real(), 0.0); continue; }
+                if (!(inside || periodic)) continue;
+                if (!(o > 4 || (o == 4 && b > a))) continue;                  // forward entries define their mirrors
+                const long long nb = ((long long)wrap(k1, n1) * n2 + wrap(k2, n2)) * RC + b;
+                svz[nb * SWP + st_slot<RC>(MASK, 8 - o, b, a)] = std::conj(v);
+            }
+        }
+    }
     for (long long i = 0; i < N * SWP; ++i) sv[i] = cmake<T2c>(svz[i].real(), svz[i].imag());
 
     const zc alpha(rnd(), rnd()), g(rnd(), rnd()), beta(rnd(), rnd()), delta(rnd(), rnd());
     StencilArgs a;
-    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.nc = nc; a.keep = keep; a.pdl = 0;
+    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.pdl = 0; a.herm = herm ? 1 : 0; a.tmap = tmap ? 1 : 0;
     a.x = x.data() + c_off / EC; a.y = y.data() + c_off / EC;
     a.z = (MODE == 1 || MODE == 2) ? z.data() + c_off / EC : nullptr;
     a.u = (MODE == 2) ? u.data() + c_off / EC : nullptr;
@@ -92,7 +112,10 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
     dim3 grid((unsigned)(np1 * np2 * c), (unsigned)strips);
     if constexpr (STAGED == 1) {
         static_assert(st_tma_smem<T, RC, MASK, T1, T2, W1, W2, CPT>() <= 227 * 1024, "patch does not fit shared memory");
-        lm_emul::launch(k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, grid, 32 * W1 * W2, a);
+        CUtensorMap tmx{x.data(), {(unsigned long long)ld * (2 * sizeof(T) / 8), (unsigned long long)n2 * RC, (unsigned long long)n1},
+                        {(unsigned long long)ld * 2 * sizeof(T), (unsigned long long)n2 * RC * ld * 2 * sizeof(T)},
+                        {(unsigned)(32 * CPT * 2), (unsigned)((P2 + 2) * RC), (unsigned)(P1 + 2)}, tmap ? 1 : 0};
+        lm_emul::run_grid(grid, dim3(32 * W1 * W2), [&] { k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>(a, tmx); });
     } else {
         lm_emul::launch(k_apply_stencil<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, grid, 32 * W1 * W2, a);
     }
@@ -115,13 +138,10 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
                 ++s;
             }
             zc ref;
-            if (MODE == 4) ref = hx;
-            else {
-                if (MODE == 2 || MODE == 3) hx += g * get_el<T>(x.data(), lde, row, col);
-                ref = alpha * hx;
-                if (MODE == 1 || MODE == 2) ref += beta * get_el<T>(z.data(), lde, row, col);
-                if (MODE == 2) ref += delta * get_el<T>(u.data(), lde, row, col);
-            }
+            if (MODE == 2 || MODE == 3) hx += g * get_el<T>(x.data(), lde, row, col);
+            ref = alpha * hx;
+            if (MODE == 1 || MODE == 2) ref += beta * get_el<T>(z.data(), lde, row, col);
+            if (MODE == 2) ref += delta * get_el<T>(u.data(), lde, row, col);
             if (!(std::abs(got - ref) <= tol * (1.0 + std::abs(ref)))) {
                 printf("FAIL %s: %dx%d %s ld=%lld window [%lld,+%lld) mode %d: row %lld col %lld got (%g,%g) want (%g,%g)\n", name, n1, n2,
                        periodic ? "periodic" : "open", ld, c_off, nc, MODE, row, col, got.real(), got.imag(), ref.real(), ref.imag());
@@ -208,22 +228,26 @@ template <int RC, st_mask_t MASK>
 static bool check_pattern(const char* name) {
     bool ok = true;
     if constexpr (RC == 1) {
-        // variant 7: 4x4 tiles, 2x2 warps
-        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 11, 9, false, 40, 0, 40, 1, 0);      // open, ragged patches, short last chunk
-        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 8, 17, true, 96, 32, 64, 2, 1);      // periodic, column strip [32, 96), plain stores
-        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 0, 32, 1, 0);        // 3x3 torus: every neighbour is a periodic image
-        ok = ok && check_apply<float, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 9, 10, true, 136, 64, 72, 1, 1);      // complex64: strip [64, 136), ragged tail
-        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 4, 1>(name, 9, 8, false, 32, 0, 32, 1, 0);       // folded values
+        // variant 7: 4x4 tiles, 2x2 warps (8 x 8 cell patches)
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 11, 9, false, 40, 1, 0);      // open, ragged patches, short last chunk, general values
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 11, 9, false, 40, 1, 1);      // same, Hermitian values + shared loads
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 27, 19, true, 96, 2, 3);      // periodic, interior patches through tensor-map boxes
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 26, 18, false, 40, 1, 3);     // open, boxes + ragged chunk (zero-filled columns)
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 1, 1);        // 3x3 torus: every neighbour is a periodic image
+        ok = ok && check_apply<float, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 19, 26, true, 136, 1, 3);      // complex64, ragged tail
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 0, 1>(name, 9, 8, false, 32, 1, 2);       // plain SpMM, general values
         ok = ok && check_observe<double, RC, MASK, 2, 2, 4, 2>(name, 11, 9, false, 37, 40, true, 1);
         ok = ok && check_observe<double, RC, MASK, 2, 2, 4, 2>(name, 8, 5, true, 130, 136, false, 2);            // pipeline wraps its 3 stages
         ok = ok && check_observe<float, RC, MASK, 2, 2, 4, 2>(name, 3, 3, true, 70, 72, true, 4);
     } else {
-        // variant 2: 4x2 tiles, 2x2 warps
-        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 11, 5, false, 40, 0, 40, 1, 0);
-        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 8, 9, true, 96, 32, 64, 2, 1);
-        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 0, 32, 1, 0);
-        ok = ok && check_apply<float, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 9, 6, true, 136, 64, 72, 1, 1);
-        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 4, 1>(name, 9, 4, false, 32, 0, 32, 1, 0);
+        // variant 2: 4x2 tiles, 2x2 warps (8 x 4 cell patches)
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 11, 5, false, 40, 1, 0);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 11, 5, false, 40, 1, 1);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 27, 11, true, 96, 2, 3);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 26, 10, false, 40, 1, 3);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 1, 1);
+        ok = ok && check_apply<float, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 19, 14, true, 136, 1, 3);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 0, 1>(name, 9, 4, false, 32, 1, 2);
         // observables shape of stencil_inst.cuh ObsShape: one cell per thread for wide forward lists
         constexpr int OT2 = st_nfwd<RC>(MASK) > 6 ? 1 : 2;
         ok = ok && check_observe<double, RC, MASK, 1, OT2, 4, 2>(name, 7, 5, false, 37, 40, true, 1);
@@ -244,10 +268,10 @@ int main(int argc, char** argv) {
     if (only < 0 || only == 6) ok = ok && check_pattern<2, LM_ST_MASK5>("rc2-full");
     if (only < 0 || only == 5) {
         // the remaining Clenshaw / Horner modes and the direct-load kernel on one pattern each
-        ok = ok && check_apply<double, 2, LM_ST_MASK4, 4, 2, 2, 2, 1, 1, 1>("haldane", 5, 5, true, 32, 0, 32, 1, 0);
-        ok = ok && check_apply<double, 2, LM_ST_MASK4, 4, 2, 2, 2, 1, 2, 1>("haldane", 5, 5, false, 32, 0, 32, 1, 0);
-        ok = ok && check_apply<double, 1, LM_ST_MASK0, 4, 4, 2, 2, 1, 3, 0>("square-nn", 9, 9, true, 72, 32, 40, 1, 0);
-        ok = ok && check_apply<double, 2, LM_ST_MASK3, 4, 2, 2, 4, 1, 3, 0>("qwz", 9, 9, false, 40, 0, 40, 1, 0);
+        ok = ok && check_apply<double, 2, LM_ST_MASK4, 4, 2, 2, 2, 1, 1, 1>("haldane", 13, 9, true, 32, 1, 3);
+        ok = ok && check_apply<double, 2, LM_ST_MASK4, 4, 2, 2, 2, 1, 2, 1>("haldane", 13, 9, false, 32, 1, 3);
+        ok = ok && check_apply<double, 1, LM_ST_MASK0, 4, 4, 2, 2, 1, 3, 0>("square-nn", 9, 9, true, 72, 1, 0);
+        ok = ok && check_apply<double, 2, LM_ST_MASK3, 4, 2, 2, 4, 1, 3, 0>("qwz", 9, 9, false, 40, 1, 0);
     }
     if (!ok) return 1;
     printf("OK %lld checks, %lld bytes through cp.async.bulk\n", nchecks, lm_emul::bulk_bytes());

@@ -29,7 +29,7 @@ _lib = import_module("lm_b200._lib")
 from oracle import evolution as EV, fields as F, lattice as L, operators as OP
 warnings.simplefilter("ignore")
 lib = _lib.load()
-lib.lm_dbg_set_step_l2_kb.argtypes = [C.c_int64]
+lib.lm_dbg_set_stencil_flags.argtypes = [C.c_int32, C.c_int32]
 seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 ncases = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 ctxs = {"c128": lm.default_context("c128"), "c64": lm.default_context("c64")}
@@ -87,8 +87,8 @@ for case in range(seed0, seed0 + ncases):
         assert e1 < 3e-14 * eps, ("spmm", e1)
         method = ["auto", "taylor", "chebyshev", "taylor_horner", "chebyshev_clenshaw", "lanczos"][int(rng.integers(0, 6))]
         dt = float(rng.choice([0.1, 0.37, -0.5, 1.3]))
-        kb = int(rng.choice([0, 0, 2 * N * 16 * 64 // 1024 + 1]))
-        lib.lm_dbg_set_step_l2_kb(kb)
+        kb = int(rng.integers(0, 4))                 # stencil kernel variant: bit 0 shared value loads (Hermitian), bit 1 tensor-map boxes
+        lib.lm_dbg_set_stencil_flags(kb & 1, kb >> 1)
         st = lm.DeviceState.from_psi(X, ctx=ctx)
         sol = lm.B200Exp(tol=1e-13 if prec == "c128" else 1e-6, method=method, ctx=ctx)
         sol.update_solver(Hd, dt)
@@ -98,7 +98,7 @@ for case in range(seed0, seed0 + ncases):
         for _ in range(nst): want = U @ want
         e2 = relerr(st.download(), want)
         assert e2 < 1e-12 * eps * 3, ("step", method, dt, kb, e2)
-        lib.lm_dbg_set_step_l2_kb(-1)
+        lib.lm_dbg_set_stencil_flags(-1, -1)
         w = rng.random(M)
         Xn = X / np.sqrt(N)
         so = lm.DeviceState.from_psi(Xn, w, ctx=ctx, n_int=Hd.n_int)
@@ -125,7 +125,7 @@ for case in range(seed0, seed0 + ncases):
             assert e5 < 1e-12 and e6 < 1e-13 and e7 < 1e-12, ("dense", e5, e6, e7)
     except Exception as e:
         nfail += 1
-        lib.lm_dbg_set_step_l2_kb(-1)
+        lib.lm_dbg_set_stencil_flags(-1, -1)
         print("FAIL", desc, "->", repr(e)[:300], flush=True)
 print("fuzz: %d cases, %d failures, %.0fs" % (ncases, nfail, time.time() - t00))
 sys.exit(1 if nfail else 0)

@@ -1,7 +1,7 @@
 """The GPU parity suite run WITHOUT a GPU: the whole library (C ABI, host orchestration in
 csrc/api.cu, every kernel) is compiled by g++ through the CUDA shim of tests/cpu_emul/ - CUDA threads
 are fibers, the runtime API is restated on host memory, stream capture records closures - and the
-gpu-marked tests of tests/test_gpu_parity.py and tests/test_zz_gpu_strips.py are executed against
+gpu-marked tests of tests/test_gpu_parity.py and tests/test_zz_gpu_patterns.py are executed against
 it through the same ctypes binding, unchanged.  Only the three full-size property tests (configs
 2-4, minutes of emulated work) and the 201-frame README workflow (the golden-fixture test runs the
 same workflow) are left to the real device.
@@ -71,9 +71,9 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     so = emul_lib
     # the emulated kernels are single-threaded per process: xdist workers, BLAS kept to two threads each
     env = dict(os.environ, LM_EMUL_LIB=so, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
-    for k in ("LM_STEP_L2_MB", "LM_STEP_PDL", "LM_APPLY_TILED", "LM_APPLY_STENCIL", "LM_STENCIL_VARIANT"):
+    for k in ("LM_STEP_PDL", "LM_STENCIL_HERM", "LM_STENCIL_TMAP", "LM_APPLY_TILED", "LM_APPLY_STENCIL", "LM_STENCIL_VARIANT"):
         env.pop(k, None)
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_gpu_strips.py"), os.path.join(ROOT, "tests", "test_zz_gpu_currents_api.py"),
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_gpu_patterns.py"), os.path.join(ROOT, "tests", "test_zz_gpu_currents_api.py"),
            "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not full_size and not readme_workflow"]
     try:
         import xdist  # noqa: F401

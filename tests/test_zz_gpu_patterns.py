@@ -1,8 +1,8 @@
-"""GPU tests of the L2-resident strip schedule of the product-form propagators (csrc/api.cu
-run_factors; opt-in through LM_STEP_L2_MB / lm_dbg_set_step_l2_kb).  The schedule only re-orders
-independent column strips, so its results must equal the plain factor-by-factor schedule BIT FOR
-BIT, and both must match the exact exponential.  Kept in its own file, sorted after the parity
-suite: written in a session without GPU time, first run is the driver's."""
+"""GPU tests of the staging / value-sharing variants of the register-tiled stencil kernel
+(csrc/stencil.cuh): shared value loads for Hermitian operators (st_tile_herm) and tensor-map boxes
+for interior patches must agree with the general row-copy kernel and with the exact exponential;
+non-Hermitian operators are refused by lm_step; asynchronous value updates; the catch-all RC = 2
+pattern; golden fixtures of the reduced configs 3 / 4."""
 import ctypes as C
 from importlib import import_module
 
@@ -19,11 +19,11 @@ pytestmark = pytest.mark.gpu
 _lib = import_module("lm_b200._lib")
 
 
-def _set_l2_kb(kb):
+def _set_flags(herm, tmap):
     lib = _lib.load()
-    lib.lm_dbg_set_step_l2_kb.argtypes = [C.c_int64]
-    lib.lm_dbg_set_step_l2_kb.restype = C.c_int32
-    _lib.check(lib.lm_dbg_set_step_l2_kb(kb))
+    lib.lm_dbg_set_stencil_flags.argtypes = [C.c_int32, C.c_int32]
+    lib.lm_dbg_set_stencil_flags.restype = C.c_int32
+    _lib.check(lib.lm_dbg_set_stencil_flags(herm, tmap))
 
 
 def _rand_block(n, m, seed):
@@ -47,7 +47,10 @@ CASES = {
 
 @pytest.mark.parametrize("precision", ["c128", "c64"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_strip_schedule_is_bitwise_equal_to_plain_schedule(case, precision):
+def test_stencil_kernel_variants_agree(case, precision):
+    """(herm, tmap) in {0,1}^2: general values + row copies (the round-1 kernel), shared value loads,
+    tensor-map boxes, both (the default).  Different summation orders: agreement to rounding, and
+    every variant against the exact exponential."""
     ctx = lm.default_context(precision)
     mk_dev, mk_or = CASES[case]
     Hd, Ho = mk_dev(), mk_or()
@@ -56,28 +59,26 @@ def test_strip_schedule_is_bitwise_equal_to_plain_schedule(case, precision):
     try:
         for M, method, dt in ((200, "chebyshev", 0.3), (333, "taylor", 0.2), (131, "chebyshev", -0.7)):
             X = _rand_block(N, M, seed=M)
-            outs, launches = [], []
-            for kb in (0, 2 * N * 16 * 64 // 1024 + 1):      # plain, then strips of 64 columns
-                _set_l2_kb(kb)
+            outs = []
+            for herm, tmap in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                _set_flags(herm, tmap)
                 st = lm.DeviceState.from_psi(X, ctx=ctx)
                 sol = lm.B200Exp(tol=tol, method=method, ctx=ctx)
                 sol.update_solver(Hd, dt)
-                n0 = ctx.launch_count()
                 for _ in range(3):                            # odd factor counts swap buffers: several steps
                     sol.step(st)
-                launches.append(ctx.launch_count() - n0)
                 outs.append(st.download())
-            assert launches[1] > launches[0], (case, M, launches)      # the strip schedule really ran
-            assert np.array_equal(outs[0], outs[1]), (case, M, method, _relerr(outs[1], outs[0]))
             U = EV.exact_propagator(Ho, dt)
             want = U @ (U @ (U @ X))
-            assert _relerr(outs[1], want) < (5e-13 if precision == "c128" else 2e-4), (case, M, method)
+            for k, o in enumerate(outs):
+                assert _relerr(o, want) < (5e-13 if precision == "c128" else 2e-4), (case, M, method, k)
+                assert _relerr(o, outs[0]) < (1e-13 if precision == "c128" else 5e-5), (case, M, method, k)
     finally:
-        _set_l2_kb(-1)
+        _set_flags(-1, -1)
 
 
-def test_strip_schedule_keeps_graph_cache_consistent():
-    """Switching the schedule between steps of the SAME state must not replay a stale step graph."""
+def test_switching_variants_keeps_graph_cache_consistent():
+    """Switching the kernel flags between steps of the SAME state must not replay a stale step graph."""
     ctx = lm.default_context("c128")
     Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(20, 20), field=lm.LandauGauge(0.1))
     Ho = OP.tightbinding_hamiltonian(L.square_lattice(20, 20), field=F.LandauGauge(0.1))
@@ -89,12 +90,98 @@ def test_strip_schedule_keeps_graph_cache_consistent():
     U = EV.exact_propagator(Ho, 0.1)
     try:
         for k in range(6):
-            _set_l2_kb(0 if k % 2 == 0 else 2 * 400 * 16 * 64 // 1024 + 1)
+            _set_flags(k % 2, (k // 2) % 2)
             sol.step(st)
             want = U @ want
         assert _relerr(st.download(), want) < 1e-12
     finally:
-        _set_l2_kb(-1)
+        _set_flags(-1, -1)
+
+
+def test_non_hermitian_operator_is_refused_by_step_and_currents():
+    """The propagators, the pair currents and the shared value loads assume H = H' (ADVICE r1): a
+    non-Hermitian matrix still multiplies (lm_spmm) but lm_step / DensityCurrents raise."""
+    import scipy.sparse as sp
+    ctx = lm.default_context("c128")
+    H = lm.tightbinding_hamiltonian(lm.SquareLattice(8, 8), field=lm.LandauGauge(0.1))
+    A = sp.csc_matrix(H.data).astype(np.complex128)
+    B = A.copy()
+    B.data = B.data.copy()
+    B.data[3] *= 1.0 + 1e-6                                   # one entry off its mirror
+    dev = lm.DeviceHam.from_csc(ctx, B, 1)
+    X = _rand_block(64, 40, seed=5)
+    st = lm.DeviceState.from_psi(X, ctx=ctx)
+    lib = _lib.load()
+    Y = np.empty_like(np.asfortranarray(X))
+    _lib.check(lib.lm_spmm(dev.handle, _lib.ptr(np.asfortranarray(X)), _lib.ptr(Y), 64, 40))
+    assert _relerr(Y, B @ X) < 1e-13
+    nmv = C.c_int32()
+    with pytest.raises(_lib.ArgumentError, match="not Hermitian"):
+        _lib.check(lib.lm_step(dev.handle, st.handle, 0.1, 1e-12, 0, C.byref(nmv)))
+    rho = np.empty(64)
+    J = np.empty(max(len(dev.pairs()[0]), 1))
+    with pytest.raises(_lib.ArgumentError, match="not Hermitian"):
+        _lib.check(lib.lm_observables(dev.handle, st.handle, _lib.ptr(rho), _lib.ptr(J)))
+    # back to Hermitian values: accepted again
+    _lib.check(lib.lm_ham_update_values(dev.handle, _lib.ptr(np.ascontiguousarray(A.data))))
+    _lib.check(lib.lm_step(dev.handle, st.handle, 0.1, 1e-12, 0, C.byref(nmv)))
+
+
+def test_async_value_updates_match_synchronous_ones_and_trip_on_a_wider_spectrum():
+    """lm_ham_update_values_async: same results as the synchronous update while the values stay inside
+    the planned enclosure (a gauge-field ramp), a sticky error at the next synchronising call when they do not."""
+    import scipy.sparse as sp
+    ctx = lm.default_context("c128")
+    lat = lm.SquareLattice(16, 12)
+    Hs = [sp.csc_matrix(lm.tightbinding_hamiltonian(lat, field=lm.LandauGauge(0.02 * k)).data).astype(np.complex128) for k in range(5)]
+    X = _rand_block(192, 64, seed=9)
+    lib = _lib.load()
+    nmv = C.c_int32()
+    outs = []
+    for use_async in (False, True):
+        dev = lm.DeviceHam.from_csc(ctx, Hs[0], 1, coords=lat.coords, lattice_dims=lat.sizes)
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        keep = []
+        for k in range(1, 5):
+            nz = np.ascontiguousarray(Hs[k].data)
+            keep.append(nz)                                   # the async call borrows the buffer until the next sync
+            _lib.check((lib.lm_ham_update_values_async if use_async else lib.lm_ham_update_values)(dev.handle, _lib.ptr(nz)))
+            _lib.check(lib.lm_step(dev.handle, st.handle, 0.1, 1e-12, 0, C.byref(nmv)))
+        _lib.check(lib.lm_ctx_synchronize(ctx.handle))
+        outs.append(st.download())
+    assert np.array_equal(outs[0], outs[1])
+    want = X
+    for k in range(1, 5):
+        want = EV.exact_propagator(Hs[k].toarray(), 0.1) @ want
+    assert _relerr(outs[1], want) < 1e-12
+    # values that leave the enclosure: reported by the next synchronising call, then cleared
+    nz = np.ascontiguousarray(3.0 * Hs[1].data)
+    _lib.check(lib.lm_ham_update_values_async(dev.handle, _lib.ptr(nz)))
+    with pytest.raises(_lib.ArgumentError, match="enclosure"):
+        _lib.check(lib.lm_ctx_synchronize(ctx.handle))
+    _lib.check(lib.lm_ctx_synchronize(ctx.handle))
+    _lib.check(lib.lm_ham_update_values(dev.handle, _lib.ptr(np.ascontiguousarray(Hs[1].data))))
+
+
+def test_synthetic_block_and_column_norms():
+    """lm_state_create_psi_synth against its numpy restatement (tests/synth.py) incl. a column shard,
+    and lm_state_column_norms2 against numpy."""
+    from synth import synth_block
+    ctx = lm.default_context("c128")
+    lib = _lib.load()
+    N, M = 300, 70
+    want = synth_block(N, M, 0, seed=1234)
+    for col0, m in ((0, M), (17, 33)):
+        h = C.c_void_p()
+        _lib.check(lib.lm_state_create_psi_synth(ctx.handle, N, m, col0, 1234, C.byref(h)))
+        out = np.empty((N, m), dtype=np.complex128, order="F")
+        _lib.check(lib.lm_state_download_psi(h, _lib.ptr(out)))
+        assert np.array_equal(out, want[:, col0:col0 + m])
+        n2 = np.empty(m)
+        _lib.check(lib.lm_state_column_norms2(h, _lib.ptr(n2)))
+        assert np.allclose(n2, (np.abs(out) ** 2).sum(axis=0), rtol=1e-13)
+        assert np.all(np.abs(n2 - 1.0) < 0.2)
+        _lib.check(lib.lm_state_destroy(h))
 
 
 # ------------------------------------------------------------------------------ catch-all RC = 2 stencil (pattern 5)
@@ -149,87 +236,6 @@ def test_catch_all_two_row_stencil_matches_oracle(case):
 
 
 # ------------------------------------------------------------------------------ online choice of the schedule
-def test_online_schedule_choice_samples_every_candidate_and_settles():
-    """LM_STEP_L2_MB=auto (here: lm_dbg_set_step_l2_kb(-2)): the first steps of a (Hamiltonian, dt,
-    tol, method) run one candidate schedule each - plain, strips of two budgets - timed with events;
-    afterwards the fastest is used.  All candidates are bit-identical, so the sampled steps are
-    ordinary steps: the trajectory must equal the plain one bit for bit."""
-    ctx = lm.default_context("c128")
-    lib = _lib.load()
-    lib.lm_dbg_set_autotune_kb.argtypes = [C.c_int64, C.c_int64]
-    lib.lm_dbg_step_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
-    Hd = lm.haldane(lm.HoneycombLattice(9, 8), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.05))
-    Ho = OP.haldane(L.honeycomb_lattice(9, 8), 1.0, 0.2, 0.1, field=F.LandauGauge(0.05))
-    N = Ho.shape[0]
-    X = _rand_block(N, 300, seed=11)
-    kb64, kb128 = 2 * N * 16 * 64 // 1024 + 1, 2 * N * 16 * 128 // 1024 + 1
-    try:
-        _set_l2_kb(0)
-        ref = lm.DeviceState.from_psi(X, ctx=ctx)
-        sol0 = lm.B200Exp(tol=1e-13, ctx=ctx)
-        sol0.update_solver(Hd, 0.2)
-        for _ in range(6):
-            sol0.step(ref)
-        _lib.check(lib.lm_dbg_set_autotune_kb(kb64, kb128))
-        _set_l2_kb(-2)
-        st = lm.DeviceState.from_psi(X, ctx=ctx)
-        sol = lm.B200Exp(tol=1e-13, ctx=ctx)
-        sol.update_solver(Hd, 0.2)
-        kb, cal = C.c_int64(), C.c_int32()
-        per_step = []
-        for k in range(6):
-            n0 = ctx.launch_count()
-            sol.step(st)
-            per_step.append(ctx.launch_count() - n0)
-            _lib.check(lib.lm_dbg_step_schedule(st.handle, C.byref(kb), C.byref(cal)))
-            assert cal.value == (1 if k < 2 else 0), (k, cal.value)
-        # step 0 plain (K launches), step 1 strips of 64 columns (5 strips), step 2 strips of 128 (3 strips)
-        assert per_step[1] == 5 * per_step[0] and per_step[2] == 3 * per_step[0], per_step
-        assert kb.value in (0, 64, 128)          # the strip width the choice settled on (0 = plain)
-        assert len(set(per_step[3:])) == 1 and per_step[3] in per_step[:3]
-        assert np.array_equal(st.download(), ref.download())
-        U = EV.exact_propagator(Ho, 0.2)
-        want = X
-        for _ in range(6):
-            want = U @ want
-        assert _relerr(st.download(), want) < 1e-12
-        # a new dt is a new calibration; a block too narrow for strips settles at once on the plain schedule
-        sol.update_solver(Hd, 0.1)
-        sol.step(st)
-        _lib.check(lib.lm_dbg_step_schedule(st.handle, C.byref(kb), C.byref(cal)))
-        assert cal.value == 1
-        narrow = lm.DeviceState.from_psi(X[:, :40].copy(), ctx=ctx)
-        sol.step(narrow)
-        _lib.check(lib.lm_dbg_step_schedule(narrow.handle, C.byref(kb), C.byref(cal)))
-        assert cal.value == 0 and kb.value == 0
-    finally:
-        _set_l2_kb(-1)
-        lib.lm_dbg_set_autotune_kb(0, 0)
-
-
-def test_strip_candidates_fill_the_machine_evenly():
-    """The widths the online choice samples: multiples of the kernel's 32-column chunk whose two strip
-    buffers stay under 60 % of the L2, ranked by wave efficiency (patches x chunks against the CTAs
-    resident on all SMs).  C2 (square 100 x 100, 5000 columns): 13 x 13 patches of 8 x 8 cells, 4
-    CTAs per SM -> 592 resident; 7 chunks = 1183 CTAs fill two waves (1184) almost exactly, 6 chunks =
-    1014 CTAs are next (0.86).  C4-sized lattices have no candidate (the plain schedule)."""
-    ctx = lm.default_context("c128")
-    lib = _lib.load()
-    lib.lm_dbg_strip_candidates.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
-    out, n = (C.c_int64 * 2)(), C.c_int32()
-    dev = lm.tightbinding_hamiltonian(lm.SquareLattice(100, 100)).device(ctx)
-    _lib.check(lib.lm_dbg_strip_candidates(dev.handle, 5000, out, C.byref(n)))
-    assert n.value == 2 and list(out) == [224, 192], (n.value, list(out))
-    for ms in out:
-        assert ms % 32 == 0 and 2 * 10**4 * ms * 16 <= 0.6 * 126 * 2**20
-    _lib.check(lib.lm_dbg_strip_candidates(dev.handle, 96, out, C.byref(n)))      # 31 MB of buffers: L2-resident as it is
-    assert n.value == 0
-    big = lm.haldane(lm.HoneycombLattice(200, 200), 1.0, 0.2, 0.1).device(ctx)     # N = 8e4: a 64-column strip pair is 164 MB
-    _lib.check(lib.lm_dbg_strip_candidates(big.handle, 4096, out, C.byref(n)))
-    assert n.value == 0
-
-
-# ------------------------------------------------------------------------------ golden fixtures of reduced configs 3 / 4
 @pytest.mark.parametrize("method", ["auto", "lanczos"])
 @pytest.mark.parametrize("name", ["config3s", "config4s"])
 def test_golden_reduced_config_fixtures_on_device(name, method):

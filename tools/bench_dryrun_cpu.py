@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]
+            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity_check"]
 
 
 def main():
@@ -67,6 +67,8 @@ def main():
     for k in ("value", "unit", "cores", "kind", "sample"):
         assert k in out["cpu_baseline"], k
     assert out["gpu_launches"] > 0 and out["value"] > 0 and out["e2e"]["value"] > 0
+    assert out["parity_check"]["max_rel"] < 1e-12, out["parity_check"]
+    assert out["roofline"]["traffic"] is None
     assert out["e2e"]["h2d_bytes_per_step"] > 0 and out["e2e"]["d2h_bytes_per_step"] > 0
     sys.stderr.write("bench dry run ok: %d launches in the timed region, keys %s" % (out["gpu_launches"], sorted(out)))
     sys.stderr.flush()
