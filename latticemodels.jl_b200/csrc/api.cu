@@ -1568,7 +1568,7 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     const long long nc = ld;
     const int variant = stencil_variant_of(h);
     int P1, P2, cpt, staged;
-    stencil_variant_shape(variant, &P1, &P2, &cpt, &staged);
+    stencil_variant_shape(variant, h->st_rc, &P1, &P2, &cpt, &staged);
     StencilArgs a;
     a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld;
     // LM_STEP_PDL=1 (opt-in): chains of factors are launched with programmatic dependent launch
@@ -2240,7 +2240,17 @@ static int observe_stencil(lm_ham* h, lm_state* s) {
     ngroups = (nchunks + cpg - 1) / cpg;
     REQUIRE(np1 * np2 * ngroups < 2147483647LL, "observe_stencil: grid too large");
     a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg; a.nchunks = (unsigned)nchunks;
-    const int st = stencil_observe(h->st_id, c->precision != LM_C128, a, (unsigned)(np1 * np2 * ngroups), c->stream);
+    CUtensorMap tmx;
+    memset(&tmx, 0, sizeof(tmx));
+    static const int tmap_env = env_int("LM_STENCIL_TMAP", 1);
+    a.tmap = 0;
+    if (g_stencil_tmap >= 0 ? g_stencil_tmap : tmap_env) {
+        const unsigned long long u8 = (unsigned long long)(c->esz() / 8);
+        a.tmap = make_tmap3d(&tmx, s->d_x, (unsigned long long)s->ld * u8, (unsigned long long)h->lat_n2 * h->st_rc, (unsigned long long)h->lat_n1,
+                             (unsigned long long)s->ld * c->esz(), (unsigned long long)h->lat_n2 * h->st_rc * (unsigned long long)s->ld * c->esz(),
+                             64u, (unsigned)((P2 + 2) * h->st_rc), (unsigned)(P1 + 1)) == 0 ? 1 : 0;
+    }
+    const int st = stencil_observe(h->st_id, c->precision != LM_C128, a, tmx, (unsigned)(np1 * np2 * ngroups), c->stream);
     if (st != 0) return fail(LM_ERR_CUDA, "observe_stencil: launch failed");
     c->launches++;
     CK(cudaGetLastError());
@@ -2267,15 +2277,21 @@ static int observe(lm_ham* h, lm_state* s, bool want_j) {
 // rank-reduced frame [rho (n_sites) | J (npairs, only if want_j)].  No host synchronisation.
 static int enqueue_observables(lm_ham* h, lm_state* s, int n_int, bool want_j) {
     lm_ctx* c = s->ctx; FWD(set_dev(c));
-    REQUIRE(!s->dense, "observables of a dense state: download it with lm_state_download_dense (diagonal) instead");
     REQUIRE(!want_j || !h || h->hermitian, "DensityCurrents: H is not Hermitian");
     const long long n_sites = s->N / n_int;
     const long long npairs = (h && want_j) ? h->npairs : 0;
-    if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
+    if (s->dense) {
+        // dense density matrix (README workflow, test/test_workflows.jl:29-62): read P itself
+        const long long E = h->N * (long long)h->W; const int th = 256;
+        if (c->precision == LM_C128) k_observe_dense<double2><<<(unsigned)((E + th - 1) / th), th, 0, c->stream>>>(h->N, h->W, s->ld, (const double2*)s->d_x, h->d_cols, h->d_dens, h->d_G);
+        else k_observe_dense<float2><<<(unsigned)((E + th - 1) / th), th, 0, c->stream>>>(h->N, h->W, s->ld, (const float2*)s->d_x, h->d_cols, h->d_dens, h->d_G);
+        c->launches++;
+        CK(cudaGetLastError());
+    } else if (c->precision == LM_C128) FWD(observe<double>(h, s, want_j)); else FWD(observe<float>(h, s, want_j));
     const long long tot = n_sites + npairs; const int th = 256;
     static const int p2p_env = env_int("LM_OBS_P2P", 1);
     // a replicated state (every rank holds the same columns) is already the whole sum on every rank
-    const bool reduce = c->nranks > 1 && !s->replicated;
+    const bool reduce = c->nranks > 1 && !s->replicated && !s->dense;      // the dense-P path is replicas only
     const bool used_p2p = reduce && c->p2p_ready && p2p_env && tot <= c->p2p_cap;
     if (used_p2p) {
         // fused finalize + push all-gather over NVLink peer memory, then local acquire + sum
@@ -2541,13 +2557,14 @@ static int corr_pairs(lm_state* s, long long nq, const int* d_a, const int* d_b,
     using T2 = typename cx2<T>::type;
     lm_ctx* c = s->ctx;
     if (nq == 0) return LM_OK;
-    k_corr_pairs<T><<<(unsigned)((nq + 7) / 8), 256, 0, c->stream>>>(nq, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
+    if (s->dense) k_corr_pairs_dense<T2><<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(nq, s->ld, (const T2*)s->d_x, d_a, d_b, d_out);
+    else k_corr_pairs<T><<<(unsigned)((nq + 7) / 8), 256, 0, c->stream>>>(nq, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
     c->launches++;
     CK(cudaGetLastError());
     return LM_OK;
 }
-static int reduce_and_fetch(lm_ctx* c, double* d_buf, size_t ndoubles, void* host_out) {
-    if (c->nranks > 1 && c->comm)
+static int reduce_and_fetch(lm_ctx* c, const lm_state* s, double* d_buf, size_t ndoubles, void* host_out) {
+    if (c->nranks > 1 && c->comm && !s->replicated && !s->dense)       // replicated / dense states are complete on every rank
         NCK(g_nccl.AllReduce(d_buf, d_buf, ndoubles, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     FWD(ensure_pinned(c, sizeof(double) * ndoubles + 4096));
     CK(cudaMemcpyAsync(c->h_pinned, d_buf, sizeof(double) * ndoubles, cudaMemcpyDeviceToHost, c->stream));
@@ -2558,7 +2575,6 @@ static int reduce_and_fetch(lm_ctx* c, double* d_buf, size_t ndoubles, void* hos
 
 extern "C" int32_t lm_local_expect(lm_state* s, int32_t n_int, const void* op, void* out) {
     REQUIRE(s && op && out, "lm_local_expect: NULL argument");
-    REQUIRE(!s->dense, "lm_local_expect: dense states are handled on the host from lm_state_download_dense");
     REQUIRE(n_int >= 1 && s->N % n_int == 0, "lm_local_expect: N is not a multiple of n_int");
     lm_ctx* c = s->ctx; FWD(set_dev(c));
     OpMat O; FWD(load_op(n_int, op, &O));
@@ -2584,13 +2600,12 @@ extern "C" int32_t lm_local_expect(lm_state* s, int32_t n_int, const void* op, v
     k_localexpect_fin<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(ns, n, O, c->d_le_G, c->d_le_out);
     c->launches++;
     CK(cudaGetLastError());
-    return reduce_and_fetch(c, (double*)c->d_le_out, (size_t)(2 * ns), out);
+    return reduce_and_fetch(c, s, (double*)c->d_le_out, (size_t)(2 * ns), out);
 }
 
 extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, double* J_out) {
     REQUIRE(h && s && op && J_out, "lm_operator_currents: NULL argument");
     REQUIRE(h->ctx == s->ctx && h->N == s->N, "lm_operator_currents: Hamiltonian/state mismatch");
-    REQUIRE(!s->dense, "lm_operator_currents: Psi-block states only");
     REQUIRE(h->n_int >= 2, "System expected to have internal degrees of freedom");
     lm_ctx* c = h->ctx; FWD(set_dev(c));
     const int n = h->n_int; const int W = h->W;
@@ -2630,7 +2645,7 @@ extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, 
     }
     c->launches++;
     CK(cudaGetLastError());
-    return reduce_and_fetch(c, h->d_oc_J, (size_t)np, J_out);
+    return reduce_and_fetch(c, s, h->d_oc_J, (size_t)np, J_out);
 }
 
 // host-only hook (tests): the product-form Chebyshev plan for exp(-i R x) on [-1, 1]

@@ -647,6 +647,30 @@ k_enclosure_check(const double* __restrict__ partial, unsigned nparts, double em
     }
 }
 
+// Observables of a DENSE density matrix (row-major P[i][j], the U P U' path): the same scratch arrays
+// the Psi-block kernels fill - dens[i] = Re P[i,i], G[e] = P[col(e), row(e)] for every ELL entry - so
+// that k_finalize_obs / the region sums / lm_bond_currents work unchanged:
+//   curr[i,j] = sum_ab 2 Im(H[i',j'] P[j',i'])      (src/zoo/currents.jl:92-102)
+template <typename T2>
+__global__ void k_observe_dense(long long N, int W, long long ld, const T2* __restrict__ P, const int* __restrict__ cols,
+                                double* __restrict__ dens, double2* __restrict__ G) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * W) return;
+    const long long i = e / W, j = cols[e];
+    const T2 v = P[j * ld + i];
+    G[e] = make_double2((double)v.x, (double)v.y);
+    if (e == i * W) dens[i] = (double)P[i * ld + i].x;
+}
+
+// generic correlators of a dense density matrix: out[q] = P[b_q, a_q]  (what k_corr_pairs sums for a Psi block)
+template <typename T2>
+__global__ void k_corr_pairs_dense(long long nq, long long ld, const T2* __restrict__ P, const int* __restrict__ a, const int* __restrict__ b, double2* __restrict__ out) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const T2 v = P[(long long)b[q] * ld + a[q]];
+    out[q] = make_double2((double)v.x, (double)v.y);
+}
+
 // scatter CSC nzval (host-assembled H) into the ELL value array
 template <typename T>
 __global__ void k_scatter_vals(long long nnz, const typename cx2<T>::type* __restrict__ nz,

@@ -61,16 +61,25 @@ static const Variant g_var[] = {
     {2, 2, 4, 2, 1, 2},   // 10: streaming (3-stage TMA pipeline over a column group), 8 x 4 patch, 256 threads
     {4, 2, 2, 2, 1, 2},   // 11: streaming, 8 x 4 patch, 128 threads
     {4, 4, 2, 2, 1, 2},   // 12: streaming, 8 x 8 patch, 128 threads          (RC = 1 only)
+    {4, 2, 1, 2, 1, 1},   // 13: staged, 4 x 4 patch, 64 threads  (RC = 2)    - more, smaller CTAs per SM: finer overlap of fill and compute
+    {4, 2, 2, 1, 1, 1},   // 14: staged, 8 x 2 patch, 64 threads  (RC = 2)
+    {4, 2, 1, 3, 1, 1},   // 15: staged, 4 x 6 patch, 96 threads  (RC = 2)
+    {4, 4, 1, 2, 1, 1},   // 16: staged, 4 x 8 patch, 64 threads  (RC = 1)
+    {4, 4, 2, 1, 1, 1},   // 17: staged, 8 x 4 patch, 64 threads  (RC = 1)
+    {0, 0, 1, 1, 1, 1},   // 18: staged, one warp per CTA: the patch is the tile (4 x 2 cells RC = 2, 4 x 4 RC = 1)
 };
 int stencil_num_variants() { return (int)(sizeof(g_var) / sizeof(g_var[0])); }
-void stencil_variant_shape(int v, int* P1, int* P2, int* cpt, int* staged) {
-    *P1 = g_var[v].w1 * g_var[v].t1; *P2 = g_var[v].w2 * g_var[v].t2; *cpt = g_var[v].cpt; *staged = g_var[v].staged;
+void stencil_variant_shape(int v, int rc, int* P1, int* P2, int* cpt, int* staged) {
+    int t1 = g_var[v].t1, t2 = g_var[v].t2;
+    if (t1 == 0) { t1 = 4; t2 = rc == 1 ? 4 : 2; }             // variant 18: the default tile of the pattern
+    *P1 = g_var[v].w1 * t1; *P2 = g_var[v].w2 * t2; *cpt = g_var[v].cpt; *staged = g_var[v].staged;
 }
 
 // CTAs of k_apply_stencil_tma resident per SM (host restatement of st_tma_smem / st_tma_blocks)
 int stencil_resident_ctas(int id, int v, bool c64) {
-    const Variant& q = g_var[v];
+    Variant q = g_var[v];
     const int rc = g_desc[id].rc, sw = stencil_stride(id, c64);
+    if (q.t1 == 0) { q.t1 = 4; q.t2 = rc == 1 ? 4 : 2; }
     const int P1 = q.w1 * q.t1, P2 = q.w2 * q.t2;
     const size_t smem = (size_t)(P1 + 2) * (P2 + 2) * rc * 32 * q.cpt * 16 + (size_t)P1 * P2 * rc * sw * (c64 ? 8 : 16);
     const int by_smem = (int)((227 * 1024) / (smem + 1024 + 64));
@@ -99,17 +108,17 @@ int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a
 }
 
 
-#define LM_ST_DECL(i) int stencil_observe_##i(bool, const StencilObsArgs&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
+#define LM_ST_DECL(i) int stencil_observe_##i(bool, const StencilObsArgs&, const CUtensorMap&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
 LM_ST_DECL(0) LM_ST_DECL(1) LM_ST_DECL(2) LM_ST_DECL(3) LM_ST_DECL(4) LM_ST_DECL(5)
 #undef LM_ST_DECL
-int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
+int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
     switch (id) {
-    case 0: return stencil_observe_0(c64, a, grid, s);
-    case 1: return stencil_observe_1(c64, a, grid, s);
-    case 2: return stencil_observe_2(c64, a, grid, s);
-    case 3: return stencil_observe_3(c64, a, grid, s);
-    case 4: return stencil_observe_4(c64, a, grid, s);
-    case 5: return stencil_observe_5(c64, a, grid, s);
+    case 0: return stencil_observe_0(c64, a, tmx, grid, s);
+    case 1: return stencil_observe_1(c64, a, tmx, grid, s);
+    case 2: return stencil_observe_2(c64, a, tmx, grid, s);
+    case 3: return stencil_observe_3(c64, a, tmx, grid, s);
+    case 4: return stencil_observe_4(c64, a, tmx, grid, s);
+    case 5: return stencil_observe_5(c64, a, tmx, grid, s);
     default: return -1;
     }
 }

@@ -84,7 +84,7 @@ __host__ __device__ constexpr int st_min_blocks(int acc_regs, int threads) {
     // accumulators + ~64 working registers per thread against the 64K-register file
     const int per_thread = acc_regs + 64;
     const int fit = 65536 / (per_thread * threads);
-    return fit < 1 ? 1 : (fit > 4 ? 4 : fit);
+    return fit < 1 ? 1 : (fit > 8 ? 8 : fit);
 }
 __device__ __forceinline__ int st_wrap(int c, int n) { c %= n; return c < 0 ? c + n : c; }
 
@@ -622,6 +622,7 @@ struct StencilObsArgs {
     const int* out;                 // [N][NF]
     double* dens; double2* G;
     unsigned ngroups, cpg, nchunks; // column groups per patch, chunks per group, chunks in total
+    int tmap;                       // 1: patches whose forward-haloed block lies inside the lattice stage it with ONE tensor-map copy per chunk
 };
 
 template <typename T> struct st_unpack;
@@ -645,7 +646,7 @@ __host__ __device__ constexpr size_t st_obs_smem() { return (size_t)ST_OBS_STAGE
 
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
 __global__ void __launch_bounds__(32 * W1 * W2, 65536 / (128 * 32 * W1 * W2) < 1 ? 1 : 65536 / (128 * 32 * W1 * W2))
-k_observe_stencil(const StencilObsArgs a) {
+k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx) {
     constexpr int NS = ST_OBS_STAGES;
     using E = typename pack<T>::E;
     constexpr int EC = pack<T>::EC;
@@ -673,9 +674,21 @@ k_observe_stencil(const StencilObsArgs a) {
         for (int q = 0; q < NS; ++q) mbar_init(&bar[q], 1);
     }
     __syncthreads();
-    auto issue = [&](unsigned ch, int stage) {              // arm the stage barrier, one bulk copy per staged row
+    // a patch whose forward-haloed block [o1, o1 + P1] x [o2 - 1, o2 + P2] lies inside the lattice is one
+    // dense box of the [n1][n2 RC][columns] view of x: ONE tensor-map copy per chunk (SASS UTMALDG).
+    // (A per-thread cp.async.bulk is serialised by the compiler into a warp-wide loop of uniform-register
+    // broadcasts - ~10 instructions per copy, a fifth of this kernel's instructions in round 1.)
+    const bool boxed = a.tmap && o1 + P1 + 1 <= a.n1 && o2 >= 1 && o2 + P2 + 1 <= a.n2;
+    auto issue = [&](unsigned ch, int stage) {              // arm the stage barrier, then the box or one bulk copy per staged row
         const long long c0 = (long long)ch * CE;
         const int cw = (int)((lde - c0) < CE ? (lde - c0) : CE);
+        if (boxed) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar[stage], (unsigned)(HR * CE * (int)sizeof(E)));
+                tma_tensor3d_g2s(sx + (size_t)stage * HR * CE, &tmx, (int)(c0 * (long long)(sizeof(E) / 8)), (o2 - 1) * RC, o1, &bar[stage]);
+            }
+            return;
+        }
         if (tid == 0) mbar_arrive_expect_tx(&bar[stage], (unsigned)(HR * cw * (int)sizeof(E)));
         // rows dealt round-robin over the WARPS (row = warp + NW * lane): every warp issues the same
         // few copies, none of them reaches the closing barrier late
@@ -759,33 +772,58 @@ k_observe_stencil(const StencilObsArgs a) {
         __syncthreads();                                    // every warp is done with `stage`
     }
     if (!active) return;
-    // fold the 32 columns of the lane dimension, one atomic per sum and column group
-    int nacc = 0;
+    // Fold the 32 columns of the lane dimension by recursive halving: at distance 16, 8, ... 1 every lane
+    // hands one half of its remaining sums to its partner and keeps the other - NV - 1 + 5 exchanges
+    // per lane instead of 5 NV for a butterfly per sum - and ends up with the complete sums number
+    // 2 lane and 2 lane + 1, which it adds to the output (one atomic per sum and group).
+    constexpr int PER = 1 + 2 * NF;                          // per row: dens, NF x Re G, NF x Im G
+    constexpr int NV = T1 * T2 * RC * PER;
+    static_assert(NV <= 64, "k_observe_stencil: more than 64 partial sums per thread");
+    double v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.0;
 #pragma unroll
     for (int v1 = 0; v1 < T1; ++v1)
 #pragma unroll
-        for (int v2 = 0; v2 < T2; ++v2) {
-            const bool valid = (q1 + v1) < a.n1 && (q2 + v2) < a.n2;
+        for (int v2 = 0; v2 < T2; ++v2)
 #pragma unroll
             for (int aa = 0; aa < RC; ++aa) {
-                const long long row = ((long long)(q1 + v1) * a.n2 + (q2 + v2)) * RC + aa;
-                const double d = st_warp_sum(dens[v1][v2][aa]);
-                if (valid && lane == (nacc & 31)) atomicAdd(a.dens + row, d);
-                ++nacc;
+                const int base = ((v1 * T2 + v2) * RC + aa) * PER;
+                v[base] = dens[v1][v2][aa];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const double sr = st_warp_sum(gr[v1][v2][aa][f]), si = st_warp_sum(gi[v1][v2][aa][f]);
-                    if (valid && lane == (nacc & 31)) {
-                        const int oe = a.out[row * NF + f];
-                        if (oe != -1) {
-                            double* g = reinterpret_cast<double*>(a.G + (oe >= 0 ? oe : -2 - oe));
-                            atomicAdd(g, sr); atomicAdd(g + 1, oe >= 0 ? si : -si);
-                        }
-                    }
-                    ++nacc;
-                }
+                for (int f = 0; f < NF; ++f) { v[base + 1 + f] = gr[v1][v2][aa][f]; v[base + 1 + NF + f] = gi[v1][v2][aa][f]; }
+            }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int off = 16 >> s, n = 32 >> s;                // n sums stay with each lane after this round (of 2 n)
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            if (i < NV) {                                    // compile-time: slot i only ever holds sums >= i
+                const double send = up ? v[i] : v[i + n];
+                const double keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
             }
         }
+    }
+    // round s (n = 32 >> s) keeps in slot i what slot i + n * [lane bit (4 - s)] held: after the last round
+    // slot k in {0, 1} of a lane holds sum number 2 lane + k
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = 2 * lane + k;
+        if (j >= NV) continue;
+        const int cell = j / (RC * PER), rem = j - cell * (RC * PER), aa = rem / PER, q = rem - aa * PER;
+        const int v1 = cell / T2, v2 = cell - v1 * T2;
+        if ((q1 + v1) >= a.n1 || (q2 + v2) >= a.n2) continue;
+        const long long row = ((long long)(q1 + v1) * a.n2 + (q2 + v2)) * RC + aa;
+        const double val = k ? v[1] : v[0];
+        if (q == 0) { atomicAdd(a.dens + row, val); continue; }
+        const int f = (q - 1) % NF; const bool imag = (q - 1) >= NF;
+        const int oe = a.out[row * NF + f];
+        if (oe == -1) continue;
+        double* g = reinterpret_cast<double*>(a.G + (oe >= 0 ? oe : -2 - oe));
+        if (!imag) atomicAdd(g, val); else atomicAdd(g + 1, oe >= 0 ? val : -val);
+    }
 }
 
 // ---- compiled patterns (stencil.cu registry; one translation unit per pattern) ----
@@ -805,12 +843,12 @@ int stencil_stride(int id, bool c64);                      // value-slot stride 
 int stencil_diag_slot(int id, int a);                      // slot of the diagonal entry of in-cell row a
 int stencil_num_variants();
 // patch size in cells, lane elements per thread and kernel family (staged = TMA) of a variant
-void stencil_variant_shape(int variant, int* P1, int* P2, int* cpt, int* staged);
+void stencil_variant_shape(int variant, int rc, int* P1, int* P2, int* cpt, int* staged);
 int stencil_resident_ctas(int id, int variant, bool c64);  // CTAs of the staged kernel resident per SM
 // launches; returns 0 on success, -1 if (id, variant, mode) is not compiled, -2 on a CUDA error
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s);
 // fused observables: patch size / forward-slot count of the compiled kernel, and its launch
 void stencil_obs_shape(int id, int* P1, int* P2, int* nf);
-int stencil_observe(int id, bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s);
+int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s);
 
 }  // namespace lm

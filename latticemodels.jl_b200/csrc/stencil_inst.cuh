@@ -68,11 +68,23 @@ static int launch_prec(bool c64, int mode, const StencilArgs& a, const CUtensorM
 }
 
 #define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MASK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, tmx, grid, s);
+// shape experiments: complex128, plain SpMM and product-form factor only (keeps the build short)
+template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT>
+static int launch_try(bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
+    if (c64) return -1;
+    if (mode == 0) return launch_one<double, RC, MASK, T1, T2, W1, W2, CPT, 0, 1>(a, tmx, grid, s);
+    if (mode == 3) return launch_one<double, RC, MASK, T1, T2, W1, W2, CPT, 3, 1>(a, tmx, grid, s);
+    return -1;
+}
+#define LM_ST_X(v, T1, T2, W1, W2, CPT) case v: return launch_try<RC, MASK, T1, T2, W1, W2, CPT>(c64, mode, a, tmx, grid, s);
 template <int RC, st_mask_t MASK>
 static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if constexpr (RC == 1) {
         switch (variant) {
             LM_ST_V(7, 4, 4, 2, 2, 1, 1)
+#ifdef LM_STENCIL_SHAPES
+            LM_ST_X(16, 4, 4, 1, 2, 1) LM_ST_X(17, 4, 4, 2, 1, 1) LM_ST_X(18, 4, 4, 1, 1, 1)
+#endif
 #ifdef LM_STENCIL_EXPLORE
             LM_ST_V(8, 4, 4, 2, 2, 1, 0) LM_ST_V(9, 4, 2, 2, 4, 2, 1) LM_ST_V(3, 4, 2, 2, 4, 1, 1) LM_ST_V(10, 2, 2, 4, 2, 1, 2) LM_ST_V(11, 4, 2, 2, 2, 1, 2) LM_ST_V(12, 4, 4, 2, 2, 1, 2)
 #endif
@@ -81,6 +93,9 @@ static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, con
     } else {
         switch (variant) {
             LM_ST_V(2, 4, 2, 2, 2, 1, 1)
+#ifdef LM_STENCIL_SHAPES
+            LM_ST_X(13, 4, 2, 1, 2, 1) LM_ST_X(14, 4, 2, 2, 1, 1) LM_ST_X(15, 4, 2, 1, 3, 1) LM_ST_X(18, 4, 2, 1, 1, 1)
+#endif
 #ifdef LM_STENCIL_EXPLORE
             LM_ST_V(0, 4, 2, 2, 4, 1, 0) LM_ST_V(1, 2, 2, 2, 4, 2, 0) LM_ST_V(3, 4, 2, 2, 4, 1, 1)
             LM_ST_V(4, 2, 2, 2, 2, 2, 1) LM_ST_V(5, 2, 4, 2, 2, 1, 1) LM_ST_V(6, 2, 2, 4, 2, 1, 1)
@@ -101,7 +116,7 @@ template <> struct ObsShape<2, false> { static constexpr int T1 = 1, T2 = 2, W1 
 template <> struct ObsShape<2, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };   // 4 x 2 cells, 256 threads
 
 template <typename T, int RC, st_mask_t MASK>
-static int launch_obs_t(const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
+static int launch_obs_t(const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
     using S = ObsShape<RC, (st_nfwd<RC>(MASK) > 6)>;
     constexpr size_t smem = st_obs_smem<T, RC, S::T1, S::T2, S::W1, S::W2>();
     static bool configured = false;
@@ -110,14 +125,14 @@ static int launch_obs_t(const StencilObsArgs& a, unsigned grid, cudaStream_t s) 
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         configured = true;
     }
-    k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2><<<grid, 32 * S::W1 * S::W2, smem, s>>>(a);
+    k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2><<<grid, 32 * S::W1 * S::W2, smem, s>>>(a, tmx);
     return 0;
 }
 template <int RC, st_mask_t MASK>
-static int launch_obs(bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
-    if (!c64) return launch_obs_t<double, RC, MASK>(a, grid, s);
+static int launch_obs(bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
+    if (!c64) return launch_obs_t<double, RC, MASK>(a, tmx, grid, s);
 #ifndef LM_STENCIL_NOC64
-    return launch_obs_t<float, RC, MASK>(a, grid, s);
+    return launch_obs_t<float, RC, MASK>(a, tmx, grid, s);
 #else
     return -1;
 #endif

@@ -9,8 +9,8 @@ int stencil_launch_2(int variant, bool c64, int mode, const StencilArgs& a, cons
     return launch_var<2, LM_ST_MASK2>(variant, c64, mode, a, tmx, grid, s);
 #endif
 }
-int stencil_observe_2(bool c64, const StencilObsArgs& a, unsigned grid, cudaStream_t s) {
-    return launch_obs<2, LM_ST_MASK2>(c64, a, grid, s);
+int stencil_observe_2(bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
+    return launch_obs<2, LM_ST_MASK2>(c64, a, tmx, grid, s);
 }
 void stencil_obs_shape_2(int* P1, int* P2, int* nf) { obs_shape<2, LM_ST_MASK2>(P1, P2, nf); }
 }  // namespace lm

@@ -40,6 +40,34 @@ class LatticeValue:
     def __getitem__(self, i):
         return self.values[i]
 
+    # value semantics for TimeSequence (copy, differentiate / integrate keep the lattice)
+    def copy(self):
+        return LatticeValue(self.lattice, self.values.copy())
+
+    def _other(self, o):
+        return o.values if isinstance(o, LatticeValue) else o
+
+    def __add__(self, o):
+        return LatticeValue(self.lattice, self.values + self._other(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return LatticeValue(self.lattice, self.values - self._other(o))
+
+    def __mul__(self, k):
+        return LatticeValue(self.lattice, self.values * self._other(k))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, k):
+        return LatticeValue(self.lattice, self.values / self._other(k))
+
+    def __eq__(self, o):
+        return isinstance(o, LatticeValue) and (o.lattice is self.lattice or o.lattice == self.lattice) and np.array_equal(o.values, self.values)
+
+    __hash__ = None
+
 
 def _device_state(state, ctx=None):
     if isinstance(state, DeviceState):
@@ -399,7 +427,7 @@ def currentsfrom(curr, src):
         _lib.check(_lib.load().lm_currents_from(dev.handle, curr.state.handle, _lib.ptr(_site_mask(ns, src)), 0, _lib.ptr(out)))
         return LatticeValue(curr.lattice, out)
     c = curr if isinstance(curr, Currents) else Currents(curr)
-    src = np.atleast_1d(np.asarray(src, int)) - 1
+    src = _to_inds(c.currents.shape[0], src)            # 1-based indices or a boolean mask (to_inds)
     m = c.currents.tocsr()
     out = np.asarray(m[src, :].sum(axis=0)).ravel()
     out[src] = 0
@@ -418,6 +446,6 @@ def currentsfromto(curr, src, dst=None):
         return float(out.value)
     c = curr if isinstance(curr, Currents) else Currents(curr)
     ns = c.currents.shape[0]
-    src = np.atleast_1d(np.asarray(src, int)) - 1
-    dst = np.setdiff1d(np.arange(ns), src) if dst is None else np.atleast_1d(np.asarray(dst, int)) - 1
+    src = _to_inds(ns, src)
+    dst = np.setdiff1d(np.arange(ns), src) if dst is None else _to_inds(ns, dst)
     return float(c.currents.tocsr()[src, :][:, dst].sum())

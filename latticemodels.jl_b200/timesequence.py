@@ -21,6 +21,11 @@ def _same(a, b):
     return bool(a == b)
 
 
+def _num(v):
+    """Operand of the calculus: lists become arrays, everything else keeps its own ``*`` / ``+``."""
+    return np.asarray(v) if isinstance(v, (list, tuple)) else v
+
+
 class TimeSequence:
     """Time-ordered ``t => value`` dictionary (src/timesequence.jl:6-61).
 
@@ -35,9 +40,14 @@ class TimeSequence:
         if f is None:
             return
         if callable(f):
+            # TimeSequence(f, evol_iter) = TimeSequence(evol_iter.times, [f(moment) for moment in evol_iter]):
+            # the keys are the NOMINAL times of the iterator (src/timesequence.jl:41-43), not the accumulated clock
             it = evol(times) if times is not None else evol
-            for moment in it:
-                self[moment.t] = f(moment)
+            vals = [self._own(f(moment)) for moment in it]
+            keys = [float(t) for t in getattr(it, "times", [])]
+            if len(keys) != len(vals):
+                raise ValueError("Keys/values length mismatch:\n%d timestamps, %d snapshots" % (len(keys), len(vals)))
+            self.times, self.snapshots = keys, vals
             return
         ts, vs = list(f), list(evol if evol is not None else [])
         if len(ts) != len(vs):
@@ -47,7 +57,16 @@ class TimeSequence:
 
     @staticmethod
     def _own(v):
-        return v if np.isscalar(v) else np.array(v, copy=True)
+        """The reference's TimeSequence{ET} holds ARBITRARY values (Currents, LatticeValue, tuples ...):
+        arrays are copied, objects with a ``copy`` method are copied through it, anything else is kept."""
+        if isinstance(v, np.ndarray):
+            return v.copy()
+        if np.isscalar(v) or isinstance(v, (tuple, str)) or v is None:
+            return v
+        if isinstance(v, list):
+            return list(v)
+        cp = getattr(v, "copy", None)
+        return cp() if callable(cp) else v
 
     # ---- dictionary interface (:54-58, 85-137) ----
     def timestamps(self):
@@ -90,7 +109,7 @@ class TimeSequence:
     def slice(self, t=(-math.inf, math.inf), index=None):
         """``tseq[args...; t = lo .. hi]`` (:106-120): the entries inside the closed interval, each value
         optionally indexed by ``index`` (a site number, a mask, ...)."""
-        pick = (lambda v: v) if index is None else (lambda v: np.asarray(v)[index])
+        pick = (lambda v: v) if index is None else (lambda v: v[index] if hasattr(v, "__getitem__") and not isinstance(v, (list, tuple)) else np.asarray(v)[index])
         keep = [k for k, tk in enumerate(self.times) if _in(tk, t)]
         return TimeSequence([self.times[k] for k in keep], [pick(self.snapshots[k]) for k in keep])
 
@@ -147,8 +166,8 @@ class TimeSequence:
         td, vs = self.times, self.snapshots
         for i in range(1, len(td)):
             dt = td[i] - td[i - 1]
-            vs[i - 1] = (1 / dt) * np.asarray(vs[i]) + (-1 / dt) * np.asarray(vs[i - 1]) if not np.isscalar(vs[i]) else \
-                (1 / dt) * vs[i] + (-1 / dt) * vs[i - 1]
+            a, b = _num(vs[i]), _num(vs[i - 1])             # the values' own arithmetic (arrays, Currents, LatticeValue-likes)
+            vs[i - 1] = (1 / dt) * a + (-1 / dt) * b
             td[i - 1] += dt / 2
         td.pop()
         vs.pop()
@@ -164,7 +183,7 @@ class TimeSequence:
         td, vs = self.times, self.snapshots
         for i in range(1, len(td)):
             dt = td[i] - td[i - 1]
-            vs[i - 1] = (dt / 2) * (np.asarray(vs[i]) if not np.isscalar(vs[i]) else vs[i]) + (dt / 2) * (np.asarray(vs[i - 1]) if not np.isscalar(vs[i - 1]) else vs[i - 1])
+            vs[i - 1] = (dt / 2) * _num(vs[i]) + (dt / 2) * _num(vs[i - 1])
         last = vs.pop()
         vs.insert(0, 0 * last)
         for i in range(1, len(td)):

@@ -157,7 +157,7 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
 // dens[i] = sum_c w_c |x[i,c]|^2,  G[e] = sum_c w_c x[j,c] conj(x[i,c]) over the forward entries
 // ---------------------------------------------------------------------------------------------
 template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
-static bool check_observe(const char* name, int n1, int n2, bool periodic, long long M, long long ld, bool weights, unsigned cpg_req) {
+static bool check_observe(const char* name, int n1, int n2, bool periodic, long long M, long long ld, bool weights, unsigned cpg_req, bool tmap = false) {
     using E = typename pack<T>::E;
     constexpr int EC = pack<T>::EC;
     constexpr int NF = st_nfwd<RC>(MASK);
@@ -202,7 +202,11 @@ static bool check_observe(const char* name, int n1, int n2, bool periodic, long 
     const long long cpg = std::max<long long>(1, std::min<long long>(cpg_req, nchunks));
     const long long ngroups = (nchunks + cpg - 1) / cpg;
     a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg; a.nchunks = (unsigned)nchunks;
-    lm_emul::launch(k_observe_stencil<T, RC, MASK, T1, T2, W1, W2>, dim3((unsigned)(np1 * np2 * ngroups)), 32 * W1 * W2, a);
+    a.tmap = tmap ? 1 : 0;
+    CUtensorMap tmx{x.data(), {(unsigned long long)ld * (2 * sizeof(T) / 8), (unsigned long long)n2 * RC, (unsigned long long)n1},
+                    {(unsigned long long)ld * 2 * sizeof(T), (unsigned long long)n2 * RC * ld * 2 * sizeof(T)},
+                    {64u, (unsigned)((P2 + 2) * RC), (unsigned)(P1 + 1)}, tmap ? 1 : 0};
+    lm_emul::run_grid(dim3((unsigned)(np1 * np2 * ngroups)), dim3(32 * W1 * W2), [&] { k_observe_stencil<T, RC, MASK, T1, T2, W1, W2>(a, tmx); });
 
     const double tol = sizeof(T) == 8 ? 1e-12 : 1e-6;   // the sums run in double for both precisions
     for (long long r = 0; r < N; ++r) {
@@ -236,9 +240,13 @@ static bool check_pattern(const char* name) {
         ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 1, 1);        // 3x3 torus: every neighbour is a periodic image
         ok = ok && check_apply<float, RC, MASK, 4, 4, 2, 2, 1, 3, 1>(name, 19, 26, true, 136, 1, 3);      // complex64, ragged tail
         ok = ok && check_apply<double, RC, MASK, 4, 4, 2, 2, 1, 0, 1>(name, 9, 8, false, 32, 1, 2);       // plain SpMM, general values
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 1, 2, 1, 3, 1>(name, 13, 19, true, 40, 1, 3);      // 64-thread CTAs (4 x 8 patches)
+        ok = ok && check_apply<double, RC, MASK, 4, 4, 1, 1, 1, 3, 1>(name, 13, 11, false, 40, 1, 3);     // one warp per CTA
         ok = ok && check_observe<double, RC, MASK, 2, 2, 4, 2>(name, 11, 9, false, 37, 40, true, 1);
         ok = ok && check_observe<double, RC, MASK, 2, 2, 4, 2>(name, 8, 5, true, 130, 136, false, 2);            // pipeline wraps its 3 stages
         ok = ok && check_observe<float, RC, MASK, 2, 2, 4, 2>(name, 3, 3, true, 70, 72, true, 4);
+        ok = ok && check_observe<double, RC, MASK, 2, 2, 4, 2>(name, 27, 14, true, 100, 104, true, 2, true);     // interior patches through tensor-map boxes
+        ok = ok && check_observe<float, RC, MASK, 2, 2, 4, 2>(name, 26, 13, false, 70, 72, false, 3, true);
     } else {
         // variant 2: 4x2 tiles, 2x2 warps (8 x 4 cell patches)
         ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 11, 5, false, 40, 1, 0);
@@ -248,11 +256,16 @@ static bool check_pattern(const char* name) {
         ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 0, 1>(name, 3, 3, true, 32, 1, 1);
         ok = ok && check_apply<float, RC, MASK, 4, 2, 2, 2, 1, 3, 1>(name, 19, 14, true, 136, 1, 3);
         ok = ok && check_apply<double, RC, MASK, 4, 2, 2, 2, 1, 0, 1>(name, 9, 4, false, 32, 1, 2);
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 1, 2, 1, 3, 1>(name, 13, 11, true, 40, 1, 3);      // 64-thread CTAs (4 x 4 patches)
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 1, 3, 1, 3, 1>(name, 13, 15, false, 40, 1, 3);     // 96 threads, 4 x 6 patches
+        ok = ok && check_apply<double, RC, MASK, 4, 2, 1, 1, 1, 3, 1>(name, 13, 7, true, 40, 1, 3);       // one warp per CTA
         // observables shape of stencil_inst.cuh ObsShape: one cell per thread for wide forward lists
         constexpr int OT2 = st_nfwd<RC>(MASK) > 6 ? 1 : 2;
         ok = ok && check_observe<double, RC, MASK, 1, OT2, 4, 2>(name, 7, 5, false, 37, 40, true, 1);
         ok = ok && check_observe<double, RC, MASK, 1, OT2, 4, 2>(name, 4, 5, true, 130, 136, false, 2);
         ok = ok && check_observe<float, RC, MASK, 1, OT2, 4, 2>(name, 3, 3, true, 70, 72, true, 4);
+        ok = ok && check_observe<double, RC, MASK, 1, OT2, 4, 2>(name, 14, 13, true, 100, 104, true, 2, true);
+        ok = ok && check_observe<float, RC, MASK, 1, OT2, 4, 2>(name, 13, 11, false, 70, 72, false, 3, true);
     }
     return ok;
 }

@@ -69,6 +69,19 @@ if os.environ.get("LM_OBS_P2P", "1") != "0":
     assert nfr.value >= 24, "peer-memory path was not taken (%d frames)" % nfr.value     # 12 densities + 12 currents
 else:
     assert nfr.value == 0
+# a single ket (every rank holds the whole vector) must NOT be summed across ranks
+ket = Psi[:, 0].copy()
+ks, kf = lm.DeviceState.from_any(ket, ctx, l, 1), lm.DeviceState.from_any(ket, ref, l, 1)
+assert ks.replicated and not kf.replicated
+Hk = h(0.3)
+for sol, st in ((sol_s, ks), (sol_f, kf)):
+    sol.update_solver(Hk, 0.1)
+    sol.step(st)
+rk_s, rk_f = lm.localdensity(ks).values, lm.localdensity(kf).values
+Jk_s, Jk_f = lm.DensityCurrents(Hk, ks).pair_values()[2], lm.DensityCurrents(Hk, kf).pair_values()[2]
+assert abs(rk_f.sum() - 1.0) < 1e-12
+worst = max(worst, np.abs(rk_s - rk_f).max() / np.abs(rk_f).max(), np.abs(Jk_s - Jk_f).max() / max(np.abs(Jk_f).max(), 1e-300))
+assert worst < 1e-12, ("replicated ket", worst)
 t = torch.tensor([worst], device="cuda", dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:

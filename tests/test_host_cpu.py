@@ -310,3 +310,54 @@ def test_stencil_kernels_execute_on_cpu(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and res.stdout.startswith("OK "), res.stdout + res.stderr
     assert int(res.stdout.split()[1]) >= 100000
+
+
+def test_timesequence_holds_arbitrary_values_and_nominal_keys():
+    """the reference's TimeSequence{ET} stores arbitrary values (src/timesequence.jl:6-19) -
+    Currents objects, LatticeValues, ragged tuples - and TimeSequence(f, evol_iter) keys its entries
+    by the iterator's NOMINAL times (:41-43)."""
+    import scipy.sparse as sp
+    from lm_b200.observables import Currents, LatticeValue
+    from lm_b200.timesequence import TimeSequence
+    lat = lm.SquareLattice(2, 2)
+    m = sp.csc_matrix(np.array([[0, 1., 0, 0], [-1., 0, 2., 0], [0, -2., 0, 0], [0, 0, 0, 0]]))
+    ts = TimeSequence()
+    ts[0.0] = Currents(m, lattice=lat)
+    ts[0.5] = Currents(2 * m, lattice=lat)
+    ts[1.0] = Currents(4 * m, lattice=lat)
+    assert isinstance(ts[0.5], Currents) and ts[0.5] == Currents(2 * m, lattice=lat)
+    d = ts.differentiate()
+    assert isinstance(d[0.25], Currents) and d[0.25] == Currents(2 * m, lattice=lat) and d[0.75] == Currents(4 * m, lattice=lat)
+    tv = TimeSequence([0.0, 1.0], [LatticeValue(lat, np.arange(4.0)), LatticeValue(lat, np.arange(4.0) + 2)])
+    iv = tv.integrate()
+    assert isinstance(iv[1.0], LatticeValue) and iv[1.0].lattice is lat and np.allclose(iv[1.0].values, np.arange(4.0) + 1)
+    tt = TimeSequence([0.0, 1.0], [(np.zeros(3), np.zeros(5)), (np.ones(3), np.ones(5))])      # ragged (rho, J) tuples
+    assert isinstance(tt[1.0], tuple) and len(tt[1.0][1]) == 5
+
+    class It:                                   # an EvolutionIterator stand-in whose clock drifts off the nominal grid
+        times = [0.0, 0.1, 0.2]
+
+        def __iter__(self):
+            class M:
+                pass
+            for k, t in enumerate(self.times):
+                mo = M()
+                mo.t = t + 1e-3 * k
+                yield mo
+    seq = TimeSequence(lambda mo: mo.t, It())
+    assert seq.timestamps() == [0.0, 0.1, 0.2] and seq[0.2] == 0.2 + 2e-3
+
+
+def test_currents_region_sums_accept_masks_on_the_host_path():
+    """currentsfrom / currentsfromto on a materialised Currents take a boolean per-site mask
+    or 1-based indices alike (`to_inds`, src/currents.jl:85-109)."""
+    import scipy.sparse as sp
+    from lm_b200.observables import Currents, currentsfrom, currentsfromto
+    a = np.zeros((4, 4))
+    a[0, 1], a[1, 2], a[2, 3] = 1.0, 2.0, 3.0
+    c = Currents(sp.csc_matrix(a - a.T))
+    mask = np.array([True, True, False, False])
+    assert np.array_equal(currentsfrom(c, mask).values, currentsfrom(c, [1, 2]).values)
+    assert np.array_equal(currentsfrom(c, [1, 2]).values, [0, 0, 2, 0])
+    assert currentsfromto(c, mask) == currentsfromto(c, [1, 2]) == 2.0
+    assert currentsfromto(c, mask, ~mask) == currentsfromto(c, [1, 2], [3, 4]) == 2.0

@@ -288,3 +288,37 @@ def test_golden_reduced_config_fixtures_complex64_mode(name):
         V = lm.DensityCurrents(m.H, m.state).pair_values()[2]
         assert _relerr(lm.localdensity(m.state).values, g["rho"][q]) < 1e-5
         assert np.abs(V - g["J"][q]).max() < 1e-5 * max(np.abs(g["J"][q]).max(), 1e-3)
+
+
+def test_currents_and_local_operators_on_a_dense_density_matrix():
+    """the reference's README loop and test/test_workflows.jl:29-62 run
+    Currents(DensityCurrents(H, P)) on a DENSE P.  Density currents, curr[i, j], Currents(...),
+    region sums, localexpect and LocalOperatorCurrents of a dense device state equal those of the
+    Psi-block form of the same P."""
+    from lm_b200.observables import Currents, LocalOperatorCurrents, currentsfrom, currentsfromto, localexpect
+    ctx = lm.default_context("c128")
+    lat = lm.SquareLattice(6, 5)
+    H = lm.qwz(lat, field=lm.LandauGauge(0.1))
+    N = 60
+    rng = np.random.default_rng(11)
+    X = _rand_block(N, 9, seed=11) / np.sqrt(N)
+    w = rng.random(9)
+    P = (X * w) @ X.conj().T
+    sd = lm.DeviceState.from_dense(P, ctx=ctx, lattice=lat, n_int=2)
+    sp_ = lm.DeviceState.from_psi(X, w, ctx=ctx, lattice=lat, n_int=2)
+    Id, Jd, Vd = lm.DensityCurrents(H, sd).pair_values()
+    Ip, Jp, Vp = lm.DensityCurrents(H, sp_).pair_values()
+    assert np.array_equal(Id, Ip) and np.array_equal(Jd, Jp) and np.abs(Vd - Vp).max() < 1e-14
+    assert np.abs(Vd).max() > 1e-4
+    Hd = H.data.toarray()
+    i, j = int(Id[3]), int(Jd[3])
+    want = 2 * np.imag(np.sum(Hd[2 * (i - 1):2 * i, 2 * (j - 1):2 * j] * P[2 * (j - 1):2 * j, 2 * (i - 1):2 * i].T))
+    assert abs(lm.DensityCurrents(H, sd)[i, j] - want) < 1e-14 and abs(lm.DensityCurrents(H, sd)[j, i] + want) < 1e-14
+    assert Currents(lm.DensityCurrents(H, sd)) == Currents(lm.DensityCurrents(H, sp_)) or \
+        abs(Currents(lm.DensityCurrents(H, sd)).currents - Currents(lm.DensityCurrents(H, sp_)).currents).max() < 1e-14
+    assert abs(currentsfromto(lm.DensityCurrents(H, sd), [1, 2, 3]) - currentsfromto(lm.DensityCurrents(H, sp_), [1, 2, 3])) < 1e-14
+    assert np.abs(currentsfrom(lm.DensityCurrents(H, sd), [1, 2, 3]).values - currentsfrom(lm.DensityCurrents(H, sp_), [1, 2, 3]).values).max() < 1e-14
+    sz = np.array([[1, 0], [0, -1]], complex)
+    assert np.abs(localexpect(sz, sd).values - localexpect(sz, sp_).values).max() < 1e-14
+    assert np.abs(LocalOperatorCurrents(H, sd, sz).pair_values()[2] - LocalOperatorCurrents(H, sp_, sz).pair_values()[2]).max() < 1e-14
+    assert np.abs(lm.localdensity(sd).values - lm.localdensity(sp_).values).max() < 1e-14
