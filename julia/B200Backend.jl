@@ -233,7 +233,7 @@ end
 function update_solver!(s::B200Exp, mat::SparseMatrixCSC{ComplexF64,Int64}, dt, force = false)   # src/evolution.jl:83-92
     s.dt = dt
     !force && s.mat === mat && s.dev !== nothing && return
-    if s.dev !== nothing && s.dev.colptr !== Int64[] && samepattern(s.dev, mat)
+    if s.dev !== nothing && !isempty(s.dev.colptr) && samepattern(s.dev, mat)
         update_values!(s.dev, mat)                                  # same sparsity pattern: nzval only
     else
         s.dev = DeviceHam(s.ctx, mat, s.n_int; lat = s.lat)
@@ -387,12 +387,10 @@ function currentsfromto(curr::DevDensityCurrents, src, dst = nothing)
     l = lattice(curr); out = Ref{Float64}(0.0)
     dev = device_ham(curr.hamiltonian, curr.state.data)
     ms = region_mask(l, src)
-    md = dst === nothing ? Ptr{UInt8}(C_NULL) : pointer(region_mask(l, dst))
-    mdkeep = dst === nothing ? nothing : region_mask(l, dst)
-    GC.@preserve mdkeep begin
-        p = mdkeep === nothing ? Ptr{UInt8}(C_NULL) : pointer(mdkeep)
+    md = dst === nothing ? UInt8[] : region_mask(l, dst)          # NULL = every site outside src
+    GC.@preserve md begin
         check(ccall((:lm_currents_fromto, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}, Int32, Ref{Float64}),
-                    dev.handle, curr.state.data.handle, ms, p, 0, out))
+                    dev.handle, curr.state.data.handle, ms, dst === nothing ? Ptr{UInt8}(C_NULL) : pointer(md), 0, out))
     end
     out[]
 end
