@@ -64,6 +64,14 @@ def workload(name):
         lat = lm.HoneycombLattice(500, 500)
         return dict(label="c4: Haldane t1=1 t2=0.2 m=0.1 on HoneycombLattice(500,500), N=5e5, M=4096, complex128, dt=0.1",
                     ham=lambda t: lm.haldane(lat, 1.0, 0.2, 0.1), M=4096, dt=0.1, time_dependent=False)
+    if name == "c1":
+        lat = lm.SquareLattice(10, 10)
+        return dict(label="c1: README example - SquareLattice(10,10), PointFlux ramp 0.2 min(t,10)/10 at (5.5,5.5), dense density matrix densitymatrix(mu=0), N=100, complex128, dt=0.1",
+                    ham=lambda t: lm.tightbinding_hamiltonian(lat, field=lm.PointFlux(0.2 * min(t, 10.0) / 10.0, (5.5, 5.5))), M=100, dt=0.1, time_dependent=True, dense=True)
+    if name == "c1x":
+        lat = lm.SquareLattice(64, 32)
+        return dict(label="c1x: dense-P path at N=2048 - SquareLattice(64,32) tight-binding, constant H, dense density matrix of 1024 occupied synthetic orbitals, complex128, dt=0.1",
+                    ham=lambda t: lm.tightbinding_hamiltonian(lat), M=2048, dt=0.1, time_dependent=False, dense=True)
     if name == "tiny":
         lat = lm.SquareLattice(20, 20)
         return dict(label="tiny: SquareLattice(20,20), M=64 (harness self-test)",
@@ -241,6 +249,272 @@ def parity_check(lm, _lib, lib, torch, dist, ctx, dev, state, Hmat, H0, rho_fram
     return out
 
 
+# ------------------------------------------------------------------------------------ the reference's published workload
+def disc_hamiltonian(n):
+    """benchmarks/models.jl:3-12: graphene disc of ~n sites (HoneycombLattice filtered by a circle centred at
+    the origin), t1 = -2.8, p-n junction potential 0.2 inside r/2, SymmetricGauge(B 1.519e-3).  Returns
+    (lattice, t -> Hamiltonian) with the ramp of benchmarks/benchmark_evolution_dynamic.jl:7: B(t) = 3 min(t/5, 1)."""
+    import math
+    import lm_b200 as lm
+    from importlib import import_module
+    LT = import_module("lm_b200.lattices")
+    r = math.sqrt(n * (math.sqrt(3) / 4) / math.pi)            # area per site = sqrt(3)/4
+    n2 = int(math.ceil(2 * r / (math.sqrt(3) / 2))) + 3
+    n1 = int(math.ceil(2 * r + n2 / 2)) + 3
+    a = np.array([[1.0, 0.5], [0.0, math.sqrt(3) / 2]])
+    basis = np.array([[0.0, 0.5], [0.0, math.sqrt(3) / 6]])
+    centre = a[:, 0] * (n1 + 1) / 2 + a[:, 1] * (n2 + 1) / 2 + basis.mean(axis=1)
+    lat = LT.BravaisLattice(a, basis - centre[:, None], (n1, n2), predicate=lambda x, y: x * x + y * y < r * r, kind="HoneycombLattice")
+    pot = np.where(lat.x ** 2 + lat.y ** 2 < r * r / 4, 0.2, 0.0)
+    return lat, (lambda t: lm.construct_hamiltonian(lat, (-2.8, lm.NearestNeighbor(1)), (1, pot),
+                                                    field=lm.SymmetricGauge(3.0 * min(t / 5.0, 1.0) * 1.519e-3)))
+
+
+def main_published(args):
+    """BASELINE.md section 1, the only first-party number of the reference: a single Ket on a graphene disc,
+    Evolution over 0:0.1:10 with a ramped SymmetricGauge (H changes every step), localdensity per frame through
+    TimeSequence; total wall seconds of the whole loop, as benchmarks/benchmark_evolution_dynamic.jl:3-13 times it.
+    Through the public host API (Evolution / TimeSequence / localdensity); the filtered lattice runs on the ELL kernels."""
+    import torch
+    import lm_b200 as lm
+    n = 10 ** int(args.workload[-1])
+    published = {4: 1.43, 5: 12.7}[int(args.workload[-1])]
+    torch.cuda.set_device(0)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    ctx = lm.Context(device=0, precision=args.precision, stream=tstream.cuda_stream)
+    lat, h = disc_hamiltonian(n)
+    N = len(lat)
+    rng = np.random.default_rng(1234)
+    psi0 = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    psi0 /= np.linalg.norm(psi0)
+    ts = np.arange(0, 101) * 0.1
+
+    def run_once():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev = lm.Evolution(lm.B200Exp(tol=args.tol, method=args.method, ctx=ctx), h, psi0)
+        dens = lm.TimeSequence(lambda m: lm.localdensity(m.state).values, ev, ts)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, dens
+    for _ in range(args.warmup):
+        run_once()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.2)
+    l0 = ctx.launch_count()
+    t_a = time.time()
+    runs = [run_once() for _ in range(args.steps)]
+    t_b = time.time()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop(t_a, t_b)
+    secs = np.array([r[0] for r in runs])
+    dens = runs[-1][1]
+    # parity of the last frame: the ket evolved on the host by a Taylor series of exp(-i H(t_k) dt)
+    import scipy.sparse as sp
+    x = psi0.copy()
+    for k in range(100):
+        A = (-0.1j) * sp.csr_matrix(h(ts[k]).data)
+        term, acc, q = x.copy(), x.copy(), 0
+        while q < 200:
+            q += 1
+            term = (A @ term) / q
+            acc += term
+            if np.abs(term).max() <= 1e-18 * np.abs(acc).max():
+                break
+        x = acc
+    rho_ref = np.abs(x) ** 2
+    rho = dens[ts[-1]]
+    total = float(np.median(secs))
+    H0 = h(0.0)
+    dev = H0.device(ctx)
+    esz = 16 if args.precision == "c128" else 8
+    out = {"metric": "total seconds, Evolution over 0:0.1:10 (100 steps, H re-evaluated every step) + localdensity per frame, single Ket, graphene disc (the reference's published workload)",
+           "value": total, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / 100, "higher_is_better": False,
+           "scaling": "replicas only", "vs_baseline": total / published, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
+           "config": {"workload": "%s: graphene disc, %d sites (target %d), t1 = -2.8, p-n potential, SymmetricGauge ramp, one Ket" % (args.workload, N, n),
+                      "published_seconds": published, "published_source": "BASELINE.md section 1 (benchmark_evolution_dynamic.jl, KrylovKitExp, Xeon 8259CL, 2 threads)",
+                      "best_seconds": float(secs.min()), "runs_timed": int(args.steps), "steps_per_second": 100.0 / total, "nnz": int(dev.nnz), "tol": args.tol,
+                      "l2": "single ket: everything is L2 resident; the loop is launch / host-latency bound, not bandwidth bound"},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": total, "unit": "s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": int(8 * N),
+                   "what": "the loop IS end to end: per step 3 field parameters to the device (phases regenerated there), lm_step, lm_local_density -> host"},
+           "roofline": {"bound": "hbm", "kernel": "lm::k_apply (ELL gather, single ket)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                        "note": "latency-bound regime (N = %d, one column): no roofline claim" % N},
+           "parity_check": {"rho_last_frame_rel": float(np.abs(rho - rho_ref).max() / rho_ref.max()), "norm": float(rho.sum()),
+                            "max_rel": float(np.abs(rho - rho_ref).max() / rho_ref.max()), "checked": "localdensity of the last frame vs a host Taylor-series evolution of the ket"}}
+    emit(out)
+
+
+# ------------------------------------------------------------------------------------ dense-P path (config 1)
+def dense_inputs(wl, H0):
+    """Initial dense density matrix: c1 = the README's densitymatrix(H(0), mu = 0) (host eigh, N = 100);
+    c1x = P = X X' of 1024 seeded synthetic orbitals (tests/synth.py)."""
+    import lm_b200 as lm
+    N = H0.structure.dim
+    if N <= 512:
+        proj = lm.densitymatrix(H0, mu=0.0)
+        return proj.dense(), proj.psi * np.sqrt(proj.weights if proj.weights is not None else 1.0)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import synth_block as synth_host
+    X = synth_host(N, N // 2, 0, seed=1234)
+    return X @ X.conj().T, X
+
+
+def cpu_dense_rate(wl, P0, n_steps):
+    """CachedExp semantics on the host (src/evolution.jl:62-128, restated in oracle/evolution.py): U = myexp!(-i H dt)
+    cached while H is unchanged, P <- U P U' as two dense products (numpy / BLAS threads) + localdensity."""
+    from oracle import evolution as EV
+    import scipy.sparse as sp
+    per_step, t = [], 0.0
+    P = P0.copy()
+    U, Hprev = None, None
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        H = sp.csc_matrix(wl["ham"](t).data)
+        if Hprev is None or (H != Hprev).nnz:
+            U, _ = EV.myexp(H, -1j * wl["dt"], threshold=1e-12)
+            U = U.toarray() if sp.issparse(U) else np.asarray(U)
+            Hprev = H
+        P = U @ P @ U.conj().T
+        np.real(np.diag(P)).copy()
+        per_step.append(time.perf_counter() - t0)
+        t += wl["dt"]
+    return 1.0 / float(np.median(per_step)), per_step
+
+
+def main_dense(args):
+    """U P U' on the FP64 tensor cores: value = device-resident steps/s, e2e = the README loop through the C ABI
+    (H values from the host every step, localdensity + currents back), roofline bound = tensor."""
+    import torch
+    import ctypes as C
+    import lm_b200 as lm
+    from importlib import import_module
+    _lib = import_module("lm_b200._lib")
+    D = import_module("lm_b200.distributed")
+    rank, world, local = D.env_rank()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    ctx = lm.Context(device=local, precision=args.precision, stream=tstream.cuda_stream)
+    lib = _lib.load()
+    wl = workload(args.workload)
+    H0 = wl["ham"](0.0)
+    N, dt = H0.structure.dim, wl["dt"]
+    P0, X0 = dense_inputs(wl, H0)
+    esz = 16 if args.precision == "c128" else 8
+    cdt = np.complex128 if esz == 16 else np.complex64
+    state = lm.DeviceState.from_dense(P0, ctx=ctx, lattice=H0.lattice, n_int=H0.n_int)
+    sol = lm.B200Exp(tol=args.tol, method=args.method, precision=args.precision, ctx=ctx)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k in range(n):
+            fn(k)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1), t0, time.time()
+
+    tcur = [0.0]
+
+    def dev_step(k):
+        sol.update_solver(wl["ham"](tcur[0]), dt)
+        sol.step(state)
+        tcur[0] += dt
+    for k in range(args.warmup):
+        dev_step(k)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = ctx.launch_count()
+    ms, t0, t1 = timed(dev_step, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop(t0, t1)
+    ms_per_step = ms / args.steps
+    # roofline: two complex GEMMs per step (8 N^3 real flops each in the 4-multiplication count) on the DMMA pipe
+    flops = 2 * 8.0 * float(N) ** 3
+    peak = C.c_double(0.0)
+    lib.lm_dbg_dmma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.lm_dbg_dmma_peak.restype = C.c_int32
+    if os.environ.get("LM_EMUL_LIB"):
+        peak.value = 40.0                     # CPU dry run of the harness (tools/bench_dryrun_cpu.py): no probe
+    else:
+        _lib.check(lib.lm_dbg_dmma_peak(ctx.handle, C.byref(peak)))
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "lm::k_zgemm_dmma_3m (complex GEMM on the FP64 tensor cores, mma.sync.m8n8k4.f64, 3M product)" if N > 256 else "lm::k_zgemm_dmma (complex GEMM on the FP64 tensor cores, 32 x 32 tiles)",
+                "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+                "peak_source": "measured in this run: register-resident DMMA chains (lm_dbg_dmma_peak); nominal B200 FP64 tensor peak 40 TFLOP/s",
+                "flops_per_step": flops, "note": "flops counted as 2 GEMMs x 8 N^3 (4-multiplication complex product); the 3M kernel executes 3/4 of them; the whole step (incl. rebuilding U when H changed) is in the time"}
+
+    # e2e: README loop through the C ABI with host buffers
+    Hmat = H0.data
+    lat = H0.lattice
+    dims = lat.sizes if len(lat) == lat.sizes[0] * lat.sizes[1] * lat.nb else None
+    dev = lm.DeviceHam.from_csc(ctx, Hmat, H0.n_int, coords=lat.coords, lattice_dims=dims)
+    nnz = dev.nnz
+    npairs, n_sites = len(dev.pairs()[0]), N // H0.n_int
+    nz_all = [np.ascontiguousarray(wl["ham"](k * dt).data.data.astype(cdt)) for k in range(args.warmup + args.steps)] if wl["time_dependent"] else None
+    nz_pinned = torch.from_numpy(np.ascontiguousarray(Hmat.data.astype(cdt)).view(np.float64 if esz == 16 else np.float32).copy()).pin_memory()
+    nz_np = nz_pinned.numpy().view(cdt)
+    rho_np, j_np = np.empty(n_sites), np.empty(max(npairs, 1))
+    st2 = lm.DeviceState.from_dense(P0, ctx=ctx, lattice=lat, n_int=H0.n_int)
+    nmv = C.c_int32()
+    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4, "chebyshev_clenshaw": 5}[args.method]
+    kk = [0]
+
+    def e2e_step(k):
+        if nz_all is not None:
+            nz_np[:] = nz_all[kk[0]]
+        kk[0] += 1
+        _lib.check(lib.lm_ham_update_values(dev.handle, _lib.ptr(nz_np)))
+        _lib.check(lib.lm_step(dev.handle, st2.handle, dt, args.tol, method, C.byref(nmv)))
+        _lib.check(lib.lm_observables(dev.handle, st2.handle, _lib.ptr(rho_np), _lib.ptr(j_np)))
+    for k in range(args.warmup):
+        e2e_step(k)
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+    e2e = {"value": 1e3 / (ms_e2e / args.steps), "unit": "steps/s", "h2d_bytes_per_step": int(nnz * esz), "d2h_bytes_per_step": int(8 * (n_sites + npairs)),
+           "what": "lm_ham_update_values(host nzval) + lm_step (U P U') + lm_observables (rho, J of the dense P -> host) per step"}
+    # parity: the e2e state against the host: orbitals evolved by a Taylor series of exp(-i H(t_k) dt), P = X W X'
+    import scipy.sparse as sp
+    w = np.ones(X0.shape[1])
+    X = X0.astype(np.complex128)
+    for k in range(args.warmup + args.steps):
+        A = (-1j * dt) * sp.csr_matrix(wl["ham"](k * dt).data)
+        term, acc, q = X.copy(), X.copy(), 0
+        while q < 200:
+            q += 1
+            term = (A @ term) / q
+            acc += term
+            if np.abs(term).max() <= 1e-18 * np.abs(acc).max():
+                break
+        X = acc
+    Pref = (X * w) @ X.conj().T
+    got = st2.download().astype(np.complex128)
+    rho_ref = np.real(np.diag(Pref)).reshape(n_sites, H0.n_int).sum(1)
+    parity = {"P_vs_host_taylor_rel": float(np.abs(got - Pref).max() / np.abs(Pref).max()),
+              "rho_rel": float(np.abs(rho_np - rho_ref).max() / np.abs(rho_ref).max()),
+              "checked": "dense P after %d e2e steps vs orbitals evolved by a host Taylor series (P = X X'); localdensity of the last frame" % (args.warmup + args.steps)}
+    parity["max_rel"] = max(parity["P_vs_host_taylor_rel"], parity["rho_rel"])
+    out = {"metric": "evolution steps/sec (dense N x N density matrix, U P U')", "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+           "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
+           "config": {"workload": wl["label"], "N": N, "nnz": int(nnz), "dt": dt, "tol": args.tol, "method": args.method,
+                      "l2": "N = %d: the three N x N buffers (%.1f MB) %s" % (N, 3 * N * N * esz / 1e6, "exceed" if 3 * N * N * esz > 126e6 else "fit in the 126 MB L2 (compute-bound path; no flush)")},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": parity}
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, per_step = cpu_dense_rate(wl, P0, 3)
+        out["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "3 steps of the CachedExp algorithm (myexp! + two dense products, numpy BLAS) on the full N = %d matrix" % N}
+    if rank == 0:
+        emit(out)
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -261,6 +535,10 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in ("pub4", "pub5"):
+        return main_published(args)
+    if workload(args.workload).get("dense"):
+        return main_dense(args)
 
     import torch
     import torch.distributed as dist

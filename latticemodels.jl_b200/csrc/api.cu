@@ -102,6 +102,7 @@ struct lm_ctx {
     double* d_frame[2] = {nullptr, nullptr}; double* h_frame[2] = {nullptr, nullptr}; size_t frame_cap[2] = {0, 0};
     long long frame_nsites[2] = {0, 0}, frame_npairs[2] = {0, 0}; bool frame_pending[2] = {false, false};
     unsigned* h_async_flag = nullptr; unsigned* d_async_flag = nullptr;   // sticky status of lm_ham_update_values_async
+    cudaStream_t up_stream = nullptr; cudaEvent_t ev_up_done = nullptr, ev_nz_free = nullptr;   // its host -> device copies
     double* d_region = nullptr;                            // region-sum scratch (lm_currents_fromto / lm_currents_from)
     unsigned char* d_mask = nullptr; size_t mask_cap = 0;
     size_t esz() const { return precision == LM_C128 ? 16 : 8; }
@@ -251,6 +252,7 @@ extern "C" int32_t lm_ctx_destroy(lm_ctx* c) {
     }
     if (c->d_region) cudaFree(c->d_region);
     if (c->d_mask) cudaFree(c->d_mask);
+    if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); cudaEventDestroy(c->ev_up_done); cudaEventDestroy(c->ev_nz_free); }
     if (c->h_async_flag) cudaFreeHost(c->h_async_flag);
     if (c->d_async_flag) cudaFree(c->d_async_flag);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -751,6 +753,7 @@ static int upload_nzval(lm_ham* h, const void* nzval) {
     k_scatter_vals<T><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const T2*)h->d_nz, h->d_csc2ell, (T2*)h->d_vals);
     c->launches++;
     CK(cudaGetLastError());
+    if (c->up_stream) CK(cudaEventRecord(c->ev_nz_free, c->stream));   // orders a later asynchronous upload after this use of d_nz
     return LM_OK;
 }
 // Gershgorin partials [grid][4] of the current ELL values into c->d_stage (k_gershgorin)
@@ -869,7 +872,28 @@ extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
         CK(cudaMalloc(&c->d_async_flag, sizeof(unsigned)));
         CK(cudaMemsetAsync(c->d_async_flag, 0, sizeof(unsigned), c->stream));
     }
-    if (c->precision == LM_C128) FWD(upload_nzval<double>(h, nzval)); else FWD(upload_nzval<float>(h, nzval));
+    // The host -> device copy runs on its own stream: the caller is ahead of the device (nothing here
+    // synchronises), so the values of step k + 1 cross PCIe while step k still computes; the main
+    // stream only waits for the copy before it scatters them into the ELL array.
+    if (!c->up_stream) {
+        CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_up_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_nz_free, cudaEventDisableTiming));
+        CK(cudaEventRecord(c->ev_nz_free, c->stream));
+    }
+    if (h->nnz > 0) {
+        const size_t bytes = c->esz() * (size_t)h->nnz;
+        CK(cudaStreamWaitEvent(c->up_stream, c->ev_nz_free, 0));       // the previous scatter has consumed d_nz
+        CK(cudaMemcpyAsync(h->d_nz, nzval, bytes, cudaMemcpyHostToDevice, c->up_stream));
+        CK(cudaEventRecord(c->ev_up_done, c->up_stream));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_up_done, 0));
+        const int th = 256; const long long bl = (h->nnz + th - 1) / th;
+        if (c->precision == LM_C128) k_scatter_vals<double><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const double2*)h->d_nz, h->d_csc2ell, (double2*)h->d_vals);
+        else k_scatter_vals<float><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const float2*)h->d_nz, h->d_csc2ell, (float2*)h->d_vals);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev_nz_free, c->stream));
+    }
     unsigned grid = 0;
     FWD(enqueue_gershgorin(h, &grid));
     const double slack = 1e-9 * std::max(std::max(h->emax - h->emin, 0.0), h->norm_inf);
@@ -1057,6 +1081,7 @@ extern "C" int32_t lm_ham_get_csc(lm_ham* h, int64_t* colptr, int64_t* rowval, v
         c->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(nzval, h->d_nz, c->esz() * (size_t)h->nnz, cudaMemcpyDeviceToHost, c->stream));
+        if (c->up_stream) CK(cudaEventRecord(c->ev_nz_free, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     return LM_OK;
@@ -1224,7 +1249,18 @@ extern "C" int32_t lm_state_download_psi(lm_state* s, void* out) {
 // C = A op(B) on the tensor-core (c128) or FFMA (c64) dense kernels
 static int dense_gemm(lm_ctx* c, bool conj_b, int Mr, int Nc, int K, const void* A, long long lda,
                       const void* B, long long ldb, void* C, long long ldc) {
-    if (c->precision == LM_C128) {
+    static const int big_env = env_int("LM_DENSE_3M_MIN", 256);     // 64 x 64 double-buffered 3M kernel from this size on
+    if (c->precision == LM_C128 && std::max(Mr, Nc) > big_env) {
+        static bool configured = false;
+        if (!configured) {
+            CK(cudaFuncSetAttribute(k_zgemm_dmma_3m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg_smem_bytes<true>()));
+            CK(cudaFuncSetAttribute(k_zgemm_dmma_3m<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg_smem_bytes<false>()));
+            configured = true;
+        }
+        dim3 g((Nc + ZG_BN - 1) / ZG_BN, (Mr + ZG_BM - 1) / ZG_BM);
+        if (conj_b) k_zgemm_dmma_3m<true><<<g, 256, zg_smem_bytes<true>(), c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
+        else k_zgemm_dmma_3m<false><<<g, 256, zg_smem_bytes<false>(), c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
+    } else if (c->precision == LM_C128) {
         dim3 g((Nc + 31) / 32, (Mr + 31) / 32);
         if (conj_b) k_zgemm_dmma<true><<<g, 128, 0, c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
         else k_zgemm_dmma<false><<<g, 128, 0, c->stream>>>(Mr, Nc, K, (const double2*)A, lda, (const double2*)B, ldb, (double2*)C, ldc);
@@ -2646,6 +2682,23 @@ extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, 
     c->launches++;
     CK(cudaGetLastError());
     return reduce_and_fetch(c, s, h->d_oc_J, (size_t)np, J_out);
+}
+
+// measured FP64 tensor-core (DMMA) throughput of this device in TFLOP/s (bench.py, dense-path roofline)
+extern "C" int32_t lm_dbg_dmma_peak(lm_ctx* c, double* tflops) {
+    REQUIRE(c && tflops, "lm_dbg_dmma_peak: NULL");
+    FWD(set_dev(c));
+    FWD(ensure_stage(c, 64));
+    const int iters = 20000, ctas = 8 * (c->sm_count > 0 ? c->sm_count : 148);
+    k_dmma_peak<<<ctas, 256, 0, c->stream>>>(1000, (double*)c->d_stage);          // warm-up
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_dmma_peak<<<ctas, 256, 0, c->stream>>>(iters, (double*)c->d_stage);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    c->launches += 2;
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *tflops = (double)ctas * 8.0 /* warps */ * iters * 8.0 /* chains */ * 512.0 /* flop per m8n8k4 */ / (ms * 1e-3) / 1e12;
+    return LM_OK;
 }
 
 // host-only hook (tests): the product-form Chebyshev plan for exp(-i R x) on [-1, 1]

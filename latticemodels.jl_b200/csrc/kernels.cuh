@@ -1255,6 +1255,127 @@ k_zgemm_dmma(int Mr, int Nc, int K, const double2* __restrict__ A, long long lda
             }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_zgemm_dmma_3m: the large-N version of the same product.  CTA = 8 warps, 64 x 64 output tile, warp
+// tile 32 x 16 (4 x 2 MMA tiles), K slabs of 16 double-buffered in shared memory (the next slab's
+// global loads are in flight while the current one is multiplied; one CTA barrier per slab).
+// Real and imaginary parts live in separate planes whose row strides (20 / 68 doubles) make every
+// fragment load conflict-free.  The complex product uses the 3M form
+//     T1 = Ar Br,  T2 = Ai Bi,  T3 = (Ar + Ai)(Br + Bi);   Cr = T1 - T2,  Ci = T3 - T1 - T2
+// i.e. three real DMMA chains instead of four (the sums cost one DADD per fragment load).
+// ------------------------------------------------------------------------------------------
+constexpr int ZG_BM = 64, ZG_BN = 64, ZG_BK = 16, ZG_LDA = 20, ZG_LDB = 68;
+template <bool CONJ_B> __host__ __device__ constexpr int zg_b_plane() { return CONJ_B ? ZG_BN * ZG_LDA : ZG_BK * ZG_LDB; }
+template <bool CONJ_B> __host__ __device__ constexpr size_t zg_smem_bytes() { return sizeof(double) * 2 * (2 * ZG_BM * ZG_LDA + 2 * zg_b_plane<CONJ_B>()); }
+
+template <bool CONJ_B>
+__global__ void __launch_bounds__(256, 1)
+k_zgemm_dmma_3m(int Mr, int Nc, int K, const double2* __restrict__ A, long long lda,
+                const double2* __restrict__ B, long long ldb, double2* __restrict__ C, long long ldc) {
+    constexpr int PA = ZG_BM * ZG_LDA, PB = zg_b_plane<CONJ_B>();
+    LM_SMEM_DYN(lm_smem);
+    double* sA = reinterpret_cast<double*>(lm_smem);                 // [buf][re | im][PA]
+    double* sB = sA + 2 * 2 * PA;                                    // [buf][re | im][PB]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * ZG_BM, n0 = blockIdx.x * ZG_BN;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const int g = lane >> 2, q = lane & 3;                           // fragment coordinates
+    double t1[4][2][2] = {}, t2[4][2][2] = {}, t3[4][2][2] = {};
+    double2 ra[4], rb[4];
+
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;
+            {   // A slab: 64 rows x 16 k
+                const int m = e >> 4, k = e & 15;
+                ra[r] = (m0 + m < Mr && k0 + k < K) ? A[(long long)(m0 + m) * lda + k0 + k] : make_double2(0, 0);
+            }
+            if (!CONJ_B) {      // B slab: 16 k x 64 columns
+                const int k = e >> 6, n = e & 63;
+                rb[r] = (k0 + k < K && n0 + n < Nc) ? B[(long long)(k0 + k) * ldb + n0 + n] : make_double2(0, 0);
+            } else {            // B^H: rows of B are the output columns
+                const int n = e >> 4, k = e & 15;
+                rb[r] = (k0 + k < K && n0 + n < Nc) ? B[(long long)(n0 + n) * ldb + k0 + k] : make_double2(0, 0);
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+        double* ar = sA + (size_t)buf * 2 * PA; double* ai = ar + PA;
+        double* br = sB + (size_t)buf * 2 * PB; double* bi = br + PB;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;
+            { const int m = e >> 4, k = e & 15; ar[m * ZG_LDA + k] = ra[r].x; ai[m * ZG_LDA + k] = ra[r].y; }
+            if (!CONJ_B) { const int k = e >> 6, n = e & 63; br[k * ZG_LDB + n] = rb[r].x; bi[k * ZG_LDB + n] = rb[r].y; }
+            else { const int n = e >> 4, k = e & 15; br[n * ZG_LDA + k] = rb[r].x; bi[n * ZG_LDA + k] = -rb[r].y; }
+        }
+    };
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += ZG_BK, buf ^= 1) {
+        const bool more = k0 + ZG_BK < K;
+        if (more) gload(k0 + ZG_BK);                                  // in flight during the multiplications below
+        const double* ar = sA + (size_t)buf * 2 * PA; const double* ai = ar + PA;
+        const double* br = sB + (size_t)buf * 2 * PB; const double* bi = br + PB;
+#pragma unroll
+        for (int kk = 0; kk < ZG_BK; kk += 4) {
+            double fa[4], fb[4], fs[4], ga[2], gb[2], gs[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int o = (wm + 8 * i + g) * ZG_LDA + kk + q;
+                fa[i] = ar[o]; fb[i] = ai[o]; fs[i] = fa[i] + fb[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int o = CONJ_B ? (wn + 8 * j + g) * ZG_LDA + kk + q : (kk + q) * ZG_LDB + wn + 8 * j + g;
+                ga[j] = br[o]; gb[j] = bi[o]; gs[j] = ga[j] + gb[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma(t1[i][j][0], t1[i][j][1], fa[i], ga[j]);
+                    dmma(t2[i][j][0], t2[i][j][1], fb[i], gb[j]);
+                    dmma(t3[i][j][0], t3[i][j][1], fs[i], gs[j]);
+                }
+        }
+        if (more) sstore(buf ^ 1);            // the other buffer was last read before the previous barrier
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + wm + 8 * i + g, n = n0 + wn + 8 * j + 2 * q + h;
+                if (m < Mr && n < Nc)
+                    C[(long long)m * ldc + n] = make_double2(t1[i][j][h] - t2[i][j][h], t3[i][j][h] - t1[i][j][h] - t2[i][j][h]);
+            }
+}
+
+// FP64 tensor-core peak probe (bench.py --workload c1x: the roofline denominator of the dense path is
+// MEASURED on the device it runs on): 8 independent register-resident DMMA chains per warp.
+__global__ void __launch_bounds__(256)
+k_dmma_peak(int iters, double* __restrict__ out) {
+    double c[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
+    const double a = 1e-9 * (double)(threadIdx.x + 1), b = 1.0 + 1e-9 * (double)blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma(c[j][0], c[j][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+    if (s == 123.456) out[0] = s;                        // keeps the chains alive
+}
+
 // FP32 (c64 mode) dense GEMM: plain FFMA tile kernel, same interface.
 template <bool CONJ_B>
 __global__ void __launch_bounds__(256)

@@ -724,12 +724,19 @@ def test_full_size_config2_properties(ctx):
     sol.step(st)
     back = st.download()
     assert np.abs(back - Psi).max() < 1e-12 * np.abs(Psi).max() * 50      # round trip
-    # linearity on a column slice against the oracle SpMM
-    Ho = H.data
+    # a column slice against the ORACLE-assembled H (oracle/operators.py): device CSC, SpMM, and one
+    # propagation step against scipy's expm_multiply
+    from scipy.sparse.linalg import expm_multiply
+    Ho = OP.tightbinding_hamiltonian(L.square_lattice(100, 100), field=F.LandauGauge(0.02)).tocsc()
+    got = H.device(ctx).to_csc()
+    assert abs(got - Ho).max() < 5e-15
     Y = np.zeros((N, 8), complex, order="F")
     X = np.asfortranarray(Psi[:, :8])
     _lib.check(_lib.load().lm_spmm(H.device(ctx).handle, _lib.ptr(X), _lib.ptr(Y), N, 8))
     assert _relerr(Y, Ho @ X) < 1e-14
+    sol.update_solver(H, 0.1)
+    sol.step(st)
+    assert _relerr(st.download()[:, :8], expm_multiply(-0.1j * Ho, back[:, :8])) < 1e-11
 
 
 @pytest.mark.parametrize("config", ["c3_qwz300", "c4_haldane500"])
@@ -773,6 +780,15 @@ def test_full_size_headline_configs_properties(ctx, config):
     lz.step(st2)
     a, b = st.download(), st2.download()
     assert np.abs(a - b).max() < 1e-11 * np.abs(a).max() * 10
+    # against the ORACLE at full size: the device-assembled H equals the oracle's CSC entry by entry, and
+    # 8 columns of the step equal scipy's expm_multiply on the oracle-assembled H
+    from scipy.sparse.linalg import expm_multiply
+    if config == "c3_qwz300":
+        Ho = OP.qwz(L.square_lattice(300, 300), field=F.LandauGauge(0.05)).tocsc()
+    else:
+        Ho = OP.haldane(L.honeycomb_lattice(500, 500), 1.0, 0.2, 0.1, field=F.LandauGauge(0.002)).tocsc()
+    assert abs(dev.to_csc() - Ho).max() < 5e-15
+    assert _relerr(a[:, :8], expm_multiply(-0.1j * Ho, Psi[:, :8])) < 1e-11
     sol.update_solver(H, -0.1)
     sol.step(st)
     assert np.abs(st.download() - Psi).max() < 5e-11 * np.abs(Psi).max()

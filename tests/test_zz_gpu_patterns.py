@@ -346,3 +346,26 @@ def test_reference_generated_golden_series_on_device(name):
         assert want_pairs == list(zip(I.tolist(), J.tolist()))
         assert _relerr(lm.localdensity(m.state).values, g["rho"][k]) < 1e-10
         assert np.abs(V - g["J"][k]).max() < 1e-10 * max(np.abs(g["J"][k]).max(), 1e-3)
+
+
+def test_dense_path_large_tiles_3m_kernel():
+    """N > 256: U P U' runs on the 64 x 64 double-buffered 3M DMMA kernel (k_zgemm_dmma_3m); ragged
+    against the tile size on purpose.  Also the Psi W Psi' escape hatch (conjugated operand)."""
+    ctx = lm.default_context("c128")
+    Ho = OP.tightbinding_hamiltonian(L.square_lattice(12, 22), field=F.LandauGauge(0.07))
+    N = Ho.shape[0]
+    rng = np.random.default_rng(3)
+    X = _rand_block(N, 40, seed=3) / np.sqrt(N)
+    w = rng.random(40)
+    P = (X * w) @ X.conj().T
+    st = lm.DeviceState.from_dense(P, ctx=ctx, n_int=1)
+    sol = lm.B200Exp(tol=1e-14, ctx=ctx, n_int=1)
+    U = EV.exact_propagator(Ho, 0.1)
+    want = P.copy()
+    for _ in range(2):
+        sol.update_solver(Ho, 0.1)
+        sol.step(st)
+        want = U @ want @ U.conj().T
+    assert _relerr(st.download(), want) < 1e-12
+    stb = lm.DeviceState.from_psi(X, w, ctx=ctx, n_int=1)
+    assert _relerr(stb.dense(), P) < 1e-13
