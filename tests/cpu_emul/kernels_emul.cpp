@@ -44,14 +44,15 @@ void emul_assemble(long long E, const double* stat, const int* cptr, const int* 
     const unsigned th = 64;
     lm_emul::launch(run_assemble, dim3((unsigned)((E + th - 1) / th)), th, AsmArgs{E, (const double2*)stat, cptr, cbond, (const double2*)camp, (const double2*)phase, (double2*)vals});
 }
-// folded Gershgorin enclosure (emin, emax, norm_inf) exactly as the host folds the per-CTA partials
-void emul_gershgorin(long long N, int W, const int* cols, const double* vals, double* out3) {
+// folded Gershgorin enclosure (emin, emax, norm_inf) and Hermiticity defect max |H_ij - conj(H_ji)| exactly as
+// the host folds the per-CTA partials (4 doubles per CTA)
+void emul_gershgorin(long long N, int W, const int* cols, const double* vals, double* out4) {
     const unsigned grid = (unsigned)((N + 255) / 256);
-    std::vector<double> partial(3 * (size_t)grid);
+    std::vector<double> partial(4 * (size_t)grid);
     lm_emul::launch(run_gersh, dim3(grid), 256, GershArgs{N, W, cols, (const double2*)vals, partial.data()});
-    double lo = 1e300, hi = -1e300, nr = 0.0;
-    for (unsigned g = 0; g < grid; ++g) { lo = std::fmin(lo, partial[3 * g]); hi = std::fmax(hi, partial[3 * g + 1]); nr = std::fmax(nr, partial[3 * g + 2]); }
-    out3[0] = lo; out3[1] = hi; out3[2] = nr;
+    double lo = 1e300, hi = -1e300, nr = 0.0, as = 0.0;
+    for (unsigned g = 0; g < grid; ++g) { lo = std::fmin(lo, partial[4 * g]); hi = std::fmax(hi, partial[4 * g + 1]); nr = std::fmax(nr, partial[4 * g + 2]); as = std::fmax(as, partial[4 * g + 3]); }
+    out4[0] = lo; out4[1] = hi; out4[2] = nr; out4[3] = as;
 }
 // y = alpha H x + gamma x + beta z + delta u through k_apply (generic ELL path, complex128) with
 // the launch geometry of api.cu apply(); mode as in the library (0 plain, 1 +beta z, 2 general, 3 factor)

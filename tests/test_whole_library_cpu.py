@@ -84,5 +84,8 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     tail = (res.stdout + res.stderr)[-4000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
-    assert m and int(m.group(1)) >= 134, tail
-    assert "failed" not in res.stdout.splitlines()[-1] and "skipped" not in res.stdout.splitlines()[-1], tail
+    assert m and int(m.group(1)) >= 140, tail
+    last = res.stdout.splitlines()[-1]
+    sk = re.search(r"(\d+) skipped", last)
+    # the only skips allowed: the three consumers of reference-generated golden series (tests/golden/ref/ absent: no Julia here)
+    assert "failed" not in last and (sk is None or int(sk.group(1)) <= 3), tail
