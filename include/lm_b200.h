@@ -202,6 +202,18 @@ int32_t lm_state_download_psi(lm_state* state, void* psi_colmajor_out);
 int32_t lm_state_download_dense(lm_state* state, void* P_colmajor_out);
 int32_t lm_state_destroy(lm_state* state);
 
+/* Lowest `nev` (<= 64) eigenpairs of H on the device: replaces
+ * diagonalize(ham, :krylovkit; n) (src/spectrum.jl:56-64) / groundstate (src/spectrum.jl:205) for sizes
+ * where the host LAPACK route is impossible.  Chebyshev-filtered subspace iteration on the SpMM kernels
+ * of the propagator; converged when every residual ||H x_j - theta_j x_j|| <= tol * max|Gershgorin bound|.
+ * evals_out: nev ascending eigenvalues; resid_out (nullable): their residual norms; vecs_out
+ * (nullable): a Psi state with nev orthonormal columns (weights NULL), ready for lm_step /
+ * lm_observables - the Fermi sphere of the nev lowest levels; iters_out (nullable): outer iterations.
+ * max_iter <= 0: 300; degree <= 0: filter degree 40.  LM_ERR_NOT_CONVERGED if max_iter is exhausted
+ * (evals_out / resid_out then hold the last Ritz values). */
+int32_t lm_eigs_lowest(lm_ham* ham, int32_t nev, double tol, int32_t max_iter, int32_t degree,
+                       double* evals_out, double* resid_out, lm_state** vecs_out, int32_t* iters_out);
+
 /* ------------------------------------------------------------------ hot path
  * lm_step replaces step!(solver, state.data, cache) (src/evolution.jl:69-78,150-154):
  * Psi <- exp(-i H dt) Psi, or P <- U P U' for a dense state.  dt < 0 is allowed here (the

@@ -208,6 +208,27 @@ psi_densitymatrix(eig::AbstractEigensystem; T::Real = 0, μ::Real = 0, mu::Real 
 
 const DevOp{B} = Operator{B,B,<:PsiProjector}
 
+# N1, second half: the lowest eigenpairs on the device (Chebyshev-filtered subspace iteration on the SpMM
+# kernels of the propagator) for sizes where the LAPACK route of `diagonalize` is impossible.  Plugs into the
+# reference's routine dispatch (src/spectrum.jl:48-67):  diagonalize(H, :b200; n = 10)
+"`eigs_lowest(ham; n, tol)` -> (eigenvalues, Operator(basis, PsiProjector)): the n lowest levels as a device block (Fermi sphere)"
+function eigs_lowest(ham::DataOperator; n::Integer = 10, tol::Real = 1e-10, maxiter::Integer = 0, degree::Integer = 0,
+                     ctx::Context = default_context())
+    mat = ham.data isa SparseMatrixCSC{ComplexF64,Int64} ? ham.data : SparseMatrixCSC{ComplexF64,Int64}(sparse(ham.data))
+    isl = basis(ham) isa LatticeModels.AbstractLatticeBasis
+    dev = DeviceHam(ctx, mat, isl ? internal_length(ham) : 1; lat = isl ? lattice(ham) : nothing)
+    vals = Vector{Float64}(undef, n); res = Vector{Float64}(undef, n)
+    h = Ref{Ptr{Cvoid}}(C_NULL); it = Ref{Int32}(0)
+    check(ccall((:lm_eigs_lowest, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}, Ref{Int32}),
+                dev.handle, n, tol, maxiter, degree, vals, res, h, it))
+    vals, Operator(basis(ham), PsiProjector(h[], size(mat, 1), ctx))
+end
+function LatticeModels.diagonalize_routine(op::DataOperator, ::Val{:b200}; n = 10, tol = 1e-10, kw...)
+    vals, P = eigs_lowest(op; n = n, tol = tol)
+    LatticeModels.Eigensystem(basis(op), psi_columns(P.data), vals)
+end
+
 # ---- the solver ---------------------------------------------------------------------------------
 mutable struct B200Exp <: EvolutionSolver
     ctx::Context
@@ -544,7 +565,7 @@ function settime!(H::B200Hamiltonian, t)
 end
 update_solver!(s::B200Exp, mat::DeviceMatrix, dt, force = false) = (s.dt = dt; s.dev = mat.dev; s.mat = mat; nothing)
 
-export B200Exp, PsiProjector, Context, B200Hamiltonian, settime!, FrameSink, psi_projector, psi_densitymatrix,
+export B200Exp, PsiProjector, Context, B200Hamiltonian, settime!, FrameSink, psi_projector, psi_densitymatrix, eigs_lowest,
        dense_state, psi_columns, shard_range, unique_id, comm_init!, peer_handle, peer_attach!, set_replicated!
 
 end # module

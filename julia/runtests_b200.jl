@@ -115,4 +115,14 @@ end
         @test seq[t].currents ≈ ref[k][2]
     end
 end
+@testset "device eigensolver (diagonalize(H, :b200; n))" begin
+    l = SquareLattice(12, 11)
+    H = qwz(l)
+    ref = diagonalize(dense(H))
+    eig = diagonalize(H, :b200, n = 10)
+    @test eig.values ≈ ref.values[1:10] atol = 1e-9
+    @test norm(H.data * eig.states - eig.states * Diagonal(eig.values)) < 1e-8
+    vals, P = eigs_lowest(H; n = 10)
+    @test localdensity(P).values ≈ localdensity(projector(ref[1:10])).values atol = 1e-7
+end
 println("B200 backend: all reference testsets passed")

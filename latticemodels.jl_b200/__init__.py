@@ -14,7 +14,8 @@ from .lattices import (Bravais, BravaisLattice, BravaisTranslation, HoneycombLat
                        NearestNeighbor, SquareLattice, honeycomb_2nn)
 from .hamiltonian import (DeviceHam, Hamiltonian, construct_hamiltonian, construct_operator,  # noqa: F401
                           haldane, qwz, tightbinding_hamiltonian)
-from .states import DeviceState, PsiProjector, densitymatrix, diagonalize, groundstate  # noqa: F401
+from .states import (DeviceState, PsiProjector, densitymatrix, diagonalize, eigs_lowest, groundstate,  # noqa: F401
+                     groundstate_device)
 from .evolution import B200Exp, Evolution, EvolutionSolver, EvolutionTimestamp  # noqa: F401
 from .observables import (Currents, DensityCurrents, LatticeValue, LocalOperatorCurrents, SubCurrents, SubLattice,  # noqa: F401
                           currentsfrom, currentsfromto, findnz, localdensity, localexpect)

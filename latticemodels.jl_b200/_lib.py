@@ -68,6 +68,7 @@ PROTOTYPES = {
     "lm_state_download_psi": [_vp, _vp],
     "lm_state_download_dense": [_vp, _vp],
     "lm_state_destroy": [_vp],
+    "lm_eigs_lowest": [_vp, _i32, _f64, _i32, _i32, _pf64, _pf64, C.POINTER(_vp), _pi32],
     "lm_step": [_vp, _vp, _f64, _f64, _i32, _pi32],
     "lm_spmm_state": [_vp, _vp, _vp],
     "lm_spmm": [_vp, _vp, _vp, _i64, _i64],

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "stencil.cuh"
 #include "taylor_roots.h"
+#include "small_la.h"
 
 #include <algorithm>
 #include <climits>
@@ -2698,6 +2699,171 @@ extern "C" int32_t lm_dbg_dmma_peak(lm_ctx* c, double* tflops) {
     c->launches += 2;
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *tflops = (double)ctas * 8.0 /* warps */ * iters * 8.0 /* chains */ * 512.0 /* flop per m8n8k4 */ / (ms * 1e-3) / 1e12;
+    return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// N1: lowest eigenpairs on the device - Chebyshev-filtered subspace iteration.
+// Replaces diagonalize(ham, :krylovkit; n) (src/spectrum.jl:56-64, KrylovKit.eigsolve :SR) where the host
+// LAPACK route of densitymatrix / groundstate is impossible (N >= 1e5).  Everything N-sized stays on the
+// device and runs on the same SpMM kernels as the propagator (a block of >= 32 columns takes the
+// register-tiled stencil path); only nb x nb Gram / Rayleigh-Ritz matrices visit the host (small_la.h).
+//   repeat:  Rayleigh-Ritz on span(X)  ->  residuals  ->  X <- p_m(H) X (Chebyshev filter damping
+//            [theta_nb, emax], emax = Gershgorin)  ->  orthonormalise (SVQB, twice)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct EigWork {
+    lm_ctx* c; long long N, ld; int nb;
+    void *X = nullptr, *Y = nullptr, *HX = nullptr, *T = nullptr, *d_small = nullptr; double2* d_g = nullptr; double* d_v = nullptr;
+    ~EigWork() { void* p[] = {X, Y, HX, T, d_small, d_g, d_v}; for (void* q : p) if (q) cudaFree(q); }
+};
+}
+static int eig_gram(EigWork& w, const void* A, const void* B, std::vector<zc>& out) {
+    lm_ctx* c = w.c; const int n = w.nb;
+    CK(cudaMemsetAsync(w.d_g, 0, sizeof(double2) * (size_t)n * n, c->stream));
+    const long long rpc = std::max<long long>(256, (w.N + 2047) / 2048);
+    const unsigned grid = (unsigned)((w.N + rpc - 1) / rpc);
+    if (c->precision == LM_C128) k_gram<double2><<<grid, 256, 0, c->stream>>>(w.N, n, w.ld, (const double2*)A, (const double2*)B, rpc, w.d_g);
+    else k_gram<float2><<<grid, 256, 0, c->stream>>>(w.N, n, w.ld, (const float2*)A, (const float2*)B, rpc, w.d_g);
+    c->launches++;
+    CK(cudaGetLastError());
+    out.resize((size_t)n * n);
+    CK(cudaMemcpyAsync(out.data(), w.d_g, sizeof(double2) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return LM_OK;
+}
+// dst = src * Msmall (nb x nb, row-major, host) on the dense GEMM kernels
+static int eig_rotate(EigWork& w, const void* src, void* dst, const std::vector<zc>& M) {
+    lm_ctx* c = w.c; const int n = w.nb;
+    if (c->precision == LM_C128) CK(cudaMemcpyAsync(w.d_small, M.data(), sizeof(zc) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+    else {
+        std::vector<std::complex<float>> f((size_t)n * n);
+        for (size_t k = 0; k < f.size(); ++k) f[k] = std::complex<float>((float)M[k].real(), (float)M[k].imag());
+        CK(cudaMemcpyAsync(w.d_small, f.data(), sizeof(std::complex<float>) * f.size(), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));          // f goes out of scope
+    }
+    FWD(dense_gemm(c, false, (int)w.N, n, n, src, w.ld, w.d_small, n, dst, w.ld));
+    if (c->precision == LM_C128) CK(cudaStreamSynchronize(c->stream));   // M is borrowed
+    return LM_OK;
+}
+// X <- orthonormal basis of span(X): G = X'X = V L V', X <- X V L^{-1/2} (SVQB), twice
+static int eig_orthonormalise(EigWork& w) {
+    const int n = w.nb;
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<zc> G, V; std::vector<double> lam;
+        FWD(eig_gram(w, w.X, w.X, G));
+        if (heig_jacobi(n, G, lam, V) < 0) return fail(LM_ERR_NOT_CONVERGED, "lm_eigs_lowest: Jacobi sweep limit (Gram matrix)");
+        const double lmax = std::max(lam.back(), 1e-300);
+        std::vector<zc> M((size_t)n * n);
+        for (int j = 0; j < n; ++j) {
+            const double sc = 1.0 / std::sqrt(std::max(lam[j], 1e-28 * lmax));
+            for (int i = 0; i < n; ++i) M[(size_t)i * n + j] = V[(size_t)i * n + j] * sc;
+        }
+        FWD(eig_rotate(w, w.X, w.T, M));
+        std::swap(w.X, w.T);
+    }
+    return LM_OK;
+}
+
+extern "C" int32_t lm_eigs_lowest(lm_ham* h, int32_t nev, double tol, int32_t max_iter, int32_t degree,
+                                  double* evals_out, double* resid_out, lm_state** vecs_out, int32_t* iters_out) {
+    REQUIRE(h && evals_out, "lm_eigs_lowest: NULL argument");
+    REQUIRE(nev >= 1 && nev <= 64, "lm_eigs_lowest: nev must be in 1..64");
+    REQUIRE(h->N >= 2 * (long long)nev + 32, "lm_eigs_lowest: matrix too small for the device solver (use the host eigen-decomposition)");
+    REQUIRE(tol > 0 && tol < 1, "lm_eigs_lowest: tol must be in (0, 1)");
+    REQUIRE(h->hermitian, "lm_eigs_lowest: H is not Hermitian");
+    lm_ctx* c = h->ctx; FWD(set_dev(c));
+    if (max_iter <= 0) max_iter = 300;
+    if (degree <= 0) degree = 40;
+    EigWork w; w.c = c; w.N = h->N;
+    w.nb = std::max(32, ((nev + std::max(8, nev / 2) + 7) / 8) * 8);
+    REQUIRE(w.nb <= 96, "lm_eigs_lowest: block too wide");
+    w.ld = pad_ld(w.nb);
+    const int n = w.nb;
+    const size_t bytes = c->esz() * (size_t)w.N * w.ld;
+    CK(cudaMalloc(&w.X, bytes)); CK(cudaMalloc(&w.Y, bytes)); CK(cudaMalloc(&w.HX, bytes)); CK(cudaMalloc(&w.T, bytes));
+    CK(cudaMalloc(&w.d_small, sizeof(zc) * (size_t)n * n)); CK(cudaMalloc(&w.d_g, sizeof(double2) * (size_t)n * n)); CK(cudaMalloc(&w.d_v, sizeof(double) * 2 * (size_t)n));
+    {   // seeded random start block
+        const long long tot = w.N * w.ld; const int th = 256;
+        if (c->precision == LM_C128) k_synth_block<double2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(w.N, n, w.ld, 0, 0x5eedull, std::sqrt(1.5 / (double)w.N), (double2*)w.X);
+        else k_synth_block<float2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(w.N, n, w.ld, 0, 0x5eedull, std::sqrt(1.5 / (double)w.N), (float2*)w.X);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    FWD(refresh_views(h));
+    FWD(eig_orthonormalise(w));
+    const double emax = h->emax, emin = h->emin, hnorm = std::max(std::max(std::fabs(emax), std::fabs(emin)), 1e-300);
+    const double floor_tol = (c->precision == LM_C128) ? 0.0 : 2e-6;
+    std::vector<double> theta(n), res(n, 1e300);
+    int it = 0; bool converged = false;
+    for (it = 1; it <= max_iter; ++it) {
+        // Rayleigh-Ritz on span(X)
+        std::vector<zc> S, Q;
+        FWD(apply(h, w.ld, w.X, w.HX, nullptr, nullptr, zc(1, 0), zc(0, 0), zc(0, 0), zc(0, 0)));
+        FWD(eig_gram(w, w.X, w.HX, S));
+        if (heig_jacobi(n, S, theta, Q) < 0) return fail(LM_ERR_NOT_CONVERGED, "lm_eigs_lowest: Jacobi sweep limit (Rayleigh-Ritz)");
+        FWD(eig_rotate(w, w.X, w.T, Q)); std::swap(w.X, w.T);
+        FWD(eig_rotate(w, w.HX, w.T, Q)); std::swap(w.HX, w.T);
+        // residuals ||H x_j - theta_j x_j||
+        CK(cudaMemcpyAsync(w.d_v, theta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(w.d_v + n, 0, sizeof(double) * n, c->stream));
+        {
+            const long long rpc = std::max<long long>(256, (w.N + 1023) / 1024);
+            dim3 grid((unsigned)((n + 31) / 32), (unsigned)((w.N + rpc - 1) / rpc));
+            if (c->precision == LM_C128) k_resid_norm2<double2><<<grid, 256, 0, c->stream>>>(w.N, n, w.ld, rpc, (const double2*)w.X, (const double2*)w.HX, w.d_v, w.d_v + n);
+            else k_resid_norm2<float2><<<grid, 256, 0, c->stream>>>(w.N, n, w.ld, rpc, (const float2*)w.X, (const float2*)w.HX, w.d_v, w.d_v + n);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(res.data(), w.d_v + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        double worst = 0.0;
+        for (int j = 0; j < n; ++j) { res[j] = std::sqrt(std::max(res[j], 0.0)); if (j < nev) worst = std::max(worst, res[j]); }
+        if (getenv("LM_DEBUG_PLAN")) fprintf(stderr, "lm_eigs_lowest: iteration %d, theta_0 %.12g, theta_nev %.12g, worst residual %.3e\n", it, theta[0], theta[nev - 1], worst);
+        if (worst <= std::max(tol, floor_tol) * hnorm) { converged = true; break; }
+        // Chebyshev filter: damp [a, b] = [theta_nb (largest Ritz value of the block), emax]; scaled three-term
+        // recurrence (no overflow): Y_1 = s1/e (H - c) X,  Y_{i+1} = 2 s_{i+1}/e (H - c) Y_i - s_i s_{i+1} Y_{i-1}
+        double a = theta[n - 1], b = emax;
+        if (!(b - a > 1e-8 * hnorm)) a = 0.5 * (theta[nev - 1] + emax);
+        const double a0 = std::min(theta[0], emin) - 1e-3 * hnorm;
+        const double e = 0.5 * (b - a), cen = 0.5 * (b + a);
+        double sig = e / (a0 - cen); const double sig1 = sig;
+        FWD(apply(h, w.ld, w.X, w.Y, nullptr, nullptr, zc(sig1 / e, 0), zc(-sig1 * cen / e, 0), zc(0, 0), zc(0, 0)));
+        for (int i = 2; i <= degree; ++i) {
+            const double sig2 = 1.0 / (2.0 / sig1 - sig);
+            // X <- 2 sig2/e (H - c) Y - sig sig2 X   (in place over the oldest term), then swap roles
+            FWD(apply(h, w.ld, w.Y, w.X, nullptr, w.X, zc(2.0 * sig2 / e, 0), zc(-2.0 * sig2 * cen / e, 0), zc(0, 0), zc(-sig * sig2, 0)));
+            std::swap(w.X, w.Y);
+            sig = sig2;
+        }
+        std::swap(w.X, w.Y);                                   // the filtered block
+        FWD(eig_orthonormalise(w));
+    }
+    if (iters_out) *iters_out = std::min(it, max_iter);
+    for (int j = 0; j < nev; ++j) { evals_out[j] = theta[j]; if (resid_out) resid_out[j] = res[j]; }
+    if (!converged) return fail(LM_ERR_NOT_CONVERGED, "lm_eigs_lowest: residual tolerance not reached within max_iter iterations");
+    if (vecs_out) {
+        lm_state* s = nullptr;
+        FWD(state_alloc(c, w.N, nev, false, &s));
+        const long long tot = w.N * s->ld; const int th = 256;
+        if (c->precision == LM_C128) k_copy_cols<double2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(w.N, nev, w.ld, (const double2*)w.X, s->ld, (double2*)s->d_x);
+        else k_copy_cols<float2><<<(unsigned)((tot + th - 1) / th), th, 0, c->stream>>>(w.N, nev, w.ld, (const float2*)w.X, s->ld, (float2*)s->d_x);
+        c->launches++;
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(c->stream);
+        if (e2 != cudaSuccess) { state_free(s); return fail(LM_ERR_CUDA, cudaGetErrorString(e2)); }
+        s->replicated = c->nranks > 1;                         // every rank computes the same vectors
+        *vecs_out = s;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return LM_OK;
+}
+// host Hermitian eigen-decomposition used above (tests): A n x n row-major complex128 -> w ascending, V columns
+extern "C" int32_t lm_dbg_heig(int32_t n, const void* A, double* w, void* V) {
+    REQUIRE(n >= 1 && A && w && V, "lm_dbg_heig: bad arguments");
+    std::vector<zc> a((const zc*)A, (const zc*)A + (size_t)n * n), v; std::vector<double> lam;
+    if (heig_jacobi(n, a, lam, v) < 0) return fail(LM_ERR_NOT_CONVERGED, "lm_dbg_heig: Jacobi sweep limit");
+    memcpy(w, lam.data(), sizeof(double) * n); memcpy(V, v.data(), sizeof(zc) * (size_t)n * n);
     return LM_OK;
 }
 

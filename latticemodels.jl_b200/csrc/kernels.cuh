@@ -736,6 +736,100 @@ k_colnorm2(long long N, long long M, long long ld, long long rows_per_cta, const
 }
 
 // ------------------------------------------------------------------------------------------
+// Device eigensolver support (lm_eigs_lowest): small-matrix reductions of
+// row-major [N][ld] blocks with n <= 96 columns.
+//   k_gram:        out[a][b] += sum_i conj(A[i][a]) B[i][b]        (out zeroed by the caller, double accumulation)
+//   k_resid_norm2: out[b]   += sum_i |HX[i][b] - theta[b] X[i][b]|^2
+//   k_copy_cols:   dst[i][c] = src[i][c] for c < n, 0 for the padding columns
+// ------------------------------------------------------------------------------------------
+constexpr int GRAM_MAXT = 6;                 // 16 x 16 threads, each up to 6 x 6 (a, b) pairs: n <= 96
+template <typename T2>
+__global__ void __launch_bounds__(256)
+k_gram(long long N, int n, long long ld, const T2* __restrict__ A, const T2* __restrict__ B, long long rows_per_cta, double2* __restrict__ out) {
+    LM_SMEM_STATIC double2 sA[8][96], sB[8][96];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long r0 = blockIdx.x * rows_per_cta, r1 = (r0 + rows_per_cta) < N ? (r0 + rows_per_cta) : N;
+    double2 acc[GRAM_MAXT][GRAM_MAXT];
+#pragma unroll
+    for (int p = 0; p < GRAM_MAXT; ++p)
+#pragma unroll
+        for (int q = 0; q < GRAM_MAXT; ++q) acc[p][q] = make_double2(0.0, 0.0);
+    for (long long rb = r0; rb < r1; rb += 8) {
+        for (int e = threadIdx.x; e < 8 * n; e += 256) {
+            const int r = e / n, c = e - r * n;
+            double2 va = make_double2(0.0, 0.0), vb = va;
+            if (rb + r < r1) {
+                const T2 x = A[(rb + r) * ld + c], y = B[(rb + r) * ld + c];
+                va = make_double2((double)x.x, (double)x.y); vb = make_double2((double)y.x, (double)y.y);
+            }
+            sA[r][c] = va; sB[r][c] = vb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < GRAM_MAXT; ++p) {
+            const int a = ty + 16 * p;
+            if (a >= n) break;
+#pragma unroll
+            for (int q = 0; q < GRAM_MAXT; ++q) {
+                const int b = tx + 16 * q;
+                if (b >= n) break;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const double2 x = sA[r][a], y = sB[r][b];            // conj(x) * y
+                    acc[p][q].x = fma(x.x, y.x, acc[p][q].x); acc[p][q].x = fma(x.y, y.y, acc[p][q].x);
+                    acc[p][q].y = fma(x.x, y.y, acc[p][q].y); acc[p][q].y = fma(-x.y, y.x, acc[p][q].y);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < GRAM_MAXT; ++p)
+#pragma unroll
+        for (int q = 0; q < GRAM_MAXT; ++q) {
+            const int a = ty + 16 * p, b = tx + 16 * q;
+            if (a < n && b < n) {
+                double* o = reinterpret_cast<double*>(out + (long long)a * n + b);
+                atomicAdd(o, acc[p][q].x); atomicAdd(o + 1, acc[p][q].y);
+            }
+        }
+}
+template <typename T2>
+__global__ void __launch_bounds__(256)
+k_resid_norm2(long long N, int n, long long ld, long long rows_per_cta, const T2* __restrict__ X, const T2* __restrict__ HX,
+              const double* __restrict__ theta, double* __restrict__ out) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long c = blockIdx.x * 32LL + tx;
+    const long long r0 = blockIdx.y * rows_per_cta, r1 = (r0 + rows_per_cta) < N ? (r0 + rows_per_cta) : N;
+    double acc = 0.0;
+    if (c < n) {
+        const double th = theta[c];
+        for (long long i = r0 + ty; i < r1; i += 8) {
+            const T2 x = X[i * ld + c], h = HX[i * ld + c];
+            const double re = (double)h.x - th * (double)x.x, im = (double)h.y - th * (double)x.y;
+            acc = fma(re, re, acc); acc = fma(im, im, acc);
+        }
+    }
+    LM_SMEM_STATIC double s[8][33];
+    s[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < n) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += s[q][tx];
+        atomicAdd(out + c, t);
+    }
+}
+template <typename T2>
+__global__ void k_copy_cols(long long N, long long n, long long ld_src, const T2* __restrict__ src, long long ld_dst, T2* __restrict__ dst) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= N * ld_dst) return;
+    const long long i = e / ld_dst, c = e - i * ld_dst;
+    T2 v; v.x = 0; v.y = 0;
+    if (c < n) v = src[i * ld_src + c];
+    dst[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------
 // layout change column-major (host) <-> row-major [N][ld] (device), 32x32 smem tiles.
 // src: N x Mc column-major with leading dimension N; dst rows i, columns c0 + [0, Mc).
 // ------------------------------------------------------------------------------------------

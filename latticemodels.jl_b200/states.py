@@ -71,6 +71,27 @@ def groundstate(ham):
     return V[:, 0].copy()
 
 
+def eigs_lowest(ham, n=10, tol=1e-10, ctx=None, max_iter=0, degree=0):
+    """Lowest ``n`` eigenpairs ON THE DEVICE (``diagonalize(ham, :krylovkit; n)``, src/spectrum.jl:56-64, for sizes
+    where the host eigen-decomposition is impossible): returns ``(E, DeviceState)`` - ascending eigenvalues and a
+    device block of the n orthonormal eigenvectors (the Fermi sphere of the n lowest levels, ready for Evolution).
+    ``eigs_lowest.info`` holds the residual norms and the iteration count of the last call."""
+    ctx = ctx or default_context()
+    dev = ham.device(ctx)
+    E, res = np.zeros(n), np.zeros(n)
+    h, it = C.c_void_p(), C.c_int32()
+    _lib.check(_lib.load().lm_eigs_lowest(dev.handle, int(n), float(tol), int(max_iter), int(degree), E.ctypes.data_as(C.POINTER(C.c_double)),
+                                          res.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h), C.byref(it)))
+    eigs_lowest.info = dict(residuals=res, iterations=it.value)
+    return E, DeviceState(ctx, h, getattr(ham, "lattice", None), getattr(ham, "n_int", 1), n, (0, n))
+
+
+def groundstate_device(ham, tol=1e-10, ctx=None):
+    """``groundstate(ham)`` (src/spectrum.jl:205) on the device: ``(E0, DeviceState)`` with one column."""
+    E, st = eigs_lowest(ham, 1, tol, ctx)
+    return float(E[0]), st
+
+
 class DeviceState:
     """Owner of an ``lm_state`` handle (a Psi block shard or a dense density matrix)."""
 

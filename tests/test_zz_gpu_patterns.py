@@ -369,3 +369,68 @@ def test_dense_path_large_tiles_3m_kernel():
     assert _relerr(st.download(), want) < 1e-12
     stb = lm.DeviceState.from_psi(X, w, ctx=ctx, n_int=1)
     assert _relerr(stb.dense(), P) < 1e-13
+
+
+@pytest.mark.parametrize("case", ["qwz", "haldane_pbc", "square_field"])
+def test_device_eigensolver_lowest_states(case):
+    """N1: lm_eigs_lowest - Chebyshev-filtered subspace iteration on the device -
+    against the host eigen-decomposition: eigenvalues, residuals, orthonormality, and the density of the
+    resulting Fermi sphere (invariant under rotations inside degenerate levels)."""
+    ctx = lm.default_context("c128")
+    if case == "qwz":
+        Hd, Ho, n_int = lm.qwz(lm.SquareLattice(12, 11)), OP.qwz(L.square_lattice(12, 11)), 2
+    elif case == "haldane_pbc":
+        Hd = lm.haldane(lm.HoneycombLattice(9, 8, boundaries=[("axis1", True)]), 1.0, 0.2, 0.1)
+        Ho, n_int = OP.haldane(L.honeycomb_lattice(9, 8, periodic=(1,)), 1.0, 0.2, 0.1), 1
+    else:
+        Hd = lm.tightbinding_hamiltonian(lm.SquareLattice(17, 13), field=lm.LandauGauge(0.11))
+        Ho, n_int = OP.tightbinding_hamiltonian(L.square_lattice(17, 13), field=F.LandauGauge(0.11)), 1
+    E, V = np.linalg.eigh(Ho.toarray())
+    for nev in (1, 10):
+        vals, st = lm.eigs_lowest(Hd, nev, tol=1e-10, ctx=ctx)
+        assert np.abs(vals - E[:nev]).max() < 1e-9, (case, nev, vals - E[:nev])
+        X = st.download()
+        assert X.shape == (Ho.shape[0], nev)
+        assert np.abs(X.conj().T @ X - np.eye(nev)).max() < 1e-12
+        R = Ho @ X - X * vals[None, :]
+        assert np.linalg.norm(R, axis=0).max() < 1e-9 * max(abs(E[0]), abs(E[-1])) * 2
+        assert np.all(lm.eigs_lowest.info["residuals"] < 1e-9 * 10)
+        if nev == 10 and E[10] - E[9] > 1e-6:                  # closed shell: the projector is unique
+            rho = lm.localdensity(st).values
+            want = (np.abs(V[:, :10]) ** 2).sum(1).reshape(-1, n_int).sum(1)
+            assert _relerr(rho, want) < 1e-7
+    e0, g = lm.groundstate_device(Hd, ctx=ctx)
+    assert abs(e0 - E[0]) < 1e-9 and g.M == 1
+
+
+def test_host_hermitian_jacobi_of_the_eigensolver():
+    """small_la.h heig_jacobi (the only host arithmetic of lm_eigs_lowest: nb x nb matrices) against numpy."""
+    lib = _lib.load()
+    lib.lm_dbg_heig.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lm_dbg_heig.restype = C.c_int32
+    rng = np.random.default_rng(8)
+    for n in (1, 5, 40):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        A = np.ascontiguousarray(A + A.conj().T)
+        w, V = np.zeros(n), np.zeros((n, n), complex)
+        _lib.check(lib.lm_dbg_heig(n, _lib.ptr(A), _lib.ptr(w), _lib.ptr(V)))
+        assert np.abs(w - np.linalg.eigvalsh(A)).max() < 1e-12 * max(1.0, np.abs(A).max()) * n
+        assert np.abs(A @ V - V * w[None, :]).max() < 1e-12 * n * max(1.0, np.abs(A).max())
+        assert np.abs(V.conj().T @ V - np.eye(n)).max() < 1e-13 * n
+
+
+def test_device_eigensolver_full_size_against_closed_form():
+    """lm_eigs_lowest at N = 2e5 (beyond any host eigen-decomposition): the open 500 x 400 square lattice has the
+    closed-form spectrum E = 2 cos(pi k / 501) + 2 cos(pi l / 401); the 12 lowest levels, their residuals against the
+    host-assembled H, and orthonormality."""
+    ctx = lm.default_context("c128")
+    n1, n2 = 500, 400
+    H = lm.tightbinding_hamiltonian(lm.SquareLattice(n1, n2))
+    k, l = np.arange(1, n1 + 1), np.arange(1, n2 + 1)
+    exact = np.sort((2 * np.cos(np.pi * k / (n1 + 1))[:, None] + 2 * np.cos(np.pi * l / (n2 + 1))[None, :]).ravel())[:12]
+    vals, st = lm.eigs_lowest(H, 12, tol=1e-9, ctx=ctx)
+    assert np.abs(vals - exact).max() < 1e-8, vals - exact
+    X = st.download()
+    assert np.abs(X.conj().T @ X - np.eye(12)).max() < 1e-11
+    R = H.data @ X - X * vals[None, :]
+    assert np.linalg.norm(R, axis=0).max() < 4e-8
