@@ -412,6 +412,7 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
     }
 
     const T2c alpha = cmake<T2c>(a.alpha[0], a.alpha[1]);
+    const bool unit_alpha = a.alpha[0] == 1.0 && a.alpha[1] == 0.0;
     const T2c beta  = cmake<T2c>(a.beta[0],  a.beta[1]);
     const T2c delta = cmake<T2c>(a.delta[0], a.delta[1]);
     E* y = (E*)a.y;
@@ -431,7 +432,8 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
                     if (cj >= nce) continue;
                     const long long e = row * lde + cj;
                     E res;
-                    pscale(res, alpha, acc[v1][v2][aa][j]);
+                    if (unit_alpha) res = acc[v1][v2][aa][j];           // scaling deferred to a later factor (run_factors)
+                    else pscale(res, alpha, acc[v1][v2][aa][j]);
                     if (MODE == 1) pfma(res, beta, ld_stream(z + e));
                     if (MODE == 2) {
                         if (z) pfma(res, beta, ld_stream(z + e));
