@@ -123,6 +123,12 @@ __device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const void* tmap, in
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
+// L2 prefetch of the same box (no shared-memory destination, no barrier): issued for the patch a LATER CTA will
+// stage, so that its tensor-map copy is served by L2 instead of HBM
+__device__ __forceinline__ void tma_tensor3d_prefetch_l2(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 :: "l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // programmatic dependent launch (griddepcontrol): no-ops for a grid launched without the attribute
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

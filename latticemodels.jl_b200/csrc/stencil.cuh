@@ -71,6 +71,7 @@ struct StencilArgs {
                                     //    and wait for the previous grid before touching global memory
     int herm;                       // 1: H is Hermitian (checked on the device): in-tile bonds share one value load (st_tile_herm)
     int tmap;                       // 1: interior patches stage their haloed block with ONE 3-D tensor-map copy (k_apply_stencil_tma)
+    unsigned pf;                    // > 0: every CTA also prefetches into L2 the box of the CTA `pf` positions later in dispatch order
     const void* x; void* y; const void* z; const void* u;
     double alpha[2], g[2], beta[2], delta[2];   // y = alpha (H x + g x) + beta z + delta u
     unsigned cps, nchunks;
@@ -377,6 +378,20 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
     }
     for (int l = NT - 1 - tid; l < vl1; l += NT)
         tma_bulk_g2s(sh + l * (P2 * RC * SWP), sv + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWP), hline, &bar);
+    // The wait for the staged block is the largest stall of this kernel (42 % of the warp samples, profiles/r2/).
+    // Opt-in (a.pf > 0, LM_STENCIL_PF): every CTA also asks the TMA engine to pull into L2 the box of the CTA that
+    // will be dispatched `pf` positions later, whose own copy is then an L2 hit.  A hint only: nothing waits on
+    // it.  Measured neutral (the wait shrinks, the kernel time does not): off by default.
+    if (a.pf && a.tmap && tid == 32 % NT) {
+        const unsigned long long lin = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x + a.pf;
+        if (lin < (unsigned long long)gridDim.x * gridDim.y) {
+            const unsigned bx = (unsigned)(lin % gridDim.x), by = (unsigned)(lin / gridDim.x);
+            const unsigned patch2 = bx / a.cps, chunk2 = by * a.cps + (bx - patch2 * a.cps);
+            const int p1 = (int)(patch2 / (unsigned)a.np2) * P1, p2 = (int)(patch2 % (unsigned)a.np2) * P2;
+            if (chunk2 < a.nchunks && p1 >= 1 && p1 + P1 + 1 <= a.n1 && p2 >= 1 && p2 + P2 + 1 <= a.n2)
+                tma_tensor3d_prefetch_l2(&tmx, (int)((long long)chunk2 * CE * (long long)(sizeof(E) / 8)), (p2 - 1) * RC, p1 - 1);
+        }
+    }
 
     const int w1 = warp / W2, w2 = warp % W2;
     const int q1 = o1 + w1 * T1, q2 = o2 + w2 * T2;         // first cell of this warp's register tile

@@ -279,6 +279,7 @@ inline void tma_tensor3d_g2s(void* dst, const void* tmap, int c0, int c1, int c2
     b.tx -= bytes; lm_emul::bulk_bytes() += bytes; lm_emul::mbar_settle(b);
     lm_emul::cta().progress = true;
 }
+inline void tma_tensor3d_prefetch_l2(const void*, int, int, int) {}      // a cache hint: nothing to emulate
 // mma.sync.aligned.m8n8k4.row.col.f64: lane l holds A[l>>2][l&3], B[l&3][l>>2], C[l>>2][2(l&3) + {0,1}]
 inline void dmma(double& d0, double& d1, double a, double b) {
     lm_emul::Cta& c = lm_emul::cta();

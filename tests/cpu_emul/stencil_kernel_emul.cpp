@@ -93,7 +93,7 @@ static bool check_apply(const char* name, int n1, int n2, bool periodic, long lo
 
     const zc alpha(rnd(), rnd()), g(rnd(), rnd()), beta(rnd(), rnd()), delta(rnd(), rnd());
     StencilArgs a;
-    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.pdl = 0; a.herm = herm ? 1 : 0; a.tmap = tmap ? 1 : 0;
+    a.svals = sv.data(); a.n1 = n1; a.n2 = n2; a.ld = ld; a.pdl = 0; a.herm = herm ? 1 : 0; a.tmap = tmap ? 1 : 0; a.pf = 5;
     a.x = x.data() + c_off / EC; a.y = y.data() + c_off / EC;
     a.z = (MODE == 1 || MODE == 2) ? z.data() + c_off / EC : nullptr;
     a.u = (MODE == 2) ? u.data() + c_off / EC : nullptr;
