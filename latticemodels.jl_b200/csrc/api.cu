@@ -707,9 +707,9 @@ static int ham_build_stencil(lm_ham* h) {
     CK(cudaMemcpy(h->d_st_out, outm.data(), sizeof(int) * outm.size(), cudaMemcpyHostToDevice));
     h->st_nf = NF;
     CK(cudaMalloc(&h->d_st_src, sizeof(int) * src.size()));
-    // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes
-    CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 256));
-    CK(cudaMemset(h->d_svals, 0, c->esz() * src.size() + 256));
+    // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes; direct loads of a ragged tile run past the last cell
+    CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 4096));
+    CK(cudaMemset(h->d_svals, 0, c->esz() * src.size() + 4096));
     CK(cudaMemcpy(h->d_st_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
     h->st_id = id; h->st_rc = rc; h->st_sw = SW; h->st_mask = mask;
     return LM_OK;
