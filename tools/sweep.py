@@ -45,13 +45,10 @@ def run_case(ctx, kind, n, M, reps, tol=1e-12, what=("spmm", "step", "triad", "o
     dev = H.device(ctx)
     N = dev.N
     esz = 16 if ctx.precision == _lib.LM_C128 else 8
-    rng = np.random.default_rng(1)
-    blk = ((rng.random((N, min(M, 64))) - 0.5) + 1j * (rng.random((N, min(M, 64))) - 0.5))
-    psi = np.asfortranarray(np.tile(blk, (1, (M + blk.shape[1] - 1) // blk.shape[1]))[:, :M].astype(_lib.cdtype(ctx.precision)))
-    x = lm.DeviceState.from_psi(psi, ctx=ctx, shard=False)
+    # device-generated block (uniform complex in [-1, 1]^2): no multi-GB host arrays
+    x = lm.DeviceState.synthetic(N, M, ctx=ctx, seed=1, shard=False)
     y = x.copy()
     z = x.copy()
-    del psi
     bytes_spmm = 2.0 * N * M * esz + dev.nnz * (esz + 4) + 4.0 * (N + 1)
     out = dict(kind=kind, n=n, N=N, M=M, W=dev.W, nnz=dev.nnz, precision="c128" if esz == 16 else "c64")
     pk = peak()
