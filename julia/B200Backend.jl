@@ -242,7 +242,8 @@ mutable struct B200Exp <: EvolutionSolver
 end
 # B200Exp(; kw...) without a Hamiltonian comes for free via IncompleteSolver (src/evolution.jl:219-231);
 # Evolution then calls B200Exp(hamiltonian; kw...) with whatever the user passed (operator, function of t, matrix)
-function B200Exp(ham; tol = 1e-12, method = 0, ctx = default_context())
+function B200Exp(ham; tol = 1e-12, method = 0, precision::Symbol = :c128,
+                 ctx = precision === :c128 ? default_context() : Context(precision = precision))
     h0 = LatticeModels._eval_ham(ham, 0.0)
     if h0 isa DataOperator && basis(h0) isa LatticeModels.AbstractLatticeBasis
         B200Exp(ctx, nothing, nothing, 0.0, tol, Int32(method), internal_length(h0), lattice(h0))
@@ -402,7 +403,11 @@ end
 # currentsfromto / currentsfrom (src/currents.jl:85-109) summed on the device: only one number / one
 # LatticeValue crosses PCIe.  Regions go through the reference's own `to_inds`.
 function region_mask(l, region)
-    m = zeros(UInt8, length(l)); m[to_inds(l, region)] .= 1; m
+    m = zeros(UInt8, length(l))
+    for i in to_inds(l, region)          # a single site gives one Int, a collection / mask a vector of them
+        m[i] = 1
+    end
+    m
 end
 function currentsfromto(curr::DevDensityCurrents, src, dst = nothing)
     l = lattice(curr); out = Ref{Float64}(0.0)
@@ -511,6 +516,20 @@ function field_descr(f::LatticeModels.FieldSum)
     parts = map(field_descr, f.fields)
     (reduce(vcat, first.(parts); init = Int32[]), reduce(vcat, last.(parts); init = Float64[]))
 end
+# every (site1, site2) pair of a bonds description, as add_term! enumerates them (src/operators/constructoperator.jl:14-38):
+# a NearestNeighbor / BravaisSiteMapping adapts to a set of translations, each of which iterates its site pairs
+function foreach_bond(f, what, l)
+    b = adapt_bonds(what, l)
+    if b isa LatticeModels.BravaisSiteMapping
+        for tr in b.translations
+            foreach_bond(f, tr, l)
+        end
+    else
+        for (a1, a2) in b
+            f(a1, a2)
+        end
+    end
+end
 """
     B200Hamiltonian(template, terms...; field = t -> NoField())
 
@@ -534,10 +553,9 @@ function B200Hamiltonian(template::LatticeModels.Hamiltonian, terms::Pair...; fi
         elseif what isa Number
             for i in 1:ns; onsite[:, :, i] .+= what .* B; end; has_onsite = true
         else
-            bonds = what isa LatticeModels.BravaisSiteMapping ? what.translations : (what,)
-            for b in bonds, (a1, a2) in adapt_bonds(b, l)
+            foreach_bond(what, l) do a1, a2
                 s1 = LatticeModels.resolve_site(l, a1); s2 = LatticeModels.resolve_site(l, a2)
-                (s1 === nothing || s2 === nothing) && continue
+                (s1 === nothing || s2 === nothing) && return
                 push!(src, s1.index); push!(dst, s2.index)
                 append!(rs, s1.old_site.coords[1:2]); append!(rd, s2.old_site.coords[1:2])
                 append!(amp, vec(B)); push!(bf, s2.factor * s1.factor')
