@@ -639,6 +639,7 @@ struct StencilObsArgs {
     const int* out;                 // [N][NF]
     double* dens; double2* G;
     unsigned ngroups, cpg, nchunks; // column groups per patch, chunks per group, chunks in total
+    unsigned npatch;                // patches (grid = ngroups x npatch, patch fastest)
     int tmap;                       // 1: patches whose forward-haloed block lies inside the lattice stage it with ONE tensor-map copy per chunk
 };
 
@@ -677,7 +678,10 @@ k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx
     LM_SMEM_STATIC __align__(8) unsigned long long bar[NS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned patch = blockIdx.x / a.ngroups, group = blockIdx.x - patch * a.ngroups;
+    // patch fastest: the CTAs of one column group sweep the lattice together, so the forward-halo rows that
+    // neighbouring patches share are read while they are still in L2 (group-fastest order with one long group
+    // per patch re-read them from HBM: 1.26x the algorithmic traffic at M = 4096, profiles/r2/bench_default_ncu_r2.md)
+    const unsigned group = blockIdx.x / a.npatch, patch = blockIdx.x - group * a.npatch;
     const int pj1 = (int)(patch / (unsigned)a.np2), pj2 = (int)(patch - (unsigned)pj1 * (unsigned)a.np2);
     const int o1 = pj1 * P1, o2 = pj2 * P2;
     const long long lde = a.ld / EC;

@@ -201,7 +201,7 @@ static bool check_observe(const char* name, int n1, int n2, bool periodic, long 
     const long long nchunks = (lde + 31) / 32;
     const long long cpg = std::max<long long>(1, std::min<long long>(cpg_req, nchunks));
     const long long ngroups = (nchunks + cpg - 1) / cpg;
-    a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg; a.nchunks = (unsigned)nchunks;
+    a.ngroups = (unsigned)ngroups; a.cpg = (unsigned)cpg; a.nchunks = (unsigned)nchunks; a.npatch = (unsigned)(np1 * np2);
     a.tmap = tmap ? 1 : 0;
     CUtensorMap tmx{x.data(), {(unsigned long long)ld * (2 * sizeof(T) / 8), (unsigned long long)n2 * RC, (unsigned long long)n1},
                     {(unsigned long long)ld * 2 * sizeof(T), (unsigned long long)n2 * RC * ld * 2 * sizeof(T)},
