@@ -530,6 +530,7 @@ def main():
     ap.add_argument("--cpu-cols", type=int, default=0, help="columns of the cpu_baseline sample (0 = 8 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--M", type=int, default=0, help="override the block width")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the c3 / c2 sub-objects")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -562,142 +563,167 @@ def main():
     if world > 1:
         D.attach_communicator(ctx)
 
-    wl = workload(args.workload)
-    if args.M:
-        wl["M"] = args.M
-    H0 = wl["ham"](0.0)
-    N, M, dt = H0.structure.dim, wl["M"], wl["dt"]
-    b, e = lm.shard_range(M, rank, world)
-    Ml = e - b
-    esz = 16 if args.precision == "c128" else 8
-    cdt = np.complex128 if args.precision == "c128" else np.complex64
-    # the block is generated on the device (a 32.8 GB host block would take minutes): this rank's
-    # column shard [b, e) of the seeded N x M block (tests/synth.py restates the generator)
-    state = lm.DeviceState.synthetic(N, M, ctx=ctx, seed=1234, lattice=H0.lattice, n_int=H0.n_int)
-    assert state.col_range == (b, e) and state.M == Ml
-    sol = lm.B200Exp(tol=args.tol, method=args.method, precision=args.precision, ctx=ctx)
     lib = _lib.load()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def run_block(wname, steps, warmup):
+        """One Psi-block workload on the already initialised context: the `value` leg, the roofline of the dominant
+        kernel, the `e2e` leg and the in-run parity checks.  Returns (bench line, workload dict)."""
+        wl = workload(wname)
+        if args.M:
+            wl["M"] = args.M
+        H0 = wl["ham"](0.0)
+        N, M, dt = H0.structure.dim, wl["M"], wl["dt"]
+        b, e = lm.shard_range(M, rank, world)
+        Ml = e - b
+        esz = 16 if args.precision == "c128" else 8
+        cdt = np.complex128 if args.precision == "c128" else np.complex64
+        # the block is generated on the device (a 32.8 GB host block would take minutes): this rank's
+        # column shard [b, e) of the seeded N x M block (tests/synth.py restates the generator)
+        state = lm.DeviceState.synthetic(N, M, ctx=ctx, seed=1234, lattice=H0.lattice, n_int=H0.n_int)
+        assert state.col_range == (b, e) and state.M == Ml
+        sol = lm.B200Exp(tol=args.tol, method=args.method, precision=args.precision, ctx=ctx)
+        lib = _lib.load()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, n, tail=None):
+            barrier()
+            t0 = time.time()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for k in range(n):
+                fn(k)
+            if tail is not None:
+                tail()
+            ev1.record()
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, t0, time.time()
+
+        # ---------------- device-resident steps (the headline `value`) ----------------
+        tcur = [0.0]
+
+        def dev_step(k):
+            sol.update_solver(wl["ham"](tcur[0]), dt)      # device phase regeneration if time dependent
+            sol.step(state)
+            tcur[0] += dt
+        for k in range(warmup):
+            dev_step(k)
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        l0 = ctx.launch_count()
+        ms, t0, t1 = timed(dev_step, steps)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop(t0, t1)
+        K = sol.n_matvec
+        ms_per_step = ms / steps
+        value = 1e3 / ms_per_step
+
+        # ---------------- roofline of the dominant kernel ----------------
+        dev = sol.dev
+        nnz = dev.nnz
+        bytes_spmm = 2.0 * N * Ml * esz + nnz * (esz + 4) + 4.0 * (N + 1)
+        n_apply = steps * K
+        avg_launch_ms = ms / max(n_apply, 1)            # the step is K back-to-back k_apply launches
+        achieved = bytes_spmm / (avg_launch_ms * 1e-3) / 1e9
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_file):
+            peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None                                   # DRAM bytes are not measured inside this run (ncu captures: profiles/)
+        sid = C.c_int32(-1)
+        lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
+        lib.lm_dbg_stencil_info(dev.handle, C.byref(sid), None, None, None)
+        kernel = ("lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells, shared value loads for Hermitian H)"
+                  if (sid.value >= 0 and state.M >= 32) else "lm::k_apply / k_apply_rows (ELL gather SpMM fused with one product-form propagator factor)")
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "bytes_per_launch": bytes_spmm, "launches_timed": n_apply, "avg_launch_ms": avg_launch_ms,
+                    "K_matvec_per_step": K}
+
+        # ---------------- end to end through the C ABI with host buffers ----------------
+        Hmat = H0.data                                    # host-assembled CSC (what t -> H(t) returns)
+        lat = H0.lattice
+        dims = lat.sizes if len(lat) == lat.sizes[0] * lat.sizes[1] * lat.nb else None   # unfiltered: rows are cell-major
+        csc_dev = lm.DeviceHam.from_csc(ctx, Hmat, H0.n_int, coords=lat.coords, lattice_dims=dims)
+        nz_pinned = torch.empty(nnz * (2 if esz == 16 else 1), dtype=torch.float64 if esz == 16 else torch.complex64).pin_memory()
+        nz_np = nz_pinned.numpy().view(cdt)
+        nz_np[:] = Hmat.data.astype(cdt)
+        npairs = len(csc_dev.pairs()[0])
+        n_sites = N // H0.n_int
+        rho_pinned = torch.empty(n_sites, dtype=torch.float64).pin_memory()
+        j_pinned = torch.empty(max(npairs, 1), dtype=torch.float64).pin_memory()
+        rho_np, j_np = rho_pinned.numpy(), j_pinned.numpy()
+        nmv = C.c_int32()
+        method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4, "chebyshev_clenshaw": 5}[args.method]
+
+        # every step: nzval host -> device, one propagation step, the frame [rho | J] device -> host through
+        # the asynchronous frame sink (double-buffered: the copy of frame k overlaps step k + 1; every
+        # frame is read back inside the timed region, the last one by `drain`)
+        pending = []
+
+        def drain():
+            while pending:
+                _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))
+
+        slot = [0]
+
+        def e2e_step(k):
+            _lib.check(lib.lm_ham_update_values_async(csc_dev.handle, _lib.ptr(nz_np)))            # H2D (pinned buffer; enclosure checked on the device)
+            _lib.check(lib.lm_step(csc_dev.handle, state.handle, dt, args.tol, method, C.byref(nmv)))
+            if len(pending) == 2:
+                _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))   # D2H of frame k - 2 lands
+            _lib.check(lib.lm_observables_async(csc_dev.handle, state.handle, slot[0], 1))
+            pending.append(slot[0])
+            slot[0] ^= 1
+        for k in range(warmup):
+            e2e_step(k)
+        drain()
+        ms_e2e, _, _ = timed(e2e_step, steps, tail=drain)
+        e2e = {"value": 1e3 / (ms_e2e / steps), "unit": "steps/s", "h2d_bytes_per_step": int(nnz * esz),
+               "d2h_bytes_per_step": int(8 * (n_sites + npairs)),
+               "what": "lm_ham_update_values_async(pinned nzval) + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
+        parity = parity_check(lm, _lib, lib, torch, dist, ctx, csc_dev, state, Hmat, H0, rho_np.copy(), N, M, dt, args, rank, world, local, cdt)
+
+        out = {"metric": "evolution steps/sec (N x Nocc Psi block)", "value": value, "unit": "steps/s", "n_gpus": world,
+               "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
+               "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
+                          "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
+                          "schedule": {"pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(steps, 1),
+                                       "stencil_shared_value_loads": int(os.environ.get("LM_STENCIL_HERM", "1") or 0), "stencil_tensor_map_boxes": int(os.environ.get("LM_STENCIL_TMAP", "1") or 0)},
+                          "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": parity}
+
+        import gc
+        del state, csc_dev, sol
+        gc.collect()
         torch.cuda.synchronize()
+        return out, wl
 
-    def timed(fn, n, tail=None):
-        barrier()
-        t0 = time.time()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for k in range(n):
-            fn(k)
-        if tail is not None:
-            tail()
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, t0, time.time()
-
-    # ---------------- device-resident steps (the headline `value`) ----------------
-    tcur = [0.0]
-
-    def dev_step(k):
-        sol.update_solver(wl["ham"](tcur[0]), dt)      # device phase regeneration if time dependent
-        sol.step(state)
-        tcur[0] += dt
-    for k in range(args.warmup):
-        dev_step(k)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    l0 = ctx.launch_count()
-    ms, t0, t1 = timed(dev_step, args.steps)
-    launches = ctx.launch_count() - l0
-    clocks = sampler.stop(t0, t1)
-    K = sol.n_matvec
-    ms_per_step = ms / args.steps
-    value = 1e3 / ms_per_step
-
-    # ---------------- roofline of the dominant kernel ----------------
-    dev = sol.dev
-    nnz = dev.nnz
-    bytes_spmm = 2.0 * N * Ml * esz + nnz * (esz + 4) + 4.0 * (N + 1)
-    n_apply = args.steps * K
-    avg_launch_ms = ms / max(n_apply, 1)            # the step is K back-to-back k_apply launches
-    achieved = bytes_spmm / (avg_launch_ms * 1e-3) / 1e9
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_file):
-        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None                                   # DRAM bytes are not measured inside this run (ncu captures: profiles/)
-    sid = C.c_int32(-1)
-    lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
-    lib.lm_dbg_stencil_info(dev.handle, C.byref(sid), None, None, None)
-    kernel = ("lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells, shared value loads for Hermitian H)"
-              if (sid.value >= 0 and state.M >= 32) else "lm::k_apply / k_apply_rows (ELL gather SpMM fused with one product-form propagator factor)")
-    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": bytes_spmm, "launches_timed": n_apply, "avg_launch_ms": avg_launch_ms,
-                "K_matvec_per_step": K}
-
-    # ---------------- end to end through the C ABI with host buffers ----------------
-    Hmat = H0.data                                    # host-assembled CSC (what t -> H(t) returns)
-    lat = H0.lattice
-    dims = lat.sizes if len(lat) == lat.sizes[0] * lat.sizes[1] * lat.nb else None   # unfiltered: rows are cell-major
-    csc_dev = lm.DeviceHam.from_csc(ctx, Hmat, H0.n_int, coords=lat.coords, lattice_dims=dims)
-    nz_pinned = torch.empty(nnz * (2 if esz == 16 else 1), dtype=torch.float64 if esz == 16 else torch.complex64).pin_memory()
-    nz_np = nz_pinned.numpy().view(cdt)
-    nz_np[:] = Hmat.data.astype(cdt)
-    npairs = len(csc_dev.pairs()[0])
-    n_sites = N // H0.n_int
-    rho_pinned = torch.empty(n_sites, dtype=torch.float64).pin_memory()
-    j_pinned = torch.empty(max(npairs, 1), dtype=torch.float64).pin_memory()
-    rho_np, j_np = rho_pinned.numpy(), j_pinned.numpy()
-    nmv = C.c_int32()
-    method = {"auto": 0, "chebyshev": 1, "taylor": 2, "taylor_horner": 4, "chebyshev_clenshaw": 5}[args.method]
-
-    # every step: nzval host -> device, one propagation step, the frame [rho | J] device -> host through
-    # the asynchronous frame sink (double-buffered: the copy of frame k overlaps step k + 1; every
-    # frame is read back inside the timed region, the last one by `drain`)
-    pending = []
-
-    def drain():
-        while pending:
-            _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))
-
-    slot = [0]
-
-    def e2e_step(k):
-        _lib.check(lib.lm_ham_update_values_async(csc_dev.handle, _lib.ptr(nz_np)))            # H2D (pinned buffer; enclosure checked on the device)
-        _lib.check(lib.lm_step(csc_dev.handle, state.handle, dt, args.tol, method, C.byref(nmv)))
-        if len(pending) == 2:
-            _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))   # D2H of frame k - 2 lands
-        _lib.check(lib.lm_observables_async(csc_dev.handle, state.handle, slot[0], 1))
-        pending.append(slot[0])
-        slot[0] ^= 1
-    for k in range(args.warmup):
-        e2e_step(k)
-    drain()
-    ms_e2e, _, _ = timed(e2e_step, args.steps, tail=drain)
-    e2e = {"value": 1e3 / (ms_e2e / args.steps), "unit": "steps/s", "h2d_bytes_per_step": int(nnz * esz),
-           "d2h_bytes_per_step": int(8 * (n_sites + npairs)),
-           "what": "lm_ham_update_values_async(pinned nzval) + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
-    parity = parity_check(lm, _lib, lib, torch, dist, ctx, csc_dev, state, Hmat, H0, rho_np.copy(), N, M, dt, args, rank, world, local, cdt)
-
-    out = {"metric": "evolution steps/sec (N x Nocc Psi block)", "value": value, "unit": "steps/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-           "scaling": "strong", "vs_baseline": None, "dtype": "complex128" if esz == 16 else "complex64", "data": "synthetic",
-           "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
-                      "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
-                      "schedule": {"pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(args.steps, 1),
-                                   "stencil_shared_value_loads": int(os.environ.get("LM_STENCIL_HERM", "1") or 0), "stencil_tensor_map_boxes": int(os.environ.get("LM_STENCIL_TMAP", "1") or 0)},
-                      "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": parity}
-
+    out, wl = run_block(args.workload, args.steps, args.warmup)
+    # continuity with round 1 and driver-run evidence for the other Psi-block configs: the default run (c4) also
+    # carries config 3 (QWZ 300 x 300, Landau ramp regenerated on the device every step) and config 2 as sub-objects
+    if args.workload == "c4" and not args.M and not args.no_secondary:
+        out["secondary"] = {}
+        for w in ("c3", "c2"):
+            try:
+                o, _ = run_block(w, args.steps, args.warmup)
+                out["secondary"][w] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
+                                       "e2e": o["e2e"]["value"], "roofline_frac": o["roofline"]["frac"], "roofline_achieved_gbs": o["roofline"]["achieved"],
+                                       "K_matvec_per_step": o["roofline"]["K_matvec_per_step"], "gpu_launches": o["gpu_launches"],
+                                       "clocks": o["clocks"], "parity_max_rel": o["parity_check"].get("max_rel")}
+            except Exception as ex:        # the headline line must not depend on the sub-objects
+                out["secondary"][w] = {"error": repr(ex)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, per_step, info = cpu_reference_rate(wl, args.cpu_cols if args.cpu_cols > 0 else -8, 3)
         out["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
