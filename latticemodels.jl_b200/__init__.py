@@ -10,10 +10,10 @@ from .build import build  # noqa: F401
 from .context import Context, default_context, shard_range  # noqa: F401
 from .fields import (FieldSum, LandauGauge, NoField, PointFlux, PointFluxes,  # noqa: F401
                      SymmetricGauge)
-from .lattices import (Bravais, BravaisLattice, BravaisTranslation, HoneycombLattice,  # noqa: F401
-                       NearestNeighbor, SquareLattice, honeycomb_2nn)
+from .lattices import (Bravais, BravaisLattice, BravaisTranslation, HoneycombLattice, KagomeLattice,  # noqa: F401
+                       NearestNeighbor, SquareLattice, TriangularLattice, honeycomb_2nn)
 from .hamiltonian import (DeviceHam, Hamiltonian, construct_hamiltonian, construct_operator,  # noqa: F401
-                          haldane, qwz, tightbinding_hamiltonian)
+                          haldane, kanemele, qwz, tightbinding_hamiltonian)
 from .states import (DeviceState, PsiProjector, densitymatrix, diagonalize, eigs_lowest, groundstate,  # noqa: F401
                      groundstate_device)
 from .evolution import B200Exp, Evolution, EvolutionSolver, EvolutionTimestamp  # noqa: F401

@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # translation units: the C ABI + the ELL kernels, and the instantiations of the register-tiled
 # stencil kernel (large fully-unrolled kernels, kept apart so that api.cu rebuilds quickly)
-UNITS = ["api.cu", "stencil.cu"] + ["stencil_k%d.cu" % i for i in range(6)]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "stencil.cuh"), os.path.join(CSRC, "stencil_inst.cuh"),
+UNITS = ["api.cu", "stencil.cu"] + ["stencil_k%d.cu" % i for i in range(9)]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "stencil.cuh"), os.path.join(CSRC, "stencil_inst.cuh"), os.path.join(CSRC, "stencil_unit.inc"),
            os.path.join(CSRC, "taylor_roots.h"), os.path.join(HERE, "..", "include", "lm_b200.h")]
 SRC = os.path.join(CSRC, "api.cu")
 DEPS = [os.path.join(CSRC, u) for u in UNITS] + HEADERS

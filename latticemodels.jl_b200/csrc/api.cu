@@ -167,6 +167,7 @@ struct lm_ham {
     int lat_n1 = 0, lat_n2 = 0;
     int st_id = -1; int st_rc = 0; int st_sw = 0; unsigned long long st_mask = 0;
     int* d_st_src = nullptr; void* d_svals = nullptr; long long svals_version = -1;
+    void* d_sreal = nullptr; int* d_ri_flag = nullptr; unsigned char* d_ri_cls = nullptr; int st_swr = 0;   // real / imaginary class copy of the values (k_gather_real)
     int* d_st_out = nullptr; int st_nf = 0;          // (row, forward slot) -> ELL entry of the pair (k_observe_stencil)
 };
 
@@ -335,7 +336,7 @@ static void ham_free(lm_ham* h) {
     void* ptrs[] = {h->d_cols, h->d_vals, h->d_upper, h->d_csc2ell, h->d_nz, h->d_pair_ptr, h->d_pair_ent,
                     h->d_r, h->d_bfac, h->d_phase, h->d_static, h->d_cptr, h->d_cbond, h->d_camp,
                     h->d_kinds, h->d_params, h->d_dens, h->d_G, h->d_obs,
-                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_st_out, h->d_pairI, h->d_pairJ};
+                    h->d_t_ptr, h->d_t_nr, h->d_t_rows, h->d_lcols, h->d_it_ptr, h->d_it_row, h->d_it_nb, h->d_it_out, h->d_oc_a, h->d_oc_b, h->d_oc_ent, h->d_oc_G, h->d_oc_J, h->d_scols, h->d_bsrc, h->d_bvals, h->d_st_src, h->d_svals, h->d_sreal, h->d_ri_flag, h->d_ri_cls, h->d_st_out, h->d_pairI, h->d_pairJ};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -625,14 +626,17 @@ static int ham_build_stencil(lm_ham* h) {
     if (h->d_st_src) { cudaFree(h->d_st_src); h->d_st_src = nullptr; }
     if (h->d_svals) { cudaFree(h->d_svals); h->d_svals = nullptr; }
     if (h->d_st_out) { cudaFree(h->d_st_out); h->d_st_out = nullptr; }
+    if (h->d_sreal) { cudaFree(h->d_sreal); h->d_sreal = nullptr; }
+    if (h->d_ri_flag) { cudaFree(h->d_ri_flag); h->d_ri_flag = nullptr; }
+    if (h->d_ri_cls) { cudaFree(h->d_ri_cls); h->d_ri_cls = nullptr; }
     h->st_id = -1; h->svals_version = -1; h->layout_epoch++;
     const long long n1 = h->lat_n1, n2 = h->lat_n2, N = h->N; const int W = h->W;
     if (n1 < 3 || n2 < 3 || N % (n1 * n2) != 0) return LM_OK;
     const int rc = (int)(N / (n1 * n2));
-    if (rc < 1 || rc > 2 || rc % h->n_int != 0) return LM_OK;
+    if (rc < 1 || rc > 4 || rc % h->n_int != 0) return LM_OK;
     auto wrapd = [](long long d, long long n) { if (d > n / 2) d -= n; if (d < -(n / 2)) d += n; return d; };
     // pass 1: pattern mask
-    unsigned long long mask = 0;
+    st_mask_t mask = {{0, 0, 0, 0}};
     for (long long i = 0; i < N; ++i) {
         const long long ci = i / rc; const int a = (int)(i % rc);
         const long long c1 = ci / n2, c2 = ci % n2;
@@ -643,7 +647,7 @@ static int ham_build_stencil(lm_ham* h) {
             if (d1 < -1 || d1 > 1 || d2 < -1 || d2 > 1) return LM_OK;        // longer hops: ELL kernels
             const int o = (int)((d1 + 1) * 3 + (d2 + 1));
             if (j == i && o != 4) return LM_OK;
-            mask |= 1ull << (o * rc * rc + a * rc + b);
+            st_set(mask, o * rc * rc + a * rc + b);
         }
     }
     const int id = stencil_find(rc, mask);
@@ -651,11 +655,11 @@ static int ham_build_stencil(lm_ham* h) {
     const StencilDesc& d = stencil_desc(id);
     const int SW = stencil_stride(id, c->precision != LM_C128);      // slot stride (complex64 rows padded to even)
     // slot of (o, b) in the list of out row a, same order as st_slot
-    int slot[9][2][2];
+    int slot[9][4][4];
     for (int a = 0; a < rc; ++a) {
         int s = 0;
         for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b) {
-            const bool set = (d.mask >> (o * rc * rc + a * rc + b)) & 1ull;
+            const bool set = st_get(d.mask, o * rc * rc + a * rc + b);
             slot[o][a][b] = set ? s : -1;
             if (set) ++s;
         }
@@ -688,7 +692,7 @@ static int ham_build_stencil(lm_ham* h) {
         const int a = (int)(i % rc);
         int f = 0;
         for (int o = 4; o < 9; ++o) for (int b = 0; b < rc; ++b) {
-            const bool set = (d.mask >> (o * rc * rc + a * rc + b)) & 1ull;
+            const bool set = st_get(d.mask, o * rc * rc + a * rc + b);
             if (!set || !(o > 4 || b > a)) continue;
             const int e = src[(size_t)i * SW + slot[o][a][b]];
             if (e >= 0) {
@@ -711,7 +715,22 @@ static int ham_build_stencil(lm_ham* h) {
     CK(cudaMalloc(&h->d_svals, c->esz() * src.size() + 4096));
     CK(cudaMemset(h->d_svals, 0, c->esz() * src.size() + 4096));
     CK(cudaMemcpy(h->d_st_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
-    h->st_id = id; h->st_rc = rc; h->st_sw = SW; h->st_mask = mask;
+    // real / imaginary value class of the pattern: per (row of the cell, slot) which component an entry may carry
+    {
+        const int SWR = stencil_rstride(id, c->precision != LM_C128);
+        std::vector<unsigned char> cls((size_t)rc * SW, 0);
+        for (int a = 0; a < rc; ++a) for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b)
+            if (slot[o][a][b] >= 0 && st_get(d.imag, o * rc * rc + a * rc + b)) cls[(size_t)a * SW + slot[o][a][b]] = 1;
+        const size_t rbytes = (size_t)N * SWR * (c->esz() / 2) + 4096;
+        CK(cudaMalloc(&h->d_sreal, rbytes));
+        CK(cudaMemset(h->d_sreal, 0, rbytes));
+        CK(cudaMalloc(&h->d_ri_flag, sizeof(int)));
+        CK(cudaMemset(h->d_ri_flag, 0, sizeof(int)));
+        CK(cudaMalloc(&h->d_ri_cls, cls.size()));
+        CK(cudaMemcpy(h->d_ri_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice));
+        h->st_swr = SWR;
+    }
+    h->st_id = id; h->st_rc = rc; h->st_sw = SW; h->st_mask = mask.w[0];
     return LM_OK;
 }
 extern "C" int32_t lm_ham_set_lattice_dims(lm_ham* h, int32_t n1, int32_t n2) {
@@ -1433,6 +1452,12 @@ static int refresh_views(lm_ham* h) {
         if (c->precision == LM_C128) k_gather_blocks<double2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_st_src, (const double2*)h->d_vals, (double2*)h->d_svals);
         else k_gather_blocks<float2><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->d_st_src, (const float2*)h->d_vals, (float2*)h->d_svals);
         c->launches++;
+        if (h->d_sreal) {
+            CK(cudaMemsetAsync(h->d_ri_flag, 1, sizeof(int), c->stream));          // non-zero until an entry leaves the class
+            if (c->precision == LM_C128) k_gather_real<double2, double><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->st_sw, h->st_swr, h->st_rc, h->d_st_src, h->d_ri_cls, (const double2*)h->d_vals, (double*)h->d_sreal, h->d_ri_flag);
+            else k_gather_real<float2, float><<<(unsigned)((nb + th - 1) / th), th, 0, c->stream>>>(nb, h->st_sw, h->st_swr, h->st_rc, h->d_st_src, h->d_ri_cls, (const float2*)h->d_vals, (float*)h->d_sreal, h->d_ri_flag);
+            c->launches++;
+        }
         h->svals_version = h->version;
     }
     CK(cudaGetLastError());
@@ -1591,11 +1616,12 @@ static int make_tmap3d(CUtensorMap* out, const void* base, unsigned long long d0
 #endif
 
 static int g_stencil_variant = -1;       // lm_dbg_set_stencil_variant (sweeps): -1 = default per pattern
+static int g_stencil_ri = -1;             // lm_dbg_set_stencil_ri (tests / sweeps): -1 = LM_STENCIL_RI (default on)
 static int g_stencil_herm = -1, g_stencil_tmap = -1;   // lm_dbg_set_stencil_flags (tests / sweeps): -1 = LM_STENCIL_HERM / LM_STENCIL_TMAP (default on)
 static int stencil_variant_of(const lm_ham* h) {
     static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
     int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
-    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : 2;
+    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : (h->st_rc == 2 ? 2 : 19);
     return variant;
 }
 static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,
@@ -1608,6 +1634,10 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     stencil_variant_shape(variant, h->st_rc, &P1, &P2, &cpt, &staged);
     StencilArgs a;
     a.svals = h->d_svals; a.n1 = h->lat_n1; a.n2 = h->lat_n2; a.ld = ld;
+    // real / imaginary value class (LM_STENCIL_RI, default on): the kernel reads the device flag k_gather_real left
+    static const int ri_env = env_int("LM_STENCIL_RI", 1);
+    const bool ri_on = (g_stencil_ri >= 0 ? g_stencil_ri : ri_env) != 0 && h->d_sreal;
+    a.sreal = ri_on ? h->d_sreal : nullptr; a.ri_flag = ri_on ? h->d_ri_flag : nullptr;
     // LM_STEP_PDL=1 (opt-in): chains of factors are launched with programmatic dependent launch
     static const int pdl_env = env_int("LM_STEP_PDL", 0);
     a.pdl = (pdl_env && staged == 1 && !z && !u) ? 1 : 0;
@@ -1680,6 +1710,22 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
 extern "C" int32_t lm_dbg_set_stencil_variant(int32_t v) { g_stencil_variant = v; ++g_sched_epoch; return LM_OK; }
 // herm: shared value loads for Hermitian operators; tmap: tensor-map boxes for interior patches (-1 = default)
 extern "C" int32_t lm_dbg_set_stencil_flags(int32_t herm, int32_t tmap) { g_stencil_herm = herm; g_stencil_tmap = tmap; ++g_sched_epoch; return LM_OK; }
+// ri: real / imaginary value class of the stencil kernel (scalar values, two FMAs per element) when the values allow it (-1 = default);
+// *in_class (may be null): whether the current values of h are in the class of its compiled pattern (synchronises)
+extern "C" int32_t lm_dbg_set_stencil_ri(int32_t ri) { g_stencil_ri = ri; ++g_sched_epoch; return LM_OK; }
+extern "C" int32_t lm_dbg_stencil_ri_state(lm_ham* h, int32_t* in_class) {
+    REQUIRE(h && in_class, "lm_dbg_stencil_ri_state: NULL argument");
+    *in_class = 0;
+    if (h->st_id < 0 || !h->d_ri_flag) return LM_OK;
+    lm_ctx* c = h->ctx;
+    FWD(set_dev(c));
+    FWD(refresh_views(h));
+    int f = 0;
+    CK(cudaMemcpyAsync(&f, h->d_ri_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *in_class = f != 0;
+    return LM_OK;
+}
 
 static int g_apply_path_override = -1;   // lm_dbg_set_apply_path (tests): 0 consecutive rows, 1 TMA tiles, 2 plan tiles, 3 site-blocked, 4 TMA quad, 5 register-tiled stencil
 // register-tiled stencil kernel (path 5 = force): default whenever the lattice matched a compiled stencil

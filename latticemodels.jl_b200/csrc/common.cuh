@@ -78,6 +78,21 @@ __device__ __forceinline__ void pfma_conj(float4& acc, const float2 v, const flo
     acc.w = fmaf(v.x, x.w, acc.w); acc.w = fmaf(-v.y, x.z, acc.w);
 }
 
+// acc += s * x for a purely REAL value s, acc += (i s) * x for a purely IMAGINARY value i s: two FMAs per complex
+// element instead of four, and the value is a 64-bit (32-bit) scalar (stencil.cuh, the "real / imaginary" value class)
+__device__ __forceinline__ void pfma_re(double2& acc, const double s, const double2 x) {
+    acc.x = fma(s, x.x, acc.x); acc.y = fma(s, x.y, acc.y);
+}
+__device__ __forceinline__ void pfma_im(double2& acc, const double s, const double2 x) {
+    acc.x = fma(-s, x.y, acc.x); acc.y = fma(s, x.x, acc.y);
+}
+__device__ __forceinline__ void pfma_re(float4& acc, const float s, const float4 x) {
+    acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y); acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
+}
+__device__ __forceinline__ void pfma_im(float4& acc, const float s, const float4 x) {
+    acc.x = fmaf(-s, x.y, acc.x); acc.y = fmaf(s, x.x, acc.y); acc.z = fmaf(-s, x.w, acc.z); acc.w = fmaf(s, x.z, acc.w);
+}
+
 // ---- shared-memory declarations of the staged kernels ----
 // (macros so that the CPU execution harness, tests/cpu_emul/, can substitute host storage;
 //  under nvcc they expand to exactly the usual CUDA declarations)

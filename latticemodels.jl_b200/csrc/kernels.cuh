@@ -239,6 +239,23 @@ __global__ void k_gather_blocks(long long n, const int* __restrict__ src, const 
     bvals[i] = v;
 }
 
+// Stencil-slot copy of the values in the pattern's real / imaginary class (stencil.cuh, StPat<>::imag): entry (row, slot)
+// keeps Re (class 0) or Im (class 1) of its value; any non-zero component of the OTHER kind clears *flag (set to
+// non-zero before the launch), and the stencil kernel then reads the complex copy instead.  cls: [RC][SW].
+template <typename T2, typename T>
+__global__ void k_gather_real(long long n, int SW, int SWR, int RC, const int* __restrict__ src, const unsigned char* __restrict__ cls,
+                              const T2* __restrict__ vals, T* __restrict__ sreal, int* flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long row = i / SW; const int slot = (int)(i - row * SW);
+    T2 v; v.x = 0; v.y = 0;
+    const int e = src[i];
+    if (e >= 0) v = vals[e];
+    const bool im = cls[(row % RC) * SW + slot] != 0;
+    if ((im ? v.x : v.y) != 0) *flag = 0;
+    sreal[row * SWR + slot] = im ? v.y : v.x;
+}
+
 template <typename T, int CPT, int NI, int MODE>
 __global__ void __launch_bounds__(256, 3)
 k_apply_sites(const SitesArgs a) {

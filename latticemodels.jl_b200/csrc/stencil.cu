@@ -12,21 +12,23 @@ namespace lm {
 //   id 3  QWZ-type: 2 orbitals, full 2x2 blocks on-site and to the 4 nearest cells
 //   id 4  Haldane: honeycomb NN + NNN + on-site
 //   id 5  any RC = 2 pattern with |d| <= 1 (honeycomb with third neighbours, 2-orbital models with diagonal hops)
+//   id 6  kagome NN + on-site (RC = 3)
+//   id 7  kagome NN + second neighbours + on-site (RC = 3)
+//   id 8  Kane-Mele: spin-1/2 honeycomb, spin-diagonal NN + second neighbours + on-site diagonal (RC = 4)
 
+#define LM_ST_DESC(id, name) {StPat<id>::rc, StPat<id>::mask, StPat<id>::imag, st_width<StPat<id>::rc>(StPat<id>::mask), name}
 static const StencilDesc g_desc[] = {
-    {1, LM_ST_MASK0, st_width<1>(LM_ST_MASK0), "square-nn"},
-    {1, LM_ST_MASK1, st_width<1>(LM_ST_MASK1), "rc1-full"},
-    {2, LM_ST_MASK2, st_width<2>(LM_ST_MASK2), "honeycomb-nn"},
-    {2, LM_ST_MASK3, st_width<2>(LM_ST_MASK3), "qwz"},
-    {2, LM_ST_MASK4, st_width<2>(LM_ST_MASK4), "haldane"},
-    {2, LM_ST_MASK5, st_width<2>(LM_ST_MASK5), "rc2-full"},
+    LM_ST_DESC(0, "square-nn"), LM_ST_DESC(1, "rc1-full"), LM_ST_DESC(2, "honeycomb-nn"),
+    LM_ST_DESC(3, "qwz"), LM_ST_DESC(4, "haldane"), LM_ST_DESC(5, "rc2-full"),
+    LM_ST_DESC(6, "kagome-nn"), LM_ST_DESC(7, "kagome-nnn"), LM_ST_DESC(8, "kanemele"),
 };
-int stencil_count() { return (int)(sizeof(g_desc) / sizeof(g_desc[0])); }
+static_assert(sizeof(g_desc) / sizeof(g_desc[0]) == LM_ST_NPAT, "pattern table out of step with StPat<>");
+int stencil_count() { return LM_ST_NPAT; }
 const StencilDesc& stencil_desc(int id) { return g_desc[id]; }
-int stencil_find(int rc, st_mask_t mask) {
+int stencil_find(int rc, const st_mask_t& mask) {
     int best = -1;
     for (int i = 0; i < stencil_count(); ++i) {
-        if (g_desc[i].rc != rc || (mask & ~g_desc[i].mask)) continue;
+        if (g_desc[i].rc != rc || !st_covers(g_desc[i].mask, mask)) continue;
         if (best < 0 || g_desc[i].sw < g_desc[best].sw) best = i;
     }
     return best;
@@ -36,13 +38,14 @@ int stencil_diag_slot(int id, int a) {
     const int rc = g_desc[id].rc;
     int s = 0;
     for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b) {
-        const bool set = (g_desc[id].mask >> (o * rc * rc + a * rc + b)) & 1ull;
+        const bool set = st_get(g_desc[id].mask, o * rc * rc + a * rc + b);
         if (o == 4 && b == a) return set ? s : -1;
         if (set) ++s;
     }
     return -1;
 }
 int stencil_stride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 1) & ~1) : g_desc[id].sw; }
+int stencil_rstride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 3) & ~3) : ((g_desc[id].sw + 1) & ~1); }
 
 // register-tile variants: T1 x T2 cells per thread, W1 x W2 warps per CTA, CPT lane elements per
 // thread; staged = haloed patch brought into shared memory by TMA bulk copies
@@ -67,6 +70,7 @@ static const Variant g_var[] = {
     {4, 4, 1, 2, 1, 1},   // 16: staged, 4 x 8 patch, 64 threads  (RC = 1)
     {4, 4, 2, 1, 1, 1},   // 17: staged, 8 x 4 patch, 64 threads  (RC = 1)
     {0, 0, 1, 1, 1, 1},   // 18: staged, one warp per CTA: the patch is the tile (4 x 2 cells RC = 2, 4 x 4 RC = 1)
+    {2, 2, 2, 2, 1, 1},   // 19: staged, 4 x 4 patch of 2 x 2 tiles, 128 threads                (RC = 3 / 4 default: 12 / 16 rows per thread)
 };
 int stencil_num_variants() { return (int)(sizeof(g_var) / sizeof(g_var[0])); }
 void stencil_variant_shape(int v, int rc, int* P1, int* P2, int* cpt, int* staged) {
@@ -88,48 +92,34 @@ int stencil_resident_ctas(int id, int v, bool c64) {
     return m < 1 ? 1 : m;
 }
 
-int stencil_launch_0(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
-int stencil_launch_1(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
-int stencil_launch_2(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
-int stencil_launch_3(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
-int stencil_launch_4(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
-int stencil_launch_5(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t);
+#define LM_ST_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define LM_ST_DECL(i) int stencil_launch_##i(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t); \
+    int stencil_observe_##i(bool, const StencilObsArgs&, const CUtensorMap&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
+LM_ST_EACH(LM_ST_DECL)
+#undef LM_ST_DECL
 
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     switch (id) {
-    case 0: return stencil_launch_0(variant, c64, mode, a, tmx, grid, s);
-    case 1: return stencil_launch_1(variant, c64, mode, a, tmx, grid, s);
-    case 2: return stencil_launch_2(variant, c64, mode, a, tmx, grid, s);
-    case 3: return stencil_launch_3(variant, c64, mode, a, tmx, grid, s);
-    case 4: return stencil_launch_4(variant, c64, mode, a, tmx, grid, s);
-    case 5: return stencil_launch_5(variant, c64, mode, a, tmx, grid, s);
+#define LM_ST_CASE(i) case i: return stencil_launch_##i(variant, c64, mode, a, tmx, grid, s);
+    LM_ST_EACH(LM_ST_CASE)
+#undef LM_ST_CASE
     default: return -1;
     }
 }
-
-
-#define LM_ST_DECL(i) int stencil_observe_##i(bool, const StencilObsArgs&, const CUtensorMap&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
-LM_ST_DECL(0) LM_ST_DECL(1) LM_ST_DECL(2) LM_ST_DECL(3) LM_ST_DECL(4) LM_ST_DECL(5)
-#undef LM_ST_DECL
 int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
     switch (id) {
-    case 0: return stencil_observe_0(c64, a, tmx, grid, s);
-    case 1: return stencil_observe_1(c64, a, tmx, grid, s);
-    case 2: return stencil_observe_2(c64, a, tmx, grid, s);
-    case 3: return stencil_observe_3(c64, a, tmx, grid, s);
-    case 4: return stencil_observe_4(c64, a, tmx, grid, s);
-    case 5: return stencil_observe_5(c64, a, tmx, grid, s);
+#define LM_ST_CASE(i) case i: return stencil_observe_##i(c64, a, tmx, grid, s);
+    LM_ST_EACH(LM_ST_CASE)
+#undef LM_ST_CASE
     default: return -1;
     }
 }
 void stencil_obs_shape(int id, int* P1, int* P2, int* nf) {
     switch (id) {
-    case 0: stencil_obs_shape_0(P1, P2, nf); break;
-    case 1: stencil_obs_shape_1(P1, P2, nf); break;
-    case 2: stencil_obs_shape_2(P1, P2, nf); break;
-    case 3: stencil_obs_shape_3(P1, P2, nf); break;
-    case 4: stencil_obs_shape_4(P1, P2, nf); break;
-    default: stencil_obs_shape_5(P1, P2, nf); break;
+#define LM_ST_CASE(i) case i: stencil_obs_shape_##i(P1, P2, nf); break;
+    LM_ST_EACH(LM_ST_CASE)
+#undef LM_ST_CASE
+    default: *P1 = *P2 = *nf = 0; break;
     }
 }
 

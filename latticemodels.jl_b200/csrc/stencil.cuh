@@ -10,7 +10,10 @@
 //
 // The sparsity pattern is a compile-time bit mask over the 9 cell offsets |d1|, |d2| <= 1:
 //   bit (o * RC*RC + a * RC + b), o = (d1+1)*3 + (d2+1)  <=>  out row a of cell c couples to
-//   in row b of cell c + (d1, d2)        (RC = rows per unit cell = basis sites x orbitals).
+//   in row b of cell c + (d1, d2)        (RC = rows per unit cell = basis sites x orbitals, <= 4).
+// A compiled pattern is a TYPE MK (struct StPat<id> at the end of this file) that carries the mask
+// and the value classes as static constexpr members: a class-type template argument cannot be
+// used for a __global__ function (nvcc 12.9), a type can.
 // Values stay per-row data (Peierls phases differ bond by bond): svals[row][slot], slots ordered
 // by (o, b); entries absent on a given row (open boundaries) hold 0 and the load wraps around.
 #pragma once
@@ -19,12 +22,19 @@
 
 namespace lm {
 
-typedef unsigned long long st_mask_t;
-
-template <int RC> __host__ __device__ constexpr bool st_bit(st_mask_t m, int o, int a, int b) {
-    return ((m >> (o * RC * RC + a * RC + b)) & 1ull) != 0;
+// 256 pattern bits: RC <= 4 rows per cell at the 9 offsets (144 bits)
+struct st_mask_t { unsigned long long w[4]; };
+__host__ __device__ constexpr bool st_get(const st_mask_t& m, int i) { return ((m.w[i >> 6] >> (i & 63)) & 1ull) != 0; }
+__host__ __device__ constexpr bool st_covers(const st_mask_t& big, const st_mask_t& small) {
+    for (int k = 0; k < 4; ++k) if (small.w[k] & ~big.w[k]) return false;
+    return true;
 }
-template <int RC> __host__ __device__ constexpr int st_slot(st_mask_t m, int o, int a, int b) {
+inline void st_set(st_mask_t& m, int i) { m.w[i >> 6] |= 1ull << (i & 63); }
+
+template <int RC> __host__ __device__ constexpr bool st_bit(const st_mask_t& m, int o, int a, int b) {
+    return st_get(m, o * RC * RC + a * RC + b);
+}
+template <int RC> __host__ __device__ constexpr int st_slot(const st_mask_t& m, int o, int a, int b) {
     int s = 0;
     for (int oo = 0; oo < 9; ++oo)
         for (int bb = 0; bb < RC; ++bb) {
@@ -33,7 +43,7 @@ template <int RC> __host__ __device__ constexpr int st_slot(st_mask_t m, int o, 
         }
     return s;
 }
-template <int RC> __host__ __device__ constexpr int st_width(st_mask_t m) {
+template <int RC> __host__ __device__ constexpr int st_width(const st_mask_t& m) {
     int w = 1;
     for (int a = 0; a < RC; ++a) {
         int s = 0;
@@ -43,7 +53,7 @@ template <int RC> __host__ __device__ constexpr int st_width(st_mask_t m) {
     return w;
 }
 // is in row b of the haloed-tile cell (u1, u2), u in [0, T + 2), read by an out row of the tile?
-template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_needed(st_mask_t m, int u1, int u2, int b) {
+template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_needed(const st_mask_t& m, int u1, int u2, int b) {
     for (int o = 0; o < 9; ++o)
         for (int a = 0; a < RC; ++a)
             if (st_bit<RC>(m, o, a, b)) {
@@ -63,6 +73,10 @@ template <int N, typename F> __device__ __forceinline__ void st_for(F&& f) {
 
 struct StencilArgs {
     const void* svals;              // [N][SW] complex, stencil-slot order
+    const void* sreal;              // [N][SWR] real scalars, same slot order: the values in the pattern's real / imaginary class
+                                    //    (Re of a real-class entry, Im of an imaginary-class entry; st_rstride)
+    const int* ri_flag;             // device flag (null = never): non-zero iff the CURRENT values are in that class (k_gather_real
+                                    //    after every value change) - read by the kernel, so a replayed step graph follows the values
     int n1, n2;                     // unit cells along the slow / fast lattice axis
     int np2;                        // CTA patches along the fast axis
     long long ld;                   // row stride of x / y / z / u (complex elements)
@@ -90,14 +104,30 @@ __host__ __device__ constexpr int st_min_blocks(int acc_regs, int threads) {
 __device__ __forceinline__ int st_wrap(int c, int n) { c %= n; return c < 0 ? c + n : c; }
 
 // value-slot stride: complex64 rows are padded to an even slot count (16-byte aligned rows for TMA)
-template <typename T, int RC, st_mask_t MASK> __host__ __device__ constexpr int st_stride() {
-    return sizeof(T) == 4 ? ((st_width<RC>(MASK) + 1) & ~1) : st_width<RC>(MASK);
+template <typename T, int RC, typename MK> __host__ __device__ constexpr int st_stride() {
+    return sizeof(T) == 4 ? ((st_width<RC>(MK::mask) + 1) & ~1) : st_width<RC>(MK::mask);
+}
+
+// scalars per row of the real / imaginary class copy: rows are 16-byte multiples (bulk copies of whole cell lines)
+template <typename T, int RC, typename MK> __host__ __device__ constexpr int st_rstride() {
+    return sizeof(T) == 4 ? ((st_width<RC>(MK::mask) + 3) & ~3) : ((st_width<RC>(MK::mask) + 1) & ~1);
+}
+// one entry: acc += h x (CONJ: conj(h) x).  CLS 0: h complex; 1: h = s purely real; 2: h = i s purely imaginary
+template <int CLS, bool CONJ, typename HV, typename E>
+__device__ __forceinline__ void st_fma(E& acc, const HV hv, const E x) {
+    if constexpr (CLS == 0) { if constexpr (CONJ) pfma_conj(acc, hv, x); else pfma(acc, hv, x); }
+    else if constexpr (CLS == 1) pfma_re(acc, hv, x);
+    else pfma_im(acc, CONJ ? -hv : hv, x);
+}
+// value class of entry (o, a, b) in a kernel that reads class scalars (VC = 1) or complex values (VC = 0)
+template <int RC, typename MK, int VC> __host__ __device__ constexpr int st_cls(int o, int a, int b) {
+    return VC ? (st_bit<RC>(MK::imag, o, a, b) ? 2 : 1) : 0;
 }
 
 // The register-tile body shared by both kernels.  load_x(U1, U2, B, j) returns lane element j of
 // in row B of haloed-tile cell (U1, U2); load_h(V1, V2, A, S) the value in slot S of out row A of
 // tile cell (V1, V2).  All indices are integral_constants: every register index is compile-time.
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int CPT, bool SELF, typename LX, typename LH>
+template <typename T, int RC, typename MK, int T1, int T2, int CPT, bool SELF, int VC, typename LX, typename LH>
 __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][CPT], const typename cx2<T>::type g,
                                         LX&& load_x, LH&& load_h) {
     using T2c = typename cx2<T>::type;
@@ -108,7 +138,7 @@ __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][C
                 constexpr int u1 = decltype(U1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
                 constexpr bool own = u1 >= 1 && u1 <= T1 && u2 >= 1 && u2 <= T2;
                 constexpr bool self = own && SELF;
-                if constexpr (st_needed<RC, T1, T2>(MASK, u1, u2, b) || self) {
+                if constexpr (st_needed<RC, T1, T2>(MK::mask, u1, u2, b) || self) {
                     E xv[CPT];
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) xv[j] = load_x(U1, U2, B, j);
@@ -116,12 +146,12 @@ __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][C
                         st_for<RC>([&](auto A) {
                             constexpr int o = decltype(O)::value, aa = decltype(A)::value;
                             constexpr int v1 = u1 - 1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
-                            if constexpr (st_bit<RC>(MASK, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
-                                constexpr int slot = st_slot<RC>(MASK, o, aa, b);
-                                const T2c hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
-                                                      A, std::integral_constant<int, slot>{});
+                            if constexpr (st_bit<RC>(MK::mask, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
+                                constexpr int slot = st_slot<RC>(MK::mask, o, aa, b);
+                                const auto hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
+                                                       A, std::integral_constant<int, slot>{});
 #pragma unroll
-                                for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xv[j]);
+                                for (int j = 0; j < CPT; ++j) st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xv[j]);
                             }
                         });
                     });
@@ -136,7 +166,7 @@ __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][C
 }
 
 // Is the pattern structurally symmetric (entry (a <- b at offset d) present iff (b <- a at -d) is)?
-template <int RC> __host__ __device__ constexpr bool st_symmetric(st_mask_t m) {
+template <int RC> __host__ __device__ constexpr bool st_symmetric(const st_mask_t& m) {
     for (int o = 0; o < 9; ++o)
         for (int a = 0; a < RC; ++a)
             for (int b = 0; b < RC; ++b)
@@ -144,7 +174,7 @@ template <int RC> __host__ __device__ constexpr bool st_symmetric(st_mask_t m) {
     return true;
 }
 // forward half of a symmetric pattern: offset (+1, *), (0, +1), or a later row of the same cell
-template <int RC> __host__ __device__ constexpr bool st_fwd_bit(st_mask_t m, int o, int a, int b) {
+template <int RC> __host__ __device__ constexpr bool st_fwd_bit(const st_mask_t& m, int o, int a, int b) {
     return st_bit<RC>(m, o, a, b) && (o > 4 || (o == 4 && b > a));
 }
 
@@ -158,12 +188,12 @@ template <int RC> __host__ __device__ constexpr bool st_fwd_bit(st_mask_t m, int
 // row and thread instead of 4 FMAs per element).  Only valid for a tile that lies completely
 // inside the lattice (the value rows of cells beyond the edge are not staged): the kernels fall
 // back to st_tile for ragged tiles.
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int CPT, bool SELF, typename LX, typename LH>
+template <typename T, int RC, typename MK, int T1, int T2, int CPT, bool SELF, int VC, typename LX, typename LH>
 __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][RC][CPT], const typename cx2<T>::type g,
                                              LX&& load_x, LH&& load_h) {
     using T2c = typename cx2<T>::type;
     using E = typename pack<T>::E;
-    static_assert(st_symmetric<RC>(MASK), "st_tile_herm needs a structurally symmetric pattern");
+    static_assert(st_symmetric<RC>(MK::mask), "st_tile_herm needs a structurally symmetric pattern");
     E xo[T1][T2][RC][CPT];
     st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
         constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
@@ -174,11 +204,19 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
     // diagonal entries (+ g) and the bonds inside the tile, one value load per bond
     st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
         constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
-        if constexpr (st_bit<RC>(MASK, 4, aa, aa)) {
-            T2c hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MASK, 4, aa, aa)>{});
-            if constexpr (SELF) { hv.x += g.x; hv.y += g.y; }
+        if constexpr (st_bit<RC>(MK::mask, 4, aa, aa)) {
+            const auto h0 = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MK::mask, 4, aa, aa)>{});
+            if constexpr (VC && !SELF) {
+                static_assert(!VC || !st_bit<RC>(MK::imag, 4, aa, aa), "the diagonal of a Hermitian operator is real");
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xo[v1][v2][aa][j]);
+                for (int j = 0; j < CPT; ++j) pfma_re(acc[v1][v2][aa][j], h0, xo[v1][v2][aa][j]);
+            } else {
+                T2c hv;
+                if constexpr (VC) { hv.x = h0; hv.y = 0; } else hv = h0;
+                if constexpr (SELF) { hv.x += g.x; hv.y += g.y; }
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xo[v1][v2][aa][j]);
+            }
         } else if constexpr (SELF) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], g, xo[v1][v2][aa][j]);
@@ -186,12 +224,12 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
         st_for<5>([&](auto OO) { st_for<RC>([&](auto B) {
             constexpr int o = decltype(OO)::value + 4, b = decltype(B)::value;
             constexpr int w1 = v1 + (o / 3 - 1), w2 = v2 + (o % 3 - 1);
-            if constexpr (st_fwd_bit<RC>(MASK, o, aa, b) && w1 >= 0 && w1 < T1 && w2 >= 0 && w2 < T2) {
-                const T2c hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MASK, o, aa, b)>{});
+            if constexpr (st_fwd_bit<RC>(MK::mask, o, aa, b) && w1 >= 0 && w1 < T1 && w2 >= 0 && w2 < T2) {
+                const auto hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MK::mask, o, aa, b)>{});
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
-                    pfma(acc[v1][v2][aa][j], hv, xo[w1][w2][b][j]);
-                    pfma_conj(acc[w1][w2][b][j], hv, xo[v1][v2][aa][j]);
+                    st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xo[w1][w2][b][j]);
+                    st_fma<st_cls<RC, MK, VC>(o, aa, b), true>(acc[w1][w2][b][j], hv, xo[v1][v2][aa][j]);
                 }
             }
         }); });
@@ -200,18 +238,18 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
     st_for<T1 + 2>([&](auto U1) { st_for<T2 + 2>([&](auto U2) { st_for<RC>([&](auto B) {
         constexpr int u1 = decltype(U1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
         constexpr bool own = u1 >= 1 && u1 <= T1 && u2 >= 1 && u2 <= T2;
-        if constexpr (!own && st_needed<RC, T1, T2>(MASK, u1, u2, b)) {
+        if constexpr (!own && st_needed<RC, T1, T2>(MK::mask, u1, u2, b)) {
             E xv[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) xv[j] = load_x(U1, U2, B, j);
             st_for<9>([&](auto O) { st_for<RC>([&](auto A) {
                 constexpr int o = decltype(O)::value, aa = decltype(A)::value;
                 constexpr int v1 = u1 - 1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
-                if constexpr (st_bit<RC>(MASK, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
-                    const T2c hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
-                                          A, std::integral_constant<int, st_slot<RC>(MASK, o, aa, b)>{});
+                if constexpr (st_bit<RC>(MK::mask, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
+                    const auto hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
+                                           A, std::integral_constant<int, st_slot<RC>(MK::mask, o, aa, b)>{});
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) pfma(acc[v1][v2][aa][j], hv, xv[j]);
+                    for (int j = 0; j < CPT; ++j) st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xv[j]);
                 }
             }); });
         }
@@ -223,13 +261,13 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
 // rows between the W1 x W2 register tiles of a CTA).  Latency-bound in practice: the loads in
 // flight are limited by the registers the accumulators leave over (profiles/).
 // ------------------------------------------------------------------------------------------
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT, int MODE>
 __global__ void __launch_bounds__(32 * W1 * W2, st_min_blocks(T1 * T2 * RC * CPT * 4, 32 * W1 * W2))
 k_apply_stencil(const StencilArgs a) {
     using T2c = typename cx2<T>::type;
     using E = typename pack<T>::E;
     constexpr int EC = pack<T>::EC;
-    constexpr int SWP = st_stride<T, RC, MASK>();
+    constexpr int SWP = st_stride<T, RC, MK>();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned patch = blockIdx.x / a.cps;
     const unsigned chunk = blockIdx.y * a.cps + (blockIdx.x - patch * a.cps);
@@ -265,7 +303,7 @@ k_apply_stencil(const StencilArgs a) {
                 for (int j = 0; j < CPT; ++j) pzero(acc[v1][v2][aa][j]);
     const T2c g = cmake<T2c>(a.g[0], a.g[1]);
 
-    st_tile<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g,
+    st_tile<T, RC, MK, T1, T2, CPT, (MODE == 2 || MODE == 3), 0>(acc, g,
         [&](auto U1, auto U2, auto B, int j) {
             const long long row = (long long)(r1[decltype(U1)::value] + r2[decltype(U2)::value]) * RC + decltype(B)::value;
             return ld_ro(x + row * lde + cidx[j]);
@@ -312,21 +350,21 @@ k_apply_stencil(const StencilArgs a) {
 // T1 x T2 register tile out of shared memory (128-bit LDS at compile-time offsets, the value
 // loads are broadcasts).  Several CTAs per SM overlap one CTA's copies with another's FMAs.
 // ------------------------------------------------------------------------------------------
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT>
 __host__ __device__ constexpr size_t st_tma_smem() {
     return (size_t)(W1 * T1 + 2) * (W2 * T2 + 2) * RC * 32 * CPT * 16
-         + (size_t)(W1 * T1) * (W2 * T2) * RC * st_stride<T, RC, MASK>() * (2 * sizeof(T));
+         + (size_t)(W1 * T1) * (W2 * T2) * RC * st_stride<T, RC, MK>() * (2 * sizeof(T));
 }
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT>
 __host__ __device__ constexpr int st_tma_blocks() {
-    const int by_smem = (int)((227 * 1024) / (st_tma_smem<T, RC, MASK, T1, T2, W1, W2, CPT>() + 1024 + 64));
+    const int by_smem = (int)((227 * 1024) / (st_tma_smem<T, RC, MK, T1, T2, W1, W2, CPT>() + 1024 + 64));
     const int by_regs = st_min_blocks(T1 * T2 * RC * CPT * 4, 32 * W1 * W2);
     const int m = by_smem < by_regs ? by_smem : by_regs;
     return m < 1 ? 1 : m;
 }
 
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE>
-__global__ void __launch_bounds__(32 * W1 * W2, st_tma_blocks<T, RC, MASK, T1, T2, W1, W2, CPT>())
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT, int MODE>
+__global__ void __launch_bounds__(32 * W1 * W2, st_tma_blocks<T, RC, MK, T1, T2, W1, W2, CPT>())
 k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx) {
     using T2c = typename cx2<T>::type;
     using E = typename pack<T>::E;
@@ -334,10 +372,11 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
     constexpr int NT = 32 * W1 * W2, P1 = W1 * T1, P2 = W2 * T2;
     constexpr int HR = (P1 + 2) * (P2 + 2) * RC;            // haloed rows of the patch
     constexpr int CE = 32 * CPT;                            // lane elements per staged row
-    constexpr int SWP = st_stride<T, RC, MASK>();
+    constexpr int SWP = st_stride<T, RC, MK>();
+    constexpr int SWR = st_rstride<T, RC, MK>();
     LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                                   // [HR][CE]
-    T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)HR * CE * sizeof(E));  // [P1][P2 * RC * SWP]
+    T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)HR * CE * sizeof(E));  // [P1][P2 * RC * SWP]  (class scalars: [P1][P2 * RC * SWR] of T)
     LM_SMEM_STATIC __align__(8) unsigned long long bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,21 +390,22 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
     const int cw = (int)((nce - c0) < CE ? (nce - c0) : CE);
     const int vl1 = (a.n1 - o1) < P1 ? (a.n1 - o1) : P1;    // own cells inside the lattice
     const int vl2 = (a.n2 - o2) < P2 ? (a.n2 - o2) : P2;
-    const unsigned hline = ((unsigned)(vl2 * RC * SWP * (int)sizeof(T2c)) + 15u) & ~15u;
     const E* __restrict__ x = (const E*)a.x;
     const T2c* __restrict__ sv = (const T2c*)a.svals;
     // a patch whose haloed block lies inside the lattice is one dense box of the [n1][n2 RC][columns]
     // view of x: ONE tensor-map copy (SASS UTMALDG; columns beyond the block are zero-filled and
     // counted) instead of HR row copies.  Patches on the rim keep the row copies (periodic images).
     const bool boxed = a.tmap && o1 >= 1 && o1 + P1 + 1 <= a.n1 && o2 >= 1 && o2 + P2 + 1 <= a.n2;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_arrive_expect_tx(&bar, (unsigned)(HR * (boxed ? CE : cw) * (int)sizeof(E)) + (unsigned)vl1 * hline);
-    }
+    if (tid == 0) mbar_init(&bar, 1);
     // a chain of factors (x <- y of the previous launch): with programmatic dependent launch the
     // CTAs of this grid are scheduled while the previous grid drains; nothing of global memory is
     // touched before the previous grid has completed and flushed
     if (a.pdl) { pdl_launch_dependents(); pdl_wait(); }
+    // real / imaginary value class (grid-uniform): the values are staged as scalars, half the bytes
+    const bool ri = a.ri_flag != nullptr && *reinterpret_cast<const volatile int*>(a.ri_flag) != 0;
+    const unsigned hline = ri ? (((unsigned)(vl2 * RC * SWR * (int)sizeof(T)) + 15u) & ~15u)
+                              : (((unsigned)(vl2 * RC * SWP * (int)sizeof(T2c)) + 15u) & ~15u);
+    if (tid == 0) mbar_arrive_expect_tx(&bar, (unsigned)(HR * (boxed ? CE : cw) * (int)sizeof(E)) + (unsigned)vl1 * hline);
     __syncthreads();
     if (boxed) {
         if (tid == 0) tma_tensor3d_g2s(sx, &tmx, (int)(c0 * (long long)(sizeof(E) / 8)), (o2 - 1) * RC, o1 - 1, &bar);
@@ -376,8 +416,14 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
             tma_bulk_g2s(sx + r * CE, x + row * lde + c0, (unsigned)(cw * (int)sizeof(E)), &bar);
         }
     }
-    for (int l = NT - 1 - tid; l < vl1; l += NT)
-        tma_bulk_g2s(sh + l * (P2 * RC * SWP), sv + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWP), hline, &bar);
+    if (ri) {
+        const T* __restrict__ sr = (const T*)a.sreal;
+        for (int l = NT - 1 - tid; l < vl1; l += NT)
+            tma_bulk_g2s(reinterpret_cast<T*>(sh) + l * (P2 * RC * SWR), sr + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWR), hline, &bar);
+    } else {
+        for (int l = NT - 1 - tid; l < vl1; l += NT)
+            tma_bulk_g2s(sh + l * (P2 * RC * SWP), sv + ((long long)(o1 + l) * a.n2 + o2) * (RC * SWP), hline, &bar);
+    }
     // The wait for the staged block is the largest stall of this kernel (42 % of the warp samples, profiles/r2/).
     // Opt-in (a.pf > 0, LM_STENCIL_PF): every CTA also asks the TMA engine to pull into L2 the box of the CTA that
     // will be dispatched `pf` positions later, whose own copy is then an L2 hit.  A hint only: nothing waits on
@@ -418,12 +464,25 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
         return hb[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWP + decltype(S)::value];
     };
     bool shared_bonds = false;
-    if constexpr (st_symmetric<RC>(MASK))
+    if constexpr (st_symmetric<RC>(MK::mask))
         shared_bonds = a.herm && q1 + T1 <= a.n1 && q2 + T2 <= a.n2;      // warp-uniform
-    if (shared_bonds) {
-        if constexpr (st_symmetric<RC>(MASK)) st_tile_herm<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g, lx, lh);
+    constexpr bool SELF = (MODE == 2 || MODE == 3);
+    if (ri) {
+        // every value is purely real or purely imaginary (the model's class, MK::imag): 64-bit uniform value
+        // loads (one shared-memory wavefront instead of two) and two FMAs per complex element instead of four
+        const T* hr = reinterpret_cast<const T*>(sh) + ((w1 * T1) * P2 + w2 * T2) * RC * SWR;
+        auto lr = [&](auto V1, auto V2, auto A, auto S) {
+            return hr[((decltype(V1)::value * P2 + decltype(V2)::value) * RC + decltype(A)::value) * SWR + decltype(S)::value];
+        };
+        if (shared_bonds) {
+            if constexpr (st_symmetric<RC>(MK::mask)) st_tile_herm<T, RC, MK, T1, T2, CPT, SELF, 1>(acc, g, lx, lr);
+        } else {
+            st_tile<T, RC, MK, T1, T2, CPT, SELF, 1>(acc, g, lx, lr);
+        }
+    } else if (shared_bonds) {
+        if constexpr (st_symmetric<RC>(MK::mask)) st_tile_herm<T, RC, MK, T1, T2, CPT, SELF, 0>(acc, g, lx, lh);
     } else {
-        st_tile<T, RC, MASK, T1, T2, CPT, (MODE == 2 || MODE == 3)>(acc, g, lx, lh);
+        st_tile<T, RC, MK, T1, T2, CPT, SELF, 0>(acc, g, lx, lh);
     }
 
     const T2c alpha = cmake<T2c>(a.alpha[0], a.alpha[1]);
@@ -472,13 +531,13 @@ k_apply_stencil_tma(const StencilArgs a, const LM_GRID_CONSTANT CUtensorMap tmx)
 // and FMAs for free.  Built only with LM_STENCIL_EXPLORE.
 // ------------------------------------------------------------------------------------------
 constexpr int ST_STREAM_STAGES = 3;
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2>
 __host__ __device__ constexpr size_t st_stream_smem() {
     return (size_t)ST_STREAM_STAGES * (W1 * T1 + 2) * (W2 * T2 + 2) * RC * 32 * 16
-         + (size_t)(W1 * T1) * (W2 * T2) * RC * st_stride<T, RC, MASK>() * (2 * sizeof(T));
+         + (size_t)(W1 * T1) * (W2 * T2) * RC * st_stride<T, RC, MK>() * (2 * sizeof(T));
 }
 
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int MODE>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int MODE>
 __global__ void __launch_bounds__(32 * W1 * W2, 1)
 k_apply_stencil_stream(const StencilArgs a) {
     using T2c = typename cx2<T>::type;
@@ -488,7 +547,7 @@ k_apply_stencil_stream(const StencilArgs a) {
     constexpr int NT = 32 * W1 * W2, P1 = W1 * T1, P2 = W2 * T2;
     constexpr int HR = (P1 + 2) * (P2 + 2) * RC;
     constexpr int CE = 32;
-    constexpr int SWP = st_stride<T, RC, MASK>();
+    constexpr int SWP = st_stride<T, RC, MK>();
     LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                                          // [NS][HR][CE]
     T2c* sh = reinterpret_cast<T2c*>(lm_smem + (size_t)NS * HR * CE * sizeof(E));    // [P1][P2 * RC * SWP]
@@ -556,7 +615,7 @@ k_apply_stencil_stream(const StencilArgs a) {
                 for (int v2 = 0; v2 < T2; ++v2)
 #pragma unroll
                     for (int aa = 0; aa < RC; ++aa) pzero(acc[v1][v2][aa][0]);
-            st_tile<T, RC, MASK, T1, T2, 1, (MODE == 2 || MODE == 3)>(acc, g,
+            st_tile<T, RC, MK, T1, T2, 1, (MODE == 2 || MODE == 3), 0>(acc, g,
                 [&](auto U1, auto U2, auto B, int) {
                     return xb[((decltype(U1)::value * (P2 + 2) + decltype(U2)::value) * RC + decltype(B)::value) * CE];
                 },
@@ -600,10 +659,10 @@ k_apply_stencil_stream(const StencilArgs a) {
 // entry that carries the pair: e >= 0 as is, e <= -2 the conjugate goes to entry -2 - e (the
 // forward neighbour sits across a periodic boundary), -1 no such bond on this row.
 // ------------------------------------------------------------------------------------------
-template <int RC> __host__ __device__ constexpr bool st_is_fwd(st_mask_t m, int o, int a, int b) {
+template <int RC> __host__ __device__ constexpr bool st_is_fwd(const st_mask_t& m, int o, int a, int b) {
     return st_bit<RC>(m, o, a, b) && (o > 4 || (o == 4 && b > a));
 }
-template <int RC> __host__ __device__ constexpr int st_fslot(st_mask_t m, int o, int a, int b) {
+template <int RC> __host__ __device__ constexpr int st_fslot(const st_mask_t& m, int o, int a, int b) {
     int s = 0;
     for (int oo = 4; oo < 9; ++oo)
         for (int bb = 0; bb < RC; ++bb) {
@@ -612,7 +671,7 @@ template <int RC> __host__ __device__ constexpr int st_fslot(st_mask_t m, int o,
         }
     return s;
 }
-template <int RC> __host__ __device__ constexpr int st_nfwd(st_mask_t m) {
+template <int RC> __host__ __device__ constexpr int st_nfwd(const st_mask_t& m) {
     int w = 1;
     for (int a = 0; a < RC; ++a) {
         int s = 0;
@@ -622,7 +681,7 @@ template <int RC> __host__ __device__ constexpr int st_nfwd(st_mask_t m) {
     return w;
 }
 // is in row b of staged cell (l1, u2) - l1 in [0, T1], u2 in [0, T2 + 2) - a forward neighbour of the tile?
-template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_fwd_needed(st_mask_t m, int l1, int u2, int b) {
+template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_fwd_needed(const st_mask_t& m, int l1, int u2, int b) {
     for (int o = 4; o < 9; ++o)
         for (int a = 0; a < RC; ++a)
             if (st_is_fwd<RC>(m, o, a, b)) {
@@ -662,7 +721,7 @@ constexpr int ST_OBS_STAGES = 3;      // TMA pipeline depth: ~2 staged chunks in
 template <typename T, int RC, int T1, int T2, int W1, int W2>
 __host__ __device__ constexpr size_t st_obs_smem() { return (size_t)ST_OBS_STAGES * (W1 * T1 + 1) * (W2 * T2 + 2) * RC * 32 * 16; }
 
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2>
 __global__ void __launch_bounds__(32 * W1 * W2, 65536 / (128 * 32 * W1 * W2) < 1 ? 1 : 65536 / (128 * 32 * W1 * W2))
 k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx) {
     constexpr int NS = ST_OBS_STAGES;
@@ -672,7 +731,7 @@ k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx
     constexpr int L2 = P2 + 2;
     constexpr int HR = (P1 + 1) * L2 * RC;                  // staged rows: own + forward cell lines
     constexpr int CE = 32;
-    constexpr int NF = st_nfwd<RC>(MASK);
+    constexpr int NF = st_nfwd<RC>(MK::mask);
     LM_SMEM_DYN(lm_smem);
     E* sx = reinterpret_cast<E*>(lm_smem);                  // [NS][HR][CE]
     LM_SMEM_STATIC __align__(8) unsigned long long bar[NS];
@@ -769,13 +828,13 @@ k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx
             }); }); });
             st_for<T1 + 1>([&](auto LL1) { st_for<T2 + 2>([&](auto U2) { st_for<RC>([&](auto B) {
                 constexpr int l1 = decltype(LL1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
-                if constexpr (st_fwd_needed<RC, T1, T2>(MASK, l1, u2, b)) {
+                if constexpr (st_fwd_needed<RC, T1, T2>(MK::mask, l1, u2, b)) {
                     const E xe = xb[((l1 * L2 + u2) * RC + b) * CE];
                     st_for<5>([&](auto OO) { st_for<RC>([&](auto A) {
                         constexpr int o = decltype(OO)::value + 4, aa = decltype(A)::value;
                         constexpr int v1 = l1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
-                        if constexpr (st_is_fwd<RC>(MASK, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
-                            constexpr int f = st_fslot<RC>(MASK, o, aa, b);
+                        if constexpr (st_is_fwd<RC>(MK::mask, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
+                            constexpr int f = st_fslot<RC>(MK::mask, o, aa, b);
 #pragma unroll
                             for (int e = 0; e < EC; ++e) {
                                 double re, im; st_unpack<T>::get(xe, e, re, im);
@@ -848,19 +907,43 @@ k_observe_stencil(const StencilObsArgs a, const LM_GRID_CONSTANT CUtensorMap tmx
 }
 
 // ---- compiled patterns (stencil.cu registry; one translation unit per pattern) ----
+// mask: the stored entries.  imag: the entries that are PURELY IMAGINARY in the pattern's "real / imaginary"
+// value class (every other entry purely real) - the class of the reference's own models without a magnetic
+// field: real hoppings and on-site terms, `im * t2` second-neighbour hops of `haldane`
+// (src/zoo/models.jl:164-170), the `-im/2` orbital-flip x-hops of `qwz` (src/zoo/models.jl:130-136).  Whether
+// the CURRENT values are in the class is decided on the device whenever they change (k_gather_real, api.cu);
+// anything else (Peierls phases, twists) runs the general complex path of the same kernel.
 #define LM_ST_MASK0 0xbaull
 #define LM_ST_MASK1 0x1ffull
 #define LM_ST_MASK2 0x404f2020ull
 #define LM_ST_MASK3 0xf0fff0f0ull
 #define LM_ST_MASK4 0xd9dfb9b0ull
 #define LM_ST_MASK5 0xfffffffffull
+#define LM_ST_IMAG3 0x60000060ull
+#define LM_ST_IMAG4 0x99909990ull
+template <int ID> struct StPat;
+template <> struct StPat<0> { static constexpr int rc = 1; static constexpr st_mask_t mask = {{LM_ST_MASK0, 0, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+template <> struct StPat<1> { static constexpr int rc = 1; static constexpr st_mask_t mask = {{LM_ST_MASK1, 0, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+template <> struct StPat<2> { static constexpr int rc = 2; static constexpr st_mask_t mask = {{LM_ST_MASK2, 0, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+template <> struct StPat<3> { static constexpr int rc = 2; static constexpr st_mask_t mask = {{LM_ST_MASK3, 0, 0, 0}}, imag = {{LM_ST_IMAG3, 0, 0, 0}}; };
+template <> struct StPat<4> { static constexpr int rc = 2; static constexpr st_mask_t mask = {{LM_ST_MASK4, 0, 0, 0}}, imag = {{LM_ST_IMAG4, 0, 0, 0}}; };
+template <> struct StPat<5> { static constexpr int rc = 2; static constexpr st_mask_t mask = {{LM_ST_MASK5, 0, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+// three and four rows per cell: the masks span two words
+//   6  kagome NN + on-site (src/zoo/lattices.jl:209, NearestNeighbor(1))       7  kagome NN + second neighbours + on-site
+//   8  Kane-Mele (src/zoo/models.jl:188-194): spin-diagonal honeycomb NN + `im t2 sigma_z` second neighbours + on-site diagonal
+template <> struct StPat<6> { static constexpr int rc = 3; static constexpr st_mask_t mask = {{0x8081ff022000400ull, 0x4ull, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+template <> struct StPat<7> { static constexpr int rc = 3; static constexpr st_mask_t mask = {{0xb191ff133090c00ull, 0x34ull, 0, 0}}, imag = {{0, 0, 0, 0}}; };
+template <> struct StPat<8> { static constexpr int rc = 4; static constexpr st_mask_t mask = {{0x84a5842184a50000ull, 0xa5218421a521a5a5ull, 0, 0}},
+                                                                                      imag = {{0x8421842184210000ull, 0x8421842184210000ull, 0, 0}}; };
+constexpr int LM_ST_NPAT = 9;
 
 // ---- host-visible registry (stencil.cu) ----
-struct StencilDesc { int rc; st_mask_t mask; int sw; const char* name; };
+struct StencilDesc { int rc; st_mask_t mask, imag; int sw; const char* name; };
 int stencil_count();
 const StencilDesc& stencil_desc(int id);
-int stencil_find(int rc, st_mask_t mask);                  // smallest compiled superset, -1 if none
+int stencil_find(int rc, const st_mask_t& mask);                  // smallest compiled superset, -1 if none
 int stencil_stride(int id, bool c64);                      // value-slot stride (complex64 rows are padded to even)
+int stencil_rstride(int id, bool c64);                     // scalars per row of the real / imaginary class copy (st_rstride)
 int stencil_diag_slot(int id, int a);                      // slot of the diagonal entry of in-cell row a
 int stencil_num_variants();
 // patch size in cells, lane elements per thread and kernel family (staged = TMA) of a variant

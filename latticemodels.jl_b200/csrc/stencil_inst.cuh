@@ -5,27 +5,27 @@
 
 namespace lm {
 
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int MODE, int STAGED>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT, int MODE, int STAGED>
 static int launch_one(const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if constexpr (STAGED == 2) {
         static_assert(CPT == 1, "the streaming kernel handles one lane element per thread");
-        constexpr size_t smem = st_stream_smem<T, RC, MASK, T1, T2, W1, W2>();
+        constexpr size_t smem = st_stream_smem<T, RC, MK, T1, T2, W1, W2>();
         static bool configured = false;
         if (!configured) {
-            if (cudaFuncSetAttribute(k_apply_stencil_stream<T, RC, MASK, T1, T2, W1, W2, MODE>,
+            if (cudaFuncSetAttribute(k_apply_stencil_stream<T, RC, MK, T1, T2, W1, W2, MODE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
             configured = true;
         }
-        k_apply_stencil_stream<T, RC, MASK, T1, T2, W1, W2, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
+        k_apply_stencil_stream<T, RC, MK, T1, T2, W1, W2, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a);
         return 0;
     } else if constexpr (STAGED == 0) {
-        k_apply_stencil<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, 0, s>>>(a);
+        k_apply_stencil<T, RC, MK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, 0, s>>>(a);
         return 0;
     } else {
-    constexpr size_t smem = st_tma_smem<T, RC, MASK, T1, T2, W1, W2, CPT>();
+    constexpr size_t smem = st_tma_smem<T, RC, MK, T1, T2, W1, W2, CPT>();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>,
+        if (cudaFuncSetAttribute(k_apply_stencil_tma<T, RC, MK, T1, T2, W1, W2, CPT, MODE>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         configured = true;
     }
@@ -38,46 +38,46 @@ static int launch_one(const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, c
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE>, a, tmx) == cudaSuccess ? 0 : -2;
+        return cudaLaunchKernelEx(&cfg, k_apply_stencil_tma<T, RC, MK, T1, T2, W1, W2, CPT, MODE>, a, tmx) == cudaSuccess ? 0 : -2;
     }
-    k_apply_stencil_tma<T, RC, MASK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a, tmx);
+    k_apply_stencil_tma<T, RC, MK, T1, T2, W1, W2, CPT, MODE><<<grid, 32 * W1 * W2, smem, s>>>(a, tmx);
     return 0;
     }
 }
 // STAGED is a compile-time family switch so that only the requested family is instantiated
-template <typename T, int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
+template <typename T, int RC, typename MK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
 static int launch_modes(int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     switch (mode) {
-    case 0: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 0, STAGED>(a, tmx, grid, s);
-    case 3: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 3, STAGED>(a, tmx, grid, s);
+    case 0: return launch_one<T, RC, MK, T1, T2, W1, W2, CPT, 0, STAGED>(a, tmx, grid, s);
+    case 3: return launch_one<T, RC, MK, T1, T2, W1, W2, CPT, 3, STAGED>(a, tmx, grid, s);
 #ifndef LM_STENCIL_FEWMODES
-    case 1: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 1, STAGED>(a, tmx, grid, s);
-    case 2: return launch_one<T, RC, MASK, T1, T2, W1, W2, CPT, 2, STAGED>(a, tmx, grid, s);
+    case 1: return launch_one<T, RC, MK, T1, T2, W1, W2, CPT, 1, STAGED>(a, tmx, grid, s);
+    case 2: return launch_one<T, RC, MK, T1, T2, W1, W2, CPT, 2, STAGED>(a, tmx, grid, s);
 #endif
     default: return -1;
     }
 }
-template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
+template <int RC, typename MK, int T1, int T2, int W1, int W2, int CPT, int STAGED>
 static int launch_prec(bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
-    if (!c64) return launch_modes<double, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
+    if (!c64) return launch_modes<double, RC, MK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
 #ifndef LM_STENCIL_NOC64
-    return launch_modes<float, RC, MASK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
+    return launch_modes<float, RC, MK, T1, T2, W1, W2, CPT, STAGED>(mode, a, tmx, grid, s);
 #else
     return -1;
 #endif
 }
 
-#define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MASK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, tmx, grid, s);
+#define LM_ST_V(v, T1, T2, W1, W2, CPT, ST) case v: return launch_prec<RC, MK, T1, T2, W1, W2, CPT, ST>(c64, mode, a, tmx, grid, s);
 // shape experiments: complex128, plain SpMM and product-form factor only (keeps the build short)
-template <int RC, st_mask_t MASK, int T1, int T2, int W1, int W2, int CPT>
+template <int RC, typename MK, int T1, int T2, int W1, int W2, int CPT>
 static int launch_try(bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if (c64) return -1;
-    if (mode == 0) return launch_one<double, RC, MASK, T1, T2, W1, W2, CPT, 0, 1>(a, tmx, grid, s);
-    if (mode == 3) return launch_one<double, RC, MASK, T1, T2, W1, W2, CPT, 3, 1>(a, tmx, grid, s);
+    if (mode == 0) return launch_one<double, RC, MK, T1, T2, W1, W2, CPT, 0, 1>(a, tmx, grid, s);
+    if (mode == 3) return launch_one<double, RC, MK, T1, T2, W1, W2, CPT, 3, 1>(a, tmx, grid, s);
     return -1;
 }
-#define LM_ST_X(v, T1, T2, W1, W2, CPT) case v: return launch_try<RC, MASK, T1, T2, W1, W2, CPT>(c64, mode, a, tmx, grid, s);
-template <int RC, st_mask_t MASK>
+#define LM_ST_X(v, T1, T2, W1, W2, CPT) case v: return launch_try<RC, MK, T1, T2, W1, W2, CPT>(c64, mode, a, tmx, grid, s);
+template <int RC, typename MK>
 static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
     if constexpr (RC == 1) {
         switch (variant) {
@@ -87,6 +87,14 @@ static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, con
 #endif
 #ifdef LM_STENCIL_EXPLORE
             LM_ST_V(8, 4, 4, 2, 2, 1, 0) LM_ST_V(9, 4, 2, 2, 4, 2, 1) LM_ST_V(3, 4, 2, 2, 4, 1, 1) LM_ST_V(10, 2, 2, 4, 2, 1, 2) LM_ST_V(11, 4, 2, 2, 2, 1, 2) LM_ST_V(12, 4, 4, 2, 2, 1, 2)
+#endif
+            default: return -1;
+        }
+    } else if constexpr (RC >= 3) {
+        switch (variant) {
+            LM_ST_V(19, 2, 2, 2, 2, 1, 1)
+#ifdef LM_STENCIL_SHAPES
+            LM_ST_X(6, 2, 2, 4, 2, 1)
 #endif
             default: return -1;
         }
@@ -114,33 +122,39 @@ template <> struct ObsShape<1, false> { static constexpr int T1 = 2, T2 = 2, W1 
 template <> struct ObsShape<1, true>  { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };
 template <> struct ObsShape<2, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 x 4 cells, 256 threads
 template <> struct ObsShape<2, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };   // 4 x 2 cells, 256 threads
+template <> struct ObsShape<3, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 3 rows x (1 + 2 NF <= 9) sums per cell
+template <> struct ObsShape<3, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };
+template <> struct ObsShape<4, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 rows x (1 + 2 NF <= 7) sums per cell
+template <> struct ObsShape<4, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };
+// WIDE: two cells per thread would exceed the 64 partial sums a thread folds (k_observe_stencil)
+template <int RC> constexpr bool obs_wide(int nf) { return RC == 3 ? nf > 4 : (RC == 4 ? nf > 3 : nf > 6); }
 
-template <typename T, int RC, st_mask_t MASK>
+template <typename T, int RC, typename MK>
 static int launch_obs_t(const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
-    using S = ObsShape<RC, (st_nfwd<RC>(MASK) > 6)>;
+    using S = ObsShape<RC, obs_wide<RC>(st_nfwd<RC>(MK::mask))>;
     constexpr size_t smem = st_obs_smem<T, RC, S::T1, S::T2, S::W1, S::W2>();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2>,
+        if (cudaFuncSetAttribute(k_observe_stencil<T, RC, MK, S::T1, S::T2, S::W1, S::W2>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         configured = true;
     }
-    k_observe_stencil<T, RC, MASK, S::T1, S::T2, S::W1, S::W2><<<grid, 32 * S::W1 * S::W2, smem, s>>>(a, tmx);
+    k_observe_stencil<T, RC, MK, S::T1, S::T2, S::W1, S::W2><<<grid, 32 * S::W1 * S::W2, smem, s>>>(a, tmx);
     return 0;
 }
-template <int RC, st_mask_t MASK>
+template <int RC, typename MK>
 static int launch_obs(bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
-    if (!c64) return launch_obs_t<double, RC, MASK>(a, tmx, grid, s);
+    if (!c64) return launch_obs_t<double, RC, MK>(a, tmx, grid, s);
 #ifndef LM_STENCIL_NOC64
-    return launch_obs_t<float, RC, MASK>(a, tmx, grid, s);
+    return launch_obs_t<float, RC, MK>(a, tmx, grid, s);
 #else
     return -1;
 #endif
 }
-template <int RC, st_mask_t MASK>
+template <int RC, typename MK>
 static void obs_shape(int* P1, int* P2, int* nf) {
-    using S = ObsShape<RC, (st_nfwd<RC>(MASK) > 6)>;
-    *P1 = S::W1 * S::T1; *P2 = S::W2 * S::T2; *nf = st_nfwd<RC>(MASK);
+    using S = ObsShape<RC, obs_wide<RC>(st_nfwd<RC>(MK::mask))>;
+    *P1 = S::W1 * S::T1; *P2 = S::W2 * S::T2; *nf = st_nfwd<RC>(MK::mask);
 }
 
 }  // namespace lm

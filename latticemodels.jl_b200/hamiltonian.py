@@ -347,3 +347,12 @@ def haldane(lat: BravaisLattice, t1, t2, m=0, field=None):
         raise _lib.ArgumentError("Invalid lattice type %s; expected HoneycombLattice" % lat.kind)
     ms = np.where(lat.b == 0, float(m), -float(m))
     return construct_hamiltonian(lat, 1, (1, ms), (t1, NearestNeighbor(1)), (1j * t2, honeycomb_2nn), field=field)
+
+
+def kanemele(lat: BravaisLattice, t1, t2, field=None):
+    """src/zoo/models.jl:188-194: spin-1/2 honeycomb model, `t1 => NearestNeighbor(1)`, `im t2 sigma_z => honeycomb_2nn`."""
+    from .lattices import honeycomb_2nn
+    if lat.kind != "HoneycombLattice":
+        raise _lib.ArgumentError("Invalid lattice type %s; expected HoneycombLattice" % lat.kind)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    return construct_hamiltonian(lat, 2, (t1, NearestNeighbor(1)), (1j * t2 * sz, honeycomb_2nn), field=field)

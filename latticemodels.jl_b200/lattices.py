@@ -240,6 +240,19 @@ def HoneycombLattice(n1, n2, boundaries=(), predicate=None):
                           _axis_boundaries((n1, n2), boundaries), predicate, "HoneycombLattice")
 
 
+def TriangularLattice(n1, n2, boundaries=(), predicate=None):
+    """src/zoo/lattices.jl:145."""
+    return BravaisLattice(np.array([[1.0, 0.5], [0.0, math.sqrt(3) / 2]]), np.zeros((2, 1)), (n1, n2),
+                          _axis_boundaries((n1, n2), boundaries), predicate, "TriangularLattice")
+
+
+def KagomeLattice(n1, n2, boundaries=(), predicate=None):
+    """src/zoo/lattices.jl:209: three sites at (0, 0), (1/2, 0), (1/4, sqrt(3)/4) per unit cell."""
+    return BravaisLattice(np.array([[1.0, 0.5], [0.0, math.sqrt(3) / 2]]),
+                          np.array([[0.0, 0.5, 0.25], [0.0, 0.0, math.sqrt(3) / 4]]), (n1, n2),
+                          _axis_boundaries((n1, n2), boundaries), predicate, "KagomeLattice")
+
+
 # src/zoo/models.jl:139-145
 honeycomb_2nn = (
     BravaisTranslation((1, 1), axis=1),

@@ -137,6 +137,23 @@ def honeycomb_lattice(a, b, periodic=(), twists=None):
     return _apply_axis_boundaries(lat, (a, b), periodic, twists)
 
 
+def triangular_lattice(a, b, periodic=(), twists=None):
+    """TriangularLattice(a, b) (src/zoo/lattices.jl:145)."""
+    uc = UnitCell(np.array([[1.0, 0.5], [0.0, math.sqrt(3) / 2]]), np.zeros((2, 1)))
+    lat = span_unitcells(uc, a, b)
+    lat.kind = "triangular"
+    return _apply_axis_boundaries(lat, (a, b), periodic, twists)
+
+
+def kagome_lattice(a, b, periodic=(), twists=None):
+    """KagomeLattice(a, b) (src/zoo/lattices.jl:209)."""
+    uc = UnitCell(np.array([[1.0, 0.5], [0.0, math.sqrt(3) / 2]]),
+                  np.array([[0.0, 0.5, 0.25], [0.0, 0.0, math.sqrt(3) / 4]]))
+    lat = span_unitcells(uc, a, b)
+    lat.kind = "kagome"
+    return _apply_axis_boundaries(lat, (a, b), periodic, twists)
+
+
 def _apply_axis_boundaries(lat, sizes, periodic, twists):
     bl = []
     twists = twists or {}

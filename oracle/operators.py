@@ -135,3 +135,12 @@ def haldane(lat, t1, t2, m=0, field=None):
         (t1, L.nearest_neighbor(lat, 1)),
         (1j * t2, L.HONEYCOMB_2NN),
     ], field)
+
+
+def kanemele(lat, t1, t2, field=None):
+    """src/zoo/models.jl:188-194."""
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    return construct_hamiltonian(lat, 2, [
+        (t1, L.nearest_neighbor(lat, 1)),
+        (1j * t2 * sz, L.HONEYCOMB_2NN),
+    ], field)

@@ -5,8 +5,8 @@
     LM_EMUL_LIB=<liblm_b200_emul.so> python tests/fuzz_parity.py [first_seed] [n_cases]     # no GPU
     python tests/fuzz_parity.py 0 200                                                         # on a B200
 
-Every case draws a lattice (square / honeycomb, 3..18 cells per axis, open / periodic / twisted
-boundaries), a model (tight binding with t1 / t2 / t3, QWZ, Haldane), a field (Landau, symmetric,
+Every case draws a lattice (square / honeycomb / kagome, 3..18 cells per axis, open / periodic / twisted
+boundaries), a model (tight binding with t1 / t2 / t3, QWZ, Haldane, Kane-Mele), a field (Landau, symmetric,
 axial and singular point fluxes, sums), a block width 1..150, a precision, a propagator method, a
 step and the schedule (plain or L2-resident strips) and checks, through the C ABI: the device
 assembled H, H X, a few evolution steps against the exact exponential, localdensity and
@@ -30,6 +30,7 @@ from oracle import evolution as EV, fields as F, lattice as L, operators as OP
 warnings.simplefilter("ignore")
 lib = _lib.load()
 lib.lm_dbg_set_stencil_flags.argtypes = [C.c_int32, C.c_int32]
+lib.lm_dbg_set_stencil_ri.argtypes = [C.c_int32]
 seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 ncases = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 ctxs = {"c128": lm.default_context("c128"), "c64": lm.default_context("c64")}
@@ -41,7 +42,7 @@ for case in range(seed0, seed0 + ncases):
     n1, n2 = int(rng.integers(3, 19)), int(rng.integers(3, 19))
     per = [bool(rng.integers(0, 2)), bool(rng.integers(0, 2))]
     tw = float(rng.uniform(0.1, 2.0)) if rng.integers(0, 3) == 0 else None
-    model = ["tb1", "tb12", "tb123", "qwz", "hc1", "haldane", "hc123"][int(rng.integers(0, 7))]
+    model = ["tb1", "tb12", "tb123", "qwz", "hc1", "haldane", "hc123", "kagome1", "kagome12", "kanemele"][int(rng.integers(0, 10))]
     fk = int(rng.integers(0, 5))
     B = float(rng.uniform(-0.2, 0.2))
     px, py = float(rng.uniform(1, n1)), float(rng.uniform(1, n2))
@@ -54,15 +55,19 @@ for case in range(seed0, seed0 + ncases):
                 bl.append(("axis2", tw)); bo_tw[2] = tw
             else:
                 bl.append(("axis%d" % ax, True)); bo_per.append(ax)
-    honey = model in ("hc1", "haldane", "hc123")
-    latd = (lm.HoneycombLattice if honey else lm.SquareLattice)(n1, n2, boundaries=bl)
-    lato = (L.honeycomb_lattice if honey else L.square_lattice)(n1, n2, periodic=tuple(bo_per), twists=bo_tw or None)
+    honey = model in ("hc1", "haldane", "hc123", "kanemele")
+    kag = model in ("kagome1", "kagome12")
+    latd = (lm.KagomeLattice if kag else lm.HoneycombLattice if honey else lm.SquareLattice)(n1, n2, boundaries=bl)
+    lato = (L.kagome_lattice if kag else L.honeycomb_lattice if honey else L.square_lattice)(n1, n2, periodic=tuple(bo_per), twists=bo_tw or None)
     try:
         if model == "tb1": Hd, Ho = lm.tightbinding_hamiltonian(latd, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, field=mkf(F))
         elif model == "tb12": Hd, Ho = lm.tightbinding_hamiltonian(latd, t1=1, t2=0.3, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, t1=1, t2=0.3, field=mkf(F))
         elif model == "tb123": Hd, Ho = lm.tightbinding_hamiltonian(latd, t1=1, t2=0.3, t3=0.1, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, t1=1, t2=0.3, t3=0.1, field=mkf(F))
         elif model == "qwz": Hd, Ho = lm.qwz(latd, field=mkf(lm)), OP.qwz(lato, field=mkf(F))
         elif model == "hc1": Hd, Ho = lm.tightbinding_hamiltonian(latd, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, field=mkf(F))
+        elif model == "kagome1": Hd, Ho = lm.tightbinding_hamiltonian(latd, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, field=mkf(F))
+        elif model == "kagome12": Hd, Ho = lm.tightbinding_hamiltonian(latd, t1=1, t2=0.3, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, t1=1, t2=0.3, field=mkf(F))
+        elif model == "kanemele": Hd, Ho = lm.kanemele(latd, 1.0, 0.2, field=mkf(lm)), OP.kanemele(lato, 1.0, 0.2, field=mkf(F))
         elif model == "haldane": Hd, Ho = lm.haldane(latd, 1.0, 0.2, 0.1, field=mkf(lm)), OP.haldane(lato, 1.0, 0.2, 0.1, field=mkf(F))
         else: Hd, Ho = lm.tightbinding_hamiltonian(latd, t1=1, t2=0.2, t3=0.1, field=mkf(lm)), OP.tightbinding_hamiltonian(lato, t1=1, t2=0.2, t3=0.1, field=mkf(F))
     except Exception as e:
@@ -87,8 +92,9 @@ for case in range(seed0, seed0 + ncases):
         assert e1 < 3e-14 * eps, ("spmm", e1)
         method = ["auto", "taylor", "chebyshev", "taylor_horner", "chebyshev_clenshaw", "lanczos"][int(rng.integers(0, 6))]
         dt = float(rng.choice([0.1, 0.37, -0.5, 1.3]))
-        kb = int(rng.integers(0, 4))                 # stencil kernel variant: bit 0 shared value loads (Hermitian), bit 1 tensor-map boxes
-        lib.lm_dbg_set_stencil_flags(kb & 1, kb >> 1)
+        kb = int(rng.integers(0, 8))                 # stencil kernel variant: bit 0 shared value loads (Hermitian), bit 1 tensor-map boxes, bit 2 no real / imaginary class scalars
+        lib.lm_dbg_set_stencil_flags(kb & 1, (kb >> 1) & 1)
+        lib.lm_dbg_set_stencil_ri(0 if kb & 4 else -1)
         st = lm.DeviceState.from_psi(X, ctx=ctx)
         sol = lm.B200Exp(tol=1e-13 if prec == "c128" else 1e-6, method=method, ctx=ctx)
         sol.update_solver(Hd, dt)
@@ -99,6 +105,7 @@ for case in range(seed0, seed0 + ncases):
         e2 = relerr(st.download(), want)
         assert e2 < 1e-12 * eps * 3, ("step", method, dt, kb, e2)
         lib.lm_dbg_set_stencil_flags(-1, -1)
+        lib.lm_dbg_set_stencil_ri(-1)
         w = rng.random(M)
         Xn = X / np.sqrt(N)
         so = lm.DeviceState.from_psi(Xn, w, ctx=ctx, n_int=Hd.n_int)
@@ -126,6 +133,7 @@ for case in range(seed0, seed0 + ncases):
     except Exception as e:
         nfail += 1
         lib.lm_dbg_set_stencil_flags(-1, -1)
+        lib.lm_dbg_set_stencil_ri(-1)
         print("FAIL", desc, "->", repr(e)[:300], flush=True)
 print("fuzz: %d cases, %d failures, %.0fs" % (ncases, nfail, time.time() - t00))
 sys.exit(1 if nfail else 0)

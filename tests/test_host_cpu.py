@@ -260,6 +260,47 @@ def test_compiled_stencil_masks_cover_reference_models():
         # tight: the compiled mask adds nothing but the on-site (same-cell) block to the model's own pattern
         extra = masks[mid] & ~m
         assert mid in (1, 5) or extra & ~(((1 << (rc * rc)) - 1) << (4 * rc * rc)) == 0
+    # patterns as the kernels see them: StPat<id> with multi-word masks (three / four rows per cell) and the
+    # "purely imaginary" entries of the real / imaginary value class
+    def word(tok):
+        tok = tok.strip()
+        return int(masks[int(tok[-1])] if tok.startswith("LM_ST_MASK") else (imags[int(tok[-1])] if tok.startswith("LM_ST_IMAG") else int(tok.rstrip("ul"), 16 if tok.startswith("0x") else 10)))
+    imags = {int(k): int(v, 16) for k, v in re.findall(r"#define LM_ST_IMAG(\d) (0x[0-9a-f]+)ull", src)}
+    pats = {}
+    for pid, rc, m, im in re.findall(r"StPat<(\d+)> \{ static constexpr int rc = (\d); static constexpr st_mask_t mask = \{\{(.*?)\}\},\s*imag = \{\{(.*?)\}\}; \};", src, re.S):
+        pats[int(pid)] = (int(rc), sum(word(t) << (64 * k) for k, t in enumerate(m.split(","))), sum(word(t) << (64 * k) for k, t in enumerate(im.split(","))))
+    assert sorted(pats) == list(range(9)) and all(pats[k][1] == masks[k] for k in masks)
+    wide = [
+        (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6), field=F.LandauGauge(0.1)), 5, 6, 3, 6),
+        (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6, periodic=(1, 2))), 5, 6, 3, 6),
+        (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6), t1=1, t2=0.3), 5, 6, 3, 7),
+        (OP.kanemele(L.honeycomb_lattice(5, 6), 1.0, 0.2), 5, 6, 4, 8),
+        (OP.kanemele(L.honeycomb_lattice(5, 6, periodic=(1, 2)), 1.0, 0.2, field=F.LandauGauge(0.05)), 5, 6, 4, 8),
+    ]
+    for H, n1, n2, rc_want, pid in wide:
+        rc, m = ST.stencil_mask(H, n1, n2)
+        assert rc == rc_want == pats[pid][0] and m is not None and m & ~pats[pid][1] == 0
+        diag = sum(1 << (4 * rc * rc + a * rc + a) for a in range(rc))
+        assert pats[pid][1] & ~m & ~diag == 0                     # tight up to the on-site diagonal
+    # value classes: without a field every stored entry of the reference models is purely real, or purely
+    # imaginary exactly where the pattern says so
+    import scipy.sparse as sp
+    for H, n1, n2, pid in [(OP.tightbinding_hamiltonian(L.square_lattice(6, 7)), 6, 7, 0), (OP.qwz(L.square_lattice(5, 6), 1.3), 5, 6, 3),
+                           (OP.haldane(L.honeycomb_lattice(5, 6, periodic=(1, 2)), 1.0, 0.2, 0.1), 5, 6, 4),
+                           (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6), t1=1, t2=0.3), 5, 6, 7),
+                           (OP.kanemele(L.honeycomb_lattice(5, 6), 1.0, 0.2), 5, 6, 8)]:
+        rc, _, imag = pats[pid]
+        csr = sp.csr_matrix(H)
+        for i in range(csr.shape[0]):
+            ci, a = divmod(i, rc)
+            for k in range(csr.indptr[i], csr.indptr[i + 1]):
+                cj, b = divmod(int(csr.indices[k]), rc)
+                d1, d2 = cj // n2 - ci // n2, cj % n2 - ci % n2
+                d1 = d1 - n1 if d1 > n1 // 2 else (d1 + n1 if d1 < -(n1 // 2) else d1)
+                d2 = d2 - n2 if d2 > n2 // 2 else (d2 + n2 if d2 < -(n2 // 2) else d2)
+                bit = ((d1 + 1) * 3 + d2 + 1) * rc * rc + a * rc + b
+                v = csr.data[k]
+                assert (v.real == 0) if (imag >> bit) & 1 else (v.imag == 0), (pid, i, int(csr.indices[k]), v)
     # third-neighbour hops couple cells two apart: no |d| <= 1 mask
     assert ST.stencil_mask(OP.tightbinding_hamiltonian(L.square_lattice(8, 8), t1=1, t3=0.1), 8, 8)[1] is None
     # Haldane: 4 forward bonds from the A row, 5 from the B row (one correlator per bond)
@@ -279,22 +320,31 @@ def test_stencil_tile_logic_executes_on_cpu(tmp_path):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
+    from concurrent.futures import ThreadPoolExecutor
     emul = os.path.join(ROOT, "tests", "cpu_emul")
-    exe = str(tmp_path / "stencil_emul")
-    subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-I", os.path.join(emul, "shim"),
-                    "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
-                    os.path.join(emul, "stencil_emul.cpp"), "-o", exe], check=True)
-    res = subprocess.run([exe], capture_output=True, text=True)
-    assert res.returncode == 0 and res.stdout.startswith("OK "), res.stdout + res.stderr
-    assert int(res.stdout.split()[1]) >= 300
+
+    def group(g):
+        exe = str(tmp_path / ("stencil_emul_%d" % g))
+        subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g, "-I", os.path.join(emul, "shim"),
+                        "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
+                        os.path.join(emul, "stencil_emul.cpp"), "-o", exe], check=True)
+        return subprocess.run([exe], capture_output=True, text=True)
+    with ThreadPoolExecutor(3) as ex:
+        results = list(ex.map(group, range(3)))
+    total = 0
+    for res in results:
+        assert res.returncode == 0 and res.stdout.startswith("OK "), res.stdout + res.stderr
+        total += int(res.stdout.split()[1])
+    assert total >= 450
 
 
 def test_stencil_kernels_execute_on_cpu(tmp_path):
     """The WHOLE stencil kernels of csrc/stencil.cuh - k_apply_stencil_tma (default SpMM / propagator
     factor), k_apply_stencil and k_observe_stencil (fused localdensity + bond correlators) - executed
     on the CPU: every CUDA thread of a CTA is an OS thread (real __syncthreads, warp-shuffle
-    mailboxes, atomics, mbarrier phase rule, alignment-checked cp.async.bulk).  All five compiled
-    patterns in the shapes the library launches, open / periodic / 3x3-torus / ragged lattices,
+    mailboxes, atomics, mbarrier phase rule, alignment-checked cp.async.bulk).  All nine compiled
+    patterns (one to four rows per unit cell) in the shapes the library launches, complex values and the
+    real / imaginary class scalars, open / periodic / 3x3-torus / ragged lattices,
     complex128 and complex64, every MODE, and the column window + plain-store flag of the
     L2-resident strip schedule (columns outside the window must stay untouched)."""
     import shutil
@@ -302,14 +352,23 @@ def test_stencil_kernels_execute_on_cpu(tmp_path):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
+    from concurrent.futures import ThreadPoolExecutor
     emul = os.path.join(ROOT, "tests", "cpu_emul")
-    exe = str(tmp_path / "stencil_kernel_emul")
-    subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-I", os.path.join(emul, "shim"),
-                    "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
-                    os.path.join(emul, "stencil_kernel_emul.cpp"), "-o", exe], check=True)
-    res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0 and res.stdout.startswith("OK "), res.stdout + res.stderr
-    assert int(res.stdout.split()[1]) >= 100000
+
+    def group(g):
+        # the fully unrolled kernels are large: four pattern groups, built as separate programs in parallel
+        exe = str(tmp_path / ("stencil_kernel_emul_%d" % g))
+        subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g, "-I", os.path.join(emul, "shim"),
+                        "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
+                        os.path.join(emul, "stencil_kernel_emul.cpp"), "-o", exe], check=True)
+        return subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    with ThreadPoolExecutor(4) as ex:
+        results = list(ex.map(group, range(4)))
+    total = 0
+    for res in results:
+        assert res.returncode == 0 and res.stdout.startswith("OK "), res.stdout + res.stderr
+        total += int(res.stdout.split()[1])
+    assert total >= 2000000
 
 
 def test_timesequence_holds_arbitrary_values_and_nominal_keys():

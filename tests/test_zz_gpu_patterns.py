@@ -434,3 +434,167 @@ def test_device_eigensolver_full_size_against_closed_form():
     assert np.abs(X.conj().T @ X - np.eye(12)).max() < 1e-11
     R = H.data @ X - X * vals[None, :]
     assert np.linalg.norm(R, axis=0).max() < 4e-8
+
+
+# ------------------------------------------------------------------------------ real / imaginary value class
+def _set_ri(v):
+    lib = _lib.load()
+    lib.lm_dbg_set_stencil_ri.argtypes = [C.c_int32]
+    lib.lm_dbg_set_stencil_ri.restype = C.c_int32
+    _lib.check(lib.lm_dbg_set_stencil_ri(v))
+
+
+def _ri_state(dev):
+    lib = _lib.load()
+    lib.lm_dbg_stencil_ri_state.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lm_dbg_stencil_ri_state.restype = C.c_int32
+    f = C.c_int32(-1)
+    _lib.check(lib.lm_dbg_stencil_ri_state(dev.handle, C.byref(f)))
+    return f.value
+
+
+RI_CASES = {
+    # (device model, oracle model, in the class of its compiled pattern?)
+    "square": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(21, 18)),
+               lambda: OP.tightbinding_hamiltonian(L.square_lattice(21, 18)), 1),
+    "square_nnn_pbc": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(12, 13, boundaries=[("axis1", True), ("axis2", True)]), t1=1, t2=0.3),
+                       lambda: OP.tightbinding_hamiltonian(L.square_lattice(12, 13, periodic=(1, 2)), t1=1, t2=0.3), 1),
+    "honeycomb": (lambda: lm.tightbinding_hamiltonian(lm.HoneycombLattice(11, 9)),
+                  lambda: OP.tightbinding_hamiltonian(L.honeycomb_lattice(11, 9)), 1),
+    "qwz": (lambda: lm.qwz(lm.SquareLattice(14, 15), 1.3), lambda: OP.qwz(L.square_lattice(14, 15), 1.3), 1),
+    "qwz_pbc": (lambda: lm.qwz(lm.SquareLattice(14, 15, boundaries=[("axis1", True)])),
+                lambda: OP.qwz(L.square_lattice(14, 15, periodic=(1,))), 1),
+    "haldane": (lambda: lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1),
+                lambda: OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1), 1),
+    "haldane_torus": (lambda: lm.haldane(lm.HoneycombLattice(9, 10, boundaries=[("axis1", True), ("axis2", True)]), 1.0, 0.2, 0.1),
+                      lambda: OP.haldane(L.honeycomb_lattice(9, 10, periodic=(1, 2)), 1.0, 0.2, 0.1), 1),
+    "haldane_field": (lambda: lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1, field=lm.LandauGauge(0.05)),
+                      lambda: OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1, field=F.LandauGauge(0.05)), 0),
+    "square_twist": (lambda: lm.tightbinding_hamiltonian(lm.SquareLattice(12, 13, boundaries=[("axis1", 0.7)])),
+                     lambda: OP.tightbinding_hamiltonian(L.square_lattice(12, 13, periodic=(1,), twists={1: 0.7})), 0),
+}
+
+
+@pytest.mark.parametrize("precision", ["c128", "c64"])
+@pytest.mark.parametrize("case", sorted(RI_CASES))
+def test_real_imaginary_value_class(case, precision):
+    """Models without a magnetic field have purely real / purely imaginary entries (real hoppings, `im t2` of
+    `haldane`, the `-im/2` orbital flips of `qwz`): the stencil kernel then reads scalar values.  The class is
+    detected on the device (lm_dbg_stencil_ri_state); scalar and complex paths agree to rounding and both match
+    the exact exponential; Peierls phases and twists stay on the complex path."""
+    ctx = lm.default_context(precision)
+    mk_dev, mk_or, in_class = RI_CASES[case]
+    Hd, Ho = mk_dev(), mk_or()
+    N = Ho.shape[0]
+    tol = 1e-13 if precision == "c128" else 1e-6
+    try:
+        outs = []
+        for ri in (0, 1):
+            _set_ri(ri)
+            X = _rand_block(N, 150, seed=11)
+            st = lm.DeviceState.from_psi(X, ctx=ctx)
+            sol = lm.B200Exp(tol=tol, method="chebyshev", ctx=ctx)
+            sol.update_solver(Hd, 0.25)
+            assert _stencil_id(sol.dev) >= 0
+            assert _ri_state(sol.dev) == in_class, case
+            for _ in range(3):
+                sol.step(st)
+            outs.append(st.download())
+        U = EV.exact_propagator(Ho, 0.25)
+        want = U @ (U @ (U @ X))
+        for o in outs:
+            assert _relerr(o, want) < (5e-13 if precision == "c128" else 2e-4), case
+        assert _relerr(outs[1], outs[0]) < (1e-13 if precision == "c128" else 5e-5), case
+    finally:
+        _set_ri(-1)
+
+
+def test_value_class_follows_value_updates():
+    """A field ramp from B = 0: the first operator is real (scalar path), later ones carry Peierls phases
+    (complex path), then back - through synchronous AND asynchronous value updates and step-graph replays.
+    The class flag lives on the device, so an asynchronous update needs no host round trip."""
+    import scipy.sparse as sp
+    ctx = lm.default_context("c128")
+    lat = lm.HoneycombLattice(12, 10)
+    Bs = [0.0, 0.0, 0.03, 0.06, 0.0, 0.0, 0.02]
+    Hs = [sp.csc_matrix(lm.haldane(lat, 1.0, 0.2, 0.1, field=lm.LandauGauge(B)).data).astype(np.complex128) for B in Bs]
+    X = _rand_block(240, 96, seed=21)
+    lib = _lib.load()
+    nmv = C.c_int32()
+    want = X
+    for H in Hs:
+        want = EV.exact_propagator(H.toarray(), 0.1) @ want
+    for use_async in (False, True):
+        dev = lm.DeviceHam.from_csc(ctx, Hs[0], 1, coords=lat.coords, lattice_dims=lat.sizes)
+        assert _stencil_id(dev) >= 0 and _ri_state(dev) == 1
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        keep = []
+        for k, H in enumerate(Hs):
+            nz = np.ascontiguousarray(H.data)
+            keep.append(nz)
+            _lib.check((lib.lm_ham_update_values_async if use_async else lib.lm_ham_update_values)(dev.handle, _lib.ptr(nz)))
+            _lib.check(lib.lm_step(dev.handle, st.handle, 0.1, 1e-13, 0, C.byref(nmv)))
+            if not use_async:
+                assert _ri_state(dev) == (1 if Bs[k] == 0.0 else 0)
+        _lib.check(lib.lm_ctx_synchronize(ctx.handle))
+        assert _relerr(st.download(), want) < 1e-12
+
+
+# ------------------------------------------------------------------------------ three / four rows per unit cell
+WIDE_CASES = {
+    # name: (device model, oracle model, compiled pattern id, in the real / imaginary class?)
+    "kagome": (lambda: lm.tightbinding_hamiltonian(lm.KagomeLattice(9, 11), field=lm.LandauGauge(0.04)),
+               lambda: OP.tightbinding_hamiltonian(L.kagome_lattice(9, 11), field=F.LandauGauge(0.04)), 6, 0),
+    "kagome_torus": (lambda: lm.tightbinding_hamiltonian(lm.KagomeLattice(8, 7, boundaries=[("axis1", True), ("axis2", True)])),
+                     lambda: OP.tightbinding_hamiltonian(L.kagome_lattice(8, 7, periodic=(1, 2))), 6, 1),
+    "kagome_t2": (lambda: lm.tightbinding_hamiltonian(lm.KagomeLattice(10, 9), t1=1, t2=0.3, field=lm.SymmetricGauge(0.02)),
+                  lambda: OP.tightbinding_hamiltonian(L.kagome_lattice(10, 9), t1=1, t2=0.3, field=F.SymmetricGauge(0.02)), 7, 0),
+    "kanemele": (lambda: lm.kanemele(lm.HoneycombLattice(9, 8), 1.0, 0.2),
+                 lambda: OP.kanemele(L.honeycomb_lattice(9, 8), 1.0, 0.2), 8, 1),
+    "kanemele_cyl_field": (lambda: lm.kanemele(lm.HoneycombLattice(9, 8, boundaries=[("axis1", True)]), 1.0, 0.2, field=lm.LandauGauge(0.03)),
+                           lambda: OP.kanemele(L.honeycomb_lattice(9, 8, periodic=(1,)), 1.0, 0.2, field=F.LandauGauge(0.03)), 8, 0),
+}
+
+
+@pytest.mark.parametrize("precision", ["c128", "c64"])
+@pytest.mark.parametrize("case", sorted(WIDE_CASES))
+def test_three_and_four_row_stencils_match_oracle(case, precision):
+    """`KagomeLattice` (three sites per cell, src/zoo/lattices.jl:209) and `kanemele` (spin-1/2 honeycomb, four rows per
+    cell, src/zoo/models.jl:188-194) run on the register-tiled stencil kernels (patterns 6 - 8, multi-word masks,
+    2 x 2-cell tiles): SpMM, every propagator, localdensity and DensityCurrents against the oracle."""
+    ctx = lm.default_context(precision)
+    mk_dev, mk_or, pid, in_class = WIDE_CASES[case]
+    Hd, Ho = mk_dev(), mk_or()
+    dev = Hd.device(ctx)
+    assert _stencil_id(dev) == pid
+    assert _ri_state(dev) == in_class
+    lib = _lib.load()
+    N = Ho.shape[0]
+    c128 = precision == "c128"
+    for M in (32, 45, 100):
+        X = _rand_block(N, M, seed=M)
+        x = lm.DeviceState.from_psi(X, ctx=ctx)
+        y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+        _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+        assert _relerr(y.download(), Ho @ X) < (1e-14 if c128 else 1e-6), (case, M)
+    X = _rand_block(N, 40, seed=5)
+    want = EV.exact_propagator(Ho, 0.3) @ X
+    for method in ("taylor", "chebyshev", "chebyshev_clenshaw", "taylor_horner"):
+        st = lm.DeviceState.from_psi(X, ctx=ctx)
+        sol = lm.B200Exp(tol=1e-14 if c128 else 1e-6, method=method, ctx=ctx)
+        sol.update_solver(Hd, 0.3)
+        sol.step(st)
+        assert _relerr(st.download(), want) < (2e-13 if c128 else 2e-5), (case, method)
+    Hdn = Ho.toarray()
+    for M in (32, 70):
+        Psi = _rand_block(N, M, seed=M) / np.sqrt(N)
+        w = np.random.default_rng(M).random(M)
+        st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, lattice=Hd.lattice, n_int=Hd.n_int)
+        I, J, V = lm.DensityCurrents(Hd, st).pair_values()
+        P = (Psi * w) @ Psi.conj().T
+        n = Hd.n_int
+        rho = np.real(np.diag(P)).reshape(-1, n).sum(axis=1)
+        assert _relerr(lm.localdensity(st).values, rho) < (1e-13 if c128 else 1e-5)
+        want_j = np.array([sum(2 * np.imag(Hdn[(i - 1) * n + a, (j - 1) * n + b] * P[(j - 1) * n + b, (i - 1) * n + a])
+                               for a in range(n) for b in range(n)) for i, j in zip(I.tolist(), J.tolist())])
+        assert np.abs(V - want_j).max() < (1e-13 if c128 else 1e-5) * max(1.0, np.abs(want_j).max()), (case, M)

@@ -85,6 +85,14 @@ def timing(ctx, cases, variants, reps):
             H = lm.tightbinding_hamiltonian(lm.SquareLattice(n, n))
         elif kind == "qwz":
             H = lm.qwz(lm.SquareLattice(n, n), field=lm.LandauGauge(0.01))
+        elif kind == "kagome":
+            H = lm.tightbinding_hamiltonian(lm.KagomeLattice(n, n), field=lm.LandauGauge(0.01))
+        elif kind == "kagome2":
+            H = lm.tightbinding_hamiltonian(lm.KagomeLattice(n, n), t1=1, t2=0.3)
+        elif kind == "kanemele":
+            H = lm.kanemele(lm.HoneycombLattice(n, n), 1.0, 0.2)
+        elif kind == "kanemele_field":
+            H = lm.kanemele(lm.HoneycombLattice(n, n), 1.0, 0.2, field=lm.LandauGauge(0.01))
         else:
             H = lm.haldane(lm.HoneycombLattice(n, n), 1.0, 0.2, 0.1)
         dev = H.device(ctx)
@@ -109,7 +117,7 @@ def timing(ctx, cases, variants, reps):
         nmv = C.c_int32()
         runs = [("ell", -1, -1)] + [("stencil", 5, v) for v in variants]
         for tag, path, v in runs:
-            lib.lm_dbg_set_apply_path(path if path >= 0 else (3 if kind == "qwz" else 2))
+            lib.lm_dbg_set_apply_path(path if path >= 0 else (3 if kind in ("qwz", "kanemele", "kanemele_field") else 2))
             lib.lm_dbg_set_stencil_variant(v)
             if lib.lm_spmm_state(dev.handle, x.handle, y.handle) != 0:
                 continue
