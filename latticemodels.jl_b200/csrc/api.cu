@@ -619,6 +619,8 @@ static int ham_build_tiles(lm_ham* h, const double* xy) {
 // every ELL entry couples cells at most one apart (periodic images included) and the pattern is
 // covered by a compiled stencil (stencil.cu), build the ELL -> stencil-slot gather map.
 // ------------------------------------------------------------------------------------------
+static int g_stencil_rtc = -1;            // lm_dbg_set_stencil_rtc (tests): -1 = LM_STENCIL_RTC (default 1: run-time specialisation when no compiled pattern matches)
+extern "C" int32_t lm_dbg_set_stencil_rtc(int32_t v) { g_stencil_rtc = v; return LM_OK; }
 static int ham_build_stencil(lm_ham* h) {
     lm_ctx* c = h->ctx;
     FWD(set_dev(c));
@@ -650,7 +652,48 @@ static int ham_build_stencil(lm_ham* h) {
             st_set(mask, o * rc * rc + a * rc + b);
         }
     }
-    const int id = stencil_find(rc, mask);
+    int id = stencil_find(rc, mask);
+    // no compiled pattern covers it (LM_STENCIL_RTC=2: also when one does, but with more slots than the pattern has): the kernels
+    // are specialised on the detected mask at run time (stencil_rtc.cu); the value classes follow the current values
+    static const int rtc_env0 = env_int("LM_STENCIL_RTC", 1);
+    const int rtc_env = g_stencil_rtc >= 0 ? g_stencil_rtc : rtc_env0;
+    if (rtc_env != 0 && (id < 0 || rtc_env == 2) && stencil_rtc_available()) {
+        bool symmetric = true;
+        for (int o = 0; o < 9 && symmetric; ++o) for (int a = 0; a < rc; ++a) for (int b = 0; b < rc; ++b)
+            if (st_get(mask, o * rc * rc + a * rc + b) != st_get(mask, (8 - o) * rc * rc + b * rc + a)) symmetric = false;
+        st_mask_t full = mask;                       // + the on-site diagonal, so that potentials never change the kernel
+        for (int a = 0; a < rc; ++a) st_set(full, 4 * rc * rc + a * rc + a);
+        if (symmetric) {
+            // purely imaginary classes: every entry of the class has no real part (and the class is not identically zero)
+            const size_t esz = c->esz();
+            std::vector<unsigned char> hv((size_t)N * W * esz);
+            CK(cudaMemcpy(hv.data(), h->d_vals, hv.size(), cudaMemcpyDeviceToHost));
+            std::vector<unsigned char> has_re(9 * 16, 0), has_im(9 * 16, 0);
+            for (long long i = 0; i < N; ++i) {
+                const long long ci = i / rc; const int a = (int)(i % rc);
+                const long long c1 = ci / n2, c2 = ci % n2;
+                for (int k = 0; k < W; ++k) {
+                    const long long j = h->h_cols[i * W + k];
+                    const long long cj = j / rc; const int b = (int)(j % rc);
+                    const int o = (int)((wrapd(cj / n2 - c1, n1) + 1) * 3 + (wrapd(cj % n2 - c2, n2) + 1));
+                    double re, im;
+                    if (esz == 16) { const double* p = (const double*)(hv.data() + ((size_t)i * W + k) * 16); re = p[0]; im = p[1]; }
+                    else { const float* p = (const float*)(hv.data() + ((size_t)i * W + k) * 8); re = p[0]; im = p[1]; }
+                    if (re != 0) has_re[o * 16 + a * 4 + b] = 1;
+                    if (im != 0) has_im[o * 16 + a * 4 + b] = 1;
+                }
+            }
+            st_mask_t imag = {{0, 0, 0, 0}};
+            for (int o = 0; o < 9; ++o) for (int a = 0; a < rc; ++a) for (int b = 0; b < rc; ++b)
+                if (!(o == 4 && a == b) && has_im[o * 16 + a * 4 + b] && !has_re[o * 16 + a * 4 + b] &&
+                    has_im[(8 - o) * 16 + b * 4 + a] && !has_re[(8 - o) * 16 + b * 4 + a]) st_set(imag, o * rc * rc + a * rc + b);
+            const int rid = stencil_rtc_register(rc, full, imag);
+            if (rid >= 0 && (id < 0 || stencil_desc(rid).sw < stencil_desc(id).sw)) {
+                if (stencil_rtc_warm(rid, c->precision != LM_C128) == 0) id = rid;
+                else if (env_int("LM_DEBUG_PLAN", 0)) fprintf(stderr, "lm: run-time stencil specialisation failed: %s\n", stencil_rtc_error());
+            }
+        }
+    }
     if (id < 0) return LM_OK;
     const StencilDesc& d = stencil_desc(id);
     const int SW = stencil_stride(id, c->precision != LM_C128);      // slot stride (complex64 rows padded to even)
@@ -687,6 +730,7 @@ static int ham_build_stencil(lm_ham* h) {
     // the entry itself, or (encoded -2 - e) the reverse entry when the neighbour wraps around
     int P1o, P2o, NF;
     stencil_obs_shape(id, &P1o, &P2o, &NF);
+    const bool obs_ok = P1o > 0;                     // run-time patterns with too many forward entries per cell keep the ELL-plan observables
     std::vector<int> outm((size_t)N * NF, -1);
     for (long long i = 0; i < N; ++i) {
         const int a = (int)(i % rc);
@@ -707,8 +751,10 @@ static int ham_build_stencil(lm_ham* h) {
             ++f;
         }
     }
-    CK(cudaMalloc(&h->d_st_out, sizeof(int) * outm.size()));
-    CK(cudaMemcpy(h->d_st_out, outm.data(), sizeof(int) * outm.size(), cudaMemcpyHostToDevice));
+    if (obs_ok) {
+        CK(cudaMalloc(&h->d_st_out, sizeof(int) * outm.size()));
+        CK(cudaMemcpy(h->d_st_out, outm.data(), sizeof(int) * outm.size(), cudaMemcpyHostToDevice));
+    }
     h->st_nf = NF;
     CK(cudaMalloc(&h->d_st_src, sizeof(int) * src.size()));
     // + slack: the bulk copy of a ragged value line is rounded up to 16 bytes; direct loads of a ragged tile run past the last cell
@@ -1621,7 +1667,7 @@ static int g_stencil_herm = -1, g_stencil_tmap = -1;   // lm_dbg_set_stencil_fla
 static int stencil_variant_of(const lm_ham* h) {
     static const int var_env = env_int("LM_STENCIL_VARIANT", -1);
     int variant = g_stencil_variant >= 0 ? g_stencil_variant : var_env;
-    if (variant < 0 || variant >= stencil_num_variants()) variant = (h->st_rc == 1) ? 7 : (h->st_rc == 2 ? 2 : 19);
+    if (variant < 0 || variant >= stencil_num_variants() || h->st_id >= LM_ST_RTC_BASE) variant = (h->st_rc == 1) ? 7 : (h->st_rc == 2 ? 2 : 19);    // run-time patterns: one shape per rows-per-cell
     return variant;
 }
 static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const void* z, const void* u,

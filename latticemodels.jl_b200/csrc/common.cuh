@@ -1,10 +1,17 @@
 // Shared device helpers of the sm_100a kernels: complex arithmetic on double2 / float2, 128-bit
 // lane elements, cache-hinted loads and stores.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of a stencil kernel for a lattice pattern that is not among the compiled ones (csrc/stencil_rtc.cpp):
+// NVRTC has the CUDA built-ins but no host headers; the tensor map is an opaque 128-byte kernel parameter
+struct alignas(64) CUtensorMap_st { unsigned long long opaque[16]; };
+typedef CUtensorMap_st CUtensorMap;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #ifndef LM_CPU_EMUL
 #include <cuda.h>               // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 #endif
 
 namespace lm {

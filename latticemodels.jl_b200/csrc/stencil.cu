@@ -24,7 +24,7 @@ static const StencilDesc g_desc[] = {
 };
 static_assert(sizeof(g_desc) / sizeof(g_desc[0]) == LM_ST_NPAT, "pattern table out of step with StPat<>");
 int stencil_count() { return LM_ST_NPAT; }
-const StencilDesc& stencil_desc(int id) { return g_desc[id]; }
+const StencilDesc& stencil_desc(int id) { return id >= LM_ST_RTC_BASE ? *stencil_rtc_desc(id) : g_desc[id]; }
 int stencil_find(int rc, const st_mask_t& mask) {
     int best = -1;
     for (int i = 0; i < stencil_count(); ++i) {
@@ -35,17 +35,18 @@ int stencil_find(int rc, const st_mask_t& mask) {
 }
 
 int stencil_diag_slot(int id, int a) {
-    const int rc = g_desc[id].rc;
+    const StencilDesc& d = stencil_desc(id);
+    const int rc = d.rc;
     int s = 0;
     for (int o = 0; o < 9; ++o) for (int b = 0; b < rc; ++b) {
-        const bool set = st_get(g_desc[id].mask, o * rc * rc + a * rc + b);
+        const bool set = st_get(d.mask, o * rc * rc + a * rc + b);
         if (o == 4 && b == a) return set ? s : -1;
         if (set) ++s;
     }
     return -1;
 }
-int stencil_stride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 1) & ~1) : g_desc[id].sw; }
-int stencil_rstride(int id, bool c64) { return c64 ? ((g_desc[id].sw + 3) & ~3) : ((g_desc[id].sw + 1) & ~1); }
+int stencil_stride(int id, bool c64) { const int sw = stencil_desc(id).sw; return c64 ? ((sw + 1) & ~1) : sw; }
+int stencil_rstride(int id, bool c64) { const int sw = stencil_desc(id).sw; return c64 ? ((sw + 3) & ~3) : ((sw + 1) & ~1); }
 
 // register-tile variants: T1 x T2 cells per thread, W1 x W2 warps per CTA, CPT lane elements per
 // thread; staged = haloed patch brought into shared memory by TMA bulk copies
@@ -82,7 +83,7 @@ void stencil_variant_shape(int v, int rc, int* P1, int* P2, int* cpt, int* stage
 // CTAs of k_apply_stencil_tma resident per SM (host restatement of st_tma_smem / st_tma_blocks)
 int stencil_resident_ctas(int id, int v, bool c64) {
     Variant q = g_var[v];
-    const int rc = g_desc[id].rc, sw = stencil_stride(id, c64);
+    const int rc = stencil_desc(id).rc, sw = stencil_stride(id, c64);
     if (q.t1 == 0) { q.t1 = 4; q.t2 = rc == 1 ? 4 : 2; }
     const int P1 = q.w1 * q.t1, P2 = q.w2 * q.t2;
     const size_t smem = (size_t)(P1 + 2) * (P2 + 2) * rc * 32 * q.cpt * 16 + (size_t)P1 * P2 * rc * sw * (c64 ? 8 : 16);
@@ -99,6 +100,7 @@ LM_ST_EACH(LM_ST_DECL)
 #undef LM_ST_DECL
 
 int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s) {
+    if (id >= LM_ST_RTC_BASE) return stencil_rtc_launch(id, c64, mode, a, tmx, grid, s);       // one shape per rows-per-cell: `variant` is ignored
     switch (id) {
 #define LM_ST_CASE(i) case i: return stencil_launch_##i(variant, c64, mode, a, tmx, grid, s);
     LM_ST_EACH(LM_ST_CASE)
@@ -107,6 +109,7 @@ int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a
     }
 }
 int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s) {
+    if (id >= LM_ST_RTC_BASE) return stencil_rtc_observe(id, c64, a, tmx, grid, s);
     switch (id) {
 #define LM_ST_CASE(i) case i: return stencil_observe_##i(c64, a, tmx, grid, s);
     LM_ST_EACH(LM_ST_CASE)
@@ -115,6 +118,14 @@ int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap
     }
 }
 void stencil_obs_shape(int id, int* P1, int* P2, int* nf) {
+    if (id >= LM_ST_RTC_BASE) {
+        const StencilDesc& d = stencil_desc(id);
+        int t1, t2, w1, w2;
+        *nf = stencil_rtc_nfwd(d.rc, d.mask);
+        if (!stencil_rtc_obs_shape(d.rc, *nf, &t1, &t2, &w1, &w2)) { *P1 = *P2 = 0; return; }       // too many forward entries per cell: ELL-plan observables
+        *P1 = w1 * t1; *P2 = w2 * t2;
+        return;
+    }
     switch (id) {
 #define LM_ST_CASE(i) case i: stencil_obs_shape_##i(P1, P2, nf); break;
     LM_ST_EACH(LM_ST_CASE)

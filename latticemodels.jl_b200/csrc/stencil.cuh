@@ -18,7 +18,6 @@
 // by (o, b); entries absent on a given row (open boundaries) hold 0 and the load wraps around.
 #pragma once
 #include "common.cuh"
-#include <utility>
 
 namespace lm {
 
@@ -29,7 +28,9 @@ __host__ __device__ constexpr bool st_covers(const st_mask_t& big, const st_mask
     for (int k = 0; k < 4; ++k) if (small.w[k] & ~big.w[k]) return false;
     return true;
 }
+#ifndef __CUDACC_RTC__
 inline void st_set(st_mask_t& m, int i) { m.w[i >> 6] |= 1ull << (i & 63); }
+#endif
 
 template <int RC> __host__ __device__ constexpr bool st_bit(const st_mask_t& m, int o, int a, int b) {
     return st_get(m, o * RC * RC + a * RC + b);
@@ -63,12 +64,17 @@ template <int RC, int T1, int T2> __host__ __device__ constexpr bool st_needed(c
     return false;
 }
 
+// compile-time loop: f(st_ic<0>{}), ..., f(st_ic<N - 1>{})  (own integer sequence: the header also compiles under NVRTC, which has no <utility>)
+template <int V> struct st_ic { static constexpr int value = V; };
+template <int... I> struct st_iseq {};
+template <int N, int... I> struct st_mkseq : st_mkseq<N - 1, N - 1, I...> {};
+template <int... I> struct st_mkseq<0, I...> { using type = st_iseq<I...>; };
 template <typename F, int... I>
-__device__ __forceinline__ void st_for_impl(F&& f, std::integer_sequence<int, I...>) {
-    (f(std::integral_constant<int, I>{}), ...);
+__device__ __forceinline__ void st_for_impl(F&& f, st_iseq<I...>) {
+    (f(st_ic<I>{}), ...);
 }
 template <int N, typename F> __device__ __forceinline__ void st_for(F&& f) {
-    st_for_impl(f, std::make_integer_sequence<int, N>{});
+    st_for_impl(f, typename st_mkseq<N>::type{});
 }
 
 struct StencilArgs {
@@ -148,8 +154,8 @@ __device__ __forceinline__ void st_tile(typename pack<T>::E (&acc)[T1][T2][RC][C
                             constexpr int v1 = u1 - 1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
                             if constexpr (st_bit<RC>(MK::mask, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
                                 constexpr int slot = st_slot<RC>(MK::mask, o, aa, b);
-                                const auto hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
-                                                       A, std::integral_constant<int, slot>{});
+                                const auto hv = load_h(st_ic<v1>{}, st_ic<v2>{},
+                                                       A, st_ic<slot>{});
 #pragma unroll
                                 for (int j = 0; j < CPT; ++j) st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xv[j]);
                             }
@@ -199,13 +205,13 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
         constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-            xo[v1][v2][aa][j] = load_x(std::integral_constant<int, v1 + 1>{}, std::integral_constant<int, v2 + 1>{}, A, j);
+            xo[v1][v2][aa][j] = load_x(st_ic<v1 + 1>{}, st_ic<v2 + 1>{}, A, j);
     }); }); });
     // diagonal entries (+ g) and the bonds inside the tile, one value load per bond
     st_for<T1>([&](auto V1) { st_for<T2>([&](auto V2) { st_for<RC>([&](auto A) {
         constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, aa = decltype(A)::value;
         if constexpr (st_bit<RC>(MK::mask, 4, aa, aa)) {
-            const auto h0 = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MK::mask, 4, aa, aa)>{});
+            const auto h0 = load_h(V1, V2, A, st_ic<st_slot<RC>(MK::mask, 4, aa, aa)>{});
             if constexpr (VC && !SELF) {
                 static_assert(!VC || !st_bit<RC>(MK::imag, 4, aa, aa), "the diagonal of a Hermitian operator is real");
 #pragma unroll
@@ -225,7 +231,7 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
             constexpr int o = decltype(OO)::value + 4, b = decltype(B)::value;
             constexpr int w1 = v1 + (o / 3 - 1), w2 = v2 + (o % 3 - 1);
             if constexpr (st_fwd_bit<RC>(MK::mask, o, aa, b) && w1 >= 0 && w1 < T1 && w2 >= 0 && w2 < T2) {
-                const auto hv = load_h(V1, V2, A, std::integral_constant<int, st_slot<RC>(MK::mask, o, aa, b)>{});
+                const auto hv = load_h(V1, V2, A, st_ic<st_slot<RC>(MK::mask, o, aa, b)>{});
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xo[w1][w2][b][j]);
@@ -246,8 +252,8 @@ __device__ __forceinline__ void st_tile_herm(typename pack<T>::E (&acc)[T1][T2][
                 constexpr int o = decltype(O)::value, aa = decltype(A)::value;
                 constexpr int v1 = u1 - 1 - (o / 3 - 1), v2 = u2 - 1 - (o % 3 - 1);
                 if constexpr (st_bit<RC>(MK::mask, o, aa, b) && v1 >= 0 && v1 < T1 && v2 >= 0 && v2 < T2) {
-                    const auto hv = load_h(std::integral_constant<int, v1>{}, std::integral_constant<int, v2>{},
-                                           A, std::integral_constant<int, st_slot<RC>(MK::mask, o, aa, b)>{});
+                    const auto hv = load_h(st_ic<v1>{}, st_ic<v2>{},
+                                           A, st_ic<st_slot<RC>(MK::mask, o, aa, b)>{});
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) st_fma<st_cls<RC, MK, VC>(o, aa, b), false>(acc[v1][v2][aa][j], hv, xv[j]);
                 }
@@ -937,6 +943,7 @@ template <> struct StPat<8> { static constexpr int rc = 4; static constexpr st_m
                                                                                       imag = {{0x8421842184210000ull, 0x8421842184210000ull, 0, 0}}; };
 constexpr int LM_ST_NPAT = 9;
 
+#ifndef __CUDACC_RTC__
 // ---- host-visible registry (stencil.cu) ----
 struct StencilDesc { int rc; st_mask_t mask, imag; int sw; const char* name; };
 int stencil_count();
@@ -954,5 +961,18 @@ int stencil_launch(int id, int variant, bool c64, int mode, const StencilArgs& a
 // fused observables: patch size / forward-slot count of the compiled kernel, and its launch
 void stencil_obs_shape(int id, int* P1, int* P2, int* nf);
 int stencil_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s);
+// ---- run-time compiled patterns (stencil_rtc.cu): ids >= LM_ST_RTC_BASE; every registry function above accepts them ----
+constexpr int LM_ST_RTC_BASE = 1000;
+bool stencil_rtc_available();                                                       // NVRTC + driver entry points found, LM_STENCIL_RTC != 0
+int stencil_rtc_register(int rc, const st_mask_t& mask, const st_mask_t& imag);     // id of the pattern (registered once), -1 if unavailable
+const StencilDesc* stencil_rtc_desc(int id);
+int stencil_rtc_warm(int id, bool c64);                                             // compile the step kernels now (0 on success)
+const char* stencil_rtc_error();
+void stencil_rtc_apply_shape(int rc, int* t1, int* t2, int* w1, int* w2);
+bool stencil_rtc_obs_shape(int rc, int nf, int* t1, int* t2, int* w1, int* w2);
+int stencil_rtc_nfwd(int rc, const st_mask_t& m);
+int stencil_rtc_launch(int id, bool c64, int mode, const StencilArgs& a, const CUtensorMap& tmx, dim3 grid, cudaStream_t s);
+int stencil_rtc_observe(int id, bool c64, const StencilObsArgs& a, const CUtensorMap& tmx, unsigned grid, cudaStream_t s);
+#endif  // __CUDACC_RTC__
 
 }  // namespace lm

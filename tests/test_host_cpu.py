@@ -420,3 +420,30 @@ def test_currents_region_sums_accept_masks_on_the_host_path():
     assert np.array_equal(currentsfrom(c, [1, 2]).values, [0, 0, 2, 0])
     assert currentsfromto(c, mask) == currentsfromto(c, [1, 2]) == 2.0
     assert currentsfromto(c, mask, ~mask) == currentsfromto(c, [1, 2], [3, 4]) == 2.0
+
+
+def test_run_time_specialisation_compiles_without_a_device():
+    """csrc/stencil_rtc.cu: the library hands its own (embedded) kernel headers to NVRTC for a lattice pattern that is not among
+    the compiled ones - here Kane-Mele with a spin-mixing nearest-neighbour term (four rows per cell), mask derived from the
+    oracle Hamiltonian.  NVRTC needs no device, so the compilation itself (apply kernel of a product-form factor, fused
+    observables kernel) is checked here; loading and launching are gpu tests (tests/test_zz_gpu_patterns.py)."""
+    import ctypes as C
+    from importlib import import_module
+    from oracle import lattice as L, operators as OP, stencil as ST
+    lib = import_module("lm_b200._lib").load()
+    lib.lm_dbg_rtc_compile.restype = C.c_longlong
+    lib.lm_dbg_rtc_compile.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.lm_dbg_rtc_error.restype = C.c_char_p
+    lat = L.honeycomb_lattice(5, 6)
+    sx = np.array([[0, 1], [1, 0]], complex)
+    H = OP.kanemele(lat, 1.0, 0.2) + OP.construct_hamiltonian(lat, 2, [(0.3j * sx, L.nearest_neighbor(lat, 1))])
+    rc, m = ST.stencil_mask(H, 5, 6)
+    assert rc == 4 and m is not None
+    m |= sum(1 << (4 * rc * rc + a * rc + a) for a in range(rc))
+    words = (C.c_uint64 * 4)(*[(m >> (64 * k)) & (2 ** 64 - 1) for k in range(4)])
+    zero = (C.c_uint64 * 4)(0, 0, 0, 0)
+    n = lib.lm_dbg_rtc_compile(rc, words, zero, 0, 3)
+    if n < 0 and b"libnvrtc" in lib.lm_dbg_rtc_error():
+        pytest.skip("libnvrtc.so.12 not installed")
+    assert n > 100000, lib.lm_dbg_rtc_error()[:2000]
+    assert lib.lm_dbg_rtc_compile(rc, words, zero, 1, -1) > 10000, lib.lm_dbg_rtc_error()[:2000]      # complex64 observables kernel

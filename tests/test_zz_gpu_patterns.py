@@ -598,3 +598,82 @@ def test_three_and_four_row_stencils_match_oracle(case, precision):
         want_j = np.array([sum(2 * np.imag(Hdn[(i - 1) * n + a, (j - 1) * n + b] * P[(j - 1) * n + b, (i - 1) * n + a])
                                for a in range(n) for b in range(n)) for i, j in zip(I.tolist(), J.tolist())])
         assert np.abs(V - want_j).max() < (1e-13 if c128 else 1e-5) * max(1.0, np.abs(want_j).max()), (case, M)
+
+
+# ------------------------------------------------------------------------------ run-time specialised patterns (NVRTC)
+def _set_rtc(v):
+    lib = _lib.load()
+    lib.lm_dbg_set_stencil_rtc.argtypes = [C.c_int32]
+    lib.lm_dbg_set_stencil_rtc.restype = C.c_int32
+    _lib.check(lib.lm_dbg_set_stencil_rtc(v))
+
+
+def _kanemele_rashba(mod_lm):
+    """Kane-Mele plus a spin-mixing nearest-neighbour term: four rows per cell, not among the compiled patterns."""
+    sz = np.array([[1, 0], [0, -1]], complex)
+    sx = np.array([[0, 1], [1, 0]], complex)
+    if mod_lm:
+        lat = lm.HoneycombLattice(9, 8, boundaries=[("axis2", True)])
+        return lm.construct_hamiltonian(lat, 2, (1.0, lm.NearestNeighbor(1)), (0.2j * sz, lm.honeycomb_2nn), (0.3j * sx, lm.NearestNeighbor(1)),
+                                        field=lm.LandauGauge(0.02))
+    lat = L.honeycomb_lattice(9, 8, periodic=(2,))
+    return OP.construct_hamiltonian(lat, 2, [(1.0, L.nearest_neighbor(lat, 1)), (0.2j * sz, L.HONEYCOMB_2NN), (0.3j * sx, L.nearest_neighbor(lat, 1))],
+                                    F.LandauGauge(0.02))
+
+
+RTC_CASES = {
+    # name: (device model, oracle model, force an exact-mask specialisation although a compiled superset exists?)
+    "kanemele_rashba": (lambda: _kanemele_rashba(True), lambda: _kanemele_rashba(False), False),
+    "kagome_t123": (lambda: lm.tightbinding_hamiltonian(lm.KagomeLattice(8, 9), t1=1, t2=0.3, t3=0.1),
+                    lambda: OP.tightbinding_hamiltonian(L.kagome_lattice(8, 9), t1=1, t2=0.3, t3=0.1), False),
+    "triangular_exact": (lambda: lm.tightbinding_hamiltonian(lm.TriangularLattice(13, 11), field=lm.SymmetricGauge(0.03)),
+                         lambda: OP.tightbinding_hamiltonian(L.triangular_lattice(13, 11), field=F.SymmetricGauge(0.03)), True),
+    "honeycomb_t123_exact": (lambda: lm.tightbinding_hamiltonian(lm.HoneycombLattice(9, 11), t1=1, t2=0.2, t3=0.1),
+                             lambda: OP.tightbinding_hamiltonian(L.honeycomb_lattice(9, 11), t1=1, t2=0.2, t3=0.1), True),
+}
+
+
+@pytest.mark.parametrize("case", sorted(RTC_CASES))
+def test_run_time_specialised_stencil_patterns(case):
+    """A lattice pattern that is not among the compiled ones (or, with LM_STENCIL_RTC=2, one whose compiled superset
+    carries empty slots) gets stencil kernels specialised on its mask at run time (csrc/stencil_rtc.cu: NVRTC on the
+    library's own headers, driver-API launch): SpMM, propagators, localdensity and DensityCurrents against the oracle."""
+    ctx = lm.default_context("c128")
+    mk_dev, mk_or, force = RTC_CASES[case]
+    try:
+        _set_rtc(2 if force else 1)
+        Hd, Ho = mk_dev(), mk_or()
+        assert abs(Hd.data - Ho).max() < 1e-14
+        dev = Hd.device(ctx)
+        assert _stencil_id(dev) >= 1000, "pattern was not specialised at run time (NVRTC unavailable?)"
+        lib = _lib.load()
+        N = Ho.shape[0]
+        for M in (32, 45, 100):
+            X = _rand_block(N, M, seed=M)
+            x = lm.DeviceState.from_psi(X, ctx=ctx)
+            y = lm.DeviceState.from_psi(np.zeros_like(X), ctx=ctx)
+            _lib.check(lib.lm_spmm_state(dev.handle, x.handle, y.handle))
+            assert _relerr(y.download(), Ho @ X) < 1e-14, (case, M)
+        X = _rand_block(N, 40, seed=5)
+        want = EV.exact_propagator(Ho, 0.3) @ X
+        for method in ("chebyshev", "taylor", "chebyshev_clenshaw", "taylor_horner"):
+            st = lm.DeviceState.from_psi(X, ctx=ctx)
+            sol = lm.B200Exp(tol=1e-14, method=method, ctx=ctx)
+            sol.update_solver(Hd, 0.3)
+            sol.step(st)
+            sol.step(st)
+            assert _relerr(st.download(), EV.exact_propagator(Ho, 0.3) @ want) < 3e-13, (case, method)
+        Hdn = Ho.toarray()
+        n = Hd.n_int
+        for M in (32, 70):
+            Psi = _rand_block(N, M, seed=M) / np.sqrt(N)
+            w = np.random.default_rng(M).random(M)
+            st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, lattice=Hd.lattice, n_int=n)
+            I, J, V = lm.DensityCurrents(Hd, st).pair_values()
+            P = (Psi * w) @ Psi.conj().T
+            assert _relerr(lm.localdensity(st).values, np.real(np.diag(P)).reshape(-1, n).sum(axis=1)) < 1e-13
+            want_j = np.array([sum(2 * np.imag(Hdn[(i - 1) * n + a, (j - 1) * n + b] * P[(j - 1) * n + b, (i - 1) * n + a])
+                                   for a in range(n) for b in range(n)) for i, j in zip(I.tolist(), J.tolist())])
+            assert np.abs(V - want_j).max() < 1e-13 * max(1.0, np.abs(want_j).max()), (case, M)
+    finally:
+        _set_rtc(-1)

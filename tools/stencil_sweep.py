@@ -89,6 +89,11 @@ def timing(ctx, cases, variants, reps):
             H = lm.tightbinding_hamiltonian(lm.KagomeLattice(n, n), field=lm.LandauGauge(0.01))
         elif kind == "kagome2":
             H = lm.tightbinding_hamiltonian(lm.KagomeLattice(n, n), t1=1, t2=0.3)
+        elif kind == "kagome3":
+            H = lm.tightbinding_hamiltonian(lm.KagomeLattice(n, n), t1=1, t2=0.3, t3=0.1)
+        elif kind == "kmr":        # Kane-Mele + spin-mixing NN term: run-time specialised pattern
+            sz, sx = np.array([[1, 0], [0, -1]], complex), np.array([[0, 1], [1, 0]], complex)
+            H = lm.construct_hamiltonian(lm.HoneycombLattice(n, n), 2, (1.0, lm.NearestNeighbor(1)), (0.2j * sz, lm.honeycomb_2nn), (0.3j * sx, lm.NearestNeighbor(1)))
         elif kind == "kanemele":
             H = lm.kanemele(lm.HoneycombLattice(n, n), 1.0, 0.2)
         elif kind == "kanemele_field":
@@ -117,7 +122,7 @@ def timing(ctx, cases, variants, reps):
         nmv = C.c_int32()
         runs = [("ell", -1, -1)] + [("stencil", 5, v) for v in variants]
         for tag, path, v in runs:
-            lib.lm_dbg_set_apply_path(path if path >= 0 else (3 if kind in ("qwz", "kanemele", "kanemele_field") else 2))
+            lib.lm_dbg_set_apply_path(path if path >= 0 else (3 if kind in ("qwz", "kanemele", "kanemele_field", "kmr") else 2))
             lib.lm_dbg_set_stencil_variant(v)
             if lib.lm_spmm_state(dev.handle, x.handle, y.handle) != 0:
                 continue
