@@ -1734,15 +1734,17 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
                                      (unsigned)(32 * cpt * 2), (unsigned)((P2 + 2) * h->st_rc), (unsigned)(P1 + 2));
         a.tmap = (st_t == 0) ? 1 : 0;
     }
-    // Opt-in L2 prefetch of the box of the CTA dispatched LM_STENCIL_PF positions later (-1 = one resident wave).
-    // Measured (profiles/r2/l2_prefetch_r2.md): the staging wait shrinks (long-scoreboard 3.2 -> 2.1 per issue, L2 hit
-    // rate 32 -> 43 %) but the kernel time does not (C4 +1 %, C3 +2 %, C2 -3 %; distances beyond one wave lose 4-14 %):
-    // DRAM sits at 72 % of ncu's peak either way.  Default off.
-    static const int pf_env = env_int("LM_STENCIL_PF", 0);
+    // L2 prefetch of the box of the CTA dispatched LM_STENCIL_PF positions later (0 = off, -1 = one resident wave; unset = auto).
+    // With complex values it was neutral (profiles/r2/l2_prefetch_r2.md).  With the value-class path the kernel waits mostly on its
+    // staging barrier and half a resident wave of look-ahead pays on the two-rows-per-cell stencils: C4 0.761 -> 0.799 (M = 4096),
+    // 0.810 -> 0.846 (512-column shard), C3 0.721 -> 0.735; one-row stencils lose 1-2 % (C2 0.904 -> 0.883) and distances beyond one
+    // wave lose (profiles/r2/value_class_r2.md, call U).  Auto: half a resident wave for RC = 2, off otherwise (RC = 3 / 4: see call V).
+    static const int pf_env = env_int("LM_STENCIL_PF", -2);
     a.pf = 0;
-    if (a.tmap && pf_env != 0)
-        a.pf = pf_env > 0 ? (unsigned)pf_env
-                          : (unsigned)(stencil_resident_ctas(h->st_id, variant, c->precision != LM_C128) * (c->sm_count > 0 ? c->sm_count : 148));
+    if (a.tmap && pf_env != 0) {
+        const unsigned wave = (unsigned)(stencil_resident_ctas(h->st_id, variant, c->precision != LM_C128) * (c->sm_count > 0 ? c->sm_count : 148));
+        a.pf = pf_env > 0 ? (unsigned)pf_env : (pf_env == -1 ? wave : (h->st_rc == 2 ? wave / 2 : 0u));
+    }
     // Hermitian operator (verified on the device at every value change): in-tile bonds share one value load
     static const int herm_env = env_int("LM_STENCIL_HERM", 1);
     a.herm = ((g_stencil_herm >= 0 ? g_stencil_herm : herm_env) && h->hermitian) ? 1 : 0;

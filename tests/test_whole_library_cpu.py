@@ -3,8 +3,8 @@ csrc/api.cu, every kernel) is compiled by g++ through the CUDA shim of tests/cpu
 are fibers, the runtime API is restated on host memory, stream capture records closures - and the
 gpu-marked tests of tests/test_gpu_parity.py and tests/test_zz_gpu_patterns.py are executed against
 it through the same ctypes binding, unchanged.  Only the three full-size property tests (configs
-2-4, minutes of emulated work) and the 201-frame README workflow (the golden-fixture test runs the
-same workflow) are left to the real device.
+2-4, minutes of emulated work), the 201-frame README workflow (the golden-fixture test runs the
+same workflow) and the run-time specialised (NVRTC) patterns are left to the real device.
 
 This is test infrastructure: the product loader (latticemodels.jl_b200/_lib.py) never sees the
 emulated library; tests/conftest.py swaps it in when LM_EMUL_LIB is set."""
@@ -74,7 +74,7 @@ def test_gpu_parity_suite_on_the_cpu_build_of_the_library(emul_lib):
     for k in ("LM_STEP_PDL", "LM_STENCIL_HERM", "LM_STENCIL_TMAP", "LM_APPLY_TILED", "LM_APPLY_STENCIL", "LM_STENCIL_VARIANT"):
         env.pop(k, None)
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_gpu_patterns.py"), os.path.join(ROOT, "tests", "test_zz_gpu_currents_api.py"),
-           "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not full_size and not readme_workflow"]
+           "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not full_size and not readme_workflow and not run_time_specialised"]      # NVRTC kernels need a device
     try:
         import xdist  # noqa: F401
         cmd += ["-n", str(min(4, os.cpu_count() or 1))]
