@@ -1738,12 +1738,13 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     // With complex values it was neutral (profiles/r2/l2_prefetch_r2.md).  With the value-class path the kernel waits mostly on its
     // staging barrier and half a resident wave of look-ahead pays on the two-rows-per-cell stencils: C4 0.761 -> 0.799 (M = 4096),
     // 0.810 -> 0.846 (512-column shard), C3 0.721 -> 0.735; one-row stencils lose 1-2 % (C2 0.904 -> 0.883) and distances beyond one
-    // wave lose (profiles/r2/value_class_r2.md, call U).  Auto: half a resident wave for RC = 2, off otherwise (RC = 3 / 4: see call V).
+    // wave lose (profiles/r2/value_class_r2.md, call U).  Three / four rows per cell gain too (call V: kagome NN + NNN SpMM 0.725 -> 0.847, Kane-Mele 0.666 -> 0.726).
+    // Auto: half a resident wave for RC >= 2, off for RC = 1.
     static const int pf_env = env_int("LM_STENCIL_PF", -2);
     a.pf = 0;
     if (a.tmap && pf_env != 0) {
         const unsigned wave = (unsigned)(stencil_resident_ctas(h->st_id, variant, c->precision != LM_C128) * (c->sm_count > 0 ? c->sm_count : 148));
-        a.pf = pf_env > 0 ? (unsigned)pf_env : (pf_env == -1 ? wave : (h->st_rc == 2 ? wave / 2 : 0u));
+        a.pf = pf_env > 0 ? (unsigned)pf_env : (pf_env == -1 ? wave : (h->st_rc >= 2 ? wave / 2 : 0u));
     }
     // Hermitian operator (verified on the device at every value change): in-tile bonds share one value load
     static const int herm_env = env_int("LM_STENCIL_HERM", 1);
