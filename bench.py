@@ -643,7 +643,13 @@ def main():
         sid = C.c_int32(-1)
         lib.lm_dbg_stencil_info.argtypes = [C.c_void_p] * 5
         lib.lm_dbg_stencil_info(dev.handle, C.byref(sid), None, None, None)
-        kernel = ("lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells, shared value loads for Hermitian H)"
+        in_class = C.c_int32(0)
+        if sid.value >= 0:
+            lib.lm_dbg_stencil_ri_state.argtypes = [C.c_void_p, C.c_void_p]
+            lib.lm_dbg_stencil_ri_state(dev.handle, C.byref(in_class))
+        ri_on = bool(in_class.value) and int(os.environ.get("LM_STENCIL_RI", "1") or 0) != 0
+        kernel = ("lm::k_apply_stencil_tma (fused lattice-stencil SpMM + one product-form propagator factor; TMA-staged patch, register-tiled unit cells, shared value loads for Hermitian H, %s)"
+                  % ("real / imaginary value class: scalar values, two FMAs per element" if ri_on else "complex values")
                   if (sid.value >= 0 and state.M >= 32) else "lm::k_apply / k_apply_rows (ELL gather SpMM fused with one product-form propagator factor)")
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -700,7 +706,8 @@ def main():
                "config": {"workload": wl["label"], "N": N, "M_total": M, "M_per_gpu": Ml, "nnz": int(nnz), "dt": dt, "tol": args.tol,
                           "method": args.method, "sharding": "Psi columns over %d GPU(s), H replicated" % world,
                           "schedule": {"pdl": int(os.environ.get("LM_STEP_PDL", "0") or 0), "launches_per_step": launches / max(steps, 1),
-                                       "stencil_shared_value_loads": int(os.environ.get("LM_STENCIL_HERM", "1") or 0), "stencil_tensor_map_boxes": int(os.environ.get("LM_STENCIL_TMAP", "1") or 0)},
+                                       "stencil_shared_value_loads": int(os.environ.get("LM_STENCIL_HERM", "1") or 0), "stencil_tensor_map_boxes": int(os.environ.get("LM_STENCIL_TMAP", "1") or 0),
+                                       "stencil_value_class_scalars": int(ri_on), "stencil_l2_lookahead": os.environ.get("LM_STENCIL_PF", "auto (half a resident wave on multi-row stencils)")},
                           "l2": "inputs larger than L2 (3 x %.0f MB Psi buffers per GPU); no flush" % (N * Ml * esz / 1e6)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": parity}
 

@@ -12,6 +12,8 @@ import shutil
 import subprocess
 from concurrent.futures import ThreadPoolExecutor
 
+import build_cache
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "latticemodels.jl_b200", "csrc")
@@ -91,7 +93,12 @@ def rewrite_launches(src):
 
 
 def build(outdir, opt="-O1", verbose=False):
-    """Returns the path of the emulated shared library (built into ``outdir``)."""
+    """Returns the path of the emulated shared library: from the content-addressed cache (build_cache.py) when the kernel
+    sources, the shim and the flags are unchanged, else built in ``outdir`` and added to the cache."""
+    return build_cache.cached("liblm_b200_emul.so", "whole-library " + opt, lambda path: shutil.copy(_build(outdir, opt, verbose), path))
+
+
+def _build(outdir, opt="-O1", verbose=False):
     gxx = shutil.which("g++")
     if gxx is None:
         raise RuntimeError("g++ not available")

@@ -41,14 +41,16 @@ static bool check_tile(const char* name) {
     const T2c gg = cmake<T2c>(g.real(), g.imag());
     st_tile<T, RC, MK, T1, T2, 1, SELF, 0>(acc, gg,
         [&](auto U1, auto U2, auto B, int) {
+            constexpr int u1 = decltype(U1)::value, u2 = decltype(U2)::value, b = decltype(B)::value;
             E e;
-            if constexpr (EC == 1) { e.x = x[U1][U2][B][0].real(); e.y = x[U1][U2][B][0].imag(); }
-            else { e.x = (float)x[U1][U2][B][0].real(); e.y = (float)x[U1][U2][B][0].imag(); e.z = (float)x[U1][U2][B][1].real(); e.w = (float)x[U1][U2][B][1].imag(); }
+            if constexpr (EC == 1) { e.x = x[u1][u2][b][0].real(); e.y = x[u1][u2][b][0].imag(); }
+            else { e.x = (float)x[u1][u2][b][0].real(); e.y = (float)x[u1][u2][b][0].imag(); e.z = (float)x[u1][u2][b][1].real(); e.w = (float)x[u1][u2][b][1].imag(); }
             return e;
         },
         [&](auto V1, auto V2, auto A, auto S) {
-            static_assert(decltype(S)::value < SW, "slot beyond the stencil width");
-            return cmake<T2c>(h[V1][V2][A][S].real(), h[V1][V2][A][S].imag());
+            constexpr int v1 = decltype(V1)::value, v2 = decltype(V2)::value, a = decltype(A)::value, sl = decltype(S)::value;
+            static_assert(sl < SW, "slot beyond the stencil width");
+            return cmake<T2c>(h[v1][v2][a][sl].real(), h[v1][v2][a][sl].imag());
         });
     const double tol = sizeof(T) == 8 ? 1e-13 : 2e-5;
     for (int v1 = 0; v1 < T1; ++v1) for (int v2 = 0; v2 < T2; ++v2) for (int a = 0; a < RC; ++a) for (int e = 0; e < EC; ++e) {

@@ -323,11 +323,15 @@ def test_stencil_tile_logic_executes_on_cpu(tmp_path):
     from concurrent.futures import ThreadPoolExecutor
     emul = os.path.join(ROOT, "tests", "cpu_emul")
 
+    sys.path.insert(0, emul)
+    import build_cache
+    sys.path.pop(0)
+
     def group(g):
-        exe = str(tmp_path / ("stencil_emul_%d" % g))
-        subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g, "-I", os.path.join(emul, "shim"),
-                        "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
-                        os.path.join(emul, "stencil_emul.cpp"), "-o", exe], check=True)
+        flags = ["-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g]
+        exe = build_cache.cached("stencil_emul_%d" % g, " ".join(flags), lambda path: subprocess.run(
+            [gxx] + flags + ["-I", os.path.join(emul, "shim"), "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
+                             os.path.join(emul, "stencil_emul.cpp"), "-o", path], check=True))
         return subprocess.run([exe], capture_output=True, text=True)
     with ThreadPoolExecutor(3) as ex:
         results = list(ex.map(group, range(3)))
@@ -355,12 +359,17 @@ def test_stencil_kernels_execute_on_cpu(tmp_path):
     from concurrent.futures import ThreadPoolExecutor
     emul = os.path.join(ROOT, "tests", "cpu_emul")
 
+    sys.path.insert(0, emul)
+    import build_cache
+    sys.path.pop(0)
+
     def group(g):
         # the fully unrolled kernels are large: four pattern groups, built as separate programs in parallel
-        exe = str(tmp_path / ("stencil_kernel_emul_%d" % g))
-        subprocess.run([gxx, "-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g, "-I", os.path.join(emul, "shim"),
-                        "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
-                        os.path.join(emul, "stencil_kernel_emul.cpp"), "-o", exe], check=True)
+        # (and kept in the content-addressed build cache while the sources are unchanged)
+        flags = ["-std=c++20", "-O0", "-w", "-pthread", "-DLM_EMUL_GROUP=%d" % g]
+        exe = build_cache.cached("stencil_kernel_emul_%d" % g, " ".join(flags), lambda path: subprocess.run(
+            [gxx] + flags + ["-I", os.path.join(emul, "shim"), "-I", os.path.join(ROOT, "latticemodels.jl_b200", "csrc"),
+                             os.path.join(emul, "stencil_kernel_emul.cpp"), "-o", path], check=True))
         return subprocess.run([exe], capture_output=True, text=True, timeout=900)
     with ThreadPoolExecutor(4) as ex:
         results = list(ex.map(group, range(4)))
