@@ -682,9 +682,15 @@ def main():
                 _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))
 
         slot = [0]
+        bcast_values = int(os.environ.get("LM_BENCH_BCAST", "1") or 0) != 0
 
         def e2e_step(k):
-            _lib.check(lib.lm_ham_update_values_async(csc_dev.handle, _lib.ptr(nz_np)))            # H2D (pinned buffer; enclosure checked on the device)
+            # H2D (pinned buffer; enclosure checked on the device).  N > 1: H(t) is the same on every rank, so rank 0 uploads it and the
+            # others receive it over NVLink (lm_ham_update_values_bcast) instead of eight PCIe uploads through host memory
+            if world > 1 and bcast_values:
+                _lib.check(lib.lm_ham_update_values_bcast(csc_dev.handle, _lib.ptr(nz_np) if rank == 0 else None, 0))
+            else:
+                _lib.check(lib.lm_ham_update_values_async(csc_dev.handle, _lib.ptr(nz_np)))
             _lib.check(lib.lm_step(csc_dev.handle, state.handle, dt, args.tol, method, C.byref(nmv)))
             if len(pending) == 2:
                 _lib.check(lib.lm_frame_wait(ctx.handle, pending.pop(0), _lib.ptr(rho_np), _lib.ptr(j_np)))   # D2H of frame k - 2 lands
@@ -697,7 +703,8 @@ def main():
         ms_e2e, _, _ = timed(e2e_step, steps, tail=drain)
         e2e = {"value": 1e3 / (ms_e2e / steps), "unit": "steps/s", "h2d_bytes_per_step": int(nnz * esz),
                "d2h_bytes_per_step": int(8 * (n_sites + npairs)),
-               "what": "lm_ham_update_values_async(pinned nzval) + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
+               "what": ("lm_ham_update_values_bcast(pinned nzval on rank 0, NVLink broadcast)" if (world > 1 and bcast_values) else "lm_ham_update_values_async(pinned nzval)")
+                       + " + lm_step + lm_observables_async / lm_frame_wait (rho, J -> host, double-buffered) per step"}
         parity = parity_check(lm, _lib, lib, torch, dist, ctx, csc_dev, state, Hmat, H0, rho_np.copy(), N, M, dt, args, rank, world, local, cdt)
 
         out = {"metric": "evolution steps/sec (N x Nocc Psi block)", "value": value, "unit": "steps/s", "n_gpus": world,

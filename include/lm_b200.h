@@ -120,6 +120,12 @@ int32_t lm_ham_update_values(lm_ham* ham, const void* nzval);
  * lm_ham_update_values.  Peierls phases never change the Gershgorin bounds, so a gauge-field ramp
  * never trips it. */
 int32_t lm_ham_update_values_async(lm_ham* ham, const void* nzval);
+/* One process per GPU, H replicated: only rank `root` supplies host values (nzval may be NULL on the other ranks); the root uploads
+ * them and every rank receives them over NVLink (ncclBroadcast), instead of one PCIe upload per rank.  Same asynchronous semantics as
+ * lm_ham_update_values_async (sticky enclosure / Hermiticity flag).  Must be called by every rank of the communicator; without a
+ * communicator it is lm_ham_update_values_async (root must be 0).  Replaces, for sharded runs, the per-process re-upload of
+ * `update_solver!(solver, mat, dt, force)` (src/evolution.jl:83-92). */
+int32_t lm_ham_update_values_bcast(lm_ham* ham, const void* nzval, int32_t root);
 
 /* Device-resident time-dependent Hamiltonian (the AbstractTimeDependentOperator branch,
  * src/evolution.jl:44-47,243).  Restates OperatorBuilder.setindex! + expand_bond

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "lm_ham_create_csc": [_vp, _i64, _i32, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_update_values": [_vp, _vp],
     "lm_ham_update_values_async": [_vp, _vp],
+    "lm_ham_update_values_bcast": [_vp, _vp, C.c_int32],
     "lm_ham_create_bonds": [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
     "lm_ham_set_fields": [_vp, _i32, _vp, _vp],
     "lm_ham_set_field_params": [_vp, _vp],

@@ -50,6 +50,7 @@ struct NcclApi {
     int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
     int (*CommInitRank)(ncclComm_h*, int, ncclUniqueId_t, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t) = nullptr;
     int (*CommDestroy)(ncclComm_h) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -62,6 +63,7 @@ static int nccl_load() {
     g_nccl.GetUniqueId = (int (*)(ncclUniqueId_t*))dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(ncclComm_h*, int, ncclUniqueId_t, int))dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_h, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
     g_nccl.CommDestroy = (int (*)(ncclComm_h))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -927,10 +929,9 @@ extern "C" int32_t lm_ham_update_values(lm_ham* h, const void* nzval) {
 // Same, without a host synchronisation: copy, scatter, and a device-side check that the new values
 // stay inside the enclosure of the last synchronous update (sticky flag, reported by the next
 // lm_frame_wait / lm_ctx_synchronize / lm_observables on the context).
-extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
-    REQUIRE(h && nzval, "lm_ham_update_values_async: NULL argument");
-    REQUIRE(!h->bond_mode, "lm_ham_update_values_async: Hamiltonian was created from bonds; use lm_ham_set_field_params");
-    REQUIRE(h->version > 0, "lm_ham_update_values_async: no synchronous update yet");
+// root < 0: every rank uploads its own copy.  root >= 0: only that rank's host values are read (uploaded on the upload stream),
+// every rank receives them over NVLink (ncclBroadcast on the compute stream, ordered after the upload and before the scatter)
+static int update_values_async(lm_ham* h, const void* nzval, int root, const char* who) {
     FWD(set_dev(h->ctx));
     lm_ctx* c = h->ctx;
     if (!c->h_async_flag) {
@@ -949,10 +950,14 @@ extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
     }
     if (h->nnz > 0) {
         const size_t bytes = c->esz() * (size_t)h->nnz;
-        CK(cudaStreamWaitEvent(c->up_stream, c->ev_nz_free, 0));       // the previous scatter has consumed d_nz
-        CK(cudaMemcpyAsync(h->d_nz, nzval, bytes, cudaMemcpyHostToDevice, c->up_stream));
-        CK(cudaEventRecord(c->ev_up_done, c->up_stream));
-        CK(cudaStreamWaitEvent(c->stream, c->ev_up_done, 0));
+        if (root < 0 || c->rank == root) {
+            if (!nzval) return fail(LM_ERR_INVALID, std::string(who) + ": NULL values on the rank that supplies them");
+            CK(cudaStreamWaitEvent(c->up_stream, c->ev_nz_free, 0));       // the previous scatter has consumed d_nz
+            CK(cudaMemcpyAsync(h->d_nz, nzval, bytes, cudaMemcpyHostToDevice, c->up_stream));
+            CK(cudaEventRecord(c->ev_up_done, c->up_stream));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_up_done, 0));
+        }
+        if (root >= 0) NCK(g_nccl.Broadcast(h->d_nz, h->d_nz, bytes, /*ncclChar*/ 0, root, c->comm, c->stream));
         const int th = 256; const long long bl = (h->nnz + th - 1) / th;
         if (c->precision == LM_C128) k_scatter_vals<double><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const double2*)h->d_nz, h->d_csc2ell, (double2*)h->d_vals);
         else k_scatter_vals<float><<<(unsigned)bl, th, 0, c->stream>>>(h->nnz, (const float2*)h->d_nz, h->d_csc2ell, (float2*)h->d_vals);
@@ -969,6 +974,28 @@ extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
     CK(cudaMemcpyAsync(c->h_async_flag, c->d_async_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     h->version++;
     return LM_OK;
+}
+extern "C" int32_t lm_ham_update_values_async(lm_ham* h, const void* nzval) {
+    REQUIRE(h && nzval, "lm_ham_update_values_async: NULL argument");
+    REQUIRE(!h->bond_mode, "lm_ham_update_values_async: Hamiltonian was created from bonds; use lm_ham_set_field_params");
+    REQUIRE(h->version > 0, "lm_ham_update_values_async: no synchronous update yet");
+    return update_values_async(h, nzval, -1, "lm_ham_update_values_async");
+}
+// One-process-per-GPU jobs: every rank holds the same H(t), so ONE rank's host values are enough - `root` uploads them, the others
+// receive them over NVLink instead of pushing seven more copies through host memory and PCIe.  nzval is read on `root` only (may be
+// NULL elsewhere).  Same asynchronous semantics as lm_ham_update_values_async; without a communicator it is that call.
+extern "C" int32_t lm_ham_update_values_bcast(lm_ham* h, const void* nzval, int32_t root) {
+    REQUIRE(h, "lm_ham_update_values_bcast: NULL argument");
+    REQUIRE(!h->bond_mode, "lm_ham_update_values_bcast: Hamiltonian was created from bonds; use lm_ham_set_field_params");
+    REQUIRE(h->version > 0, "lm_ham_update_values_bcast: no synchronous update yet");
+    lm_ctx* c = h->ctx;
+    if (c->nranks <= 1 || !c->comm) {
+        REQUIRE(nzval && root == 0, "lm_ham_update_values_bcast: single-rank context: root must be 0 and supply the values");
+        return update_values_async(h, nzval, -1, "lm_ham_update_values_bcast");
+    }
+    REQUIRE(root >= 0 && root < c->nranks, "lm_ham_update_values_bcast: root out of range");
+    REQUIRE(g_nccl.Broadcast, "lm_ham_update_values_bcast: libnccl lacks ncclBroadcast");
+    return update_values_async(h, nzval, root, "lm_ham_update_values_bcast");
 }
 
 static int ham_regen(lm_ham* h) {

@@ -82,6 +82,29 @@ Jk_s, Jk_f = lm.DensityCurrents(Hk, ks).pair_values()[2], lm.DensityCurrents(Hk,
 assert abs(rk_f.sum() - 1.0) < 1e-12
 worst = max(worst, np.abs(rk_s - rk_f).max() / np.abs(rk_f).max(), np.abs(Jk_s - Jk_f).max() / max(np.abs(Jk_f).max(), 1e-300))
 assert worst < 1e-12, ("replicated ket", worst)
+# lm_ham_update_values_bcast: only rank 0 supplies the host values of H(t) (the others pass NULL and hold garbage), every rank
+# receives them over NVLink; same frames as synchronous per-rank updates on the unsharded reference
+import scipy.sparse as sp  # noqa: E402
+_L = import_module("lm_b200._lib")
+Hs = [sp.csc_matrix(h(0.1 * k).data).astype(np.complex128) for k in range(5)]
+dev_s = lm.DeviceHam.from_csc(ctx, Hs[0], 1, coords=l.coords, lattice_dims=l.sizes)
+dev_f = lm.DeviceHam.from_csc(ref, Hs[0], 1, coords=l.coords, lattice_dims=l.sizes)
+sb = lm.DeviceState.from_psi(Psi, w, ctx=ctx, lattice=l)
+fb = lm.DeviceState.from_psi(Psi, w, ctx=ref, lattice=l, shard=False)
+nmv = C.c_int32()
+keep = []
+for k in range(1, 5):
+    nz = np.ascontiguousarray(Hs[k].data)
+    keep.append(nz)
+    _L.check(_lib.lm_ham_update_values_bcast(dev_s.handle, _L.ptr(nz) if rank == 0 else None, 0))
+    _L.check(_lib.lm_step(dev_s.handle, sb.handle, 0.1, 1e-13, 0, C.byref(nmv)))
+    _L.check(_lib.lm_ham_update_values(dev_f.handle, _L.ptr(nz)))
+    _L.check(_lib.lm_step(dev_f.handle, fb.handle, 0.1, 1e-13, 0, C.byref(nmv)))
+_L.check(_lib.lm_ctx_synchronize(ctx.handle))
+b0, b1 = lm.shard_range(M, rank, world)
+dev_b = np.abs(sb.download() - fb.download()[:, b0:b1]).max()
+assert dev_b < 1e-13, ("broadcast value update", dev_b)
+worst = max(worst, dev_b)
 t = torch.tensor([worst], device="cuda", dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
