@@ -1,6 +1,7 @@
 // Registry of the compiled stencil patterns and register-tile variants (kernels: stencil.cuh,
 // instantiated per pattern in stencil_k<id>.cu).
 #include "stencil.cuh"
+#include <cstdlib>
 
 namespace lm {
 
@@ -15,20 +16,22 @@ namespace lm {
 //   id 6  kagome NN + on-site (RC = 3)
 //   id 7  kagome NN + second neighbours + on-site (RC = 3)
 //   id 8  Kane-Mele: spin-1/2 honeycomb, spin-diagonal NN + second neighbours + on-site diagonal (RC = 4)
+//   id 9  QWZ with a diagonal on-site term (what `qwz` builds): 9 entries per row instead of the 10 of id 3
 
 #define LM_ST_DESC(id, name) {StPat<id>::rc, StPat<id>::mask, StPat<id>::imag, st_width<StPat<id>::rc>(StPat<id>::mask), name}
 static const StencilDesc g_desc[] = {
     LM_ST_DESC(0, "square-nn"), LM_ST_DESC(1, "rc1-full"), LM_ST_DESC(2, "honeycomb-nn"),
     LM_ST_DESC(3, "qwz"), LM_ST_DESC(4, "haldane"), LM_ST_DESC(5, "rc2-full"),
-    LM_ST_DESC(6, "kagome-nn"), LM_ST_DESC(7, "kagome-nnn"), LM_ST_DESC(8, "kanemele"),
+    LM_ST_DESC(6, "kagome-nn"), LM_ST_DESC(7, "kagome-nnn"), LM_ST_DESC(8, "kanemele"), LM_ST_DESC(9, "qwz-diag"),
 };
 static_assert(sizeof(g_desc) / sizeof(g_desc[0]) == LM_ST_NPAT, "pattern table out of step with StPat<>");
 int stencil_count() { return LM_ST_NPAT; }
 const StencilDesc& stencil_desc(int id) { return id >= LM_ST_RTC_BASE ? *stencil_rtc_desc(id) : g_desc[id]; }
 int stencil_find(int rc, const st_mask_t& mask) {
+    static const long skip = getenv("LM_STENCIL_SKIP") ? strtol(getenv("LM_STENCIL_SKIP"), nullptr, 0) : 0;     // debug / A-B runs: bit i hides pattern i
     int best = -1;
     for (int i = 0; i < stencil_count(); ++i) {
-        if (g_desc[i].rc != rc || !st_covers(g_desc[i].mask, mask)) continue;
+        if (g_desc[i].rc != rc || !st_covers(g_desc[i].mask, mask) || ((skip >> i) & 1)) continue;
         if (best < 0 || g_desc[i].sw < g_desc[best].sw) best = i;
     }
     return best;
@@ -93,7 +96,7 @@ int stencil_resident_ctas(int id, int v, bool c64) {
     return m < 1 ? 1 : m;
 }
 
-#define LM_ST_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define LM_ST_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 #define LM_ST_DECL(i) int stencil_launch_##i(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t); \
     int stencil_observe_##i(bool, const StencilObsArgs&, const CUtensorMap&, unsigned, cudaStream_t); void stencil_obs_shape_##i(int*, int*, int*);
 LM_ST_EACH(LM_ST_DECL)

@@ -941,7 +941,9 @@ template <> struct StPat<6> { static constexpr int rc = 3; static constexpr st_m
 template <> struct StPat<7> { static constexpr int rc = 3; static constexpr st_mask_t mask = {{0xb191ff133090c00ull, 0x34ull, 0, 0}}, imag = {{0, 0, 0, 0}}; };
 template <> struct StPat<8> { static constexpr int rc = 4; static constexpr st_mask_t mask = {{0x84a5842184a50000ull, 0xa5218421a521a5a5ull, 0, 0}},
                                                                                       imag = {{0x8421842184210000ull, 0x8421842184210000ull, 0, 0}}; };
-constexpr int LM_ST_NPAT = 9;
+//   9  QWZ as the reference builds it (src/zoo/models.jl:130-136): the on-site term `sigma_z m` is diagonal, 9 instead of 10 entries per row
+template <> struct StPat<9> { static constexpr int rc = 2; static constexpr st_mask_t mask = {{0xf0f9f0f0ull, 0, 0, 0}}, imag = {{LM_ST_IMAG3, 0, 0, 0}}; };
+constexpr int LM_ST_NPAT = 10;
 
 #ifndef __CUDACC_RTC__
 // ---- host-visible registry (stencil.cu) ----

@@ -1,7 +1,7 @@
 // Run-time specialisation of the register-tiled stencil kernels (stencil.cuh) on a DETECTED lattice pattern.
 //
 // The kernels are templates over the pattern (a type with the sparsity mask and the value classes as constexpr members);
-// nine patterns are compiled into the library (stencil.cu).  Any other pattern of at most four rows per unit cell that
+// ten patterns are compiled into the library (stencil.cu).  Any other pattern of at most four rows per unit cell that
 // couples adjacent cells - kagome with third neighbours, Kane-Mele with a spin-mixing term, a two-orbital model on the
 // honeycomb lattice, ... - gets its own instantiation here: the same headers (embedded in the library as text,
 // gen_rtc_headers.inc) are compiled by NVRTC for sm_100a with the detected mask, loaded through the driver API and

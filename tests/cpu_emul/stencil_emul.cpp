@@ -118,6 +118,7 @@ int main() {
     ok = ok && check_pattern<1, StPat<1>>("rc1-full");
     ok = ok && check_pattern<2, StPat<2>>("honeycomb-nn");
     ok = ok && check_pattern<2, StPat<3>>("qwz");
+    ok = ok && check_pattern<2, StPat<9>>("qwz-diag");
 #endif
 #if !defined(LM_EMUL_GROUP) || LM_EMUL_GROUP == 1
     ok = ok && check_pattern<2, StPat<4>>("haldane");

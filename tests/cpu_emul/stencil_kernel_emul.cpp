@@ -329,6 +329,7 @@ int main(int argc, char** argv) {
 #if LM_IN_GROUP(0)
     if (only < 0 || only == 0) ok = ok && check_pattern<1, StPat<0>>("square-nn");
     if (only < 0 || only == 1) ok = ok && check_pattern<1, StPat<1>>("rc1-full");
+    if (only < 0 || only == 10) ok = ok && check_pattern<2, StPat<9>>("qwz-diag");
     if (only < 0 || only == 5) {
         // the remaining Clenshaw / Horner modes and the direct-load kernel on one pattern each
         ok = ok && check_apply<double, 2, StPat<4>, 4, 2, 2, 2, 1, 1, 1>("haldane", 13, 9, true, 32, 1, 3);

@@ -172,7 +172,14 @@ STENCIL_CASES = {
     "honeycomb_nn": (lambda: lm.tightbinding_hamiltonian(lm.HoneycombLattice(7, 12), field=lm.LandauGauge(0.03)),
                      lambda: OP.tightbinding_hamiltonian(L.honeycomb_lattice(7, 12), field=F.LandauGauge(0.03)), 2),
     "qwz_pbc": (lambda: lm.qwz(lm.SquareLattice(14, 15, boundaries=[("axis1", True)]), field=lm.LandauGauge(0.5)),
-                lambda: OP.qwz(L.square_lattice(14, 15, periodic=(1,)), field=F.LandauGauge(0.5)), 3),
+                lambda: OP.qwz(L.square_lattice(14, 15, periodic=(1,)), field=F.LandauGauge(0.5)), 9),        # diagonal on-site term: exact mask
+    # QWZ plus an on-site orbital-mixing term sigma_x: full 2 x 2 blocks everywhere (pattern 3)
+    "qwz_sx": (lambda: lm.construct_hamiltonian(lm.SquareLattice(11, 12), 2, (np.array([[1, 0], [0, -1]], complex), 1.0), (np.array([[0, 1], [1, 0]], complex), 0.3),
+                                                (np.array([[1, -1j], [-1j, -1]], complex) / 2, lm.BravaisTranslation(axis=1)),
+                                                (np.array([[1, -1], [1, -1]], complex) / 2, lm.BravaisTranslation(axis=2)), field=lm.LandauGauge(0.1)),
+               lambda: OP.construct_hamiltonian(L.square_lattice(11, 12), 2, [(np.array([[1, 0], [0, -1]], complex), 1.0), (np.array([[0, 1], [1, 0]], complex), 0.3),
+                                                                              (np.array([[1, -1j], [-1j, -1]], complex) / 2, L.translation(axis=1, nu=2)),
+                                                                              (np.array([[1, -1], [1, -1]], complex) / 2, L.translation(axis=2, nu=2))], F.LandauGauge(0.1)), 3),
     "haldane": (lambda: lm.haldane(lm.HoneycombLattice(13, 11), 1.0, 0.2, 0.1, field=lm.SymmetricGauge(0.03)),
                 lambda: OP.haldane(L.honeycomb_lattice(13, 11), 1.0, 0.2, 0.1, field=F.SymmetricGauge(0.03)), 4),
     "haldane_torus": (lambda: lm.haldane(lm.HoneycombLattice(9, 16, boundaries=[("axis1", True), ("axis2", True)]), 1.0, 0.2, 0.1),

@@ -269,7 +269,10 @@ def test_compiled_stencil_masks_cover_reference_models():
     pats = {}
     for pid, rc, m, im in re.findall(r"StPat<(\d+)> \{ static constexpr int rc = (\d); static constexpr st_mask_t mask = \{\{(.*?)\}\},\s*imag = \{\{(.*?)\}\}; \};", src, re.S):
         pats[int(pid)] = (int(rc), sum(word(t) << (64 * k) for k, t in enumerate(m.split(","))), sum(word(t) << (64 * k) for k, t in enumerate(im.split(","))))
-    assert sorted(pats) == list(range(9)) and all(pats[k][1] == masks[k] for k in masks)
+    assert sorted(pats) == list(range(10)) and all(pats[k][1] == masks[k] for k in masks)
+    # `qwz` itself has a diagonal on-site term: pattern 9 is its exact mask (9 entries per row), pattern 3 the full-block superset
+    rcq, mq = ST.stencil_mask(OP.qwz(L.square_lattice(5, 6), field=F.LandauGauge(0.2)), 5, 6)
+    assert rcq == 2 and mq == pats[9][1] and mq & ~pats[3][1] == 0 and pats[9][2] == pats[3][2]
     wide = [
         (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6), field=F.LandauGauge(0.1)), 5, 6, 3, 6),
         (OP.tightbinding_hamiltonian(L.kagome_lattice(5, 6, periodic=(1, 2))), 5, 6, 3, 6),
@@ -346,7 +349,7 @@ def test_stencil_kernels_execute_on_cpu(tmp_path):
     """The WHOLE stencil kernels of csrc/stencil.cuh - k_apply_stencil_tma (default SpMM / propagator
     factor), k_apply_stencil and k_observe_stencil (fused localdensity + bond correlators) - executed
     on the CPU: every CUDA thread of a CTA is an OS thread (real __syncthreads, warp-shuffle
-    mailboxes, atomics, mbarrier phase rule, alignment-checked cp.async.bulk).  All nine compiled
+    mailboxes, atomics, mbarrier phase rule, alignment-checked cp.async.bulk).  All ten compiled
     patterns (one to four rows per unit cell) in the shapes the library launches, complex values and the
     real / imaginary class scalars, open / periodic / 3x3-torus / ragged lattices,
     complex128 and complex64, every MODE, and the column window + plain-store flag of the
