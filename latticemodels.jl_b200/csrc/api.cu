@@ -2734,12 +2734,19 @@ static int load_op(int n, const void* op_colmajor, OpMat* out) {
     }
     return LM_OK;
 }
+// `block` > 1: the pairs come in groups of block x block - all orbital pairs of one site (localexpect) or of one pair of sites
+// (LocalOperatorCurrents), consecutive rows on either side: one warp per group reads the rows once (k_corr_blocks)
 template <typename T>
-static int corr_pairs(lm_state* s, long long nq, const int* d_a, const int* d_b, double2* d_out) {
+static int corr_pairs(lm_state* s, long long nq, const int* d_a, const int* d_b, double2* d_out, int block = 1) {
     using T2 = typename cx2<T>::type;
     lm_ctx* c = s->ctx;
     if (nq == 0) return LM_OK;
+    static const int blocks_env = env_int("LM_CORR_BLOCKS", 1);
+    const long long ng = block > 1 ? nq / ((long long)block * block) : 0;
     if (s->dense) k_corr_pairs_dense<T2><<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(nq, s->ld, (const T2*)s->d_x, d_a, d_b, d_out);
+    else if (blocks_env && block == 2) k_corr_blocks<T, 2><<<(unsigned)((ng + 7) / 8), 256, 0, c->stream>>>(ng, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
+    else if (blocks_env && block == 3) k_corr_blocks<T, 3><<<(unsigned)((ng + 7) / 8), 256, 0, c->stream>>>(ng, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
+    else if (blocks_env && block == 4) k_corr_blocks<T, 4><<<(unsigned)((ng + 7) / 8), 256, 0, c->stream>>>(ng, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
     else k_corr_pairs<T><<<(unsigned)((nq + 7) / 8), 256, 0, c->stream>>>(nq, s->M, s->ld, (const T2*)s->d_x, s->d_w, d_a, d_b, d_out);
     c->launches++;
     CK(cudaGetLastError());
@@ -2777,8 +2784,8 @@ extern "C" int32_t lm_local_expect(lm_state* s, int32_t n_int, const void* op, v
         CK(cudaMemcpy(c->d_le_b, b.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
         c->le_N = s->N; c->le_n = n;
     }
-    if (c->precision == LM_C128) FWD(corr_pairs<double>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G));
-    else FWD(corr_pairs<float>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G));
+    if (c->precision == LM_C128) FWD(corr_pairs<double>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G, n));
+    else FWD(corr_pairs<float>(s, nq, c->d_le_a, c->d_le_b, c->d_le_G, n));
     k_localexpect_fin<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(ns, n, O, c->d_le_G, c->d_le_out);
     c->launches++;
     CK(cudaGetLastError());
@@ -2819,10 +2826,10 @@ extern "C" int32_t lm_operator_currents(lm_ham* h, lm_state* s, const void* op, 
         CK(cudaMemcpy(h->d_oc_ent, ent.data(), sizeof(int) * nq, cudaMemcpyHostToDevice));
     }
     if (c->precision == LM_C128) {
-        FWD(corr_pairs<double>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G));
+        FWD(corr_pairs<double>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G, n));
         k_opcurrents_fin<double><<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(np, n, O, h->d_oc_G, h->d_oc_ent, (const double2*)h->d_vals, h->d_oc_J);
     } else {
-        FWD(corr_pairs<float>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G));
+        FWD(corr_pairs<float>(s, nq, h->d_oc_a, h->d_oc_b, h->d_oc_G, n));
         k_opcurrents_fin<float><<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(np, n, O, h->d_oc_G, h->d_oc_ent, (const float2*)h->d_vals, h->d_oc_J);
     }
     c->launches++;

@@ -1114,6 +1114,53 @@ k_corr_pairs(long long nq, long long M, long long ld, const typename cx2<T>::typ
     gr = warp_sum(gr); gi = warp_sum(gi);
     if (lane == 0) out[q] = make_double2(gr, gi);
 }
+// Block form of the same correlators: localexpect and LocalOperatorCurrents ask for ALL NI x NI orbital pairs of a site (or of a
+// pair of sites), out[(g NI + al) NI + be] = P[rowB_g + be, rowA_g + al].  One warp per group loads the NI + NI rows once (NI when both
+// sides are the same site) and feeds NI^2 accumulators: 2 NI (NI) row reads per group instead of 2 NI^2.  rowA / rowB are the
+// per-pair arrays of k_corr_pairs; a group's base rows are its first entries.
+template <typename T, int NI>
+__global__ void __launch_bounds__(256)
+k_corr_blocks(long long ng, long long M, long long ld, const typename cx2<T>::type* __restrict__ x,
+              const double* __restrict__ w, const int* __restrict__ rowA, const int* __restrict__ rowB,
+              double2* __restrict__ out) {
+    using T2 = typename cx2<T>::type;
+    const int lane = threadIdx.x & 31;
+    const long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= ng) return;
+    const int ra = rowA[g * NI * NI], rb = rowB[g * NI * NI];
+    const bool same = ra == rb;                                    // warp-uniform
+    const T2* pa = x + (long long)ra * ld;
+    const T2* pb = x + (long long)rb * ld;
+    double gr[NI][NI], gi[NI][NI];
+#pragma unroll
+    for (int al = 0; al < NI; ++al)
+#pragma unroll
+        for (int be = 0; be < NI; ++be) { gr[al][be] = 0.0; gi[al][be] = 0.0; }
+    for (long long c = lane; c < M; c += 32) {
+        const double wc = w ? w[c] : 1.0;
+        T2 va[NI], vb[NI];
+#pragma unroll
+        for (int al = 0; al < NI; ++al) va[al] = ld_ro(pa + al * ld + c);
+#pragma unroll
+        for (int be = 0; be < NI; ++be) vb[be] = same ? va[be] : ld_ro(pb + be * ld + c);
+#pragma unroll
+        for (int al = 0; al < NI; ++al) {
+            const double ar = wc * (double)va[al].x, ai = wc * (double)va[al].y;
+#pragma unroll
+            for (int be = 0; be < NI; ++be) {
+                gr[al][be] = fma((double)vb[be].x, ar, gr[al][be]); gr[al][be] = fma((double)vb[be].y, ai, gr[al][be]);
+                gi[al][be] = fma((double)vb[be].y, ar, gi[al][be]); gi[al][be] = fma(-(double)vb[be].x, ai, gi[al][be]);
+            }
+        }
+    }
+#pragma unroll
+    for (int al = 0; al < NI; ++al)
+#pragma unroll
+        for (int be = 0; be < NI; ++be) {
+            const double r = warp_sum(gr[al][be]), i = warp_sum(gi[al][be]);
+            if (lane == 0) out[(g * NI + al) * NI + be] = make_double2(r, i);
+        }
+}
 struct OpMat { double2 m[64]; };     // n_int x n_int operator, row-major m[j * n + k], n_int <= 8
 // localexpect (src/operators/latticeutils.jl:13-20): out_s = sum_{j,k} op[j,k] P[(s,k),(s,j)],
 // G laid out [site][j][k] with G = P[(s,k),(s,j)]
