@@ -677,3 +677,30 @@ def test_run_time_specialised_stencil_patterns(case):
             assert np.abs(V - want_j).max() < 1e-13 * max(1.0, np.abs(want_j).max()), (case, M)
     finally:
         _set_rtc(-1)
+
+
+def test_spin_currents_on_kanemele():
+    """`LocalOperatorCurrents(H, P, sigma_z)` and `localexpect(sigma_z, P)` on the Kane-Mele model (src/zoo/models.jl:188-194; the
+    reference's spin-current use case, src/zoo/currents.jl:150-184): four rows per cell on the stencil kernels, correlators by the
+    block kernel (one warp per site / bond block), against the oracle; up + down = density currents."""
+    ctx = lm.default_context("c128")
+    l, lo = lm.HoneycombLattice(7, 6), L.honeycomb_lattice(7, 6)
+    Hd = lm.kanemele(l, 1.0, 0.2, field=lm.LandauGauge(0.04))
+    Ho = OP.kanemele(lo, 1.0, 0.2, field=F.LandauGauge(0.04))
+    from oracle import observables as OB
+    N = Ho.shape[0]
+    Psi = _rand_block(N, 41, seed=13) / np.sqrt(N)
+    w = np.random.default_rng(4).random(41)
+    st = lm.DeviceState.from_psi(Psi, w, ctx=ctx, lattice=l, n_int=2)
+    ost = OB.State(Psi, w, block=True)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    sx = np.array([[0, 1], [1, 0]], complex)
+    for op in (sz, sx, sz + 0.5j * sx @ sz):
+        assert np.abs(lm.localexpect(op, st).values - OB.localexpect(op, ost, 2)).max() < 1e-13
+        I, J, V = lm.LocalOperatorCurrents(Hd, st, op).pair_values()
+        want = np.array([OB.operator_current(Ho, ost, op, i, j, 2) for i, j in zip(I, J)])
+        assert np.abs(V - want).max() < 1e-13
+    dc = lm.Currents(lm.DensityCurrents(Hd, st))
+    up = lm.Currents(lm.LocalOperatorCurrents(Hd, st, [[1, 0], [0, 0]]))
+    dn = lm.Currents(lm.LocalOperatorCurrents(Hd, st, [[0, 0], [0, 1]]))
+    assert abs((up + dn).currents - dc.currents).max() < 1e-13
