@@ -117,15 +117,19 @@ static int launch_var(int variant, bool c64, int mode, const StencilArgs& a, con
 
 // observables kernel shape per RC: T1 x T2 cells per thread, W1 x W2 warps per CTA
 // (WIDE = more than 6 forward entries per row: one cell per thread keeps the partial sums in registers)
+#ifndef LM_OBS_WIDE_W1
+#define LM_OBS_WIDE_W1 4
+#define LM_OBS_WIDE_W2 4
+#endif
 template <int RC, bool WIDE> struct ObsShape;
 template <> struct ObsShape<1, false> { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };   // 8 x 4 cells, 256 threads
 template <> struct ObsShape<1, true>  { static constexpr int T1 = 2, T2 = 2, W1 = 4, W2 = 2; };
 template <> struct ObsShape<2, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 x 4 cells, 256 threads
 template <> struct ObsShape<2, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };   // 4 x 2 cells, 256 threads
 template <> struct ObsShape<3, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 3 rows x (1 + 2 NF <= 9) sums per cell
-template <> struct ObsShape<3, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };
+template <> struct ObsShape<3, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };   // (512-thread CTAs measured slower on kagome NN + NNN: 3.37 -> 4.09 ms)
 template <> struct ObsShape<4, false> { static constexpr int T1 = 1, T2 = 2, W1 = 4, W2 = 2; };   // 4 rows x (1 + 2 NF <= 7) sums per cell
-template <> struct ObsShape<4, true>  { static constexpr int T1 = 1, T2 = 1, W1 = 4, W2 = 2; };
+template <> struct ObsShape<4, true>  { static constexpr int T1 = 1, T2 = 1, W1 = LM_OBS_WIDE_W1, W2 = LM_OBS_WIDE_W2; };   // one cell per thread: 4 x 4-cell patches (512 threads) keep the staged / own row ratio at 1.9 (Kane-Mele 2.34 -> 2.10 ms)
 // WIDE: two cells per thread would exceed the 64 partial sums a thread folds (k_observe_stencil)
 template <int RC> constexpr bool obs_wide(int nf) { return RC == 3 ? nf > 4 : (RC == 4 ? nf > 3 : nf > 6); }
 

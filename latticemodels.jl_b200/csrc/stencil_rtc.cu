@@ -62,6 +62,9 @@ bool stencil_rtc_obs_shape(int rc, int nf, int* t1, int* t2, int* w1, int* w2) {
     if (per_cell > 64) return false;
     if (rc == 1 && 4 * per_cell <= 64) { *t1 = 2; *t2 = 2; return true; }
     *t1 = 1; *t2 = (2 * per_cell <= 64) ? 2 : 1;
+    // one cell per thread: 4 x 4-cell patches (512 threads) for four rows per cell and for the widest three-row patterns
+    // (measured: Kane-Mele + spin mixing 2.69 -> 2.30 ms, kagome t1 t2 t3 6.48 -> 5.39 ms; kagome NN + NNN loses, 3.37 -> 4.09 ms)
+    if (*t2 == 1 && (rc == 4 || (rc == 3 && per_cell > 48))) *w2 = 4;
     return true;
 }
 

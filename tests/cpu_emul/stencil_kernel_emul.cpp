@@ -284,10 +284,11 @@ static bool check_pattern(const char* name) {
         ok = ok && check_apply<float, RC, MK, 2, 2, 2, 2, 1, 3, 1>(name, 9, 7, true, 136, 1, 7);
         constexpr int NFW = st_nfwd<RC>(MK::mask);
         constexpr int OT2 = (RC == 3 ? NFW > 4 : NFW > 3) ? 1 : 2;
-        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, 2>(name, 7, 5, false, 37, 40, true, 1);
-        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, 2>(name, 4, 5, true, 130, 136, false, 2);
-        ok = ok && check_observe<float, RC, MK, 1, OT2, 4, 2>(name, 3, 3, true, 70, 72, true, 4);
-        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, 2>(name, 14, 13, true, 100, 104, true, 2, true);
+        constexpr int OW2 = (OT2 == 1 && RC == 4) ? 4 : 2;   // four rows, one cell per thread: 4 x 4-cell patches, 512 threads (ObsShape<4, true>)
+        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, OW2>(name, 7, 5, false, 37, 40, true, 1);
+        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, OW2>(name, 4, 5, true, 130, 136, false, 2);
+        ok = ok && check_observe<float, RC, MK, 1, OT2, 4, OW2>(name, 3, 3, true, 70, 72, true, 4);
+        ok = ok && check_observe<double, RC, MK, 1, OT2, 4, OW2>(name, 14, 13, true, 100, 104, true, 2, true);
     } else {
         // variant 2: 4x2 tiles, 2x2 warps (8 x 4 cell patches)
         ok = ok && check_apply<double, RC, MK, 4, 2, 2, 2, 1, 3, 1>(name, 11, 5, false, 40, 1, 0);
