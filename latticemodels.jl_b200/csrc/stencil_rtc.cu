@@ -25,6 +25,7 @@ struct RtcKernel { void* mod = nullptr; void* fn = nullptr; bool tried = false; 
 struct RtcPattern {
     StencilDesc desc;
     std::string name;
+    int device = 0;                 // the modules live in this device's primary context (one process per GPU: always the same one)
     RtcKernel apply[2][4];          // [complex64][MODE]
     RtcKernel obs[2];
 };
@@ -329,11 +330,16 @@ int stencil_rtc_warm(int, bool) { return -1; }
 // register a detected pattern (or find it again); returns its id >= LM_ST_RTC_BASE, -1 if run-time compilation is not available
 int stencil_rtc_register(int rc, const st_mask_t& mask, const st_mask_t& imag) {
     if (rc < 1 || rc > 4 || !stencil_rtc_available()) return -1;
+    int dev = 0;
+#ifndef LM_CPU_EMUL
+    cudaGetDevice(&dev);
+#endif
     for (size_t i = 0; i < g_rtc.size(); ++i) {
         const StencilDesc& d = g_rtc[i]->desc;
-        if (d.rc == rc && !memcmp(&d.mask, &mask, sizeof(mask)) && !memcmp(&d.imag, &imag, sizeof(imag))) return LM_ST_RTC_BASE + (int)i;
+        if (g_rtc[i]->device == dev && d.rc == rc && !memcmp(&d.mask, &mask, sizeof(mask)) && !memcmp(&d.imag, &imag, sizeof(imag))) return LM_ST_RTC_BASE + (int)i;
     }
     RtcPattern* p = new RtcPattern;
+    p->device = dev;
     char nm[96];
     snprintf(nm, sizeof(nm), "rtc-rc%d-%llx:%llx:%llx", rc, mask.w[2], mask.w[1], mask.w[0]);
     p->name = nm;
