@@ -127,6 +127,16 @@ function update_values!(d::DeviceHam, m::SparseMatrixCSC{ComplexF64,Int64})
     check(ccall((:lm_ham_update_values, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}), d.handle, m.nzval))
     d.src = m; d
 end
+# Multi-process runs (one Julia process per GPU, the same H(t) in every process): only `root` hands its host values over, the other
+# ranks receive them over NVLink (ncclBroadcast) instead of one PCIe upload per process.  Asynchronous like lm_ham_update_values_async:
+# `m.nzval` must stay alive until the next synchronising call (lm_frame_wait / lm_ctx_synchronize / an observable); every rank of the
+# communicator must make the call.
+function update_values_bcast!(d::DeviceHam, m::Union{Nothing,SparseMatrixCSC{ComplexF64,Int64}}, root::Integer = 0)
+    check(ccall((:lm_ham_update_values_bcast, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int32),
+                d.handle, m === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(m.nzval), root))
+    m === nothing || (d.src = m)
+    d
+end
 function currents_pairs(d::DeviceHam)
     d.pairs === nothing || return d.pairs
     np = Ref{Int64}(0)
@@ -584,6 +594,6 @@ end
 update_solver!(s::B200Exp, mat::DeviceMatrix, dt, force = false) = (s.dt = dt; s.dev = mat.dev; s.mat = mat; nothing)
 
 export B200Exp, PsiProjector, Context, B200Hamiltonian, settime!, FrameSink, psi_projector, psi_densitymatrix, eigs_lowest,
-       dense_state, psi_columns, shard_range, unique_id, comm_init!, peer_handle, peer_attach!, set_replicated!
+       dense_state, psi_columns, shard_range, unique_id, comm_init!, peer_handle, peer_attach!, set_replicated!, update_values_bcast!
 
 end # module
