@@ -69,7 +69,15 @@ bool stencil_rtc_obs_shape(int rc, int nf, int* t1, int* t2, int* w1, int* w2) {
     return true;
 }
 
-#ifndef LM_CPU_EMUL
+// gen_rtc_headers.inc is written by build.py; a bare `nvcc -c stencil_rtc.cu` without it still compiles (run-time specialisation off)
+#if defined(LM_CPU_EMUL)
+#define LM_RTC_OFF 1
+#elif defined(__has_include)
+#if !__has_include("gen_rtc_headers.inc")
+#define LM_RTC_OFF 1
+#endif
+#endif
+#ifndef LM_RTC_OFF
 #include "gen_rtc_headers.inc"      // g_rtc_common_cuh, g_rtc_stencil_cuh: the text of common.cuh / stencil.cuh (written by build.py)
 
 // ---- NVRTC through dlopen ----
@@ -319,7 +327,7 @@ int stencil_rtc_warm(int id, bool c64) {
     }
     return 0;
 }
-#else   // CPU execution harness: no run-time compilation
+#else   // CPU execution harness / no embedded headers: no run-time compilation
 long long stencil_rtc_compile_only(int, const st_mask_t&, const st_mask_t&, bool, int) { return -1; }
 bool stencil_rtc_available() { return false; }
 int stencil_rtc_launch(int, bool, int, const StencilArgs&, const CUtensorMap&, dim3, cudaStream_t) { return -1; }
