@@ -35,6 +35,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define REQUIRE(cond, msg) do { if (!(cond)) return fail(LM_ERR_INVALID, msg); } while (0)
 #define FWD(expr) do { int _s = (expr); if (_s != LM_OK) return _s; } while (0)
 // tuning knobs (environment overrides are for the sweep harness only)
+static const int LM_RTC_MISS = -1000;       // internal: a run-time specialised kernel is not available, take the generic path (never leaves the library)
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
 extern "C" const char* lm_last_error(void) { return g_err.c_str(); }
@@ -1777,6 +1778,7 @@ static int apply_stencil(lm_ham* h, long long ld, const void* x, void* y, const 
     static const int herm_env = env_int("LM_STENCIL_HERM", 1);
     a.herm = ((g_stencil_herm >= 0 ? g_stencil_herm : herm_env) && h->hermitian) ? 1 : 0;
     const int st = stencil_launch(h->st_id, variant, c->precision != LM_C128, mode, a, tmx, grid, c->stream);
+    if (st == -1 && h->st_id >= LM_ST_RTC_BASE) return LM_RTC_MISS;      // run-time compilation of this term form failed: apply() falls back to the ELL kernels
     if (st == -1) return fail(LM_ERR_UNSUPPORTED, "apply_stencil: kernel variant not compiled");
     if (st != 0) return fail(LM_ERR_CUDA, "apply_stencil: cudaFuncSetAttribute failed");
     c->launches++;
@@ -1821,8 +1823,10 @@ static int apply(lm_ham* h, long long ld, const void* x, void* y, const void* z,
     //                 2 = register gather over plan tiles (L1 patch reuse)
     // n_int = 2 models: site-blocked gather (3 = force, default on when the block view exists)
     static const int sites_env = env_int("LM_APPLY_SITES", 1);
-    if (stencil_path(h, ld) && alpha != zc(0, 0))
-        return apply_stencil(h, ld, x, y, z, u, alpha, gamma, beta, delta);
+    if (stencil_path(h, ld) && alpha != zc(0, 0)) {
+        const int st = apply_stencil(h, ld, x, y, z, u, alpha, gamma, beta, delta);
+        if (st != LM_RTC_MISS) return st;
+    }
     if (h->d_scols && ld >= 32 && ((tiled_env < 0 && sites_env) || tiled_env == 3)) return apply_sites(h, ld, x, y, z, u, alpha, gamma, beta, delta);
     // default: tile-order register gather whenever the host supplied site coordinates
     if (h->plan_from_coords && ld >= 32 && (tiled_env == 2 || tiled_env < 0)) return apply_rows(h, ld, x, y, z, u, alpha, gamma, beta, delta);
@@ -2433,6 +2437,7 @@ static int observe_stencil(lm_ham* h, lm_state* s) {
                              64u, (unsigned)((P2 + 2) * h->st_rc), (unsigned)(P1 + 1)) == 0 ? 1 : 0;
     }
     const int st = stencil_observe(h->st_id, c->precision != LM_C128, a, tmx, (unsigned)(np1 * np2 * ngroups), c->stream);
+    if (st == -1 && h->st_id >= LM_ST_RTC_BASE) return LM_RTC_MISS;      // run-time compilation of the observables kernel failed: observe() falls back
     if (st != 0) return fail(LM_ERR_CUDA, "observe_stencil: launch failed");
     c->launches++;
     CK(cudaGetLastError());
@@ -2442,7 +2447,10 @@ static int observe_stencil(lm_ham* h, lm_state* s) {
 template <typename T>
 static int observe(lm_ham* h, lm_state* s, bool want_j) {
     static const int obs_stencil_env = env_int("LM_OBS_STENCIL", 1);
-    if (h->st_id >= 0 && h->d_st_out && want_j && s->M >= 32 && obs_stencil_env && g_apply_path_override < 0) return observe_stencil(h, s);
+    if (h->st_id >= 0 && h->d_st_out && want_j && s->M >= 32 && obs_stencil_env && g_apply_path_override < 0) {
+        const int st = observe_stencil(h, s);
+        if (st != LM_RTC_MISS) return st;
+    }
     static const int obs_tiled_env = env_int("LM_OBS_TILED", -1);
     if (h->obs_tiled && want_j && s->M >= 16 && obs_tiled_env != 0) return observe_tiled<T>(h, s);
     // ELL slots are processed WB at a time; a density-only pass has no active slot (k0 = W)
