@@ -12,8 +12,10 @@ A "step" is one application of exp(-i H dt) to the whole Psi block (all ranks' c
 Strong scaling: the block is fixed, its columns are sharded over the ranks, H is replicated.
   value     : steps/s with Psi resident in HBM (K lm_step calls, CUDA events, max over ranks)
   e2e       : steps/s through the C ABI with HOST buffers every step: H values uploaded from
-              pinned host memory (host-assembled time-dependent H path), step, fused
+              pinned host memory (host-assembled time-dependent H path; N > 1: rank 0 uploads, the
+              other ranks receive them over NVLink, lm_ham_update_values_bcast), step, fused
               localdensity + bond currents reduced (all-reduced for N > 1) and copied back
+  secondary : the default run (c4) also carries configs 3 and 2 as sub-objects (same legs and checks)
   roofline  : the dominant kernel (k_apply_stencil_tma = lattice-stencil SpMM fused with one
               product-form propagator factor): algorithmic bytes per launch / average launch
               duration vs the measured HBM copy bandwidth
